@@ -1,0 +1,31 @@
+# Top-level build: the CUDA library (C ABI), the `sickle` CLI host, and the test oracle.
+#   make lib     -> sickle_b200/libsickle_b200.so   (sm_100a only)
+#   make cli     -> bin/sickle                       (drop-in `sickle se|pe` host over the C ABI)
+#   make oracle  -> oracle/_build/*, oracle/_ref/* (the latter only where /root/reference exists)
+NVCC      ?= /usr/local/cuda/bin/nvcc
+ARCH      := -gencode arch=compute_100a,code=sm_100a
+NVFLAGS   := $(ARCH) -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function -Xptxas -v
+CSRC      := sickle_b200/csrc
+LIB       := sickle_b200/libsickle_b200.so
+KERNELS   := $(wildcard $(CSRC)/*.cuh) include/sickle_b200.h
+
+.PHONY: all lib cli oracle clean
+all: lib cli oracle
+
+lib: $(LIB)
+$(LIB): $(CSRC)/capi.cu $(KERNELS)
+	$(NVCC) $(NVFLAGS) -shared $(CSRC)/capi.cu -o $@ 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; exit 1)
+	@grep -E "error|warning: v|spill" $(CSRC)/ptxas.log | grep -v "0 bytes spill" || true
+
+cli: bin/sickle
+bin/sickle: host/sickle_main.cpp host/trimmer.cpp host/trimmer.h include/sickle_b200.h $(LIB)
+	@mkdir -p bin
+	g++ -O2 -std=c++17 -Wall -Iinclude host/sickle_main.cpp host/trimmer.cpp -o $@ \
+	    -Lsickle_b200 -lsickle_b200 -lz -lpthread -Wl,-rpath,'$$ORIGIN/../sickle_b200'
+
+oracle:
+	$(MAKE) -C oracle all
+
+clean:
+	rm -rf $(LIB) bin $(CSRC)/ptxas.log
+	$(MAKE) -C oracle clean

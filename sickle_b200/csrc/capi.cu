@@ -1,0 +1,463 @@
+// capi.cu -- host runtime behind include/sickle_b200.h: slots, pinned double buffering, streams,
+// kernel launches.  The only public symbols are the extern "C" entry points of the header.
+//
+// Pipeline per slot (one CUDA stream per slot; slots overlap each other's copies and kernels):
+//   H2D(in) -> K1 line index (per input) -> K2 trim+route+scan -> K3 emit -> finalize -> D2H(summary)
+//   sk_wait: wait summary, D2H(out streams, exact sizes), return pointers into pinned memory.
+// This replaces the reference's two-stage overlap (detached output thread while the main thread
+// reads the next batch: src/trim_single.cpp:336-339, src/trim_paired.cpp:444-458).
+#include "../../include/sickle_b200.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "k1_index.cuh"
+#include "k2_trim.cuh"
+#include "k3_emit.cuh"
+#include "sk_device.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+void set_err(const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof g_err, fmt, ap);
+    va_end(ap);
+}
+
+#define SK_CUDA(call)                                                                        \
+    do {                                                                                     \
+        cudaError_t e__ = (call);                                                            \
+        if (e__ != cudaSuccess) {                                                            \
+            set_err("CUDA error %s at %s:%d: %s", cudaGetErrorName(e__), __FILE__, __LINE__, \
+                    cudaGetErrorString(e__));                                                \
+            return SK_E_CUDA;                                                                \
+        }                                                                                    \
+    } while (0)
+
+constexpr uint64_t kPad = 64;           // readable padding after every device input buffer
+constexpr uint64_t kMaxSlotBytes = (1ull << 31) - 4096;
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_done = nullptr;
+    cudaEvent_t ev_stage[3] = {nullptr, nullptr, nullptr};   // after K1, after K2, after K3
+    char *h_in[2] = {nullptr, nullptr};
+    char *h_out[3] = {nullptr, nullptr, nullptr};
+    uint8_t *d_in[2] = {nullptr, nullptr};
+    uint8_t *d_out[3] = {nullptr, nullptr, nullptr};
+    uint64_t out_cap[3] = {0, 0, 0};
+    uint32_t *d_line_end[2] = {nullptr, nullptr};
+    sk::RecDesc *d_desc[2] = {nullptr, nullptr};
+    unsigned long long *d_status_k1[2] = {nullptr, nullptr};
+    unsigned long long *d_status_k2 = nullptr;
+    sk::Control *d_ctl = nullptr;
+    sk::DevResult *d_res = nullptr;
+    sk::DevResult *h_res = nullptr;
+    uint32_t epoch = 0;
+    bool busy = false;
+    bool device_mode = false;
+    uint64_t up_lo[2] = {0, 0}, up_hi[2] = {0, 0};   // byte range already uploaded by sk_upload
+    uint64_t base[2] = {0, 0};                       // buffer offset of DevInput.data for the batch
+    uint32_t first[2] = {0, 0};                      // start - base (0..15)
+    uint8_t *ext_out[3] = {nullptr, nullptr, nullptr};
+    uint32_t launches = 0;
+};
+
+}  // namespace
+
+struct sk_ctx {
+    int device = 0;
+    int sm_count = 148;
+    uint64_t slot_bytes = 0;
+    uint32_t line_cap = 0;       // lines per input
+    uint32_t k1_tiles_cap = 0;
+    uint32_t k2_tiles_cap = 0;
+    int n_inputs = 1;
+    sk_params params{};
+    sk::DevParams dev{};
+    std::vector<Slot> slots;
+    bool host_buffers = false;
+};
+
+namespace {
+
+int make_dev_params(const sk_params &p, sk::DevParams &d) {
+    // quality_constants {offset, min, max}: reference src/sickle.h:85-91
+    switch (p.qualtype) {
+        case SK_QUAL_SANGER: d.qoff = 33; d.qmin = 33; d.qmax = 126; break;
+        case SK_QUAL_SOLEXA: d.qoff = 64; d.qmin = 58; d.qmax = 112; break;
+        case SK_QUAL_ILLUMINA: d.qoff = 64; d.qmin = 64; d.qmax = 110; break;
+        default: set_err("invalid qualtype %d", p.qualtype); return SK_E_ARG;
+    }
+    if (p.qual_threshold < 0 || p.length_threshold < 0) { set_err("thresholds must be >= 0"); return SK_E_ARG; }
+    if (p.mode < SK_MODE_SE || p.mode > SK_MODE_PE_INTER_M) { set_err("invalid mode %d", p.mode); return SK_E_ARG; }
+    d.qthr = p.qual_threshold;
+    d.lthr = p.length_threshold;
+    d.no_fiveprime = p.no_fiveprime ? 1 : 0;
+    d.trunc_n = p.trunc_n ? 1 : 0;
+    d.mode = p.mode;
+    d.emu_threads = p.emulate_threads > 1 ? p.emulate_threads : 1;
+    d.has_singles = p.has_singles ? 1 : 0;
+    return SK_OK;
+}
+
+void free_slot(Slot &s) {
+    for (int i = 0; i < 2; ++i) {
+        if (s.h_in[i]) cudaFreeHost(s.h_in[i]);
+        if (s.d_in[i]) cudaFree(s.d_in[i]);
+        if (s.d_line_end[i]) cudaFree(s.d_line_end[i]);
+        if (s.d_desc[i]) cudaFree(s.d_desc[i]);
+        if (s.d_status_k1[i]) cudaFree(s.d_status_k1[i]);
+    }
+    for (int i = 0; i < 3; ++i) {
+        if (s.h_out[i]) cudaFreeHost(s.h_out[i]);
+        if (s.d_out[i]) cudaFree(s.d_out[i]);
+    }
+    if (s.d_status_k2) cudaFree(s.d_status_k2);
+    if (s.d_ctl) cudaFree(s.d_ctl);
+    if (s.d_res) cudaFree(s.d_res);
+    if (s.h_res) cudaFreeHost(s.h_res);
+    if (s.ev_begin) cudaEventDestroy(s.ev_begin);
+    if (s.ev_end) cudaEventDestroy(s.ev_end);
+    if (s.ev_done) cudaEventDestroy(s.ev_done);
+    for (auto &e : s.ev_stage) if (e) cudaEventDestroy(e);
+    if (s.stream) cudaStreamDestroy(s.stream);
+    s = Slot{};
+}
+
+int alloc_slot(sk_ctx *c, Slot &s, bool host_buffers) {
+    const uint64_t sb = c->slot_bytes;
+    SK_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+    SK_CUDA(cudaEventCreate(&s.ev_begin));
+    SK_CUDA(cudaEventCreate(&s.ev_end));
+    for (auto &e : s.ev_stage) SK_CUDA(cudaEventCreate(&e));
+    SK_CUDA(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
+    for (int i = 0; i < c->n_inputs; ++i) {
+        if (host_buffers) {
+            SK_CUDA(cudaHostAlloc((void **)&s.h_in[i], sb + kPad, cudaHostAllocDefault));
+            SK_CUDA(cudaMalloc((void **)&s.d_in[i], sb + kPad));
+            SK_CUDA(cudaMemset(s.d_in[i], 0, sb + kPad));
+        }
+        SK_CUDA(cudaMalloc((void **)&s.d_line_end[i], (size_t)c->line_cap * sizeof(uint32_t) + 64));
+        SK_CUDA(cudaMalloc((void **)&s.d_desc[i], ((size_t)c->line_cap / 4 + 1) * sizeof(sk::RecDesc)));
+        SK_CUDA(cudaMalloc((void **)&s.d_status_k1[i], (size_t)c->k1_tiles_cap * 8));
+        SK_CUDA(cudaMemset(s.d_status_k1[i], 0, (size_t)c->k1_tiles_cap * 8));
+    }
+    SK_CUDA(cudaMalloc((void **)&s.d_status_k2, (size_t)c->k2_tiles_cap * 8 * sk::kMaxStreams));
+    SK_CUDA(cudaMemset(s.d_status_k2, 0, (size_t)c->k2_tiles_cap * 8 * sk::kMaxStreams));
+    if (host_buffers) {
+        // stream capacities: an output stream never exceeds the bytes of the inputs feeding it
+        const int mode = c->params.mode;
+        uint64_t cap[3] = {sb, 0, 0};
+        if (mode == SK_MODE_PE_2FILE) { cap[1] = sb; cap[2] = c->params.has_singles ? 2 * sb : 0; }
+        if (mode == SK_MODE_PE_INTER) cap[2] = c->params.has_singles ? sb : 0;
+        for (int k = 0; k < 3; ++k) {
+            s.out_cap[k] = cap[k];
+            if (!cap[k]) continue;
+            SK_CUDA(cudaHostAlloc((void **)&s.h_out[k], cap[k] + kPad, cudaHostAllocDefault));
+            SK_CUDA(cudaMalloc((void **)&s.d_out[k], cap[k] + kPad));
+        }
+    }
+    SK_CUDA(cudaMalloc((void **)&s.d_ctl, sizeof(sk::Control)));
+    sk::Control z;
+    memset(&z, 0, sizeof z);
+    z.err_key = sk::kNoError;
+    SK_CUDA(cudaMemcpy(s.d_ctl, &z, sizeof z, cudaMemcpyHostToDevice));
+    SK_CUDA(cudaMalloc((void **)&s.d_res, sizeof(sk::DevResult)));
+    SK_CUDA(cudaHostAlloc((void **)&s.h_res, sizeof(sk::DevResult), cudaHostAllocDefault));
+    return SK_OK;
+}
+
+// Enqueue K1..K3 + finalize for one batch on `st`.
+// Input i is bytes [first_i, n_i) relative to the 16-byte aligned pointer in_i (first_i <= 15).
+int launch_batch(sk_ctx *c, Slot &s, const uint8_t *in0, uint32_t first0, uint64_t n0, const uint8_t *in1,
+                 uint32_t first1, uint64_t n1, uint8_t *const out[3], const uint64_t out_cap[3], cudaStream_t st) {
+    s.epoch += 1;
+    if ((s.epoch & (uint32_t)sk::kEpochMask) == 0) {  // epoch tag wrapped: clear the status words once
+        for (int i = 0; i < c->n_inputs; ++i) SK_CUDA(cudaMemsetAsync(s.d_status_k1[i], 0, (size_t)c->k1_tiles_cap * 8, st));
+        SK_CUDA(cudaMemsetAsync(s.d_status_k2, 0, (size_t)c->k2_tiles_cap * 8 * sk::kMaxStreams, st));
+        s.epoch += 1;
+    }
+    sk::DevInput di[2];
+    const uint8_t *ins[2] = {in0, in1};
+    const uint64_t ns[2] = {n0, n1};
+    const uint32_t firsts[2] = {first0, first1};
+    for (int i = 0; i < 2; ++i) {
+        di[i].data = ins[i];
+        di[i].first = firsts[i];
+        di[i].nbytes = (uint32_t)ns[i];
+        di[i].line_end = s.d_line_end[i];
+        di[i].line_cap = c->line_cap;
+    }
+    if (c->n_inputs == 1) { di[1].data = nullptr; di[1].first = 0; di[1].nbytes = 0; di[1].line_end = nullptr; di[1].line_cap = 0; }
+    sk::OutPtrs op;
+    for (int k = 0; k < 3; ++k) { op.p[k] = out[k]; op.cap[k] = out[k] ? out_cap[k] : 0; }
+
+    s.launches = 0;
+    SK_CUDA(cudaEventRecord(s.ev_begin, st));
+    const int resident = c->sm_count * 8;
+    for (int i = 0; i < c->n_inputs; ++i) {
+        const uint32_t tiles = (uint32_t)((ns[i] + sk::kK1TileBytes - 1) / sk::kK1TileBytes);
+        if (!tiles) continue;
+        const int grid = tiles < (uint32_t)resident ? (int)tiles : resident;
+        sk::k1_line_index<<<grid, sk::kK1Threads, 0, st>>>(di[i], s.d_ctl, i, s.d_status_k1[i], tiles, s.epoch);
+        s.launches++;
+    }
+    SK_CUDA(cudaEventRecord(s.ev_stage[0], st));
+    {
+        // units <= bytes / 4 (a line is at least its '\n'); usually ~bytes/325
+        const uint64_t max_units = (ns[0] + ns[1]) / 4 + 1;
+        uint64_t tiles = (max_units + sk::kK2UnitsPerTile - 1) / sk::kK2UnitsPerTile;
+        const int grid = tiles < (uint64_t)resident ? (int)tiles : resident;
+        sk::k2_trim_route<<<grid, sk::kK2Threads, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, s.d_desc[0], s.d_desc[1],
+                                                           s.d_status_k2, c->k2_tiles_cap, s.epoch);
+        SK_CUDA(cudaEventRecord(s.ev_stage[1], st));
+        sk::k3_emit<<<resident, sk::kK3Threads, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, s.d_desc[0], s.d_desc[1], op);
+        SK_CUDA(cudaEventRecord(s.ev_stage[2], st));
+        sk::k_finalize<<<1, 32, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, op, s.d_res);
+        s.launches += 3;
+    }
+    SK_CUDA(cudaEventRecord(s.ev_end, st));
+    SK_CUDA(cudaGetLastError());
+    return SK_OK;
+}
+
+void fill_result(const Slot &s, sk_result *res) {
+    const sk::DevResult &r = *s.h_res;
+    memset(res, 0, sizeof *res);
+    for (int k = 0; k < 3; ++k) res->out_bytes[k] = r.out_bytes[k];
+    for (int k = 0; k < 2; ++k) {
+        // device offsets are relative to the aligned-down batch pointer; consumed counts from `start`
+        const uint64_t first = s.first[k];
+        res->consumed[k] = r.consumed[k] > first ? r.consumed[k] - first : 0;
+        res->records[k] = r.records[k];
+    }
+    res->kept = r.counters[0]; res->discard = r.counters[1];
+    res->kept_p = r.counters[2]; res->discard_p = r.counters[3];
+    res->kept_s1 = r.counters[4]; res->kept_s2 = r.counters[5];
+    res->discard_s1 = r.counters[6]; res->discard_s2 = r.counters[7];
+    res->error.kind = r.err_kind; res->error.file = r.err_file; res->error.record = r.err_record;
+    res->error.position = r.err_position; res->error.byte = r.err_byte;
+    for (int k = 0; k < 4; ++k) {
+        res->error.line_off[k] = r.err_line_off[k] + s.base[r.err_file & 1];
+        res->error.line_len[k] = r.err_line_len[k];
+    }
+    res->kernel_launches = s.launches;
+}
+
+int stage_times(const Slot &s, sk_result *res) {
+    SK_CUDA(cudaEventElapsedTime(&res->kernel_ms, s.ev_begin, s.ev_end));
+    SK_CUDA(cudaEventElapsedTime(&res->stage_ms[0], s.ev_begin, s.ev_stage[0]));
+    SK_CUDA(cudaEventElapsedTime(&res->stage_ms[1], s.ev_stage[0], s.ev_stage[1]));
+    SK_CUDA(cudaEventElapsedTime(&res->stage_ms[2], s.ev_stage[1], s.ev_stage[2]));
+    SK_CUDA(cudaEventElapsedTime(&res->stage_ms[3], s.ev_stage[2], s.ev_end));
+    return SK_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+int sk_abi_version(void) { return SK_ABI_VERSION; }
+
+int sk_device_count(void) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess) { set_err("cudaGetDeviceCount: %s", cudaGetErrorString(e)); return -1; }
+    return n;
+}
+
+const char *sk_last_error(void) { return g_err; }
+
+uint64_t sk_slot_bytes(const sk_ctx *ctx) { return ctx ? ctx->slot_bytes : 0; }
+
+sk_ctx *sk_create(int device, uint64_t slot_bytes, int n_slots, const sk_params *params) {
+    if (!params || slot_bytes == 0 || slot_bytes > kMaxSlotBytes || n_slots < 0 || n_slots > 64) {
+        set_err("sk_create: bad arguments (slot_bytes=%llu n_slots=%d)", (unsigned long long)slot_bytes, n_slots);
+        return nullptr;
+    }
+    sk::DevParams dp;
+    if (make_dev_params(*params, dp) != SK_OK) return nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) {
+        set_err("sk_create: CUDA device %d not available (%d devices) -- there is no CPU fallback", device, ndev);
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) { set_err("cudaSetDevice(%d) failed", device); return nullptr; }
+    sk_ctx *c = new (std::nothrow) sk_ctx();
+    if (!c) { set_err("out of memory"); return nullptr; }
+    c->device = device;
+    cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, device);
+    c->slot_bytes = (slot_bytes + 15) & ~15ull;
+    c->params = *params;
+    c->dev = dp;
+    c->n_inputs = params->mode == SK_MODE_PE_2FILE ? 2 : 1;
+    // line index capacity: average line >= SICKLE_B200_MIN_LINE_BYTES bytes (default 4, '\n' included)
+    uint64_t min_line = 4;
+    if (const char *e = getenv("SICKLE_B200_MIN_LINE_BYTES")) { long v = atol(e); if (v >= 1 && v <= 1024) min_line = (uint64_t)v; }
+    c->line_cap = (uint32_t)(c->slot_bytes / min_line + 8) & ~3u;
+    c->k1_tiles_cap = (uint32_t)((c->slot_bytes + sk::kK1TileBytes - 1) / sk::kK1TileBytes) + 1;
+    c->k2_tiles_cap = (uint32_t)(((uint64_t)c->line_cap / 4 + sk::kK2UnitsPerTile - 1) / sk::kK2UnitsPerTile) + 2;
+    c->host_buffers = n_slots > 0;
+    const int ns = n_slots > 0 ? n_slots : 1;
+    c->slots.resize(ns);
+    for (int i = 0; i < ns; ++i) {
+        if (alloc_slot(c, c->slots[i], c->host_buffers) != SK_OK) {
+            for (auto &s : c->slots) free_slot(s);
+            delete c;
+            return nullptr;
+        }
+    }
+    return c;
+}
+
+void sk_destroy(sk_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    for (auto &s : ctx->slots) {
+        if (s.stream) cudaStreamSynchronize(s.stream);
+        free_slot(s);
+    }
+    delete ctx;
+}
+
+char *sk_in_buffer(sk_ctx *ctx, int slot, int which) {
+    if (!ctx || !ctx->host_buffers || slot < 0 || slot >= (int)ctx->slots.size() || which < 0 || which >= ctx->n_inputs) {
+        set_err("sk_in_buffer: bad slot/which");
+        return nullptr;
+    }
+    return ctx->slots[slot].h_in[which];
+}
+
+int sk_upload(sk_ctx *ctx, int slot, int which, uint64_t offset, uint64_t nbytes) {
+    if (!ctx || !ctx->host_buffers || slot < 0 || slot >= (int)ctx->slots.size() || which < 0 || which >= ctx->n_inputs) {
+        set_err("sk_upload: bad slot/which");
+        return SK_E_ARG;
+    }
+    Slot &s = ctx->slots[slot];
+    if (s.busy) { set_err("sk_upload: slot %d still busy (call sk_wait first)", slot); return SK_E_ARG; }
+    if (offset + nbytes > ctx->slot_bytes || s.up_hi[which] != s.up_lo[which]) {
+        set_err("sk_upload: range outside the slot, or a range was already uploaded for this batch");
+        return SK_E_ARG;
+    }
+    if (!nbytes) return SK_OK;
+    SK_CUDA(cudaSetDevice(ctx->device));
+    SK_CUDA(cudaMemcpyAsync(s.d_in[which] + offset, s.h_in[which] + offset, nbytes, cudaMemcpyHostToDevice, s.stream));
+    s.up_lo[which] = offset;
+    s.up_hi[which] = offset + nbytes;
+    return SK_OK;
+}
+
+int sk_submit(sk_ctx *ctx, int slot, uint64_t start0, uint64_t end0, uint64_t start1, uint64_t end1) {
+    if (!ctx || !ctx->host_buffers || slot < 0 || slot >= (int)ctx->slots.size()) { set_err("sk_submit: bad slot"); return SK_E_ARG; }
+    const uint64_t st[2] = {start0, start1}, en[2] = {end0, end1};
+    for (int i = 0; i < 2; ++i) {
+        if (st[i] > en[i] || en[i] > ctx->slot_bytes || (i >= ctx->n_inputs && en[i] != st[i])) {
+            set_err("sk_submit: bad byte range [%llu, %llu) for input %d (slot_bytes %llu)", (unsigned long long)st[i],
+                    (unsigned long long)en[i], i, (unsigned long long)ctx->slot_bytes);
+            return SK_E_ARG;
+        }
+    }
+    Slot &s = ctx->slots[slot];
+    if (s.busy) { set_err("sk_submit: slot %d still busy (call sk_wait first)", slot); return SK_E_ARG; }
+    SK_CUDA(cudaSetDevice(ctx->device));
+    for (int i = 0; i < ctx->n_inputs; ++i) {
+        // upload what sk_upload has not covered: [start, min(end, up_lo)) and [max(start, up_hi), end)
+        uint64_t lo = s.up_lo[i], hi = s.up_hi[i];
+        if (hi == lo) { lo = hi = st[i]; }
+        if (lo < st[i]) lo = st[i];
+        if (hi > en[i]) hi = en[i];
+        if (hi < lo) hi = lo;
+        if (lo > st[i])
+            SK_CUDA(cudaMemcpyAsync(s.d_in[i] + st[i], s.h_in[i] + st[i], lo - st[i], cudaMemcpyHostToDevice, s.stream));
+        if (en[i] > hi)
+            SK_CUDA(cudaMemcpyAsync(s.d_in[i] + hi, s.h_in[i] + hi, en[i] - hi, cudaMemcpyHostToDevice, s.stream));
+        s.up_lo[i] = s.up_hi[i] = 0;
+        s.base[i] = st[i] & ~15ull;
+        s.first[i] = (uint32_t)(st[i] - s.base[i]);
+    }
+    int rc = launch_batch(ctx, s, s.d_in[0] + s.base[0], s.first[0], en[0] - s.base[0],
+                          ctx->n_inputs > 1 ? s.d_in[1] + s.base[1] : nullptr, s.first[1],
+                          ctx->n_inputs > 1 ? en[1] - s.base[1] : 0, s.d_out, s.out_cap, s.stream);
+    if (rc != SK_OK) return rc;
+    SK_CUDA(cudaMemcpyAsync(s.h_res, s.d_res, sizeof(sk::DevResult), cudaMemcpyDeviceToHost, s.stream));
+    SK_CUDA(cudaEventRecord(s.ev_done, s.stream));
+    s.busy = true;
+    s.device_mode = false;
+    return SK_OK;
+}
+
+int sk_wait(sk_ctx *ctx, int slot, sk_result *res) {
+    if (!ctx || !res || slot < 0 || slot >= (int)ctx->slots.size()) { set_err("sk_wait: bad arguments"); return SK_E_ARG; }
+    Slot &s = ctx->slots[slot];
+    if (!s.busy || s.device_mode) { set_err("sk_wait: slot %d has no submitted batch", slot); return SK_E_ARG; }
+    SK_CUDA(cudaSetDevice(ctx->device));
+    SK_CUDA(cudaEventSynchronize(s.ev_done));
+    s.busy = false;
+    fill_result(s, res);
+    if (s.h_res->index_overflow & 1u) {
+        set_err("batch has more than %u lines per input; raise SICKLE_B200_MIN_LINE_BYTES granularity or shrink the batch",
+                ctx->line_cap);
+        return SK_E_CAPACITY;
+    }
+    if (s.h_res->index_overflow & 2u) { set_err("output stream larger than its buffer"); return SK_E_CAPACITY; }
+    if (int rc = stage_times(s, res)) return rc;
+    if (res->error.kind == 0) {
+        for (int k = 0; k < 3; ++k) {
+            if (res->out_bytes[k] && s.h_out[k])
+                SK_CUDA(cudaMemcpyAsync(s.h_out[k], s.d_out[k], res->out_bytes[k], cudaMemcpyDeviceToHost, s.stream));
+            res->out[k] = s.h_out[k];
+        }
+        SK_CUDA(cudaStreamSynchronize(s.stream));
+    } else {
+        for (int k = 0; k < 3; ++k) res->out_bytes[k] = 0;
+    }
+    return SK_OK;
+}
+
+int sk_trim_device(sk_ctx *ctx, int slot, const void *in0, uint64_t n0, const void *in1, uint64_t n1,
+                   void *const out[3], const uint64_t out_cap[3], void *stream) {
+    if (!ctx || slot < 0 || slot >= (int)ctx->slots.size() || !out || !out_cap) { set_err("sk_trim_device: bad arguments"); return SK_E_ARG; }
+    if (n0 > ctx->slot_bytes || n1 > ctx->slot_bytes || (ctx->n_inputs == 1 && n1) ||
+        (reinterpret_cast<uintptr_t>(in0) & 15) || (reinterpret_cast<uintptr_t>(in1) & 15)) {
+        set_err("sk_trim_device: inputs must be 16-byte aligned and <= slot_bytes");
+        return SK_E_ARG;
+    }
+    Slot &s = ctx->slots[slot];
+    if (s.busy && !s.device_mode) { set_err("sk_trim_device: slot %d busy", slot); return SK_E_ARG; }
+    SK_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+    uint8_t *o[3] = {(uint8_t *)out[0], (uint8_t *)out[1], (uint8_t *)out[2]};
+    s.base[0] = s.base[1] = 0;
+    s.first[0] = s.first[1] = 0;
+    int rc = launch_batch(ctx, s, (const uint8_t *)in0, 0, n0, (const uint8_t *)in1, 0, n1, o, out_cap, st);
+    if (rc != SK_OK) return rc;
+    s.busy = true;
+    s.device_mode = true;
+    return SK_OK;
+}
+
+int sk_result_device(sk_ctx *ctx, int slot, void *stream, sk_result *res) {
+    if (!ctx || !res || slot < 0 || slot >= (int)ctx->slots.size()) { set_err("sk_result_device: bad arguments"); return SK_E_ARG; }
+    Slot &s = ctx->slots[slot];
+    if (!s.busy || !s.device_mode) { set_err("sk_result_device: nothing submitted on slot %d", slot); return SK_E_ARG; }
+    SK_CUDA(cudaSetDevice(ctx->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+    SK_CUDA(cudaMemcpyAsync(s.h_res, s.d_res, sizeof(sk::DevResult), cudaMemcpyDeviceToHost, st));
+    SK_CUDA(cudaStreamSynchronize(st));
+    s.busy = false;
+    fill_result(s, res);
+    if (int rc = stage_times(s, res)) return rc;
+    if (s.h_res->index_overflow & 1u) { set_err("batch has more than %u lines per input", ctx->line_cap); return SK_E_CAPACITY; }
+    if (s.h_res->index_overflow & 2u) { set_err("output stream larger than its buffer"); return SK_E_CAPACITY; }
+    return SK_OK;
+}
+
+}  // extern "C"

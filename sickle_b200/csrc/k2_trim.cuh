@@ -1,0 +1,333 @@
+// k2_trim.cuh -- K2: per-read sliding-window trimming + keep/discard/singles routing + output scan.
+//
+// Replaces Abstract_Trimmer::sliding_window / get_quality_num (src/trim.cpp:3-140), the record
+// checks of FQEntry::validate (src/FQEntry.cpp:53-97), the keep flags of processing_thread
+// (src/trim_single.cpp:357-372, src/trim_paired.cpp:483-504) and the routing decisions of
+// output_single / output_paired (src/trim_single.cpp:382-404, src/trim_paired.cpp:531-567).
+//
+// Arithmetic is integer only.  The reference compares (double)total/(double)ws with the threshold;
+// that is exactly  total >= qthr*ws  (IEEE division is correctly rounded and monotone; SURVEY.md
+// section 8-a2), and (int)(0.1*L) == L/10 for every L < 5e6.
+//
+// This is the general ("any read length") formulation: one warp walks one read, 32 window
+// positions per step, window totals from a warp-shuffle prefix scan of q[i+ws]-q[i].  A warp
+// handles 32 consecutive units (reads, or pairs) so that lane k ends up holding unit k's result;
+// routing, the 3-stream output-length scan (warp scan + decoupled look-back) and the per-record
+// descriptors are then lane-parallel.
+#pragma once
+
+#include "sk_device.cuh"
+
+namespace sk {
+
+constexpr int kK2Threads = 256;
+constexpr int kK2UnitsPerTile = kK2Threads;  // 8 warps x 32 units
+
+struct Cut {
+    int five, three;  // three < 0 => discard (src/trim_single.cpp:368)
+};
+
+// record / unit counts of the batch, derived from the line counts K1 produced
+struct Geometry {
+    uint32_t nrec0, nrec1, nunits;
+};
+__device__ __forceinline__ Geometry batch_geometry(const Control *ctl, const DevParams &P) {
+    Geometry g;
+    const bool ovf = ctl->index_overflow != 0;
+    g.nrec0 = ovf ? 0u : ctl->nlines[0] >> 2;
+    g.nrec1 = ovf ? 0u : ctl->nlines[1] >> 2;
+    if (P.mode == 0) { g.nunits = g.nrec0; g.nrec1 = 0; }
+    else if (P.mode == 1) { g.nunits = min(g.nrec0, g.nrec1); g.nrec0 = g.nrec1 = g.nunits; }
+    else { g.nunits = g.nrec0 >> 1; g.nrec0 = g.nunits * 2; g.nrec1 = 0; }
+    return g;
+}
+
+// Output position p (0-based, in the reference's write order) -> unit index.
+// Reference: records are dealt round-robin to N queues and written queue by queue;
+// se: record k -> queue (k+1)%N (src/trim_single.cpp:263,273-274); pe: pair k -> queue k%N
+// (src/trim_paired.cpp:349,388,403).
+__device__ __forceinline__ uint32_t position_to_unit(uint32_t p, uint32_t U, int N, bool paired) {
+    if (N <= 1) return p;
+    const uint32_t n = (uint32_t)N, a = U / n, b = U % n;
+    if (!paired) {
+        // queue 0 holds residue N-1 (a elements, since b <= N-1), queues 1.. hold residues 0..N-2
+        if (p < a) return p * n + (n - 1);
+        p -= a;
+    }
+    if (p < b * (a + 1)) return (p % (a + 1)) * n + p / (a + 1);
+    p -= b * (a + 1);
+    return (p % a) * n + b + p / a;
+}
+
+// FQEntry::validate, src/FQEntry.cpp:53-97.  Line 3 is not inspected by the reference.
+__device__ __forceinline__ int validate_record(const uint8_t *__restrict__ d, const RecLines &r) {
+    if (r.len[0] <= 1) return 1;
+    if (d[r.start[0]] != '@') return 2;
+    if (r.len[1] < 1) return 3;
+    if (r.len[3] < 1) return 4;
+    if (r.len[3] != r.len[1]) return 5;
+    return 0;
+}
+
+// One warp, one read.  All lanes return the same Cut.  err_pos >= 0: a quality byte outside
+// [qmin,qmax] was met at that position inside the prefix the reference's scalar loop visits.
+__device__ __noinline__ Cut warp_sliding_window(const uint8_t *__restrict__ d, uint32_t seq_off, uint32_t L,
+                                                uint32_t qual_off, const DevParams &P, int lane, int &err_pos) {
+    const Cut discard = {-1, -1};
+    err_pos = -1;
+    if (L < (uint32_t)P.lthr) return discard;                    // trim.cpp:21-26 (nothing validated)
+    const uint8_t *__restrict__ q = d + qual_off;
+    uint32_t ws = L / 10u;                                       // trim.cpp:8
+    if (ws == 0) ws = L;                                         // trim.cpp:30
+    const long long thr_total = (long long)P.qthr * (long long)ws;
+
+    int part = 0;                                                // trim.cpp:31-33
+    for (uint32_t j0 = 0; j0 < ws; j0 += 32) {
+        const uint32_t j = j0 + lane;
+        bool bad = false;
+        if (j < ws) {
+            const int b = q[j];
+            bad = (b < P.qmin) | (b > P.qmax);
+            part += b - P.qoff;
+        }
+        const uint32_t bm = __ballot_sync(0xffffffffu, bad);
+        if (bm) { err_pos = (int)(j0 + __ffs(bm) - 1); return discard; }
+    }
+    int carry = warp_sum_i(part);
+
+    const uint32_t nwin = L - ws + 1u;                           // trim.cpp:34
+    bool found = false;
+    int i5 = -1, i3 = -1;
+    for (uint32_t c = 0; c < nwin; c += 32) {
+        const uint32_t i = c + lane;
+        const bool valid = i < nwin;
+        int dlt = 0;
+        bool bad = false;
+        if (valid && i > 0) {                                    // trim.cpp:76-79 for window i-1
+            const int lead = q[i - 1 + ws], trail = q[i - 1];
+            bad = (lead < P.qmin) | (lead > P.qmax);
+            dlt = lead - trail;
+        }
+        const int T = carry + warp_incl_scan_i(dlt, lane);
+        carry = __shfl_sync(0xffffffffu, T, 31);
+        const bool good = valid && (long long)T >= thr_total;    // trim.cpp:36,42,61
+        const uint32_t vm = __ballot_sync(0xffffffffu, valid);
+        const uint32_t gm = __ballot_sync(0xffffffffu, good);
+        bool can3 = found || P.no_fiveprime;
+        uint32_t from = 0;
+        if (!can3 && gm) {                                       // first good window: trim.cpp:42
+            from = __ffs(gm) - 1;
+            i5 = (int)(c + from);
+            found = true;
+            can3 = true;
+        }
+        uint32_t brk = 32;
+        if (can3) {                                              // first bad window after it: trim.cpp:61
+            const uint32_t bm = vm & ~gm & (0xffffffffu << from);
+            if (bm) { brk = __ffs(bm) - 1; i3 = (int)(c + brk); }
+        }
+        // a lead byte is range-checked iff its window is reached, i.e. lane <= brk
+        const uint32_t reach = brk >= 31 ? 0xffffffffu : ((2u << brk) - 1u);
+        const uint32_t badm = __ballot_sync(0xffffffffu, bad) & reach;
+        if (badm) { err_pos = (int)(c + (__ffs(badm) - 1) - 1 + ws); return discard; }
+        if (i3 >= 0) break;
+    }
+
+    int five = 0, three = (int)L;
+    if (found) {                                                 // trim.cpp:46-51
+        for (uint32_t j0 = (uint32_t)i5; j0 < (uint32_t)i5 + ws; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            const bool hit = j < (uint32_t)i5 + ws && (int)q[j] - P.qoff >= P.qthr;
+            const uint32_t hm = __ballot_sync(0xffffffffu, hit);
+            if (hm) { five = (int)(j0 + __ffs(hm) - 1); break; }
+        }
+    }
+    if (i3 >= 0) {                                               // trim.cpp:65-70
+        for (uint32_t j0 = (uint32_t)i3; j0 < (uint32_t)i3 + ws; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            const bool hit = j < (uint32_t)i3 + ws && (int)q[j] - P.qoff < P.qthr;
+            const uint32_t hm = __ballot_sync(0xffffffffu, hit);
+            if (hm) { three = (int)(j0 + __ffs(hm) - 1); break; }
+        }
+    }
+    if (P.trunc_n) {                                             // trim.cpp:86-98 (bug kept: 'N' only => -2)
+        const uint8_t *__restrict__ s = d + seq_off;
+        int pn = -1;
+        bool anyN = false;
+        for (uint32_t j0 = 0; j0 < L; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            const int b = j < L ? s[j] : 0;
+            const uint32_t mn = __ballot_sync(0xffffffffu, b == 'n');
+            anyN |= __ballot_sync(0xffffffffu, b == 'N') != 0;
+            if (mn) { pn = (int)(j0 + __ffs(mn) - 1); break; }
+        }
+        if (pn >= 0) three = pn - 1;
+        else if (anyN) three = -2;
+    }
+    if ((!found && !P.no_fiveprime) || (three - five < P.lthr)) return discard;  // trim.cpp:103
+    return Cut{five, three};
+}
+
+__device__ __forceinline__ unsigned long long make_err_key(bool quality, uint32_t unit, int mate, uint32_t pos) {
+    return ((unsigned long long)(quality ? 1u : 0u) << 63) | ((unsigned long long)(unit & 0x7fffffffu) << 32) |
+           ((unsigned long long)(mate & 1) << 31) | (unsigned long long)(pos & 0x7fffffffu);
+}
+
+struct MateInfo {
+    Cut cut;
+    uint32_t fixed_len;  // name_len + plus_len + 4 newlines
+};
+
+// Trim one record with the whole warp; reports data errors through ctl->err_key.
+__device__ __forceinline__ MateInfo trim_mate(const DevInput &in, uint32_t rec, uint32_t unit, int mate,
+                                              const DevParams &P, Control *ctl, int lane) {
+    const RecLines r = record_lines(in, rec);
+    MateInfo m;
+    m.fixed_len = r.len[0] + r.len[2] + 4u;
+    const int bad = validate_record(in.data, r);
+    if (bad) {
+        if (lane == 0) atomicMin(&ctl->err_key, make_err_key(false, unit, mate, 0));
+        m.cut = Cut{-1, -1};
+        return m;
+    }
+    int err_pos;
+    m.cut = warp_sliding_window(in.data, r.start[1], r.len[1], r.start[3], P, lane, err_pos);
+    if (err_pos >= 0 && lane == 0) atomicMin(&ctl->err_key, make_err_key(true, unit, mate, (uint32_t)err_pos));
+    return m;
+}
+
+__global__ void __launch_bounds__(kK2Threads)
+k2_trim_route(DevInput in0, DevInput in1, DevParams P, Control *__restrict__ ctl, RecDesc *__restrict__ desc0,
+              RecDesc *__restrict__ desc1, unsigned long long *__restrict__ status /* [3][max_tiles] */,
+              uint32_t status_stride, uint32_t epoch) {
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t warp_tot[kK2Threads / 32][kMaxStreams];
+    __shared__ unsigned long long tile_prefix[kMaxStreams];
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const Geometry g = batch_geometry(ctl, P);
+    const uint32_t num_tiles = (g.nunits + kK2UnitsPerTile - 1) / kK2UnitsPerTile;
+    const bool paired = P.mode != 0;
+    const bool inter = P.mode >= 2;
+    const bool mmode = P.mode == 3;
+
+    while (true) {
+        if (tid == 0) s_tile = atomicAdd(&ctl->tile_counter[2], 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= num_tiles) break;
+
+        // ---- phase 1: the warp trims its 32 units one after the other; lane k keeps unit k ----
+        const uint32_t p0 = tile * kK2UnitsPerTile + wid * 32;
+        MateInfo mine0 = {{-1, -1}, 0}, mine1 = {{-1, -1}, 0};
+        uint32_t my_unit = 0;
+        for (int k = 0; k < 32; ++k) {
+            const uint32_t p = p0 + k;
+            if (p >= g.nunits) break;
+            const uint32_t u = position_to_unit(p, g.nunits, P.emu_threads, paired);
+            const MateInfo a = trim_mate(in0, inter ? 2 * u : u, u, 0, P, ctl, lane);
+            MateInfo b = {{-1, -1}, 0};
+            if (paired) b = inter ? trim_mate(in0, 2 * u + 1, u, 1, P, ctl, lane) : trim_mate(in1, u, u, 1, P, ctl, lane);
+            if (lane == k) { mine0 = a; mine1 = b; my_unit = u; }
+        }
+
+        // ---- phase 2: routing (lane = unit) ----
+        const bool active = p0 + lane < g.nunits;
+        const bool k1 = active && mine0.cut.three >= 0;
+        const bool k2 = active && paired && mine1.cut.three >= 0;
+        const uint32_t n1 = k1 ? (uint32_t)(mine0.cut.three - mine0.cut.five) : 0u;
+        const uint32_t n2 = k2 ? (uint32_t)(mine1.cut.three - mine1.cut.five) : 0u;
+        const uint32_t len1 = mine0.fixed_len + 2u * n1, len2 = mine1.fixed_len + 2u * n2;  // kept record bytes
+        const uint32_t nlen1 = mine0.fixed_len + 2u, nlen2 = mine1.fixed_len + 2u;          // "N record" bytes
+        uint32_t add[kMaxStreams] = {0, 0, 0};
+        uint32_t route1 = 0, route2 = 0, rel2 = 0;  // rel2: offset of mate 2 after mate 1 in a shared stream
+        if (active) {
+            if (!paired) {
+                if (k1) { add[0] = len1; route1 = kRouteEmit | 0u; }
+            } else if (k1 && k2) {                                   // trim_paired.cpp:543-551
+                route1 = kRouteEmit | 0u;
+                if (inter) { add[0] = len1 + len2; route2 = kRouteEmit | 0u; rel2 = len1; }
+                else { add[0] = len1; add[1] = len2; route2 = kRouteEmit | 1u; }
+            } else if (k1 || k2) {                                   // trim_paired.cpp:552-563
+                if (mmode) {
+                    route1 = kRouteEmit | (k1 ? 0u : kRouteNRec);
+                    route2 = kRouteEmit | (k2 ? 0u : kRouteNRec);
+                    rel2 = k1 ? len1 : nlen1;
+                    add[0] = rel2 + (k2 ? len2 : nlen2);
+                } else if (P.has_singles) {                          // trim_paired.cpp:601,609
+                    if (k1) { route1 = kRouteEmit | 2u; add[2] = len1; }
+                    else { route2 = kRouteEmit | 2u; add[2] = len2; }
+                }
+            } else if (mmode) {                                      // both fail under -M: two N records
+                route1 = route2 = kRouteEmit | kRouteNRec;
+                rel2 = nlen1;
+                add[0] = nlen1 + nlen2;
+            }
+        }
+
+        // ---- phase 3: 3-stream exclusive scan over the tile, look-back across tiles ----
+        uint32_t incl[kMaxStreams];
+#pragma unroll
+        for (int s = 0; s < kMaxStreams; ++s) {
+            incl[s] = warp_incl_scan(add[s], lane);
+            if (lane == 31) warp_tot[wid][s] = incl[s];
+        }
+        __syncthreads();
+        if (wid < kMaxStreams) {
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < kK2Threads / 32; ++w) total += warp_tot[w][wid];
+            const unsigned long long pre = lookback_exclusive(status + (size_t)wid * status_stride, tile, total, epoch, lane);
+            if (lane == 0) {
+                tile_prefix[wid] = pre;
+                if (tile == num_tiles - 1) ctl->out_bytes[wid] = pre + total;
+            }
+        }
+        __syncthreads();
+        uint32_t off[kMaxStreams];
+#pragma unroll
+        for (int s = 0; s < kMaxStreams; ++s) {
+            uint32_t wbase = 0;
+            for (int w = 0; w < wid; ++w) wbase += warp_tot[w][s];
+            off[s] = (uint32_t)tile_prefix[s] + wbase + incl[s] - add[s];
+        }
+
+        // ---- phase 4: descriptors + counters ----
+        if (active) {
+            RecDesc d1;
+            d1.route = route1;
+            d1.dst_off = off[route1 & 3u];
+            d1.five = k1 ? (uint32_t)mine0.cut.five : 0u;
+            d1.nkeep = n1;
+            desc0[inter ? 2 * my_unit : my_unit] = d1;
+            if (paired) {
+                RecDesc d2;
+                d2.route = route2;
+                d2.dst_off = off[route2 & 3u] + rel2;
+                d2.five = k2 ? (uint32_t)mine1.cut.five : 0u;
+                d2.nkeep = n2;
+                (inter ? desc0 : desc1)[inter ? 2 * my_unit + 1 : my_unit] = d2;
+            }
+        }
+        // counters: trim_single.cpp:391,397; trim_paired.cpp:551,557-562,566
+        const uint32_t m_both = __ballot_sync(0xffffffffu, active && paired && k1 && k2);
+        const uint32_t m_only1 = __ballot_sync(0xffffffffu, active && paired && k1 && !k2);
+        const uint32_t m_only2 = __ballot_sync(0xffffffffu, active && paired && !k1 && k2);
+        const uint32_t m_none = __ballot_sync(0xffffffffu, active && paired && !k1 && !k2);
+        const uint32_t m_sekeep = __ballot_sync(0xffffffffu, active && !paired && k1);
+        const uint32_t m_sedrop = __ballot_sync(0xffffffffu, active && !paired && !k1);
+        if (lane == 0) {
+            if (m_sekeep) atomicAdd(&ctl->counters[0], (unsigned long long)__popc(m_sekeep));
+            if (m_sedrop) atomicAdd(&ctl->counters[1], (unsigned long long)__popc(m_sedrop));
+            if (m_both) atomicAdd(&ctl->counters[2], 2ull * __popc(m_both));
+            if (m_none) atomicAdd(&ctl->counters[3], 2ull * __popc(m_none));
+            if (m_only1) { atomicAdd(&ctl->counters[4], (unsigned long long)__popc(m_only1));
+                           atomicAdd(&ctl->counters[7], (unsigned long long)__popc(m_only1)); }
+            if (m_only2) { atomicAdd(&ctl->counters[5], (unsigned long long)__popc(m_only2));
+                           atomicAdd(&ctl->counters[6], (unsigned long long)__popc(m_only2)); }
+        }
+        __syncthreads();  // warp_tot / tile_prefix reused by the next tile
+    }
+}
+
+}  // namespace sk

@@ -1,0 +1,138 @@
+// k3_emit.cuh -- K3: stream compaction + FASTQ formatting, and the batch summary.
+//
+// Replaces the stringstream formatting of Trim_Single::output_single (src/trim_single.cpp:393-396)
+// and Trim_Paired::get_read_string / output_paired (src/trim_paired.cpp:506-513,543-567): every kept
+// record is written as  name '\n' seq[five:three] '\n' line3 '\n' qual[five:three] '\n'  (line 3 is
+// echoed verbatim, as the reference does) at the byte offset K2's scan assigned to it, directly in
+// the output stream's buffer.  -M "N records" follow README.md:116-120 (parity unpinned).
+#pragma once
+
+#include "k2_trim.cuh"
+#include "sk_device.cuh"
+
+namespace sk {
+
+constexpr int kK3Threads = 256;
+
+// Warp-cooperative copy of n bytes, arbitrary alignment on both sides.  Destination words are
+// written 4-byte aligned; source words are fetched aligned and funnel-shifted.  May read up to 3
+// bytes past src+n (inside the 16-byte padding every input buffer carries).
+__device__ __forceinline__ void warp_copy(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, uint32_t n,
+                                          int lane) {
+    uint32_t head = (4u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 3u)) & 3u;
+    if (head > n) head = n;
+    if ((uint32_t)lane < head) dst[lane] = src[lane];
+    dst += head; src += head; n -= head;
+    const uint32_t nw = n >> 2;
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
+    const uint32_t *__restrict__ s32 = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
+    uint32_t *__restrict__ d32 = reinterpret_cast<uint32_t *>(dst);
+    for (uint32_t k = lane; k < nw; k += 32) {
+        const uint32_t lo = s32[k];
+        const uint32_t hi = sh ? s32[k + 1] : 0u;
+        d32[k] = __funnelshift_r(lo, hi, sh);
+    }
+    const uint32_t tail = n & 3u;
+    if ((uint32_t)lane < tail) dst[4 * nw + lane] = src[4 * nw + lane];
+}
+
+__device__ __forceinline__ void emit_record(const DevInput &in, uint32_t rec, const RecDesc d, uint8_t *const *outs,
+                                            const DevParams &P, int lane) {
+    const RecLines r = record_lines(in, rec);
+    const uint8_t *__restrict__ src = in.data;
+    uint8_t *dst = outs[d.route & 3u] + d.dst_off;
+    warp_copy(dst, src + r.start[0], r.len[0] + 1u, lane);           // name line incl. its '\n'
+    dst += r.len[0] + 1u;
+    if (d.route & kRouteNRec) {
+        if (lane == 0) { dst[0] = 'N'; dst[1] = '\n'; }
+        dst += 2;
+        warp_copy(dst, src + r.start[2], r.len[2] + 1u, lane);       // line 3 verbatim incl. '\n'
+        dst += r.len[2] + 1u;
+        if (lane == 0) { dst[0] = (uint8_t)P.qmin; dst[1] = '\n'; }
+        return;
+    }
+    warp_copy(dst, src + r.start[1] + d.five, d.nkeep, lane);        // seq[five:three]
+    dst += d.nkeep;
+    if (lane == 0) *dst = '\n';
+    dst += 1;
+    warp_copy(dst, src + r.start[2], r.len[2] + 1u, lane);           // line 3 verbatim incl. '\n'
+    dst += r.len[2] + 1u;
+    warp_copy(dst, src + r.start[3] + d.five, d.nkeep, lane);        // qual[five:three]
+    dst += d.nkeep;
+    if (lane == 0) *dst = '\n';
+}
+
+struct OutPtrs {
+    uint8_t *p[kMaxStreams];
+    unsigned long long cap[kMaxStreams];
+};
+
+__global__ void __launch_bounds__(kK3Threads)
+k3_emit(DevInput in0, DevInput in1, DevParams P, const Control *__restrict__ ctl, const RecDesc *__restrict__ desc0,
+        const RecDesc *__restrict__ desc1, OutPtrs outs) {
+    const int lane = threadIdx.x & 31;
+    const Geometry g = batch_geometry(ctl, P);
+    if (ctl->err_key != kNoError) return;  // outputs of a failing batch are never used
+#pragma unroll
+    for (int s = 0; s < kMaxStreams; ++s)
+        if (ctl->out_bytes[s] > outs.cap[s]) return;  // reported by finalize as a capacity error
+    const uint32_t total = g.nrec0 + g.nrec1;
+    const uint32_t nwarps = gridDim.x * (kK3Threads / 32);
+    for (uint32_t w = blockIdx.x * (kK3Threads / 32) + (threadIdx.x >> 5); w < total; w += nwarps) {
+        const bool second = w >= g.nrec0;
+        const uint32_t rec = second ? w - g.nrec0 : w;
+        const RecDesc d = second ? desc1[rec] : desc0[rec];
+        if (!(d.route & kRouteEmit)) continue;
+        emit_record(second ? in1 : in0, rec, d, outs.p, P, lane);
+    }
+}
+
+// One thread: batch summary (sizes, consumed bytes, counters, first data error); resets the control block.
+__global__ void k_finalize(DevInput in0, DevInput in1, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
+                           DevResult *__restrict__ res) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const Geometry g = batch_geometry(ctl, P);
+    DevResult r;
+    for (int s = 0; s < kMaxStreams; ++s) r.out_bytes[s] = ctl->out_bytes[s];
+    r.records[0] = g.nrec0;
+    r.records[1] = g.nrec1;
+    r.consumed[0] = g.nrec0 ? (unsigned long long)in0.line_end[4ull * g.nrec0 - 1] + 1ull : 0ull;
+    r.consumed[1] = g.nrec1 ? (unsigned long long)in1.line_end[4ull * g.nrec1 - 1] + 1ull : 0ull;
+    for (int k = 0; k < 8; ++k) r.counters[k] = (long long)ctl->counters[k];
+    r.index_overflow = ctl->index_overflow;
+    for (int s = 0; s < kMaxStreams; ++s)
+        if (ctl->out_bytes[s] > outs.cap[s]) r.index_overflow |= 2u;
+    r.pad = 0;
+    r.err_kind = 0; r.err_file = 0; r.err_record = 0; r.err_position = 0; r.err_byte = 0;
+    for (int k = 0; k < 4; ++k) { r.err_line_off[k] = 0; r.err_line_len[k] = 0; }
+    const unsigned long long key = ctl->err_key;
+    if (key != kNoError) {
+        const bool quality = (key >> 63) != 0;
+        const uint32_t unit = (uint32_t)((key >> 32) & 0x7fffffffu);
+        const int mate = (int)((key >> 31) & 1u);
+        const uint32_t pos = (uint32_t)(key & 0x7fffffffu);
+        const bool inter = P.mode >= 2;
+        const bool second = (P.mode == 1 && mate == 1);
+        const DevInput &in = second ? in1 : in0;
+        const uint32_t rec = inter ? 2 * unit + mate : unit;
+        const RecLines l = record_lines(in, rec);
+        r.err_file = second ? 1 : 0;
+        r.err_record = rec;
+        for (int k = 0; k < 4; ++k) { r.err_line_off[k] = l.start[k]; r.err_line_len[k] = l.len[k]; }
+        if (quality) {
+            r.err_kind = 6;
+            r.err_position = (int)pos;
+            r.err_byte = (int)(signed char)in.data[l.start[3] + pos];
+        } else {
+            r.err_kind = validate_record(in.data, l);
+        }
+    }
+    *res = r;
+    // leave the control block clean for the slot's next batch (no per-batch memset on the stream)
+    Control z;
+    memset(&z, 0, sizeof z);
+    z.err_key = kNoError;
+    *ctl = z;
+}
+
+}  // namespace sk

@@ -1,0 +1,177 @@
+// sk_device.cuh -- device-side structures and small helpers shared by the kernels.
+// sm_100a only.  See DESIGN.md for the data layout.
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace sk {
+
+constexpr int kMaxStreams = 3;
+
+// Trimming parameters in the form the kernels want (built from sk_params on the host).
+struct DevParams {
+    int32_t qoff, qmin, qmax;  // quality_constants row, reference src/sickle.h:85-91
+    int32_t qthr;              // -q
+    int32_t lthr;              // -l
+    int32_t no_fiveprime;      // -x
+    int32_t trunc_n;           // -n
+    int32_t mode;              // SK_MODE_*
+    int32_t emu_threads;       // >= 1
+    int32_t has_singles;
+};
+
+// One input buffer of a batch and its line index.
+struct DevInput {
+    const uint8_t *data;   // 16-byte aligned; 16 bytes of readable padding after nbytes
+    uint32_t first;        // 0..15: the batch starts at data[first] (bytes before it are ignored)
+    uint32_t nbytes;       // the batch ends at data[nbytes]
+    uint32_t *line_end;    // line_end[l] = byte offset of the l-th '\n'
+    uint32_t line_cap;     // capacity of line_end
+};
+
+// Per-record descriptor written by K2 and consumed by K3 (16 bytes).
+//   dst_off : byte offset of the record inside its output stream
+//   five    : 5' cut (first kept base)
+//   nkeep   : number of kept bases (three - five)
+//   route   : bits 0-1 output stream, bit 2 = emit, bit 3 = emit as "N record" (-M)
+struct __align__(16) RecDesc {
+    uint32_t dst_off;
+    uint32_t five;
+    uint32_t nkeep;
+    uint32_t route;
+};
+constexpr uint32_t kRouteEmit = 4u;
+constexpr uint32_t kRouteNRec = 8u;
+
+// Device-resident control block of a slot; reset by k_finalize at the end of every batch.
+struct Control {
+    uint32_t tile_counter[4];     // dynamic tile tickets: K1 input 0, K1 input 1, K2, K3
+    uint32_t nlines[2];           // written by K1's last tile
+    uint32_t index_overflow;      // a line index ran out of capacity
+    uint32_t pad0;
+    unsigned long long err_key;   // min over offending (class, unit, mate, position); ~0 = none
+    unsigned long long counters[8];  // kept, discard, kept_p, discard_p, kept_s1, kept_s2, discard_s1, discard_s2
+    unsigned long long out_bytes[kMaxStreams];
+};
+constexpr unsigned long long kNoError = ~0ull;
+
+// Summary produced by the finalize kernel and copied to the host (mirrors sk_result's scalars).
+struct DevResult {
+    unsigned long long out_bytes[kMaxStreams];
+    unsigned long long consumed[2];
+    unsigned long long records[2];
+    long long counters[8];
+    int32_t err_kind, err_file;
+    long long err_record;
+    int32_t err_position, err_byte;
+    unsigned long long err_line_off[4], err_line_len[4];
+    uint32_t index_overflow;
+    uint32_t pad;
+};
+
+// ---- decoupled look-back tile status word ------------------------------------------------------
+//   [63:62] flag (0 = not ready, 1 = tile aggregate, 2 = inclusive prefix)
+//   [61:34] epoch of the batch that wrote it (a word from another epoch counts as "not ready",
+//           so the status arrays are never cleared between batches)
+//   [33:0]  value (line counts / output bytes of one batch: < 2^32)
+constexpr unsigned long long kFlagAggregate = 1ull;
+constexpr unsigned long long kFlagInclusive = 2ull;
+constexpr int kEpochShift = 34;
+constexpr unsigned long long kEpochMask = (1ull << 28) - 1;
+constexpr unsigned long long kValueMask = (1ull << 34) - 1;
+
+__device__ __forceinline__ unsigned long long pack_status(unsigned long long flag, uint32_t epoch,
+                                                          unsigned long long value) {
+    return (flag << 62) | (((unsigned long long)epoch & kEpochMask) << kEpochShift) | (value & kValueMask);
+}
+// flag of a status word as seen from `epoch` (0 if the word is stale)
+__device__ __forceinline__ uint32_t status_flag(unsigned long long w, uint32_t epoch) {
+    return (((w >> kEpochShift) & kEpochMask) == ((unsigned long long)epoch & kEpochMask)) ? (uint32_t)(w >> 62) : 0u;
+}
+__device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// Called by all 32 lanes of ONE warp.  Publishes this tile's aggregate, walks back over the
+// predecessors' status words and returns the exclusive prefix of `tile` (same value in all lanes).
+// Tiles are handed out by an atomic ticket, so every predecessor is running or done.
+__device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long long *status, uint32_t tile,
+                                                                 unsigned long long aggregate, uint32_t epoch,
+                                                                 int lane) {
+    if (tile == 0) {
+        if (lane == 0) st_status(&status[0], pack_status(kFlagInclusive, epoch, aggregate));
+        return 0ull;
+    }
+    if (lane == 0) st_status(&status[tile], pack_status(kFlagAggregate, epoch, aggregate));
+    unsigned long long exclusive = 0;
+    int64_t idx = (int64_t)tile - 1;
+    while (true) {
+        const int64_t my = idx - lane;
+        uint32_t flag = 2;  // tiles before 0: inclusive prefix 0
+        unsigned long long v = 0;
+        if (my >= 0) {
+            unsigned long long w;
+            do { w = ld_status(&status[my]); flag = status_flag(w, epoch); } while (flag == 0);
+            v = w & kValueMask;
+        }
+        const uint32_t incl = __ballot_sync(0xffffffffu, flag == 2);
+        if (incl) {
+            const int first = __ffs(incl) - 1;
+            if (lane > first) v = 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        exclusive += v;
+        if (incl) break;
+        idx -= 32;
+    }
+    if (lane == 0) st_status(&status[tile], pack_status(kFlagInclusive, epoch, exclusive + aggregate));
+    return exclusive;
+}
+
+__device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        uint32_t t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ int warp_incl_scan_i(int v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Byte offsets of a record's four lines inside its input buffer.
+struct RecLines {
+    uint32_t start[4];
+    uint32_t len[4];
+};
+__device__ __forceinline__ RecLines record_lines(const DevInput &in, uint32_t rec) {
+    RecLines r;
+    const uint32_t *__restrict__ line_end = in.line_end;
+    const uint4 e = *reinterpret_cast<const uint4 *>(line_end + 4ull * rec);
+    const uint32_t prev = rec ? __ldg(line_end + 4ull * rec - 1) + 1u : in.first;
+    r.start[0] = prev;      r.len[0] = e.x - prev;
+    r.start[1] = e.x + 1u;  r.len[1] = e.y - e.x - 1u;
+    r.start[2] = e.y + 1u;  r.len[2] = e.z - e.y - 1u;
+    r.start[3] = e.z + 1u;  r.len[3] = e.w - e.z - 1u;
+    return r;
+}
+
+}  // namespace sk

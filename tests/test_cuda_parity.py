@@ -1,0 +1,263 @@
+"""Parity of the CUDA path (through the C ABI) with the reference / the CPU oracle.  All -m gpu.
+
+* golden.json: outputs of the unmodified reference binary on the committed fixtures (md5, sizes,
+  counters, error kind/position/record), incl. `-a N` order through the reference batch geometry;
+* seeded random inputs compared byte for byte with the oracle (SE, PE two-file, interleaved, -M);
+* batch-size invariance and the early-upload (pipelined) submit path.
+Bar: bit-exact (this path is byte/integer work).
+"""
+import re
+
+import numpy as np
+import pytest
+
+import golden_util as gu
+import oracle_py as orc
+
+pytestmark = pytest.mark.gpu
+
+ERRKIND = {"Sequence ID is to short.": 1, "Invalid char at the beggining of ID.": 2,
+           "Sequence line is empty": 3, "Quality line is empty.": 4,
+           "Sequence and quality lines have different lengths:": 5, "ERROR: Quality value": 6}
+
+
+@pytest.fixture(scope="module")
+def capi():
+    from sickle_b200 import capi as m
+
+    m.load()
+    return m
+
+
+def _modes(capi):
+    return {"se": capi.MODE_SE, "pei": capi.MODE_PE_INTER, "pe2": capi.MODE_PE_2FILE}
+
+
+def _run_cuda(capi, mode, flags, in0, in1=b"", slot_bytes=1 << 16, has_singles=True, threads=1, pipelined=False,
+              n_slots=1, headroom=None):
+    from sickle_b200 import runner
+
+    p = capi.make_params(flags["qualtype"], flags["q"], flags["l"], flags["x"], flags["n"], mode=mode,
+                         emulate_threads=threads, has_singles=has_singles)
+    with capi.Context(p, slot_bytes, n_slots) as ctx:
+        if threads > 1:
+            return runner.trim_stream_reference_order(ctx, in0, in1)
+        return runner.trim_stream(ctx, in0, in1, pipelined=pipelined, headroom=headroom)
+
+
+def test_golden_cases(capi, golden):
+    from sickle_b200 import runner
+
+    bad = []
+    nok = nerr = 0
+    for case in golden["cases"]:
+        kind, in0, in1 = gu.load_inputs(case, golden["dir"])
+        f = gu.parse_flags(case["flags"])
+        has_singles = "-s" in case["outputs"]
+        # slots small enough to force several batches, large enough for the longest record (24 KB)
+        slot = 1 << 16 if case["threads"] == 1 else 1 << 20
+        try:
+            r = _run_cuda(capi, _modes(capi)[kind], f, in0, in1, slot_bytes=slot, has_singles=has_singles,
+                          threads=case["threads"])
+            err = None
+        except runner.DataError as e:
+            r, err = None, e
+        if case["rc"] == 0:
+            nok += 1
+            if err is not None:
+                bad.append((case["id"], "unexpected data error", err.kind))
+                continue
+            exp = gu.expected_streams(case)
+            for s in range(3):
+                if exp[s] is not None and (gu.md5(r["out"][s]), len(r["out"][s])) != exp[s]:
+                    bad.append((case["id"], "stream", s, len(r["out"][s]), exp[s][1]))
+            c, g = r["counters"], case["counts"]
+            if case["mode"] == "se":
+                if (c["kept"], c["discard"]) != (g["kept"], g["discard"]):
+                    bad.append((case["id"], "counts", c, g))
+            elif (c["kept_p"], c["discard_p"], c["kept_s1"] + c["kept_s2"], c["discard_s1"] + c["discard_s2"]) != \
+                    (g["kept_p"], g["discard_p"], g["kept_s"], g["discard_s"]):
+                bad.append((case["id"], "counts", c, g))
+        else:
+            nerr += 1
+            want = [k for msg, k in ERRKIND.items() if msg in case["stderr"]][0]
+            if err is None or err.kind != want:
+                bad.append((case["id"], "error kind", None if err is None else err.kind, want))
+                continue
+            if want == 6:
+                pos = int(re.search(r"Quality position: (\d+)", case["stderr"]).group(1))
+                val = int(re.search(r"Quality value \((-?\d+)\)", case["stderr"]).group(1))
+                rec = re.search(r"FastQ record: (\S+)", case["stderr"]).group(1)
+                if (err.position + 1, err.byte, err.lines[0].decode()) != (pos, val, rec):
+                    bad.append((case["id"], "error detail", err.position, err.byte, err.lines[0], pos, val, rec))
+    assert not bad, bad[:10]
+    assert nok > 190 and nerr >= 6
+
+
+def _random_fastq(rng, n, lmax, qualtype, lower_n=True, plus_name=True):
+    off = {"sanger": 33, "illumina": 64, "solexa": 64}[qualtype]
+    lo, hi = {"sanger": (0, 60), "illumina": (0, 46), "solexa": (-6, 48)}[qualtype]
+    out = []
+    for i in range(n):
+        L = int(rng.integers(1, lmax + 1))
+        seq = np.frombuffer(b"ACGT", dtype=np.uint8)[rng.integers(0, 4, L)].copy()
+        r = rng.random(L)
+        seq[r < 0.01] = ord("N")
+        if lower_n:
+            seq[(r > 0.01) & (r < 0.013)] = ord("n")
+        style = rng.integers(0, 4)
+        if style == 0:
+            q = rng.integers(lo, hi + 1, L)
+        elif style == 1:
+            q = np.clip(np.sort(rng.integers(lo, hi + 1, L))[::-1] + rng.integers(-3, 4, L), lo, hi)
+        elif style == 2:
+            q = np.clip(np.sort(rng.integers(lo, hi + 1, L)) + rng.integers(-3, 4, L), lo, hi)
+        else:
+            q = np.full(L, int(rng.integers(lo, hi + 1)))
+            a, b = sorted(rng.integers(0, L + 1, 2))
+            q[a:b] = int(rng.integers(lo, hi + 1))
+        name = b"@r%d" % i + (b" x" * int(rng.integers(0, 3)))
+        plus = b"+" + name[1:] if (plus_name and i % 3 == 0) else b"+"
+        out.append(name + b"\n" + seq.tobytes() + b"\n" + plus + b"\n" + (q + off).astype(np.uint8).tobytes() + b"\n")
+    return out
+
+
+FLAGSETS = [dict(q=20, l=20, x=False, n=False), dict(q=30, l=5, x=True, n=False), dict(q=10, l=0, x=False, n=True),
+            dict(q=25, l=1, x=True, n=True), dict(q=0, l=0, x=False, n=False), dict(q=41, l=30, x=False, n=False)]
+
+
+@pytest.mark.parametrize("qualtype", ["sanger", "illumina", "solexa"])
+@pytest.mark.parametrize("lmax", [12, 70, 400, 3000])
+def test_random_se_vs_oracle(capi, qualtype, lmax):
+    rng = np.random.default_rng([1, lmax, len(qualtype)])
+    recs = _random_fastq(rng, 3000 if lmax <= 400 else 300, lmax, qualtype)
+    data = b"".join(recs)
+    for fl in FLAGSETS:
+        flags = dict(qualtype=qualtype, **fl)
+        want = orc.run(orc.MODE_SE, orc.make_params(qualtype, fl["q"], fl["l"], fl["x"], fl["n"]), data)
+        assert want["rc"] == 0
+        got = _run_cuda(capi, capi.MODE_SE, flags, data, slot_bytes=1 << (17 if lmax > 70 else 14))
+        assert got["out"][0] == want["out"][0], (qualtype, lmax, fl)
+        assert (got["counters"]["kept"], got["counters"]["discard"]) == (want["counters"]["kept"], want["counters"]["discard"])
+        assert got["batches"] > 1
+
+
+@pytest.mark.parametrize("mode_name", ["pe2", "pei", "pei_nosingles", "peiM"])
+def test_random_pe_vs_oracle(capi, mode_name):
+    rng = np.random.default_rng([2, len(mode_name)])
+    a = _random_fastq(rng, 2500, 200, "sanger")
+    b = _random_fastq(rng, 2500, 120, "sanger")
+    has_singles = mode_name != "pei_nosingles"
+    if mode_name == "pe2":
+        in0, in1, omode, cmode = b"".join(a), b"".join(b), orc.MODE_PE_2FILE, capi.MODE_PE_2FILE
+    else:
+        in0 = b"".join(x + y for x, y in zip(a, b))
+        in1 = b""
+        omode = orc.MODE_PE_INTER_M if mode_name == "peiM" else orc.MODE_PE_INTER
+        cmode = capi.MODE_PE_INTER_M if mode_name == "peiM" else capi.MODE_PE_INTER
+    for fl in FLAGSETS:
+        # batch_len huge: one reference batch (the reference pairs two files only when their
+        # per-batch line counts agree; this path pairs by record number)
+        want = orc.run(omode, orc.make_params("sanger", fl["q"], fl["l"], fl["x"], fl["n"]), in0, in1,
+                       has_singles=has_singles, batch_len=1 << 40)
+        assert want["rc"] == 0
+        got = _run_cuda(capi, cmode, dict(qualtype="sanger", **fl), in0, in1, slot_bytes=1 << 17, has_singles=has_singles)
+        for s in range(3):
+            assert got["out"][s] == want["out"][s], (mode_name, fl, s)
+        for k in ("kept_p", "discard_p", "kept_s1", "kept_s2", "discard_s1", "discard_s2"):
+            assert got["counters"][k] == want["counters"][k], (mode_name, fl, k)
+
+
+@pytest.mark.parametrize("threads", [2, 3, 7])
+def test_emulated_thread_order_vs_oracle(capi, threads):
+    """-a N output order (queue dealing inside reference batches), SE and PE."""
+    rng = np.random.default_rng([3, threads])
+    data = b"".join(_random_fastq(rng, 4001, 90, "sanger"))
+    from sickle_b200 import runner
+
+    bl = runner.recommended_batch_len(len(data), 512, False)
+    want = orc.run(orc.MODE_SE, orc.make_params("sanger"), data, threads=threads, batch_len=bl)
+    got = _run_cuda(capi, capi.MODE_SE, dict(qualtype="sanger", q=20, l=20, x=False, n=False), data,
+                    slot_bytes=1 << 20, threads=threads)
+    assert got["out"][0] == want["out"][0]
+    a = _random_fastq(rng, 1500, 100, "sanger")
+    b = _random_fastq(rng, 1500, 100, "sanger")
+    inter = b"".join(x + y for x, y in zip(a, b))
+    bl = runner.recommended_batch_len(len(inter), 512, True)
+    want = orc.run(orc.MODE_PE_INTER, orc.make_params("sanger"), inter, threads=threads, batch_len=bl)
+    got = _run_cuda(capi, capi.MODE_PE_INTER, dict(qualtype="sanger", q=20, l=20, x=False, n=False), inter,
+                    slot_bytes=1 << 20, threads=threads)
+    assert got["out"][0] == want["out"][0] and got["out"][2] == want["out"][2]
+
+
+def test_batch_size_invariance_and_pipelined_upload(capi):
+    """Same bytes whatever the slot size, and through the early-upload (sk_upload) submit path."""
+    from sickle_b200 import synth
+
+    data = synth.fixed_length_records(20000, 150, "sanger", seed=11).tobytes()
+    flags = dict(qualtype="sanger", q=20, l=20, x=False, n=False)
+    want = orc.run(orc.MODE_SE, orc.make_params("sanger"), data)
+    ref = None
+    for slot, pipe, nslots, head in ((1 << 22, False, 1, None), (1 << 16, False, 1, None), (100003 & ~15, False, 1, None),
+                                     (1 << 18, True, 2, 4096), (1 << 18, True, 3, 1 << 12), (1 << 16, True, 2, 777)):
+        got = _run_cuda(capi, capi.MODE_SE, flags, data, slot_bytes=slot, pipelined=pipe, n_slots=nslots, headroom=head)
+        assert got["out"][0] == want["out"][0], (slot, pipe)
+        assert got["counters"]["kept"] == want["counters"]["kept"]
+        ref = got
+    assert ref["records"][0] == 20000
+
+
+def test_edge_inputs(capi):
+    flags = dict(qualtype="sanger", q=20, l=20, x=False, n=False)
+    # empty input, a single record, a record without final newline, trailing partial record, lone newlines
+    rec = b"@a1\n" + b"ACGT" * 10 + b"\n+\n" + b"I" * 40 + b"\n"
+    for data in (b"", rec, rec * 3 + b"@partial\nAC\n", rec[:-1], rec * 2 + b"@x\n"):
+        from sickle_b200 import runner
+
+        want = orc.run(orc.MODE_SE, orc.make_params("sanger"), data)
+        got = err = None
+        try:
+            got = _run_cuda(capi, capi.MODE_SE, flags, data, slot_bytes=4096)
+        except runner.DataError as e:
+            err = e
+        if want["rc"] == 0:
+            assert err is None and got["out"][0] == want["out"][0], data[-20:]
+        else:
+            assert err is not None and err.kind == want["rc"], (data[-20:], err)
+    # lthr = 0 can emit empty sequence lines
+    data = b"@z9\nACGTACGTAC\n+\n" + b"#" * 10 + b"\n" + rec
+    want = orc.run(orc.MODE_SE, orc.make_params("sanger", q=20, l=0, x=True), data)
+    got = _run_cuda(capi, capi.MODE_SE, dict(qualtype="sanger", q=20, l=0, x=True, n=False), data, slot_bytes=4096)
+    assert got["out"][0] == want["out"][0] and b"@z9\n\n+\n\n" in got["out"][0]
+
+
+def test_large_batch_properties(capi):
+    """Bench-sized batch (1M x R150, 325 MB) on the device-resident path: oracle parity on a
+    200k-read prefix, conservation of records, and order-independent structure checks."""
+    import torch
+
+    from sickle_b200 import synth
+
+    n = 1_000_000
+    dev = torch.device("cuda:0")
+    rec = synth.r150_records_torch(n, 0, dev, seed=5)
+    inp = torch.zeros(rec.numel() + 64, dtype=torch.uint8, device=dev)
+    inp[: rec.numel()] = rec.reshape(-1)
+    out = torch.empty(rec.numel() + 64, dtype=torch.uint8, device=dev)
+    p = capi.make_params("sanger")
+    with capi.Context(p, rec.numel() + 16, 0) as ctx:
+        st = torch.cuda.current_stream().cuda_stream
+        ctx.trim_device(inp.data_ptr(), rec.numel(), 0, 0, [out.data_ptr(), 0, 0], [out.numel(), 0, 0], st)
+        res = ctx.result_device(st)
+    assert res.error.kind == 0
+    assert res.records[0] == n and res.kept + res.discard == n and res.consumed[0] == rec.numel()
+    assert 0 < res.discard < n // 2
+    got = out[: res.out_bytes[0]].cpu().numpy().tobytes()
+    assert got.count(b"\n") == 4 * res.kept
+    m = 200_000
+    host = rec[:m].cpu().numpy().tobytes()
+    want = orc.run(orc.MODE_SE, orc.make_params("sanger"), host)
+    assert got[: len(want["out"][0])] == want["out"][0]
+    # every kept record: len(seq) == len(qual) and starts with '@SRR'
+    lines = got.split(b"\n")
+    assert all(len(lines[i + 1]) == len(lines[i + 3]) and lines[i].startswith(b"@SRR") for i in range(0, 4000, 4))
