@@ -259,7 +259,7 @@ def run_cuda_arm(args):
     achieved = alg_bytes / (ms_per_step / 1e3) / 1e9
 
     # --- e2e: host-facing C ABI, pinned host buffers, H2D + kernels + D2H every step
-    e2e = run_e2e(args, torch, dist, capi, inp, nb, nbytes, local, world, dev)
+    e2e = None if args.kernel_only else run_e2e(args, torch, dist, capi, inp, nb, nbytes, local, world, dev)
     clk = clocks.stop() if rank == 0 else None
 
     if rank != 0:
@@ -285,7 +285,7 @@ def run_cuda_arm(args):
         "gpu_launches": launches * args.steps,
         "clocks": clk,
     }
-    if world == 1 and not args.no_cpu_baseline:
+    if world == 1 and not args.no_cpu_baseline and not args.kernel_only:
         try:
             v, cores, kind, label, times = time_reference(args.cpu_reads, 1, 0)
             line["cpu_baseline"] = {"value": v, "unit": "reads/s", "cores": cores, "kind": kind,
@@ -355,6 +355,7 @@ def main():
     ap.add_argument("--cpu-reads", type=int, default=4_000_000, help="sample size of the cpu_baseline leg")
     ap.add_argument("--ref-reads", type=int, default=250_000, help="reads per step of --impl reference")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--kernel-only", action="store_true", help="skip the e2e and cpu_baseline legs (for ncu runs)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference_arm(args)
