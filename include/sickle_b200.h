@@ -107,6 +107,7 @@ typedef struct sk_result {
     float kernel_ms;         /* device time of the batch's kernels (CUDA events)              */
     float stage_ms[4];       /* of which: K1 line index, K2 trim+route, K3 emit, summary      */
     uint32_t kernel_launches;/* kernels launched for the batch                                */
+    uint32_t fused;          /* 1: the single-pass fused kernel produced the batch; 0: K1/K2/K3 */
 } sk_result;
 
 typedef struct sk_ctx sk_ctx;

@@ -38,7 +38,8 @@ class Result(C.Structure):
                 ("records", C.c_uint64 * 2), ("kept", C.c_int64), ("discard", C.c_int64), ("kept_p", C.c_int64),
                 ("discard_p", C.c_int64), ("kept_s1", C.c_int64), ("kept_s2", C.c_int64),
                 ("discard_s1", C.c_int64), ("discard_s2", C.c_int64), ("error", ErrorInfo),
-                ("kernel_ms", C.c_float), ("stage_ms", C.c_float * 4), ("kernel_launches", C.c_uint32)]
+                ("kernel_ms", C.c_float), ("stage_ms", C.c_float * 4), ("kernel_launches", C.c_uint32),
+                ("fused", C.c_uint32)]
 
     COUNTERS = ("kept", "discard", "kept_p", "discard_p", "kept_s1", "kept_s2", "discard_s1", "discard_s2")
 

@@ -2,8 +2,12 @@
 // kernel launches.  The only public symbols are the extern "C" entry points of the header.
 //
 // Pipeline per slot (one CUDA stream per slot; slots overlap each other's copies and kernels):
-//   H2D(in) -> K1 line index (per input) -> K2 trim+route+scan -> K3 emit -> finalize -> D2H(summary)
-//   sk_wait: wait summary, D2H(out streams, exact sizes), return pointers into pinned memory.
+//   H2D(in) -> kernels -> D2H(summary);  sk_wait: wait summary, D2H(out streams, exact sizes).
+// Kernels of a batch are either
+//   fused   : kf_fused (parse+trim+route+emit in one pass) + kf_finalize      [short records, input order]
+//   general : K1 line index (per input) -> K2 trim+route+scan -> K3 emit -> k_finalize   [everything]
+// The fused kernel flags what it cannot do exactly (long records, data errors, ...); the batch is then
+// re-run on the general path before the result is returned, and the context backs off for a while.
 // This replaces the reference's two-stage overlap (detached output thread while the main thread
 // reads the next batch: src/trim_single.cpp:336-339, src/trim_paired.cpp:444-458).
 #include "../../include/sickle_b200.h"
@@ -18,6 +22,7 @@
 #include "k1_index.cuh"
 #include "k2_trim.cuh"
 #include "k3_emit.cuh"
+#include "kf_fused.cuh"
 #include "sk_device.cuh"
 
 namespace {
@@ -43,6 +48,17 @@ void set_err(const char *fmt, ...) {
 
 constexpr uint64_t kPad = 64;           // readable padding after every device input buffer
 constexpr uint64_t kMaxSlotBytes = (1ull << 31) - 4096;
+constexpr int kFusedMinTile = sk::FusedCfg<5>::kTile;   // smallest tile of the instantiated configs
+
+// what a batch was launched with (kept so that a fused batch can be re-run on the general path)
+struct BatchArgs {
+    const uint8_t *in[2] = {nullptr, nullptr};
+    uint32_t first[2] = {0, 0};
+    uint64_t n[2] = {0, 0};
+    uint8_t *out[3] = {nullptr, nullptr, nullptr};
+    uint64_t cap[3] = {0, 0, 0};
+    cudaStream_t st = nullptr;
+};
 
 struct Slot {
     cudaStream_t stream = nullptr;
@@ -57,16 +73,18 @@ struct Slot {
     sk::RecDesc *d_desc[2] = {nullptr, nullptr};
     unsigned long long *d_status_k1[2] = {nullptr, nullptr};
     unsigned long long *d_status_k2 = nullptr;
+    unsigned long long *d_status_f = nullptr;   // fused: [3][fused_tiles_cap] (newlines, main, singles)
     sk::Control *d_ctl = nullptr;
     sk::DevResult *d_res = nullptr;
     sk::DevResult *h_res = nullptr;
     uint32_t epoch = 0;
     bool busy = false;
     bool device_mode = false;
+    bool last_fused = false;
     uint64_t up_lo[2] = {0, 0}, up_hi[2] = {0, 0};   // byte range already uploaded by sk_upload
     uint64_t base[2] = {0, 0};                       // buffer offset of DevInput.data for the batch
     uint32_t first[2] = {0, 0};                      // start - base (0..15)
-    uint8_t *ext_out[3] = {nullptr, nullptr, nullptr};
+    BatchArgs last;
     uint32_t launches = 0;
 };
 
@@ -79,11 +97,18 @@ struct sk_ctx {
     uint32_t line_cap = 0;       // lines per input
     uint32_t k1_tiles_cap = 0;
     uint32_t k2_tiles_cap = 0;
+    uint32_t fused_tiles_cap = 0;
     int n_inputs = 1;
     sk_params params{};
     sk::DevParams dev{};
     std::vector<Slot> slots;
     bool host_buffers = false;
+    // path selection
+    bool fused_eligible = false;   // mode / order the fused kernel supports
+    int fused_ch = 7;              // 16-byte chunks per thread (5, 7, 9 or 11)
+    int fused_grid = 0;
+    int fused_backoff = 0;         // batches left on the general path after a fused failure
+    uint64_t n_fused = 0, n_general = 0, n_rerun = 0;
 };
 
 namespace {
@@ -121,6 +146,7 @@ void free_slot(Slot &s) {
         if (s.d_out[i]) cudaFree(s.d_out[i]);
     }
     if (s.d_status_k2) cudaFree(s.d_status_k2);
+    if (s.d_status_f) cudaFree(s.d_status_f);
     if (s.d_ctl) cudaFree(s.d_ctl);
     if (s.d_res) cudaFree(s.d_res);
     if (s.h_res) cudaFreeHost(s.h_res);
@@ -152,6 +178,10 @@ int alloc_slot(sk_ctx *c, Slot &s, bool host_buffers) {
     }
     SK_CUDA(cudaMalloc((void **)&s.d_status_k2, (size_t)c->k2_tiles_cap * 8 * sk::kMaxStreams));
     SK_CUDA(cudaMemset(s.d_status_k2, 0, (size_t)c->k2_tiles_cap * 8 * sk::kMaxStreams));
+    if (c->fused_eligible) {
+        SK_CUDA(cudaMalloc((void **)&s.d_status_f, (size_t)c->fused_tiles_cap * 8 * 3));
+        SK_CUDA(cudaMemset(s.d_status_f, 0, (size_t)c->fused_tiles_cap * 8 * 3));
+    }
     if (host_buffers) {
         // stream capacities: an output stream never exceeds the bytes of the inputs feeding it
         const int mode = c->params.mode;
@@ -175,57 +205,145 @@ int alloc_slot(sk_ctx *c, Slot &s, bool host_buffers) {
     return SK_OK;
 }
 
-// Enqueue K1..K3 + finalize for one batch on `st`.
-// Input i is bytes [first_i, n_i) relative to the 16-byte aligned pointer in_i (first_i <= 15).
-int launch_batch(sk_ctx *c, Slot &s, const uint8_t *in0, uint32_t first0, uint64_t n0, const uint8_t *in1,
-                 uint32_t first1, uint64_t n1, uint8_t *const out[3], const uint64_t out_cap[3], cudaStream_t st) {
-    s.epoch += 1;
-    if ((s.epoch & (uint32_t)sk::kEpochMask) == 0) {  // epoch tag wrapped: clear the status words once
-        for (int i = 0; i < c->n_inputs; ++i) SK_CUDA(cudaMemsetAsync(s.d_status_k1[i], 0, (size_t)c->k1_tiles_cap * 8, st));
-        SK_CUDA(cudaMemsetAsync(s.d_status_k2, 0, (size_t)c->k2_tiles_cap * 8 * sk::kMaxStreams, st));
-        s.epoch += 1;
-    }
-    sk::DevInput di[2];
-    const uint8_t *ins[2] = {in0, in1};
-    const uint64_t ns[2] = {n0, n1};
-    const uint32_t firsts[2] = {first0, first1};
+void make_inputs(const sk_ctx *c, const Slot &s, const BatchArgs &a, sk::DevInput di[2], sk::OutPtrs &op) {
     for (int i = 0; i < 2; ++i) {
-        di[i].data = ins[i];
-        di[i].first = firsts[i];
-        di[i].nbytes = (uint32_t)ns[i];
+        di[i].data = a.in[i];
+        di[i].first = a.first[i];
+        di[i].nbytes = (uint32_t)a.n[i];
         di[i].line_end = s.d_line_end[i];
         di[i].line_cap = c->line_cap;
     }
     if (c->n_inputs == 1) { di[1].data = nullptr; di[1].first = 0; di[1].nbytes = 0; di[1].line_end = nullptr; di[1].line_cap = 0; }
-    sk::OutPtrs op;
-    for (int k = 0; k < 3; ++k) { op.p[k] = out[k]; op.cap[k] = out[k] ? out_cap[k] : 0; }
+    for (int k = 0; k < 3; ++k) { op.p[k] = a.out[k]; op.cap[k] = a.out[k] ? a.cap[k] : 0; }
+}
 
+int next_epoch(sk_ctx *c, Slot &s, cudaStream_t st) {
+    s.epoch += 1;
+    if ((s.epoch & (uint32_t)sk::kEpochMask) == 0) {  // epoch tag wrapped: clear the status words once
+        for (int i = 0; i < c->n_inputs; ++i) SK_CUDA(cudaMemsetAsync(s.d_status_k1[i], 0, (size_t)c->k1_tiles_cap * 8, st));
+        SK_CUDA(cudaMemsetAsync(s.d_status_k2, 0, (size_t)c->k2_tiles_cap * 8 * sk::kMaxStreams, st));
+        if (s.d_status_f) SK_CUDA(cudaMemsetAsync(s.d_status_f, 0, (size_t)c->fused_tiles_cap * 8 * 3, st));
+        s.epoch += 1;
+    }
+    return SK_OK;
+}
+
+// General path: K1 (per input) -> K2 -> K3 -> finalize.
+int launch_general(sk_ctx *c, Slot &s, const BatchArgs &a) {
+    cudaStream_t st = a.st;
+    if (int rc = next_epoch(c, s, st)) return rc;
+    sk::DevInput di[2];
+    sk::OutPtrs op;
+    make_inputs(c, s, a, di, op);
     s.launches = 0;
     SK_CUDA(cudaEventRecord(s.ev_begin, st));
     const int resident = c->sm_count * 8;
     for (int i = 0; i < c->n_inputs; ++i) {
-        const uint32_t tiles = (uint32_t)((ns[i] + sk::kK1TileBytes - 1) / sk::kK1TileBytes);
+        const uint32_t tiles = (uint32_t)((a.n[i] + sk::kK1TileBytes - 1) / sk::kK1TileBytes);
         if (!tiles) continue;
         const int grid = tiles < (uint32_t)resident ? (int)tiles : resident;
         sk::k1_line_index<<<grid, sk::kK1Threads, 0, st>>>(di[i], s.d_ctl, i, s.d_status_k1[i], tiles, s.epoch);
         s.launches++;
     }
     SK_CUDA(cudaEventRecord(s.ev_stage[0], st));
-    {
-        // units <= bytes / 4 (a line is at least its '\n'); usually ~bytes/325
-        const uint64_t max_units = (ns[0] + ns[1]) / 4 + 1;
-        uint64_t tiles = (max_units + sk::kK2UnitsPerTile - 1) / sk::kK2UnitsPerTile;
-        const int grid = tiles < (uint64_t)resident ? (int)tiles : resident;
-        sk::k2_trim_route<<<grid, sk::kK2Threads, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, s.d_desc[0], s.d_desc[1],
-                                                           s.d_status_k2, c->k2_tiles_cap, s.epoch);
-        SK_CUDA(cudaEventRecord(s.ev_stage[1], st));
-        sk::k3_emit<<<resident, sk::kK3Threads, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, s.d_desc[0], s.d_desc[1], op);
-        SK_CUDA(cudaEventRecord(s.ev_stage[2], st));
-        sk::k_finalize<<<1, 32, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, op, s.d_res);
-        s.launches += 3;
-    }
+    // units <= bytes / 4 (a line is at least its '\n'); usually ~bytes/325
+    const uint64_t max_units = (a.n[0] + a.n[1]) / 4 + 1;
+    const uint64_t tiles = (max_units + sk::kK2UnitsPerTile - 1) / sk::kK2UnitsPerTile;
+    const int grid = tiles < (uint64_t)resident ? (int)tiles : resident;
+    sk::k2_trim_route<<<grid, sk::kK2Threads, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, s.d_desc[0], s.d_desc[1],
+                                                       s.d_status_k2, c->k2_tiles_cap, s.epoch);
+    SK_CUDA(cudaEventRecord(s.ev_stage[1], st));
+    sk::k3_emit<<<resident, sk::kK3Threads, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, s.d_desc[0], s.d_desc[1], op);
+    SK_CUDA(cudaEventRecord(s.ev_stage[2], st));
+    sk::k_finalize<<<1, 32, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, op, s.d_res);
+    s.launches += 3;
     SK_CUDA(cudaEventRecord(s.ev_end, st));
     SK_CUDA(cudaGetLastError());
+    s.last_fused = false;
+    c->n_general++;
+    return SK_OK;
+}
+
+template <int CH>
+int launch_fused_ch(sk_ctx *c, Slot &s, const BatchArgs &a, const sk::DevInput &di, const sk::OutPtrs &op) {
+    using Cfg = sk::FusedCfg<CH>;
+    cudaStream_t st = a.st;
+    const uint32_t tiles = (uint32_t)((a.n[0] + Cfg::kTile - 1) / Cfg::kTile);
+    if (tiles) {
+        const int grid = tiles < (uint32_t)c->fused_grid ? (int)tiles : c->fused_grid;
+        sk::kf_fused<CH><<<grid, sk::kFThreads, Cfg::kSmem, st>>>(di, c->dev, s.d_ctl, op, s.d_status_f,
+                                                                 s.d_status_f + c->fused_tiles_cap, c->fused_tiles_cap,
+                                                                 tiles, s.epoch);
+        s.launches++;
+    }
+    return SK_OK;
+}
+
+template <int CH>
+int setup_fused_ch(sk_ctx *c) {
+    using Cfg = sk::FusedCfg<CH>;
+    SK_CUDA(cudaFuncSetAttribute(sk::kf_fused<CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
+    int per_sm = 0;
+    SK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sk::kf_fused<CH>, sk::kFThreads, Cfg::kSmem));
+    if (per_sm < 1) { set_err("fused kernel does not fit on this device"); return SK_E_CUDA; }
+    c->fused_grid = per_sm * c->sm_count;
+    return SK_OK;
+}
+
+int setup_fused(sk_ctx *c) {
+    switch (c->fused_ch) {
+        case 5: return setup_fused_ch<5>(c);
+        case 9: return setup_fused_ch<9>(c);
+        case 11: return setup_fused_ch<11>(c);
+        default: c->fused_ch = 7; return setup_fused_ch<7>(c);
+    }
+}
+
+// Fused path: one kernel + summary.
+int launch_fused(sk_ctx *c, Slot &s, const BatchArgs &a) {
+    cudaStream_t st = a.st;
+    if (int rc = next_epoch(c, s, st)) return rc;
+    sk::DevInput di[2];
+    sk::OutPtrs op;
+    make_inputs(c, s, a, di, op);
+    s.launches = 0;
+    SK_CUDA(cudaEventRecord(s.ev_begin, st));
+    int rc;
+    switch (c->fused_ch) {
+        case 5: rc = launch_fused_ch<5>(c, s, a, di[0], op); break;
+        case 9: rc = launch_fused_ch<9>(c, s, a, di[0], op); break;
+        case 11: rc = launch_fused_ch<11>(c, s, a, di[0], op); break;
+        default: rc = launch_fused_ch<7>(c, s, a, di[0], op); break;
+    }
+    if (rc) return rc;
+    SK_CUDA(cudaEventRecord(s.ev_stage[0], st));
+    SK_CUDA(cudaEventRecord(s.ev_stage[1], st));
+    SK_CUDA(cudaEventRecord(s.ev_stage[2], st));
+    sk::kf_finalize<<<1, 32, 0, st>>>(di[0], c->dev, s.d_ctl, s.d_res);
+    s.launches++;
+    SK_CUDA(cudaEventRecord(s.ev_end, st));
+    SK_CUDA(cudaGetLastError());
+    s.last_fused = true;
+    c->n_fused++;
+    return SK_OK;
+}
+
+int launch_batch(sk_ctx *c, Slot &s, const BatchArgs &a) {
+    s.last = a;
+    if (c->fused_eligible && c->fused_backoff == 0) return launch_fused(c, s, a);
+    if (c->fused_backoff > 0) c->fused_backoff--;
+    return launch_general(c, s, a);
+}
+
+// The summary of the slot's batch is in h_res.  If the fused kernel gave up, run the batch again on
+// the general path (same stream) and wait for its summary.
+int rerun_if_needed(sk_ctx *c, Slot &s) {
+    if (!s.last_fused || !(s.h_res->index_overflow & 4u)) return SK_OK;
+    c->fused_backoff = 16;
+    c->n_rerun++;
+    if (int rc = launch_general(c, s, s.last)) return rc;
+    SK_CUDA(cudaMemcpyAsync(s.h_res, s.d_res, sizeof(sk::DevResult), cudaMemcpyDeviceToHost, s.last.st));
+    SK_CUDA(cudaStreamSynchronize(s.last.st));
     return SK_OK;
 }
 
@@ -250,6 +368,7 @@ void fill_result(const Slot &s, sk_result *res) {
         res->error.line_len[k] = r.err_line_len[k];
     }
     res->kernel_launches = s.launches;
+    res->fused = s.last_fused ? 1u : 0u;
 }
 
 int stage_times(const Slot &s, sk_result *res) {
@@ -258,6 +377,15 @@ int stage_times(const Slot &s, sk_result *res) {
     SK_CUDA(cudaEventElapsedTime(&res->stage_ms[1], s.ev_stage[0], s.ev_stage[1]));
     SK_CUDA(cudaEventElapsedTime(&res->stage_ms[2], s.ev_stage[1], s.ev_stage[2]));
     SK_CUDA(cudaEventElapsedTime(&res->stage_ms[3], s.ev_stage[2], s.ev_end));
+    return SK_OK;
+}
+
+int check_capacity(const sk_ctx *c, const Slot &s) {
+    if (s.h_res->index_overflow & 1u) {
+        set_err("batch has more than %u lines per input; lower SICKLE_B200_MIN_LINE_BYTES or shrink the batch", c->line_cap);
+        return SK_E_CAPACITY;
+    }
+    if (s.h_res->index_overflow & 2u) { set_err("output stream larger than its buffer"); return SK_E_CAPACITY; }
     return SK_OK;
 }
 
@@ -305,6 +433,12 @@ sk_ctx *sk_create(int device, uint64_t slot_bytes, int n_slots, const sk_params 
     c->line_cap = (uint32_t)(c->slot_bytes / min_line + 8) & ~3u;
     c->k1_tiles_cap = (uint32_t)((c->slot_bytes + sk::kK1TileBytes - 1) / sk::kK1TileBytes) + 1;
     c->k2_tiles_cap = (uint32_t)(((uint64_t)c->line_cap / 4 + sk::kK2UnitsPerTile - 1) / sk::kK2UnitsPerTile) + 2;
+    c->fused_tiles_cap = (uint32_t)(c->slot_bytes / kFusedMinTile) + 2;
+    // SICKLE_B200_PATH = auto (default) | general | fused ; SICKLE_B200_FUSED_CH = 5 | 7 | 9 | 11
+    c->fused_eligible = params->mode != SK_MODE_PE_2FILE && dp.emu_threads == 1;
+    if (const char *e = getenv("SICKLE_B200_PATH")) { if (!strcmp(e, "general")) c->fused_eligible = false; }
+    if (const char *e = getenv("SICKLE_B200_FUSED_CH")) c->fused_ch = atoi(e);
+    if (c->fused_eligible && setup_fused(c) != SK_OK) { delete c; return nullptr; }
     c->host_buffers = n_slots > 0;
     const int ns = n_slots > 0 ? n_slots : 1;
     c->slots.resize(ns);
@@ -368,6 +502,7 @@ int sk_submit(sk_ctx *ctx, int slot, uint64_t start0, uint64_t end0, uint64_t st
     Slot &s = ctx->slots[slot];
     if (s.busy) { set_err("sk_submit: slot %d still busy (call sk_wait first)", slot); return SK_E_ARG; }
     SK_CUDA(cudaSetDevice(ctx->device));
+    BatchArgs a;
     for (int i = 0; i < ctx->n_inputs; ++i) {
         // upload what sk_upload has not covered: [start, min(end, up_lo)) and [max(start, up_hi), end)
         uint64_t lo = s.up_lo[i], hi = s.up_hi[i];
@@ -382,10 +517,13 @@ int sk_submit(sk_ctx *ctx, int slot, uint64_t start0, uint64_t end0, uint64_t st
         s.up_lo[i] = s.up_hi[i] = 0;
         s.base[i] = st[i] & ~15ull;
         s.first[i] = (uint32_t)(st[i] - s.base[i]);
+        a.in[i] = s.d_in[i] + s.base[i];
+        a.first[i] = s.first[i];
+        a.n[i] = en[i] - s.base[i];
     }
-    int rc = launch_batch(ctx, s, s.d_in[0] + s.base[0], s.first[0], en[0] - s.base[0],
-                          ctx->n_inputs > 1 ? s.d_in[1] + s.base[1] : nullptr, s.first[1],
-                          ctx->n_inputs > 1 ? en[1] - s.base[1] : 0, s.d_out, s.out_cap, s.stream);
+    for (int k = 0; k < 3; ++k) { a.out[k] = s.d_out[k]; a.cap[k] = s.out_cap[k]; }
+    a.st = s.stream;
+    int rc = launch_batch(ctx, s, a);
     if (rc != SK_OK) return rc;
     SK_CUDA(cudaMemcpyAsync(s.h_res, s.d_res, sizeof(sk::DevResult), cudaMemcpyDeviceToHost, s.stream));
     SK_CUDA(cudaEventRecord(s.ev_done, s.stream));
@@ -401,13 +539,9 @@ int sk_wait(sk_ctx *ctx, int slot, sk_result *res) {
     SK_CUDA(cudaSetDevice(ctx->device));
     SK_CUDA(cudaEventSynchronize(s.ev_done));
     s.busy = false;
+    if (int rc = rerun_if_needed(ctx, s)) return rc;
     fill_result(s, res);
-    if (s.h_res->index_overflow & 1u) {
-        set_err("batch has more than %u lines per input; raise SICKLE_B200_MIN_LINE_BYTES granularity or shrink the batch",
-                ctx->line_cap);
-        return SK_E_CAPACITY;
-    }
-    if (s.h_res->index_overflow & 2u) { set_err("output stream larger than its buffer"); return SK_E_CAPACITY; }
+    if (int rc = check_capacity(ctx, s)) return rc;
     if (int rc = stage_times(s, res)) return rc;
     if (res->error.kind == 0) {
         for (int k = 0; k < 3; ++k) {
@@ -433,11 +567,14 @@ int sk_trim_device(sk_ctx *ctx, int slot, const void *in0, uint64_t n0, const vo
     Slot &s = ctx->slots[slot];
     if (s.busy && !s.device_mode) { set_err("sk_trim_device: slot %d busy", slot); return SK_E_ARG; }
     SK_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
-    uint8_t *o[3] = {(uint8_t *)out[0], (uint8_t *)out[1], (uint8_t *)out[2]};
+    BatchArgs a;
+    a.in[0] = (const uint8_t *)in0; a.in[1] = (const uint8_t *)in1;
+    a.n[0] = n0; a.n[1] = n1;
+    for (int k = 0; k < 3; ++k) { a.out[k] = (uint8_t *)out[k]; a.cap[k] = out_cap[k]; }
+    a.st = stream ? (cudaStream_t)stream : s.stream;
     s.base[0] = s.base[1] = 0;
     s.first[0] = s.first[1] = 0;
-    int rc = launch_batch(ctx, s, (const uint8_t *)in0, 0, n0, (const uint8_t *)in1, 0, n1, o, out_cap, st);
+    int rc = launch_batch(ctx, s, a);
     if (rc != SK_OK) return rc;
     s.busy = true;
     s.device_mode = true;
@@ -449,15 +586,15 @@ int sk_result_device(sk_ctx *ctx, int slot, void *stream, sk_result *res) {
     Slot &s = ctx->slots[slot];
     if (!s.busy || !s.device_mode) { set_err("sk_result_device: nothing submitted on slot %d", slot); return SK_E_ARG; }
     SK_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = stream ? (cudaStream_t)stream : s.stream;
+    cudaStream_t st = s.last.st;
+    (void)stream;
     SK_CUDA(cudaMemcpyAsync(s.h_res, s.d_res, sizeof(sk::DevResult), cudaMemcpyDeviceToHost, st));
     SK_CUDA(cudaStreamSynchronize(st));
     s.busy = false;
+    if (int rc = rerun_if_needed(ctx, s)) return rc;
     fill_result(s, res);
     if (int rc = stage_times(s, res)) return rc;
-    if (s.h_res->index_overflow & 1u) { set_err("batch has more than %u lines per input", ctx->line_cap); return SK_E_CAPACITY; }
-    if (s.h_res->index_overflow & 2u) { set_err("output stream larger than its buffer"); return SK_E_CAPACITY; }
-    return SK_OK;
+    return check_capacity(ctx, s);
 }
 
 }  // extern "C"

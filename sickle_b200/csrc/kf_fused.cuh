@@ -1,0 +1,538 @@
+// kf_fused.cuh -- single-pass fused kernel for short records: parse + trim + route + emit.
+//
+// One pass over the batch: every input byte is read from HBM once and every output byte written
+// once (the general K1/K2/K3 path reads the input three times and round-trips a line index and a
+// descriptor table).  Same results as K1+K2+K3 -- it covers, per tile,
+//   * the Batch/FQEntry line split              (reference src/GZReader.cpp:76-92, src/FQEntry.cpp:8-18)
+//   * FQEntry::validate                         (src/FQEntry.cpp:53-97)
+//   * sliding_window / get_quality_num          (src/trim.cpp:3-140)
+//   * keep / singles / discard routing          (src/trim_single.cpp:382-404, src/trim_paired.cpp:531-567)
+//   * record formatting                         (src/trim_single.cpp:393-396, src/trim_paired.cpp:506-513)
+// for SK_MODE_SE, SK_MODE_PE_INTER and SK_MODE_PE_INTER_M in input order (emulate_threads == 1).
+//
+// Tile structure (256 threads, persistent CTAs, tiles handed out by an atomic ticket):
+//   S1  region = tile (224 threads x CH x 16 B) + halo (32 threads x CH x 16 B) -> shared memory,
+//       coalesced 16-byte loads.  The halo lets a record that starts in the tile finish.
+//   S2  each thread scans its CH*16 contiguous bytes (odd CH => conflict-free LDS.128): SWAR newline
+//       test -> bit masks -> popc.
+//   S3  block scan -> rank of every newline; positions to shared memory (u16).
+//   S4  decoupled look-back #1 over the tiles' newline counts -> global line number of the tile.
+//   S5  records are lines 4r..4r+3; a record (pair) belongs to the tile holding the newline in
+//       front of it.  One thread per record from here on.
+//   S6  validate + sliding window out of shared memory (word loads, dp4a window sums, SWAR range
+//       check), thread-per-read.
+//   S7  routing, 2-stream block scan, decoupled look-back #2 -> byte offsets in the output streams.
+//   S8  each thread copies its trimmed record into a shared staging buffer laid out like the
+//       destination (same 16-byte phase), then the CTA flushes it with aligned 16-byte stores.
+// Anything this kernel cannot handle exactly -- a record longer than the halo, more than 256
+// records or 2048 newlines in a tile, or ANY data error -- sets Control::fast_fail; the host then
+// re-runs the batch through the general path, which also produces the reference's error details.
+#pragma once
+
+#include "k1_index.cuh"
+#include "k2_trim.cuh"
+#include "sk_device.cuh"
+
+namespace sk {
+
+constexpr int kFThreads = 256;
+constexpr int kFTileThreads = 224;   // 7 warps own tile bytes, the 8th warp scans the halo
+constexpr int kFMaxNl = 2048;
+
+template <int CH>
+struct FusedCfg {
+    static_assert(CH % 2 == 1, "CH must be odd (conflict-free 16-byte shared loads at stride CH*16)");
+    static constexpr int kBytesPerThread = CH * 16;
+    static constexpr int kRegion = kFThreads * kBytesPerThread;
+    static constexpr int kTile = kFTileThreads * kBytesPerThread;
+    static constexpr int kInBytes = kRegion + 32;        // word loads may run 8 bytes past the data
+    static constexpr int kOutBytes = kRegion + 96;       // + two 16-byte phase shifts + slack
+    static constexpr size_t kSmem = (size_t)kInBytes + kOutBytes + kFMaxNl * 2 + 256;
+};
+
+// four successive bytes at a time from an arbitrary shared-memory byte offset
+struct Stream4 {
+    const uint32_t *w;
+    uint32_t cur, nxt, sh;
+    __device__ __forceinline__ void init(const uint8_t *sm, uint32_t off) {
+        w = reinterpret_cast<const uint32_t *>(sm + (off & ~3u));
+        sh = (off & 3u) * 8u;
+        cur = w[0];
+        nxt = w[1];
+        w += 2;
+    }
+    __device__ __forceinline__ uint32_t next() {
+        const uint32_t r = __funnelshift_r(cur, nxt, sh);
+        cur = nxt;
+        nxt = *w++;
+        return r;
+    }
+};
+
+struct RangeCheck {
+    uint32_t kmin, kmax;   // qmin * 0x01010101, (qmax | 0x80) * 0x01010101
+    __device__ __forceinline__ void init(const DevParams &P) {
+        kmin = (uint32_t)P.qmin * 0x01010101u;
+        kmax = ((uint32_t)P.qmax | 0x80u) * 0x01010101u;
+    }
+    // non-zero iff any of the 4 bytes of x is outside [qmin, qmax] (qmax <= 126)
+    __device__ __forceinline__ uint32_t bad4(uint32_t x) const {
+        const uint32_t lo = (x | 0x80808080u) - kmin;          // bit 7 set iff (b & 0x7f) >= qmin
+        const uint32_t up = kmax - (x & 0x7F7F7F7Fu);          // bit 7 set iff (b & 0x7f) <= qmax
+        return ~(lo & up & ~x) & 0x80808080u;
+    }
+};
+
+struct TrimOut {
+    int five, three;   // three < 0 => discard
+    bool error;        // a quality byte outside the encoding's range inside the visited prefix
+};
+
+// Thread-per-read sliding window over shared memory.  Same decisions as warp_sliding_window.
+__device__ __forceinline__ TrimOut thread_sliding_window(const uint8_t *__restrict__ sm, uint32_t seq_off, uint32_t L,
+                                                         uint32_t qual_off, const DevParams &P, const RangeCheck &rc) {
+    TrimOut o;
+    o.five = -1; o.three = -1; o.error = false;
+    if (L < (uint32_t)P.lthr) return o;                                  // trim.cpp:21-26
+    const uint8_t *__restrict__ q = sm + qual_off;
+    uint32_t ws = L / 10u;                                               // trim.cpp:8
+    if (ws == 0) ws = L;                                                 // trim.cpp:30
+    const long long thr_ll = (long long)P.qthr * (long long)ws;
+    // window totals of a record that fits a tile are < 2^23; clamp so that T - thr cannot overflow
+    const int thr = thr_ll > 0x3fffffffLL ? 0x3fffffff : (int)thr_ll;
+
+    // ---- initial window (trim.cpp:31-33): dp4a sums + SWAR range check, 4 bytes at a time
+    int T = 0;
+    {
+        Stream4 s;
+        s.init(sm, qual_off);
+        uint32_t j = 0;
+        uint32_t bad = 0;
+        for (; j + 4 <= ws; j += 4) {
+            const uint32_t x = s.next();
+            bad |= rc.bad4(x);
+            T = (int)__dp4a(x, 0x01010101u, (uint32_t)T);
+        }
+        for (; j < ws; ++j) {
+            const int b = q[j];
+            bad |= (uint32_t)((b < P.qmin) | (b > P.qmax));
+            T += b;
+        }
+        if (bad) { o.error = true; return o; }
+        T -= (int)ws * P.qoff;
+    }
+    int Tm = T - thr;                          // window i is "good" iff Tm >= 0   (trim.cpp:36,42,61)
+    const uint32_t nwin = L - ws + 1u;         // trim.cpp:34
+    bool found = P.no_fiveprime != 0;          // -x: behave as if the 5' end was already found
+    int i5 = -1, i3 = -1;
+    uint32_t i = 0;
+
+    // window i with total Tm: returns true when the 3' break happens here
+#define SK_WINDOW_STEP(idx)                                               \
+    {                                                                     \
+        const bool good = Tm >= 0;                                        \
+        if (!found && good) { found = true; i5 = (int)(idx); }            \
+        if (!good && found) { i3 = (int)(idx); }                          \
+    }
+
+    Stream4 lead, trail;
+    lead.init(sm, qual_off + ws);
+    trail.init(sm, qual_off);
+    // groups of four windows i..i+3, needing lead bytes q[i+ws..i+ws+3] (all < L)
+    while (i3 < 0 && i + 4 < nwin) {
+        const uint32_t lw = lead.next(), tw = trail.next();
+        const uint32_t bad = rc.bad4(lw);
+        const int d0 = (int)(lw & 0xffu) - (int)(tw & 0xffu);
+        const int d1 = (int)((lw >> 8) & 0xffu) - (int)((tw >> 8) & 0xffu);
+        const int d2 = (int)((lw >> 16) & 0xffu) - (int)((tw >> 16) & 0xffu);
+        const int d3 = (int)(lw >> 24) - (int)(tw >> 24);
+        const int T1 = Tm + d0, T2 = T1 + d1, T3 = T2 + d2, T4 = T3 + d3;
+        if (found && !bad && ((Tm | T1 | T2 | T3) >= 0)) {   // common case: four good windows
+            Tm = T4;
+            i += 4;
+            continue;
+        }
+        // resolve this group window by window (5' not found yet, a bad window, or a suspicious byte)
+        const int Tk[4] = {Tm, T1, T2, T3};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            if (i3 < 0) {
+                Tm = Tk[k];
+                SK_WINDOW_STEP(i + k);
+                // the lead byte of window i+k+1 is fetched only if the loop goes on (trim.cpp:76-79)
+                if (i3 < 0 && ((bad >> (8 * k)) & 0x80u)) { o.error = true; return o; }
+            }
+        }
+        if (i3 < 0) { Tm = T4; i += 4; }
+    }
+    // remaining windows one by one
+    while (i3 < 0 && i < nwin) {
+        SK_WINDOW_STEP(i);
+        if (i3 >= 0 || i + 1 >= nwin) break;
+        const int b = q[i + ws];
+        if ((b < P.qmin) | (b > P.qmax)) { o.error = true; return o; }
+        Tm += b - (int)q[i];
+        ++i;
+    }
+#undef SK_WINDOW_STEP
+    found = found && (i5 >= 0 || P.no_fiveprime);
+
+    int five = 0, three = (int)L;
+    if (i5 >= 0) {                                                       // trim.cpp:46-51
+        for (uint32_t j = (uint32_t)i5; j < (uint32_t)i5 + ws; ++j)
+            if ((int)q[j] - P.qoff >= P.qthr) { five = (int)j; break; }
+    }
+    if (i3 >= 0) {                                                       // trim.cpp:65-70
+        for (uint32_t j = (uint32_t)i3; j < (uint32_t)i3 + ws; ++j)
+            if ((int)q[j] - P.qoff < P.qthr) { three = (int)j; break; }
+    }
+    if (P.trunc_n) {                                                     // trim.cpp:86-98
+        const uint8_t *__restrict__ s = sm + seq_off;
+        int pn = -1;
+        bool anyN = false;
+        for (uint32_t j = 0; j < L; ++j) {
+            const int b = s[j];
+            if (b == 'n') { pn = (int)j; break; }
+            anyN |= (b == 'N');
+        }
+        if (pn >= 0) three = pn - 1;
+        else if (anyN) three = -2;
+    }
+    const bool have5 = (i5 >= 0) || P.no_fiveprime;
+    if (!have5 || (three - five < P.lthr)) return o;                     // trim.cpp:103
+    o.five = five;
+    o.three = three;
+    return o;
+}
+
+// thread-sequential copy inside shared memory, arbitrary alignment on both sides
+__device__ __forceinline__ void smem_copy(uint8_t *__restrict__ out, uint32_t dst, const uint8_t *__restrict__ in,
+                                          uint32_t src, uint32_t len) {
+    while (len && (dst & 3u)) { out[dst++] = in[src++]; --len; }
+    const uint32_t nw = len >> 2;
+    if (nw) {
+        const uint32_t sh = (src & 3u) * 8u;
+        const uint32_t *__restrict__ w = reinterpret_cast<const uint32_t *>(in + (src & ~3u));
+        uint32_t *__restrict__ d = reinterpret_cast<uint32_t *>(out + dst);
+        uint32_t cur = w[0];
+        for (uint32_t k = 0; k < nw; ++k) {
+            const uint32_t nxt = w[k + 1];
+            d[k] = __funnelshift_r(cur, nxt, sh);
+            cur = nxt;
+        }
+        dst += nw * 4; src += nw * 4; len -= nw * 4;
+    }
+    while (len) { out[dst++] = in[src++]; --len; }
+}
+
+template <int CH>
+__global__ void __launch_bounds__(kFThreads)
+kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
+         unsigned long long *__restrict__ status_nl, unsigned long long *__restrict__ status_out /* [2][stride] */,
+         uint32_t status_stride, uint32_t num_tiles, uint32_t epoch) {
+    using Cfg = FusedCfg<CH>;
+    extern __shared__ __align__(16) uint8_t smem[];
+    uint8_t *s_in = smem;
+    uint8_t *s_out = smem + Cfg::kInBytes;
+    uint16_t *s_nl = reinterpret_cast<uint16_t *>(smem + Cfg::kInBytes + Cfg::kOutBytes);
+    __shared__ uint32_t s_tile;
+    __shared__ uint32_t warp_tot[kFThreads / 32];
+    __shared__ uint32_t warp_tot2[kFThreads / 32][2];
+    __shared__ unsigned long long s_G;
+    __shared__ unsigned long long s_O[2];
+    __shared__ uint32_t s_fail;
+
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const uint4 *__restrict__ src = reinterpret_cast<const uint4 *>(in.data);
+    const uint32_t nchunks = (in.nbytes + 15u) >> 4;
+    const bool paired = P.mode != 0;
+    const bool mmode = P.mode == 3;
+    const uint32_t lpu = paired ? 8u : 4u;   // lines per unit
+    RangeCheck rc;
+    rc.init(P);
+
+    while (true) {
+        if (tid == 0) { s_tile = atomicAdd(&ctl->tile_counter[3], 1u); s_fail = 0; }
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= num_tiles) break;
+        const uint32_t t0 = tile * (uint32_t)Cfg::kTile;
+
+        // ---- S1: region -> shared memory
+#pragma unroll
+        for (int k = 0; k < CH; ++k) {
+            const uint32_t c = k * kFThreads + tid;
+            uint4 v = make_uint4(0, 0, 0, 0);
+            const uint32_t g = (t0 >> 4) + c;
+            if (g < nchunks) v = __ldcs(src + g);
+            reinterpret_cast<uint4 *>(s_in)[c] = v;
+        }
+        __syncthreads();
+
+        // ---- S2: newline masks of this thread's CH*16 contiguous bytes
+        const uint32_t b0 = tid * Cfg::kBytesPerThread;          // region-relative
+        uint32_t m[CH];
+        uint32_t cnt = 0;
+        {
+            const uint32_t lo = (tile == 0) ? in.first : 0u;     // bytes before the batch start
+            const uint32_t hi = in.nbytes > t0 ? in.nbytes - t0 : 0u;   // bytes at/after the batch end
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                const uint4 v = reinterpret_cast<const uint4 *>(s_in)[CH * tid + k];
+                uint32_t mk = newline_mask16(v);
+                const uint32_t cb = b0 + 16u * k;
+                if (cb + 16u > hi) mk &= cb >= hi ? 0u : ((1u << (hi - cb)) - 1u);
+                if (cb < lo) mk &= cb + 16u <= lo ? 0u : (0xffffu << (lo - cb));
+                m[k] = mk;
+                cnt += __popc(mk);
+            }
+        }
+        // ---- S3: ranks
+        const uint32_t incl = warp_incl_scan(cnt, lane);
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        uint32_t wbase = 0, n_all = 0, c_t = 0;
+#pragma unroll
+        for (int w = 0; w < kFThreads / 32; ++w) {
+            const uint32_t t = warp_tot[w];
+            if (w < wid) wbase += t;
+            if (w < kFTileThreads / 32) c_t += t;
+            n_all += t;
+        }
+        const bool nl_overflow = n_all > (uint32_t)kFMaxNl;
+        if (!nl_overflow) {
+            uint32_t rank = wbase + incl - cnt;
+#pragma unroll
+            for (int k = 0; k < CH; ++k) {
+                uint32_t mk = m[k];
+                while (mk) {
+                    const int b = __ffs(mk) - 1;
+                    mk &= mk - 1;
+                    s_nl[rank++] = (uint16_t)(b0 + 16u * k + b);
+                }
+            }
+        }
+        // ---- S4: global line number of the tile
+        if (wid == 0) {
+            const unsigned long long p = lookback_exclusive(status_nl, tile, c_t, epoch, lane);
+            if (lane == 0) s_G = p;
+        }
+        __syncthreads();
+        const uint32_t G = (uint32_t)s_G;
+
+        // ---- S5: units owned by this tile.  Newline j (j < c_t) is global newline G+j; the line
+        // after it is line G+j+1; a unit starts at every line that is a multiple of lpu.  Tile 0
+        // also owns the unit starting at the batch's first byte ("newline -1").
+        int j_s = (int)((lpu - (G + 1u) % lpu) % lpu);
+        if (tile == 0) j_s = -1;
+        const uint32_t n_units = (j_s < (int)c_t) ? (uint32_t)((int)c_t - 1 - j_s) / lpu + 1u : 0u;
+        const uint32_t rpu = paired ? 2u : 1u;
+        const uint32_t nrec_t = n_units * rpu;
+        bool fail = nl_overflow || nrec_t > (uint32_t)kFThreads;
+
+        // per-record state (thread = record)
+        const bool has_rec = !fail && (uint32_t)tid < nrec_t;
+        bool complete = false;
+        uint32_t start = 0, e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+        if (has_rec) {
+            const int j = j_s + (int)(lpu * ((uint32_t)tid / rpu)) + 4 * (int)((uint32_t)tid % rpu);
+            if ((uint32_t)(j + 4) < n_all) {
+                complete = true;
+                start = j < 0 ? in.first : (uint32_t)s_nl[j] + 1u;
+                e0 = s_nl[j + 1]; e1 = s_nl[j + 2]; e2 = s_nl[j + 3]; e3 = s_nl[j + 4];
+            }
+        }
+        if (paired) {   // a pair is complete only if both mates are (all lanes take part in the shuffle)
+            const int mate_complete = __shfl_xor_sync(0xffffffffu, (int)complete, 1);
+            complete = complete && mate_complete != 0;
+        }
+        // an incomplete unit is fine only as the unfinished tail of the batch
+        const bool region_to_end = (unsigned long long)t0 + Cfg::kRegion >= in.nbytes;
+        if (has_rec && !complete && !region_to_end) fail = true;
+
+        // ---- S6: validate + trim
+        TrimOut cut;
+        cut.five = -1; cut.three = -1; cut.error = false;
+        uint32_t name_len = 0, plus_len = 0, L = 0;
+        if (has_rec && complete) {
+            name_len = e0 - start;
+            L = e1 - e0 - 1u;
+            plus_len = e2 - e1 - 1u;
+            const uint32_t qlen = e3 - e2 - 1u;
+            // FQEntry::validate (src/FQEntry.cpp:53-97): any violation is a data error
+            if (name_len <= 1u || s_in[start] != '@' || L < 1u || qlen < 1u || qlen != L) fail = true;
+            else {
+                cut = thread_sliding_window(s_in, e0 + 1u, L, e2 + 1u, P, rc);
+                if (cut.error) fail = true;
+            }
+        }
+        if (fail) s_fail = 1u;
+
+        // ---- S7: routing + output offsets (lane = record; mates are lanes 2k, 2k+1)
+        const bool live = has_rec && complete;
+        const bool keep = live && cut.three >= 0;
+        const uint32_t nkeep = keep ? (uint32_t)(cut.three - cut.five) : 0u;
+        const uint32_t fixed = name_len + plus_len + 4u;
+        uint32_t add0 = 0, add1 = 0;        // bytes for the main stream / the singles stream
+        bool nrec_out = false;              // emit as an "N record" (-M)
+        int stream = -1;
+        const bool other = paired && __shfl_xor_sync(0xffffffffu, (int)keep, 1) != 0;   // mate's keep flag
+        if (live) {
+            if (!paired) {
+                if (keep) { stream = 0; add0 = fixed + 2u * nkeep; }
+            } else {
+                if (mmode) {                                        // README.md:116-120
+                    stream = 0;
+                    nrec_out = !keep;
+                    add0 = keep ? fixed + 2u * nkeep : fixed + 2u;
+                } else if (keep && other) { stream = 0; add0 = fixed + 2u * nkeep; }     // trim_paired.cpp:543-551
+                else if (keep && P.has_singles) { stream = 1; add1 = fixed + 2u * nkeep; } // trim_paired.cpp:552-563
+            }
+        }
+        const uint32_t inc0 = warp_incl_scan(add0, lane);
+        const uint32_t inc1 = warp_incl_scan(add1, lane);
+        if (lane == 31) { warp_tot2[wid][0] = inc0; warp_tot2[wid][1] = inc1; }
+        __syncthreads();
+        const bool tile_fail = s_fail != 0;
+        if (wid < 2) {
+            uint32_t total = 0;
+#pragma unroll
+            for (int w = 0; w < kFThreads / 32; ++w) total += warp_tot2[w][wid];
+            if (tile_fail) total = 0;
+            const unsigned long long pre =
+                lookback_exclusive(status_out + (size_t)wid * status_stride, tile, total, epoch, lane);
+            if (lane == 0) {
+                s_O[wid] = pre;
+                if (tile == num_tiles - 1) ctl->out_bytes[wid == 0 ? 0 : 2] = pre + total;
+            }
+        }
+        if (tile_fail) {
+            if (tid == 0) ctl->fast_fail = 1u;
+            __syncthreads();
+            continue;
+        }
+        uint32_t wb0 = 0, wb1 = 0, tot0 = 0, tot1 = 0;
+#pragma unroll
+        for (int w = 0; w < kFThreads / 32; ++w) {
+            const uint32_t a = warp_tot2[w][0], b = warp_tot2[w][1];
+            if (w < wid) { wb0 += a; wb1 += b; }
+            tot0 += a; tot1 += b;
+        }
+        __syncthreads();
+        const unsigned long long O0 = s_O[0], O1 = s_O[1];
+        uint8_t *g0 = outs.p[0] + O0;
+        uint8_t *g1 = outs.p[2] ? outs.p[2] + O1 : nullptr;
+        const uint32_t ph0 = (uint32_t)(reinterpret_cast<uintptr_t>(g0) & 15u);
+        const uint32_t ph1 = (uint32_t)(reinterpret_cast<uintptr_t>(g1) & 15u);
+        const uint32_t base1 = ((ph0 + tot0 + 15u) & ~15u) + ph1;      // singles staged after the main bytes
+        const bool cap_ok = O0 + tot0 <= outs.cap[0] && (tot1 == 0 || (g1 && O1 + tot1 <= outs.cap[2]));
+        if (!cap_ok) {
+            if (tid == 0) ctl->index_overflow = 2u;
+            __syncthreads();
+            continue;
+        }
+
+        // ---- S8a: thread-per-record copy into the staging buffer (destination-phase aligned)
+        if (stream >= 0) {
+            uint32_t d = stream == 0 ? ph0 + wb0 + inc0 - add0 : base1 + wb1 + inc1 - add1;
+            smem_copy(s_out, d, s_in, start, name_len + 1u);            // name line and its '\n'
+            d += name_len + 1u;
+            if (nrec_out) {
+                s_out[d] = 'N'; s_out[d + 1] = '\n';
+                d += 2;
+                smem_copy(s_out, d, s_in, e1 + 1u, plus_len + 1u);      // line 3 verbatim
+                d += plus_len + 1u;
+                s_out[d] = (uint8_t)P.qmin; s_out[d + 1] = '\n';
+            } else {
+                const uint32_t five = (uint32_t)cut.five;
+                if (five + nkeep == L) {
+                    // nothing cut at the 3' end: seq tail, '\n', line 3, '\n' are contiguous in the source
+                    smem_copy(s_out, d, s_in, e0 + 1u + five, nkeep + 1u + plus_len + 1u);
+                    d += nkeep + plus_len + 2u;
+                    smem_copy(s_out, d, s_in, e2 + 1u + five, nkeep + 1u);
+                } else {
+                    smem_copy(s_out, d, s_in, e0 + 1u + five, nkeep);
+                    d += nkeep;
+                    smem_copy(s_out, d, s_in, e1, plus_len + 2u);       // '\n' + line 3 + '\n'
+                    d += plus_len + 2u;
+                    smem_copy(s_out, d, s_in, e2 + 1u + five, nkeep);
+                    d += nkeep;
+                    s_out[d] = '\n';
+                }
+            }
+        }
+        __syncthreads();
+
+        // ---- S8b: flush with destination-aligned 16-byte stores (byte stores on the ragged ends)
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            const uint32_t tot = s == 0 ? tot0 : tot1;
+            if (tot == 0) continue;
+            const uint32_t ph = s == 0 ? ph0 : ph1;
+            const uint32_t sb = s == 0 ? 0u : base1 - ph1;             // staging offset of the 16-byte grid
+            uint8_t *gal = (s == 0 ? g0 : g1) - ph;                    // 16-byte aligned
+            const uint32_t nch = (ph + tot + 15u) >> 4;
+            for (uint32_t c = tid; c < nch; c += kFThreads) {
+                const uint32_t lo = c == 0 ? ph : 0u;
+                const uint32_t hi = min(16u, ph + tot - 16u * c);
+                if (lo == 0 && hi == 16) {
+                    __stcs(reinterpret_cast<uint4 *>(gal) + c, *reinterpret_cast<const uint4 *>(s_out + sb + 16u * c));
+                } else {
+                    for (uint32_t b = lo; b < hi; ++b) gal[16u * c + b] = s_out[sb + 16u * c + b];
+                }
+            }
+        }
+
+        // ---- bookkeeping: consumed bytes, record count, counters
+        {
+            // end of the last complete record of this tile (absolute offset in the input buffer)
+            uint32_t end = live ? t0 + e3 + 1u : 0u;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) end = max(end, __shfl_xor_sync(0xffffffffu, end, o));
+            const uint32_t m_live = __ballot_sync(0xffffffffu, live);
+            const uint32_t m_keep = __ballot_sync(0xffffffffu, keep);
+            uint32_t m_other = 0;
+            if (paired) {
+                // bit k = keep flag of lane k's mate
+                m_other = ((m_keep & 0x55555555u) << 1) | ((m_keep & 0xAAAAAAAAu) >> 1);
+            }
+            if (lane == 0 && m_live) {
+                atomicMax(&ctl->fast_consumed, end);
+                atomicAdd(&ctl->fast_records, (uint32_t)__popc(m_live));
+                if (!paired) {
+                    atomicAdd(&ctl->counters[0], (unsigned long long)__popc(m_keep));
+                    atomicAdd(&ctl->counters[1], (unsigned long long)__popc(m_live & ~m_keep));
+                } else {
+                    const uint32_t even = 0x55555555u & m_live;          // one bit per pair (mate 1's lane)
+                    const uint32_t k1 = m_keep & even, k2 = m_other & even;
+                    atomicAdd(&ctl->counters[2], 2ull * __popc(k1 & k2));           // kept_p
+                    atomicAdd(&ctl->counters[3], 2ull * __popc(even & ~k1 & ~k2));  // discard_p
+                    atomicAdd(&ctl->counters[4], (unsigned long long)__popc(k1 & ~k2));   // kept_s1
+                    atomicAdd(&ctl->counters[7], (unsigned long long)__popc(k1 & ~k2));   // discard_s2
+                    atomicAdd(&ctl->counters[5], (unsigned long long)__popc(k2 & ~k1));   // kept_s2
+                    atomicAdd(&ctl->counters[6], (unsigned long long)__popc(k2 & ~k1));   // discard_s1
+                }
+            }
+        }
+        __syncthreads();   // staging buffers and scan scratch are reused by the next tile
+    }
+}
+
+// Batch summary of the fused path (no line index exists): one thread.
+__global__ void kf_finalize(DevInput in, DevParams P, Control *__restrict__ ctl, DevResult *__restrict__ res) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    DevResult r;
+    memset(&r, 0, sizeof r);
+    for (int s = 0; s < kMaxStreams; ++s) r.out_bytes[s] = ctl->out_bytes[s];
+    r.records[0] = ctl->fast_records;
+    r.consumed[0] = ctl->fast_consumed;
+    for (int k = 0; k < 8; ++k) r.counters[k] = (long long)ctl->counters[k];
+    r.index_overflow = (ctl->index_overflow & 2u) | (ctl->fast_fail ? 4u : 0u);
+    *res = r;
+    Control z;
+    memset(&z, 0, sizeof z);
+    z.err_key = kNoError;
+    *ctl = z;
+}
+
+}  // namespace sk

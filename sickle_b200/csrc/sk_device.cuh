@@ -48,8 +48,10 @@ constexpr uint32_t kRouteNRec = 8u;
 struct Control {
     uint32_t tile_counter[4];     // dynamic tile tickets: K1 input 0, K1 input 1, K2, K3
     uint32_t nlines[2];           // written by K1's last tile
-    uint32_t index_overflow;      // a line index ran out of capacity
-    uint32_t pad0;
+    uint32_t index_overflow;      // bit 0: a line index ran out of capacity; bit 1: an output buffer did
+    uint32_t fast_fail;           // fused path met something it does not handle: re-run on the general path
+    uint32_t fast_consumed;       // fused path: end of the last complete unit (max over tiles)
+    uint32_t fast_records;        // fused path: complete records
     unsigned long long err_key;   // min over offending (class, unit, mate, position); ~0 = none
     unsigned long long counters[8];  // kept, discard, kept_p, discard_p, kept_s1, kept_s2, discard_s1, discard_s2
     unsigned long long out_bytes[kMaxStreams];

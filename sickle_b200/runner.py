@@ -36,7 +36,7 @@ def trim_stream(ctx: capi.Context, in0: bytes, in1: bytes = b"", pipelined: bool
     outs = [[], [], []]
     totals = dict.fromkeys(capi.Result.COUNTERS, 0)
     records = [0, 0]
-    stats = dict(batches=0, kernel_ms=0.0, launches=0)
+    stats = dict(batches=0, kernel_ms=0.0, launches=0, fused_batches=0)
 
     def absorb(res, slot, base_records):
         if res.error.kind:
@@ -52,6 +52,7 @@ def trim_stream(ctx: capi.Context, in0: bytes, in1: bytes = b"", pipelined: bool
         stats["batches"] += 1
         stats["kernel_ms"] += res.kernel_ms
         stats["launches"] += res.kernel_launches
+        stats["fused_batches"] += res.fused
         for i in range(2):
             records[i] += res.records[i]
 

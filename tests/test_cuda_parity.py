@@ -45,7 +45,15 @@ def _run_cuda(capi, mode, flags, in0, in1=b"", slot_bytes=1 << 16, has_singles=T
         return runner.trim_stream(ctx, in0, in1, pipelined=pipelined, headroom=headroom)
 
 
-def test_golden_cases(capi, golden):
+@pytest.fixture(params=["auto", "general"])
+def kernel_path(request, monkeypatch):
+    """auto = single-pass fused kernel where it applies (falls back to K1/K2/K3 per batch);
+    general = K1/K2/K3 always."""
+    monkeypatch.setenv("SICKLE_B200_PATH", request.param)
+    return request.param
+
+
+def test_golden_cases(capi, golden, kernel_path):
     from sickle_b200 import runner
 
     bad = []
@@ -128,7 +136,7 @@ FLAGSETS = [dict(q=20, l=20, x=False, n=False), dict(q=30, l=5, x=True, n=False)
 
 @pytest.mark.parametrize("qualtype", ["sanger", "illumina", "solexa"])
 @pytest.mark.parametrize("lmax", [12, 70, 400, 3000])
-def test_random_se_vs_oracle(capi, qualtype, lmax):
+def test_random_se_vs_oracle(capi, qualtype, lmax, kernel_path):
     rng = np.random.default_rng([1, lmax, len(qualtype)])
     recs = _random_fastq(rng, 3000 if lmax <= 400 else 300, lmax, qualtype)
     data = b"".join(recs)
@@ -143,7 +151,7 @@ def test_random_se_vs_oracle(capi, qualtype, lmax):
 
 
 @pytest.mark.parametrize("mode_name", ["pe2", "pei", "pei_nosingles", "peiM"])
-def test_random_pe_vs_oracle(capi, mode_name):
+def test_random_pe_vs_oracle(capi, mode_name, kernel_path):
     rng = np.random.default_rng([2, len(mode_name)])
     a = _random_fastq(rng, 2500, 200, "sanger")
     b = _random_fastq(rng, 2500, 120, "sanger")
@@ -203,6 +211,7 @@ def test_batch_size_invariance_and_pipelined_upload(capi):
         got = _run_cuda(capi, capi.MODE_SE, flags, data, slot_bytes=slot, pipelined=pipe, n_slots=nslots, headroom=head)
         assert got["out"][0] == want["out"][0], (slot, pipe)
         assert got["counters"]["kept"] == want["counters"]["kept"]
+        assert got["fused_batches"] == got["batches"], "150 bp reads must take the single-pass kernel"
         ref = got
     assert ref["records"][0] == 20000
 
