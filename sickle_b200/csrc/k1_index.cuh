@@ -22,17 +22,18 @@ constexpr int kK1BytesPerThread = 64;
 constexpr int kK1TileBytes = kK1Threads * kK1BytesPerThread;  // 16384
 
 // 0x80 in every byte of w that equals '\n' (exact, no false positives).
+// Three ALU ops per word: the low 7 bits of (w ^ 0x0A..) are zero iff +0x7F leaves bit 7 clear, and
+// the byte's own bit 7 (unchanged by the xor) must be clear as well.
 __device__ __forceinline__ uint32_t newline_flags(uint32_t w) {
-    const uint32_t x = w ^ 0x0A0A0A0Au;
-    const uint32_t t = ((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x;
-    return ~(t | 0x7F7F7F7Fu);
+    const uint32_t t = ((w ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+    return ~(t | w) & 0x80808080u;
 }
-// 4 flag bits (bit i = byte i is '\n') from a word of 0x80 flags.
-__device__ __forceinline__ uint32_t flags_to_nibble(uint32_t f) { return ((f >> 7) * 0x10204080u) >> 28; }
+// 4 flag bits (bit i = byte i flagged) from a word of 0x80 flags: bits 7/15/23/31 -> 28/29/30/31.
+__device__ __forceinline__ uint32_t flags_to_nibble(uint32_t f) { return (f * 0x00204081u) >> 28; }
 
 __device__ __forceinline__ uint32_t newline_mask16(const uint4 v) {
-    return flags_to_nibble(newline_flags(v.x)) | (flags_to_nibble(newline_flags(v.y)) << 4) |
-           (flags_to_nibble(newline_flags(v.z)) << 8) | (flags_to_nibble(newline_flags(v.w)) << 12);
+    return flags_to_nibble(newline_flags(v.x)) + (flags_to_nibble(newline_flags(v.y)) << 4) +
+           (flags_to_nibble(newline_flags(v.z)) << 8) + (flags_to_nibble(newline_flags(v.w)) << 12);
 }
 
 // swizzled position (in 16-byte chunks) of logical chunk c inside the staging tile

@@ -14,13 +14,14 @@
 //   S1  region = tile (224 threads x CH x 16 B) + halo (32 threads x CH x 16 B) -> shared memory,
 //       coalesced 16-byte loads.  The halo lets a record that starts in the tile finish.
 //   S2  each thread scans its CH*16 contiguous bytes (odd CH => conflict-free LDS.128): SWAR newline
-//       test -> bit masks -> popc.
+//       test (3 ALU ops / word) -> bit masks -> popc.
 //   S3  block scan -> rank of every newline; positions to shared memory (u16).
 //   S4  decoupled look-back #1 over the tiles' newline counts -> global line number of the tile.
 //   S5  records are lines 4r..4r+3; a record (pair) belongs to the tile holding the newline in
 //       front of it.  One thread per record from here on.
-//   S6  validate + sliding window out of shared memory (word loads, dp4a window sums, SWAR range
-//       check), thread-per-read.
+//   S6  validate + sliding window out of shared memory, thread-per-read and branch-free: 32 windows
+//       per step, window totals by dp4a straight from the packed quality words, good/bad windows and
+//       out-of-range bytes collected as bit masks and resolved once per step.
 //   S7  routing, 2-stream block scan, decoupled look-back #2 -> byte offsets in the output streams.
 //   S8  each thread copies its trimmed record into a shared staging buffer laid out like the
 //       destination (same 16-byte phase), then the CTA flushes it with aligned 16-byte stores.
@@ -45,7 +46,7 @@ struct FusedCfg {
     static constexpr int kBytesPerThread = CH * 16;
     static constexpr int kRegion = kFThreads * kBytesPerThread;
     static constexpr int kTile = kFTileThreads * kBytesPerThread;
-    static constexpr int kInBytes = kRegion + 32;        // word loads may run 8 bytes past the data
+    static constexpr int kInBytes = kRegion + 128;       // the window loop reads up to ~80 bytes past a record
     static constexpr int kOutBytes = kRegion + 96;       // + two 16-byte phase shifts + slack
     static constexpr size_t kSmem = (size_t)kInBytes + kOutBytes + kFMaxNl * 2 + 256;
 };
@@ -75,7 +76,7 @@ struct RangeCheck {
         kmin = (uint32_t)P.qmin * 0x01010101u;
         kmax = ((uint32_t)P.qmax | 0x80u) * 0x01010101u;
     }
-    // non-zero iff any of the 4 bytes of x is outside [qmin, qmax] (qmax <= 126)
+    // 0x80 in every byte of x that is outside [qmin, qmax] (qmax <= 126)
     __device__ __forceinline__ uint32_t bad4(uint32_t x) const {
         const uint32_t lo = (x | 0x80808080u) - kmin;          // bit 7 set iff (b & 0x7f) >= qmin
         const uint32_t up = kmax - (x & 0x7F7F7F7Fu);          // bit 7 set iff (b & 0x7f) <= qmax
@@ -88,7 +89,18 @@ struct TrimOut {
     bool error;        // a quality byte outside the encoding's range inside the visited prefix
 };
 
+// dp4a with unsigned bytes in a and signed bytes in b
+__device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
+    int d;
+    asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+    return d;
+}
+
 // Thread-per-read sliding window over shared memory.  Same decisions as warp_sliding_window.
+// Window i is "good" iff total(i) >= qthr*ws (trim.cpp:36,42,61).  Let i5 = first good window,
+// i3 = first bad window after it (or the first bad window at all with -x).  Quality bytes are range-
+// checked exactly where the reference's scalar loop touches them: the first window always, and the
+// byte entering window i+1 iff the loop gets past window i (i < i3 and i+1 < nwin).
 __device__ __forceinline__ TrimOut thread_sliding_window(const uint8_t *__restrict__ sm, uint32_t seq_off, uint32_t L,
                                                          uint32_t qual_off, const DevParams &P, const RangeCheck &rc) {
     TrimOut o;
@@ -101,7 +113,7 @@ __device__ __forceinline__ TrimOut thread_sliding_window(const uint8_t *__restri
     // window totals of a record that fits a tile are < 2^23; clamp so that T - thr cannot overflow
     const int thr = thr_ll > 0x3fffffffLL ? 0x3fffffff : (int)thr_ll;
 
-    // ---- initial window (trim.cpp:31-33): dp4a sums + SWAR range check, 4 bytes at a time
+    // ---- first window (trim.cpp:31-33): dp4a sums + SWAR range check, 4 bytes at a time
     int T = 0;
     {
         Stream4 s;
@@ -121,61 +133,57 @@ __device__ __forceinline__ TrimOut thread_sliding_window(const uint8_t *__restri
         if (bad) { o.error = true; return o; }
         T -= (int)ws * P.qoff;
     }
-    int Tm = T - thr;                          // window i is "good" iff Tm >= 0   (trim.cpp:36,42,61)
+    int Tm = T - thr;                          // sign bit set <=> window is bad
     const uint32_t nwin = L - ws + 1u;         // trim.cpp:34
     bool found = P.no_fiveprime != 0;          // -x: behave as if the 5' end was already found
     int i5 = -1, i3 = -1;
-    uint32_t i = 0;
-
-    // window i with total Tm: returns true when the 3' break happens here
-#define SK_WINDOW_STEP(idx)                                               \
-    {                                                                     \
-        const bool good = Tm >= 0;                                        \
-        if (!found && good) { found = true; i5 = (int)(idx); }            \
-        if (!good && found) { i3 = (int)(idx); }                          \
-    }
 
     Stream4 lead, trail;
     lead.init(sm, qual_off + ws);
     trail.init(sm, qual_off);
-    // groups of four windows i..i+3, needing lead bytes q[i+ws..i+ws+3] (all < L)
-    while (i3 < 0 && i + 4 < nwin) {
-        const uint32_t lw = lead.next(), tw = trail.next();
-        const uint32_t bad = rc.bad4(lw);
-        const int d0 = (int)(lw & 0xffu) - (int)(tw & 0xffu);
-        const int d1 = (int)((lw >> 8) & 0xffu) - (int)((tw >> 8) & 0xffu);
-        const int d2 = (int)((lw >> 16) & 0xffu) - (int)((tw >> 16) & 0xffu);
-        const int d3 = (int)(lw >> 24) - (int)(tw >> 24);
-        const int T1 = Tm + d0, T2 = T1 + d1, T3 = T2 + d2, T4 = T3 + d3;
-        if (found && !bad && ((Tm | T1 | T2 | T3) >= 0)) {   // common case: four good windows
-            Tm = T4;
-            i += 4;
-            continue;
-        }
-        // resolve this group window by window (5' not found yet, a bad window, or a suspicious byte)
-        const int Tk[4] = {Tm, T1, T2, T3};
+    for (uint32_t base = 0; base < nwin && i3 < 0; base += 32) {
+        uint32_t negw = 0;   // bit k: window base+k is bad
+        uint32_t oorw = 0;   // bit k: the byte entering window base+k+1 is outside the encoding's range
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            if (i3 < 0) {
-                Tm = Tk[k];
-                SK_WINDOW_STEP(i + k);
-                // the lead byte of window i+k+1 is fetched only if the loop goes on (trim.cpp:76-79)
-                if (i3 < 0 && ((bad >> (8 * k)) & 0x80u)) { o.error = true; return o; }
-            }
+        for (int g = 0; g < 8; ++g) {
+            const uint32_t lw = lead.next(), tw = trail.next();
+            // totals of windows base+4g+1 .. +4: prefix sums of (lead - trail), independent of each other
+            const int T1 = dp4a_us(lw, 0x00000001, dp4a_us(tw, 0x000000FF, Tm));
+            const int T2 = dp4a_us(lw, 0x00000101, dp4a_us(tw, 0x0000FFFF, Tm));
+            const int T3 = dp4a_us(lw, 0x00010101, dp4a_us(tw, 0x00FFFFFF, Tm));
+            const int T4 = dp4a_us(lw, 0x01010101, dp4a_us(tw, (int)0xFFFFFFFF, Tm));
+            // sign bytes of windows base+4g .. +3 -> 4 flag bits
+            const uint32_t s01 = __byte_perm((uint32_t)Tm, (uint32_t)T1, 0x0073);
+            const uint32_t s23 = __byte_perm((uint32_t)T2, (uint32_t)T3, 0x0073);
+            const uint32_t sg = __byte_perm(s01, s23, 0x5410) & 0x80808080u;
+            negw += flags_to_nibble(sg) << (4 * g);
+            oorw += flags_to_nibble(rc.bad4(lw)) << (4 * g);
+            Tm = T4;
         }
-        if (i3 < 0) { Tm = T4; i += 4; }
+        // ---- resolve the 32 windows of this step
+        const uint32_t left = nwin - base;                               // windows from base on (>= 1)
+        const uint32_t vmask = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
+        const uint32_t goodw = ~negw & vmask;
+        uint32_t after = 0xffffffffu;
+        if (!found) {                                                    // first good window: trim.cpp:42
+            if (goodw) {
+                const int k = __ffs(goodw) - 1;
+                i5 = (int)base + k;
+                found = true;
+                after = 0xffffffffu << k;
+            } else after = 0;
+        }
+        const uint32_t cand = negw & vmask & after;                      // first bad window after it: trim.cpp:61
+        uint32_t visited;                                                // which entering bytes were really fetched
+        if (cand) {
+            const int k3 = __ffs(cand) - 1;
+            i3 = (int)base + k3;
+            visited = (1u << k3) - 1u;                                   // windows before the break
+        } else {
+            visited = left > 32 ? 0xffffffffu : ((1u << (left - 1u)) - 1u);   // all but the last window
+        }
+        if (oorw & visited) { o.error = true; return o; }
     }
-    // remaining windows one by one
-    while (i3 < 0 && i < nwin) {
-        SK_WINDOW_STEP(i);
-        if (i3 >= 0 || i + 1 >= nwin) break;
-        const int b = q[i + ws];
-        if ((b < P.qmin) | (b > P.qmax)) { o.error = true; return o; }
-        Tm += b - (int)q[i];
-        ++i;
-    }
-#undef SK_WINDOW_STEP
-    found = found && (i5 >= 0 || P.no_fiveprime);
 
     int five = 0, three = (int)L;
     if (i5 >= 0) {                                                       // trim.cpp:46-51
@@ -205,23 +213,40 @@ __device__ __forceinline__ TrimOut thread_sliding_window(const uint8_t *__restri
     return o;
 }
 
-// thread-sequential copy inside shared memory, arbitrary alignment on both sides
+// Thread-sequential copy inside shared memory, arbitrary alignment on both sides.  The bulk moves
+// as 16-byte destination-aligned stores fed by funnel-shifted source words.
 __device__ __forceinline__ void smem_copy(uint8_t *__restrict__ out, uint32_t dst, const uint8_t *__restrict__ in,
                                           uint32_t src, uint32_t len) {
+    // head: bytes up to a 4-byte destination boundary, then words up to a 16-byte boundary
     while (len && (dst & 3u)) { out[dst++] = in[src++]; --len; }
-    const uint32_t nw = len >> 2;
-    if (nw) {
-        const uint32_t sh = (src & 3u) * 8u;
-        const uint32_t *__restrict__ w = reinterpret_cast<const uint32_t *>(in + (src & ~3u));
-        uint32_t *__restrict__ d = reinterpret_cast<uint32_t *>(out + dst);
-        uint32_t cur = w[0];
-        for (uint32_t k = 0; k < nw; ++k) {
-            const uint32_t nxt = w[k + 1];
-            d[k] = __funnelshift_r(cur, nxt, sh);
-            cur = nxt;
-        }
-        dst += nw * 4; src += nw * 4; len -= nw * 4;
+    const uint32_t sh = (src & 3u) * 8u;
+    const uint32_t *__restrict__ w = reinterpret_cast<const uint32_t *>(in + (src & ~3u));
+    uint32_t cur = w[0];
+    uint32_t nw = len >> 2;                       // whole destination words left
+    uint32_t *__restrict__ d = reinterpret_cast<uint32_t *>(out + dst);
+    uint32_t k = 0;
+    while (k < nw && ((dst + 4u * k) & 15u)) {
+        const uint32_t nxt = w[k + 1];
+        d[k] = __funnelshift_r(cur, nxt, sh);
+        cur = nxt;
+        ++k;
     }
+    for (; k + 4 <= nw; k += 4) {
+        const uint32_t a = w[k + 1], b = w[k + 2], c = w[k + 3], e = w[k + 4];
+        uint4 v;
+        v.x = __funnelshift_r(cur, a, sh);
+        v.y = __funnelshift_r(a, b, sh);
+        v.z = __funnelshift_r(b, c, sh);
+        v.w = __funnelshift_r(c, e, sh);
+        *reinterpret_cast<uint4 *>(d + k) = v;
+        cur = e;
+    }
+    for (; k < nw; ++k) {
+        const uint32_t nxt = w[k + 1];
+        d[k] = __funnelshift_r(cur, nxt, sh);
+        cur = nxt;
+    }
+    dst += nw * 4; src += nw * 4; len -= nw * 4;
     while (len) { out[dst++] = in[src++]; --len; }
 }
 
@@ -269,24 +294,29 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         }
         __syncthreads();
 
-        // ---- S2: newline masks of this thread's CH*16 contiguous bytes
+        // ---- S2: newline masks of this thread's CH*16 contiguous bytes (two 64-bit halves)
         const uint32_t b0 = tid * Cfg::kBytesPerThread;          // region-relative
-        uint32_t m[CH];
-        uint32_t cnt = 0;
+        unsigned long long mlo = 0, mhi = 0;                     // bytes [0,64) and [64, CH*16)
         {
-            const uint32_t lo = (tile == 0) ? in.first : 0u;     // bytes before the batch start
-            const uint32_t hi = in.nbytes > t0 ? in.nbytes - t0 : 0u;   // bytes at/after the batch end
+            // only the first tile (bytes before the batch start) and the tiles touching the end of
+            // the batch have bytes to mask off
+            const bool edge = tile == 0 || (unsigned long long)t0 + Cfg::kRegion > in.nbytes;
+            const uint32_t lo = (tile == 0) ? in.first : 0u;
+            const uint32_t hi = in.nbytes > t0 ? in.nbytes - t0 : 0u;
 #pragma unroll
             for (int k = 0; k < CH; ++k) {
                 const uint4 v = reinterpret_cast<const uint4 *>(s_in)[CH * tid + k];
                 uint32_t mk = newline_mask16(v);
-                const uint32_t cb = b0 + 16u * k;
-                if (cb + 16u > hi) mk &= cb >= hi ? 0u : ((1u << (hi - cb)) - 1u);
-                if (cb < lo) mk &= cb + 16u <= lo ? 0u : (0xffffu << (lo - cb));
-                m[k] = mk;
-                cnt += __popc(mk);
+                if (edge) {
+                    const uint32_t cb = b0 + 16u * k;
+                    if (cb + 16u > hi) mk &= cb >= hi ? 0u : ((1u << (hi - cb)) - 1u);
+                    if (cb < lo) mk &= cb + 16u <= lo ? 0u : (0xffffu << (lo - cb));
+                }
+                if (k < 4) mlo |= (unsigned long long)mk << (16 * k);
+                else mhi |= (unsigned long long)mk << (16 * (k - 4));
             }
         }
+        const uint32_t cnt = __popcll(mlo) + __popcll(mhi);
         // ---- S3: ranks
         const uint32_t incl = warp_incl_scan(cnt, lane);
         if (lane == 31) warp_tot[wid] = incl;
@@ -300,16 +330,18 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             n_all += t;
         }
         const bool nl_overflow = n_all > (uint32_t)kFMaxNl;
+        // publish the tile's newline count as early as possible (S4 part 1 happens inside look-back)
         if (!nl_overflow) {
             uint32_t rank = wbase + incl - cnt;
-#pragma unroll
-            for (int k = 0; k < CH; ++k) {
-                uint32_t mk = m[k];
-                while (mk) {
-                    const int b = __ffs(mk) - 1;
-                    mk &= mk - 1;
-                    s_nl[rank++] = (uint16_t)(b0 + 16u * k + b);
-                }
+            while (mlo) {
+                const int b = __ffsll((long long)mlo) - 1;
+                mlo &= mlo - 1;
+                s_nl[rank++] = (uint16_t)(b0 + b);
+            }
+            while (mhi) {
+                const int b = __ffsll((long long)mhi) - 1;
+                mhi &= mhi - 1;
+                s_nl[rank++] = (uint16_t)(b0 + 64 + b);
             }
         }
         // ---- S4: global line number of the tile
@@ -390,7 +422,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             }
         }
         const uint32_t inc0 = warp_incl_scan(add0, lane);
-        const uint32_t inc1 = warp_incl_scan(add1, lane);
+        const uint32_t inc1 = paired ? warp_incl_scan(add1, lane) : 0u;
         if (lane == 31) { warp_tot2[wid][0] = inc0; warp_tot2[wid][1] = inc1; }
         __syncthreads();
         const bool tile_fail = s_fail != 0;
@@ -435,9 +467,9 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         // ---- S8a: thread-per-record copy into the staging buffer (destination-phase aligned)
         if (stream >= 0) {
             uint32_t d = stream == 0 ? ph0 + wb0 + inc0 - add0 : base1 + wb1 + inc1 - add1;
-            smem_copy(s_out, d, s_in, start, name_len + 1u);            // name line and its '\n'
-            d += name_len + 1u;
             if (nrec_out) {
+                smem_copy(s_out, d, s_in, start, name_len + 1u);        // name line and its '\n'
+                d += name_len + 1u;
                 s_out[d] = 'N'; s_out[d + 1] = '\n';
                 d += 2;
                 smem_copy(s_out, d, s_in, e1 + 1u, plus_len + 1u);      // line 3 verbatim
@@ -445,14 +477,20 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 s_out[d] = (uint8_t)P.qmin; s_out[d + 1] = '\n';
             } else {
                 const uint32_t five = (uint32_t)cut.five;
-                if (five + nkeep == L) {
-                    // nothing cut at the 3' end: seq tail, '\n', line 3, '\n' are contiguous in the source
-                    smem_copy(s_out, d, s_in, e0 + 1u + five, nkeep + 1u + plus_len + 1u);
-                    d += nkeep + plus_len + 2u;
-                    smem_copy(s_out, d, s_in, e2 + 1u + five, nkeep + 1u);
+                // source runs: [name '\n'] [seq five..three) ['\n' line3 '\n'] [qual five..three) ['\n'];
+                // neighbours that are contiguous in the source are copied together
+                if (five == 0) {
+                    smem_copy(s_out, d, s_in, start, name_len + 1u + nkeep);
+                    d += name_len + 1u + nkeep;
                 } else {
+                    smem_copy(s_out, d, s_in, start, name_len + 1u);
+                    d += name_len + 1u;
                     smem_copy(s_out, d, s_in, e0 + 1u + five, nkeep);
                     d += nkeep;
+                }
+                if (five == 0 && nkeep == L) {
+                    smem_copy(s_out, d, s_in, e1, plus_len + 2u + nkeep + 1u);   // rest of the record
+                } else {
                     smem_copy(s_out, d, s_in, e1, plus_len + 2u);       // '\n' + line 3 + '\n'
                     d += plus_len + 2u;
                     smem_copy(s_out, d, s_in, e2 + 1u + five, nkeep);

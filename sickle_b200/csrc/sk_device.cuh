@@ -119,7 +119,12 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long l
         unsigned long long v = 0;
         if (my >= 0) {
             unsigned long long w;
-            do { w = ld_status(&status[my]); flag = status_flag(w, epoch); } while (flag == 0);
+            while (true) {
+                w = ld_status(&status[my]);
+                flag = status_flag(w, epoch);
+                if (flag) break;
+                __nanosleep(40);   // predecessor still working: do not burn issue slots
+            }
             v = w & kValueMask;
         }
         const uint32_t incl = __ballot_sync(0xffffffffu, flag == 2);
