@@ -25,8 +25,8 @@
 //   S7  routing, 2-stream block scan, decoupled look-back #2 -> byte offsets in the output streams.
 //   S8  each thread copies its trimmed record into a shared staging buffer laid out like the
 //       destination (same 16-byte phase), then the CTA flushes it with aligned 16-byte stores.
-// Anything this kernel cannot handle exactly -- a record longer than the halo, more than 256
-// records or 2048 newlines in a tile, or ANY data error -- sets Control::fast_fail; the host then
+// Anything this kernel cannot handle exactly -- a record longer than the halo, more than 128
+// records or 1024 newlines in a tile, or ANY data error -- sets Control::fast_fail; the host then
 // re-runs the batch through the general path, which also produces the reference's error details.
 #pragma once
 
@@ -38,7 +38,7 @@ namespace sk {
 
 constexpr int kFThreads = 256;
 constexpr int kFTileThreads = 224;   // 7 warps own tile bytes, the 8th warp scans the halo
-constexpr int kFMaxNl = 2048;
+constexpr int kFMaxNl = 1024;        // newline positions per region (2 KB; also holds 128 record descriptors)
 
 template <int CH>
 struct FusedCfg {
@@ -46,9 +46,10 @@ struct FusedCfg {
     static constexpr int kBytesPerThread = CH * 16;
     static constexpr int kRegion = kFThreads * kBytesPerThread;
     static constexpr int kTile = kFTileThreads * kBytesPerThread;
-    static constexpr int kInBytes = kRegion + 128;       // the window loop reads up to ~80 bytes past a record
-    static constexpr int kOutBytes = kRegion + 96;       // + two 16-byte phase shifts + slack
-    static constexpr size_t kSmem = (size_t)kInBytes + kOutBytes + kFMaxNl * 2 + 256;
+    static constexpr int kInBytes = kRegion + 96;        // the window loop reads up to ~50 bytes past a record
+    static constexpr int kOutBytes = kTile + 768 + 96;   // a tile of output + the last record's overhang + phase shifts
+    // CH = 7: 56,896 B -> four CTAs per SM (4 x (56,896 + 144 static + 1,024 reserved) <= 232,448)
+    static constexpr size_t kSmem = (size_t)kInBytes + kOutBytes + kFMaxNl * 2 + 128;
 };
 
 // four successive bytes at a time from an arbitrary shared-memory byte offset
@@ -185,23 +186,46 @@ __device__ __forceinline__ TrimOut thread_sliding_window(const uint8_t *__restri
         if (oorw & visited) { o.error = true; return o; }
     }
 
+    // The two in-window scans only touch bytes the loop above has range-checked (all < 128), so
+    // "q - qoff >= qthr" is the SWAR test "(b | 0x80) - c has bit 7 set" with c = qthr + qoff.
     int five = 0, three = (int)L;
+    const int cthr = P.qthr + P.qoff;
+    const uint32_t c4 = (uint32_t)(cthr < 1 ? 0 : (cthr > 128 ? 128 : cthr)) * 0x01010101u;
     if (i5 >= 0) {                                                       // trim.cpp:46-51
-        for (uint32_t j = (uint32_t)i5; j < (uint32_t)i5 + ws; ++j)
-            if ((int)q[j] - P.qoff >= P.qthr) { five = (int)j; break; }
+        Stream4 s;
+        s.init(sm, qual_off + (uint32_t)i5);
+        for (uint32_t j = 0; j < ws; j += 4) {
+            const uint32_t ge = ((s.next() | 0x80808080u) - c4) & 0x80808080u;
+            uint32_t nib = flags_to_nibble(ge);
+            if (ws - j < 4) nib &= (1u << (ws - j)) - 1u;
+            if (nib) { five = i5 + (int)j + __ffs(nib) - 1; break; }
+        }
     }
     if (i3 >= 0) {                                                       // trim.cpp:65-70
-        for (uint32_t j = (uint32_t)i3; j < (uint32_t)i3 + ws; ++j)
-            if ((int)q[j] - P.qoff < P.qthr) { three = (int)j; break; }
+        Stream4 s;
+        s.init(sm, qual_off + (uint32_t)i3);
+        for (uint32_t j = 0; j < ws; j += 4) {
+            const uint32_t lt = ~((s.next() | 0x80808080u) - c4) & 0x80808080u;
+            uint32_t nib = flags_to_nibble(lt);
+            if (ws - j < 4) nib &= (1u << (ws - j)) - 1u;
+            if (nib) { three = i3 + (int)j + __ffs(nib) - 1; break; }
+        }
     }
     if (P.trunc_n) {                                                     // trim.cpp:86-98
-        const uint8_t *__restrict__ s = sm + seq_off;
+        Stream4 s;
+        s.init(sm, seq_off);
         int pn = -1;
-        bool anyN = false;
-        for (uint32_t j = 0; j < L; ++j) {
-            const int b = s[j];
-            if (b == 'n') { pn = (int)j; break; }
-            anyN |= (b == 'N');
+        uint32_t anyN = 0;
+        for (uint32_t j = 0; j < L; j += 4) {
+            const uint32_t x = s.next();
+            // exact zero-byte tests of x ^ 'n' and x ^ 'N' (same trick as newline_flags)
+            const uint32_t tn = ((x ^ 0x6E6E6E6Eu) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+            const uint32_t tN = ((x ^ 0x4E4E4E4Eu) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+            uint32_t fn = flags_to_nibble(~(tn | x) & 0x80808080u);
+            uint32_t fN = flags_to_nibble(~(tN | x) & 0x80808080u);
+            if (L - j < 4) { const uint32_t m = (1u << (L - j)) - 1u; fn &= m; fN &= m; }
+            if (fn) { pn = (int)j + __ffs(fn) - 1; break; }
+            anyN |= fN;
         }
         if (pn >= 0) three = pn - 1;
         else if (anyN) three = -2;
@@ -217,20 +241,30 @@ __device__ __forceinline__ TrimOut thread_sliding_window(const uint8_t *__restri
 // as 16-byte destination-aligned stores fed by funnel-shifted source words.
 __device__ __forceinline__ void smem_copy(uint8_t *__restrict__ out, uint32_t dst, const uint8_t *__restrict__ in,
                                           uint32_t src, uint32_t len) {
-    // head: bytes up to a 4-byte destination boundary, then words up to a 16-byte boundary
-    while (len && (dst & 3u)) { out[dst++] = in[src++]; --len; }
+    // Straight-line (predicated) ragged ends keep the lanes of a warp converged; only the 16-byte
+    // loop has a data-dependent trip count, and that is nearly the same for reads of similar length.
+    // head: up to 3 bytes to a 4-byte destination boundary
+    const uint32_t h = min(len, (0u - dst) & 3u);
+#pragma unroll
+    for (uint32_t j = 0; j < 3; ++j)
+        if (j < h) out[dst + j] = in[src + j];
+    dst += h; src += h; len -= h;
     const uint32_t sh = (src & 3u) * 8u;
     const uint32_t *__restrict__ w = reinterpret_cast<const uint32_t *>(in + (src & ~3u));
-    uint32_t cur = w[0];
-    uint32_t nw = len >> 2;                       // whole destination words left
     uint32_t *__restrict__ d = reinterpret_cast<uint32_t *>(out + dst);
-    uint32_t k = 0;
-    while (k < nw && ((dst + 4u * k) & 15u)) {
-        const uint32_t nxt = w[k + 1];
-        d[k] = __funnelshift_r(cur, nxt, sh);
-        cur = nxt;
-        ++k;
+    const uint32_t nw = len >> 2;                 // whole destination words
+    uint32_t cur = w[0];
+    // up to 3 words to a 16-byte destination boundary
+    const uint32_t pre = min(nw, ((0u - dst) >> 2) & 3u);
+#pragma unroll
+    for (uint32_t j = 0; j < 3; ++j) {
+        if (j < pre) {
+            const uint32_t nxt = w[j + 1];
+            d[j] = __funnelshift_r(cur, nxt, sh);
+            cur = nxt;
+        }
     }
+    uint32_t k = pre;
     for (; k + 4 <= nw; k += 4) {
         const uint32_t a = w[k + 1], b = w[k + 2], c = w[k + 3], e = w[k + 4];
         uint4 v;
@@ -241,17 +275,23 @@ __device__ __forceinline__ void smem_copy(uint8_t *__restrict__ out, uint32_t ds
         *reinterpret_cast<uint4 *>(d + k) = v;
         cur = e;
     }
-    for (; k < nw; ++k) {
-        const uint32_t nxt = w[k + 1];
-        d[k] = __funnelshift_r(cur, nxt, sh);
-        cur = nxt;
+    const uint32_t rem = nw - k;                  // 0..3 trailing words
+#pragma unroll
+    for (uint32_t j = 0; j < 3; ++j) {
+        if (j < rem) {
+            const uint32_t nxt = w[k + j + 1];
+            d[k + j] = __funnelshift_r(cur, nxt, sh);
+            cur = nxt;
+        }
     }
-    dst += nw * 4; src += nw * 4; len -= nw * 4;
-    while (len) { out[dst++] = in[src++]; --len; }
+    dst += nw * 4; src += nw * 4; len -= nw * 4;  // 0..3 trailing bytes
+#pragma unroll
+    for (uint32_t j = 0; j < 3; ++j)
+        if (j < len) out[dst + j] = in[src + j];
 }
 
 template <int CH>
-__global__ void __launch_bounds__(kFThreads)
+__global__ void __launch_bounds__(kFThreads, 4)
 kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
          unsigned long long *__restrict__ status_nl, unsigned long long *__restrict__ status_out /* [2][stride] */,
          uint32_t status_stride, uint32_t num_tiles, uint32_t epoch) {
@@ -260,6 +300,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
     uint8_t *s_in = smem;
     uint8_t *s_out = smem + Cfg::kInBytes;
     uint16_t *s_nl = reinterpret_cast<uint16_t *>(smem + Cfg::kInBytes + Cfg::kOutBytes);
+    uint4 *s_desc = reinterpret_cast<uint4 *>(s_nl);   // S7/S8a record descriptors alias the newline positions
     __shared__ uint32_t s_tile;
     __shared__ uint32_t warp_tot[kFThreads / 32];
     __shared__ uint32_t warp_tot2[kFThreads / 32][2];
@@ -296,7 +337,9 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
 
         // ---- S2: newline masks of this thread's CH*16 contiguous bytes (two 64-bit halves)
         const uint32_t b0 = tid * Cfg::kBytesPerThread;          // region-relative
-        unsigned long long mlo = 0, mhi = 0;                     // bytes [0,64) and [64, CH*16)
+        uint32_t mw[(CH + 1) / 2];                               // newline bits, 32 bytes per word
+#pragma unroll
+        for (int k = 0; k < (CH + 1) / 2; ++k) mw[k] = 0;
         {
             // only the first tile (bytes before the batch start) and the tiles touching the end of
             // the batch have bytes to mask off
@@ -312,11 +355,12 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                     if (cb + 16u > hi) mk &= cb >= hi ? 0u : ((1u << (hi - cb)) - 1u);
                     if (cb < lo) mk &= cb + 16u <= lo ? 0u : (0xffffu << (lo - cb));
                 }
-                if (k < 4) mlo |= (unsigned long long)mk << (16 * k);
-                else mhi |= (unsigned long long)mk << (16 * (k - 4));
+                mw[k >> 1] |= mk << (16 * (k & 1));
             }
         }
-        const uint32_t cnt = __popcll(mlo) + __popcll(mhi);
+        uint32_t cnt = 0;
+#pragma unroll
+        for (int k = 0; k < (CH + 1) / 2; ++k) cnt += __popc(mw[k]);
         // ---- S3: ranks
         const uint32_t incl = warp_incl_scan(cnt, lane);
         if (lane == 31) warp_tot[wid] = incl;
@@ -332,16 +376,24 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         const bool nl_overflow = n_all > (uint32_t)kFMaxNl;
         // publish the tile's newline count as early as possible (S4 part 1 happens inside look-back)
         if (!nl_overflow) {
+            // a 32-byte word of a FASTQ file holds 0, 1 or (around the '+' line) 2 newlines: two
+            // straight-line extractions, a loop only for pathological input
             uint32_t rank = wbase + incl - cnt;
-            while (mlo) {
-                const int b = __ffsll((long long)mlo) - 1;
-                mlo &= mlo - 1;
-                s_nl[rank++] = (uint16_t)(b0 + b);
-            }
-            while (mhi) {
-                const int b = __ffsll((long long)mhi) - 1;
-                mhi &= mhi - 1;
-                s_nl[rank++] = (uint16_t)(b0 + 64 + b);
+#pragma unroll
+            for (int k = 0; k < (CH + 1) / 2; ++k) {
+                uint32_t m = mw[k];
+                if (m) {
+                    s_nl[rank++] = (uint16_t)(b0 + 32u * k + (uint32_t)__ffs(m) - 1u);
+                    m &= m - 1;
+                    if (m) {
+                        s_nl[rank++] = (uint16_t)(b0 + 32u * k + (uint32_t)__ffs(m) - 1u);
+                        m &= m - 1;
+                        while (m) {
+                            s_nl[rank++] = (uint16_t)(b0 + 32u * k + (uint32_t)__ffs(m) - 1u);
+                            m &= m - 1;
+                        }
+                    }
+                }
             }
         }
         // ---- S4: global line number of the tile
@@ -360,7 +412,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         const uint32_t n_units = (j_s < (int)c_t) ? (uint32_t)((int)c_t - 1 - j_s) / lpu + 1u : 0u;
         const uint32_t rpu = paired ? 2u : 1u;
         const uint32_t nrec_t = n_units * rpu;
-        bool fail = nl_overflow || nrec_t > (uint32_t)kFThreads;
+        bool fail = nl_overflow || nrec_t > (uint32_t)kFThreads / 2u;   // S8a gives every record two lanes
 
         // per-record state (thread = record)
         const bool has_rec = !fail && (uint32_t)tid < nrec_t;
@@ -425,12 +477,18 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         const uint32_t inc1 = paired ? warp_incl_scan(add1, lane) : 0u;
         if (lane == 31) { warp_tot2[wid][0] = inc0; warp_tot2[wid][1] = inc1; }
         __syncthreads();
-        const bool tile_fail = s_fail != 0;
-        if (wid < 2) {
-            uint32_t total = 0;
+        uint32_t wb0 = 0, wb1 = 0, tot0 = 0, tot1 = 0;
 #pragma unroll
-            for (int w = 0; w < kFThreads / 32; ++w) total += warp_tot2[w][wid];
-            if (tile_fail) total = 0;
+        for (int w = 0; w < kFThreads / 32; ++w) {
+            const uint32_t a = warp_tot2[w][0], b = warp_tot2[w][1];
+            if (w < wid) { wb0 += a; wb1 += b; }
+            tot0 += a; tot1 += b;
+        }
+        // the staging buffer holds a tile's worth of output; a tile whose (long, untrimmed) records
+        // reach far into the halo can exceed it -> general path
+        const bool tile_fail = s_fail != 0 || tot0 + tot1 + 64u > (uint32_t)Cfg::kOutBytes;
+        if (wid < 2) {
+            const uint32_t total = tile_fail ? 0u : (wid == 0 ? tot0 : tot1);
             const unsigned long long pre =
                 lookback_exclusive(status_out + (size_t)wid * status_stride, tile, total, epoch, lane);
             if (lane == 0) {
@@ -443,12 +501,17 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             __syncthreads();
             continue;
         }
-        uint32_t wb0 = 0, wb1 = 0, tot0 = 0, tot1 = 0;
-#pragma unroll
-        for (int w = 0; w < kFThreads / 32; ++w) {
-            const uint32_t a = warp_tot2[w][0], b = warp_tot2[w][1];
-            if (w < wid) { wb0 += a; wb1 += b; }
-            tot0 += a; tot1 += b;
+        // record descriptors for S8a (two lanes per record); they reuse the newline-position array,
+        // which nobody reads after S5
+        if (has_rec) {   // every slot S8a may look at is rewritten (x == 0: nothing to emit)
+            uint4 dsc;
+            dsc.x = stream < 0 ? 0u
+                               : ((stream == 1 ? wb1 + inc1 - add1 : wb0 + inc0 - add0) |
+                                  (stream == 1 ? 0x80000000u : 0u) | (nrec_out ? 0x40000000u : 0u) | 0x20000000u);
+            dsc.y = start | (e0 << 16);
+            dsc.z = e1 | (e2 << 16);
+            dsc.w = (keep ? (uint32_t)cut.five : 0u) | (nkeep << 16);
+            s_desc[tid] = dsc;
         }
         __syncthreads();
         const unsigned long long O0 = s_O[0], O1 = s_O[1];
@@ -464,38 +527,45 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             continue;
         }
 
-        // ---- S8a: thread-per-record copy into the staging buffer (destination-phase aligned)
-        if (stream >= 0) {
-            uint32_t d = stream == 0 ? ph0 + wb0 + inc0 - add0 : base1 + wb1 + inc1 - add1;
-            if (nrec_out) {
-                smem_copy(s_out, d, s_in, start, name_len + 1u);        // name line and its '\n'
-                d += name_len + 1u;
-                s_out[d] = 'N'; s_out[d + 1] = '\n';
-                d += 2;
-                smem_copy(s_out, d, s_in, e1 + 1u, plus_len + 1u);      // line 3 verbatim
-                d += plus_len + 1u;
-                s_out[d] = (uint8_t)P.qmin; s_out[d + 1] = '\n';
-            } else {
-                const uint32_t five = (uint32_t)cut.five;
-                // source runs: [name '\n'] [seq five..three) ['\n' line3 '\n'] [qual five..three) ['\n'];
-                // neighbours that are contiguous in the source are copied together
-                if (five == 0) {
-                    smem_copy(s_out, d, s_in, start, name_len + 1u + nkeep);
-                    d += name_len + 1u + nkeep;
+        // ---- S8a: two lanes per record copy it into the staging buffer (destination-phase aligned):
+        // lane 0 takes [name '\n' seq), lane 1 takes ['\n' line3 '\n' qual '\n')
+        {
+            const uint32_t r = (uint32_t)tid >> 1, sub = (uint32_t)tid & 1u;
+            uint4 dsc = make_uint4(0, 0, 0, 0);
+            if (r < nrec_t) dsc = s_desc[r];
+            if (dsc.x & 0x20000000u) {
+                const uint32_t r_start = dsc.y & 0xffffu, r_e0 = dsc.y >> 16, r_e1 = dsc.z & 0xffffu, r_e2 = dsc.z >> 16;
+                const uint32_t five = dsc.w & 0xffffu, n = dsc.w >> 16;
+                const uint32_t nlen = r_e0 - r_start, plen = r_e2 - r_e1 - 1u;
+                uint32_t d = ((dsc.x & 0x80000000u) ? base1 : ph0) + (dsc.x & 0xffffu);
+                if (dsc.x & 0x40000000u) {                                 // "N record"
+                    if (sub == 0) {
+                        smem_copy(s_out, d, s_in, r_start, nlen + 1u);     // name line and its '\n'
+                        s_out[d + nlen + 1u] = 'N';
+                        s_out[d + nlen + 2u] = '\n';
+                    } else {
+                        d += nlen + 3u;
+                        smem_copy(s_out, d, s_in, r_e1 + 1u, plen + 1u);   // line 3 verbatim
+                        s_out[d + plen + 1u] = (uint8_t)P.qmin;
+                        s_out[d + plen + 2u] = '\n';
+                    }
+                } else if (sub == 0) {
+                    if (five == 0) {
+                        smem_copy(s_out, d, s_in, r_start, nlen + 1u + n); // contiguous in the source
+                    } else {
+                        smem_copy(s_out, d, s_in, r_start, nlen + 1u);
+                        smem_copy(s_out, d + nlen + 1u, s_in, r_e0 + 1u + five, n);
+                    }
                 } else {
-                    smem_copy(s_out, d, s_in, start, name_len + 1u);
-                    d += name_len + 1u;
-                    smem_copy(s_out, d, s_in, e0 + 1u + five, nkeep);
-                    d += nkeep;
-                }
-                if (five == 0 && nkeep == L) {
-                    smem_copy(s_out, d, s_in, e1, plus_len + 2u + nkeep + 1u);   // rest of the record
-                } else {
-                    smem_copy(s_out, d, s_in, e1, plus_len + 2u);       // '\n' + line 3 + '\n'
-                    d += plus_len + 2u;
-                    smem_copy(s_out, d, s_in, e2 + 1u + five, nkeep);
-                    d += nkeep;
-                    s_out[d] = '\n';
+                    d += nlen + 1u + n;
+                    const uint32_t Lr = r_e1 - r_e0 - 1u;
+                    if (five == 0 && n == Lr) {
+                        smem_copy(s_out, d, s_in, r_e1, plen + 2u + n + 1u);   // rest of the record
+                    } else {
+                        smem_copy(s_out, d, s_in, r_e1, plen + 2u);        // '\n' + line 3 + '\n'
+                        smem_copy(s_out, d + plen + 2u, s_in, r_e2 + 1u + five, n);
+                        s_out[d + plen + 2u + n] = '\n';
+                    }
                 }
             }
         }
