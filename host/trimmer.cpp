@@ -1,0 +1,711 @@
+// trimmer.cpp -- see trimmer.h.  Host logic only: option parsing, file I/O, batch cutting, carrying
+// the incomplete tail between batches, ordered output, counters, the reference's messages.
+// All per-read work happens on the GPU behind include/sickle_b200.h; there is no CPU trimming here.
+#include "trimmer.h"
+
+#include <fcntl.h>
+#include <getopt.h>
+#include <sys/stat.h>
+#include <unistd.h>
+#include <zlib.h>
+
+#include <algorithm>
+#include <chrono>
+#include <climits>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+namespace host {
+
+static double now_s() {
+    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+// ---------------------------------------------------------------------------------------------
+ByteSource::~ByteSource() {
+    if (gz_) gzclose((gzFile)gz_);
+    if (fd_ >= 0) ::close(fd_);
+}
+
+bool ByteSource::open(const char *path) {
+    int fd = ::open(path, O_RDONLY);
+    if (fd < 0) return false;
+    struct stat st;
+    if (fstat(fd, &st) == 0) size_ = (unsigned long long)st.st_size;
+    unsigned char magic[2] = {0, 0};
+    const ssize_t got = ::pread(fd, magic, 2, 0);
+    if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
+        gzFile g = gzdopen(fd, "rb");
+        if (!g) { ::close(fd); return false; }
+        gzbuffer(g, 1u << 20);
+        gz_ = g;
+    } else {
+        fd_ = fd;
+#ifdef POSIX_FADV_SEQUENTIAL
+        posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
+#endif
+    }
+    return true;
+}
+
+long long ByteSource::read(char *dst, unsigned long long n) {
+    unsigned long long done = 0;
+    if (gz_) {
+        const double t0 = now_s();
+        while (done < n) {
+            const unsigned want = (unsigned)std::min<unsigned long long>(n - done, 1u << 30);
+            const int r = gzread((gzFile)gz_, dst + done, want);
+            if (r < 0) return -1;
+            if (r == 0) break;
+            done += (unsigned long long)r;
+        }
+        inflate_s_ += now_s() - t0;
+        return (long long)done;
+    }
+    while (done < n) {
+        const ssize_t r = ::read(fd_, dst + done, (size_t)std::min<unsigned long long>(n - done, 1ull << 30));
+        if (r < 0) return -1;
+        if (r == 0) break;
+        done += (unsigned long long)r;
+    }
+    return (long long)done;
+}
+
+ByteSink::~ByteSink() { close(); }
+
+bool ByteSink::open(const char *path, bool gzip) {
+    if (gzip) {
+        gzFile g = gzopen(path, "wb");
+        if (!g) return false;
+        gzbuffer(g, 1u << 20);
+        gz_ = g;
+        return true;
+    }
+    fd_ = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
+    return fd_ >= 0;
+}
+
+bool ByteSink::write(const char *src, unsigned long long n) {
+    unsigned long long done = 0;
+    while (done < n) {
+        if (gz_) {
+            const unsigned want = (unsigned)std::min<unsigned long long>(n - done, 1u << 30);
+            const int r = gzwrite((gzFile)gz_, src + done, want);
+            if (r <= 0) return false;
+            done += (unsigned long long)r;
+        } else {
+            const ssize_t r = ::write(fd_, src + done, (size_t)std::min<unsigned long long>(n - done, 1ull << 30));
+            if (r < 0) return false;
+            done += (unsigned long long)r;
+        }
+    }
+    return true;
+}
+
+void ByteSink::close() {
+    if (gz_) { gzclose((gzFile)gz_); gz_ = nullptr; }
+    if (fd_ >= 0) { ::close(fd_); fd_ = -1; }
+}
+
+// Trim_Single::recommended_batch_len / Trim_Paired::recommended_batch_len
+// (reference src/trim_single.cpp:194-211, src/trim_paired.cpp:246-263)
+static long long recommended_batch_len(unsigned long long file_size, long long b_mib, bool paired) {
+    unsigned long long mx = (unsigned)(int)(1024 * 1024 * b_mib);
+    if (paired) mx /= 2;
+    const unsigned long long rec = file_size / 8;
+    if (rec < 20) return 20;
+    if (rec > mx) return (long long)mx;
+    return (long long)rec;
+}
+
+// Cuts a byte stream into the batches GZReader::read_lines would form (reference
+// src/GZReader.cpp:59-132): lines are added until the sum of their lengths (without '\n') reaches
+// batch_len, a multiple of `minlines` lines is kept and the rest carried.  Only needed to reproduce
+// the reference's `-a N` output order, which is defined per reference batch.
+class RefBatcher {
+public:
+    RefBatcher(ByteSource *src, long long batch_len, int minlines) : src_(src), batch_len_(batch_len), minlines_(minlines) {}
+    // Fills dst (capacity cap) with the next batch; returns its size, 0 at the end, -1 if it does not fit.
+    long long next(char *dst, unsigned long long cap) {
+        if (eof_) return 0;
+        unsigned long long n = 0;
+        std::vector<unsigned long long> ends;   // end offset (after '\n') of every line in dst
+        long long remaining = batch_len_;
+        // carried lines first
+        if (!carry_.empty()) {
+            if (carry_.size() > cap) return -1;
+            memcpy(dst, carry_.data(), carry_.size());
+            unsigned long long p = 0;
+            while (p < carry_.size()) {
+                const char *nl = (const char *)memchr(carry_.data() + p, '\n', carry_.size() - p);
+                const unsigned long long e = nl ? (unsigned long long)(nl - carry_.data()) + 1 : carry_.size();
+                remaining -= (long long)(e - p - 1);
+                ends.push_back(e);
+                p = e;
+            }
+            n = carry_.size();
+            carry_.clear();
+        }
+        do {
+            const char *line;
+            unsigned long long len;
+            if (!next_line(&line, &len)) { eof_ = true; break; }
+            if (n + len > cap) return -1;
+            memcpy(dst + n, line, len);
+            if (dst[n + len - 1] != '\n') dst[n + len - 1] = '\n';   // unterminated last line: GZReader.cpp:81-88
+            n += len;
+            ends.push_back(n);
+            remaining -= (long long)(len - 1);
+        } while (remaining > 0);
+        const size_t extra = ends.size() % (size_t)minlines_;
+        const size_t keep = ends.size() - extra;
+        if (keep == 0) return 0;
+        const unsigned long long end = ends[keep - 1];
+        carry_.assign(dst + end, dst + n);
+        return (long long)end;
+    }
+
+private:
+    bool next_line(const char **line, unsigned long long *len) {
+        while (true) {
+            if (pos_ < buf_.size()) {
+                const char *p = buf_.data() + pos_;
+                const char *nl = (const char *)memchr(p, '\n', buf_.size() - pos_);
+                if (nl) { *line = p; *len = (unsigned long long)(nl - p) + 1; pos_ += *len; return true; }
+                if (src_done_) { *line = p; *len = buf_.size() - pos_; pos_ = buf_.size(); return *len > 0; }
+            } else if (src_done_) return false;
+            // refill, keeping the unfinished line
+            std::vector<char> nb(buf_.begin() + (long)pos_, buf_.end());
+            const size_t keep = nb.size();
+            nb.resize(keep + (8u << 20));
+            const long long r = src_->read(nb.data() + keep, 8u << 20);
+            nb.resize(keep + (size_t)std::max<long long>(r, 0));
+            if (r <= 0) src_done_ = true;
+            buf_.swap(nb);
+            pos_ = 0;
+        }
+    }
+    ByteSource *src_;
+    long long batch_len_;
+    int minlines_;
+    bool eof_ = false, src_done_ = false;
+    std::vector<char> buf_, carry_;
+    size_t pos_ = 0;
+};
+
+}  // namespace host
+
+using host::ByteSink;
+using host::ByteSource;
+using host::Totals;
+
+static const char *kTypeNames[4] = {"Phred", "Sanger", "Solexa", "Illumina"};   // reference src/sickle.h:68-73
+static const int kQualityConstants[4][3] = {{0, 4, 60}, {33, 33, 126}, {64, 58, 112}, {64, 64, 110}};   // src/sickle.h:85-91
+
+// Print what the reference prints before exit(1): FQEntry::validate (src/FQEntry.cpp:55-94) and
+// get_quality_num (src/trim.cpp:130-135).  `record_no` is the 0-based record number in its file.
+int Abstract_Trimmer::report_data_error(const sk_result &r, const char *buf0, const char *buf1) {
+    const sk_error_info &e = r.error;
+    const char *buf = e.file ? buf1 : buf0;
+    std::string line[4];
+    for (int k = 0; k < 4; ++k) line[k].assign(buf + e.line_off[k], (size_t)e.line_len[k]);
+    const long long position = e.record + 1;   // FQEntry::position
+    auto err = [](const std::string &s) { fprintf(stderr, "[ERROR] %s\n", s.c_str()); };
+    const std::string where = "In " + line[0] + "(line " + std::to_string(position * 4 - 4) + ")";
+    switch (e.kind) {
+        case SK_DATA_ID_SHORT:
+            err(where); err("Sequence ID is to short."); err("ID:" + line[0]); err("Sequence: " + line[1]);
+            err("Comment: " + line[2]); err("Qualities: " + line[3]);
+            break;
+        case SK_DATA_ID_CHAR:
+            err(where); err("Invalid char at the beggining of ID."); err("Sequence: " + line[1]);
+            err("Comment: " + line[2]); err("Qualities: " + line[3]);
+            break;
+        case SK_DATA_SEQ_EMPTY: err("Sequence line is empty"); break;
+        case SK_DATA_QUAL_EMPTY: err("Quality line is empty."); break;
+        case SK_DATA_LEN_MISMATCH:
+            err("Sequence and quality lines have different lengths:"); err(line[1]); err(line[3]);
+            break;
+        case SK_DATA_QUAL_RANGE:
+            fprintf(stderr, "ERROR: Quality value (%d) does not fall within correct range for %s encoding.\n", e.byte,
+                    kTypeNames[qualtype]);
+            fprintf(stderr, "Range for %s encoding: %d-%d\n", kTypeNames[qualtype], kQualityConstants[qualtype][1],
+                    kQualityConstants[qualtype][2]);
+            fprintf(stderr, "FastQ record: %s\n", line[0].c_str());
+            fprintf(stderr, "Quality string: %s\n", line[3].c_str());
+            fprintf(stderr, "Quality char: '%c'\n", (char)e.byte);
+            fprintf(stderr, "Quality position: %d\n", e.position + 1);
+            break;
+        default: fprintf(stderr, "[ERROR] unknown data error %d\n", e.kind);
+    }
+    fflush(stderr);
+    return EXIT_FAILURE;
+}
+
+namespace {
+
+struct Ctx {
+    sk_ctx *c = nullptr;
+    ~Ctx() { if (c) sk_destroy(c); }
+};
+
+bool write_outputs(const sk_result &r, ByteSink *outs[3]) {
+    for (int k = 0; k < 3; ++k)
+        if (r.out_bytes[k] && outs[k] && outs[k]->is_open())
+            if (!outs[k]->write(r.out[k], r.out_bytes[k])) return false;
+    return true;
+}
+
+void add_totals(Totals &t, const sk_result &r) {
+    t.kept += r.kept; t.discard += r.discard;
+    t.kept_p += r.kept_p; t.discard_p += r.discard_p;
+    t.kept_s1 += r.kept_s1; t.kept_s2 += r.kept_s2;
+    t.discard_s1 += r.discard_s1; t.discard_s2 += r.discard_s2;
+    t.records[0] += (long long)r.records[0]; t.records[1] += (long long)r.records[1];
+    t.kernel_ms += r.kernel_ms;
+    t.batches++;
+    t.fused_batches += r.fused;
+}
+
+unsigned long long env_u64(const char *name, unsigned long long dflt) {
+    const char *e = getenv(name);
+    if (!e || !*e) return dflt;
+    return strtoull(e, nullptr, 10);
+}
+
+// The reference drops the last character of an unterminated final line (src/GZReader.cpp:81-88):
+// overwrite it with the newline the reader would have seen.
+inline void patch_eof(char *buf, unsigned long long end) {
+    if (end > 0 && buf[end - 1] != '\n') buf[end - 1] = '\n';
+}
+
+}  // namespace
+
+int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, ByteSink *outs[3], bool has_singles,
+                                 Totals &tot) {
+    sk_params p;
+    memset(&p, 0, sizeof p);
+    p.qualtype = qualtype;
+    p.qual_threshold = qual_threshold;
+    p.length_threshold = length_threshold;
+    p.no_fiveprime = no_fiveprime;
+    p.trunc_n = trunc_n;
+    p.mode = mode;
+    p.emulate_threads = threads > 1 ? threads : 1;
+    p.has_singles = has_singles ? 1 : 0;
+    const int device = (int)env_u64("SICKLE_B200_DEVICE", 0);
+    const bool two = mode == SK_MODE_PE_2FILE;
+    const bool paired = mode != SK_MODE_SE;
+
+    if (sk_device_count() <= 0) {
+        fprintf(stderr, "****Error: no usable CUDA device (%s). This build has no CPU path.\n\n", sk_last_error());
+        return EXIT_FAILURE;
+    }
+
+    // ---------------------------------------------------------------------------------------
+    // (A) reference output order requested (-a N, N > 1): batches follow the reference's batch
+    //     geometry (src/GZReader.cpp:59-132); one slot, synchronous.
+    // ---------------------------------------------------------------------------------------
+    if (p.emulate_threads > 1) {
+        const long long bl = host::recommended_batch_len(in0->file_size(), batch_mib, paired);
+        unsigned long long slot = (unsigned long long)bl + (unsigned long long)bl / 16 + (4ull << 20);
+        slot = std::min<unsigned long long>(slot, (1ull << 31) - 8192);
+        Ctx ctx;
+        ctx.c = sk_create(device, slot, 1, &p);
+        if (!ctx.c) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
+        host::RefBatcher b0(in0, bl, (mode == SK_MODE_PE_INTER || mode == SK_MODE_PE_INTER_M) ? 8 : 4);
+        host::RefBatcher b1(in1 ? in1 : in0, bl, 4);
+        char *h0 = sk_in_buffer(ctx.c, 0, 0), *h1 = two ? sk_in_buffer(ctx.c, 0, 1) : nullptr;
+        long long base[2] = {0, 0};
+        while (true) {
+            const long long n0 = b0.next(h0, slot);
+            if (n0 < 0) { fprintf(stderr, "****Error: a reference batch does not fit in a %llu-byte slot.\n\n", slot); return EXIT_FAILURE; }
+            if (n0 == 0) break;
+            long long n1 = 0;
+            if (two) {
+                n1 = b1.next(h1, slot);
+                if (n1 <= 0) break;
+            }
+            if (sk_submit(ctx.c, 0, 0, (uint64_t)n0, 0, (uint64_t)n1) != SK_OK) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
+            sk_result r;
+            if (sk_wait(ctx.c, 0, &r) != SK_OK) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
+            if (r.error.kind) { r.error.record += base[r.error.file]; return report_data_error(r, h0, h1); }
+            if (!write_outputs(r, outs)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
+            add_totals(tot, r);
+            base[0] += (long long)r.records[0]; base[1] += (long long)r.records[1];
+        }
+        return EXIT_SUCCESS;
+    }
+
+    const unsigned long long slot = env_u64("SICKLE_B200_SLOT_MB", 256) << 20;
+    const int nslots = two ? 2 : 3;
+    Ctx ctx;
+    ctx.c = sk_create(device, slot, nslots, &p);
+    if (!ctx.c) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
+
+    // ---------------------------------------------------------------------------------------
+    // (B) two input files: pairs are matched by record number.  Each batch is the carried tail of
+    //     either file plus new bytes; the next batch is submitted before the previous one's output
+    //     is written, so file writes overlap the GPU.
+    // ---------------------------------------------------------------------------------------
+    if (two) {
+        ByteSource *src[2] = {in0, in1};
+        unsigned long long carry_len[2] = {0, 0};
+        const char *carry_ptr[2] = {nullptr, nullptr};
+        bool eof[2] = {false, false};
+        long long base[2] = {0, 0};
+        int slot_i = 0;
+        bool have_prev = false;
+        sk_result prev;
+        while (true) {
+            char *h[2] = {sk_in_buffer(ctx.c, slot_i, 0), sk_in_buffer(ctx.c, slot_i, 1)};
+            unsigned long long n[2] = {0, 0};
+            bool grew = false;
+            for (int i = 0; i < 2; ++i) {
+                if (carry_len[i]) memmove(h[i], carry_ptr[i], carry_len[i]);
+                n[i] = carry_len[i];
+                if (!eof[i]) {
+                    const long long r = src[i]->read(h[i] + n[i], slot - n[i]);
+                    if (r < 0) { fprintf(stderr, "****Error: read failed\n\n"); return EXIT_FAILURE; }
+                    if ((unsigned long long)r < slot - n[i]) eof[i] = true;
+                    if (r > 0) grew = true;
+                    n[i] += (unsigned long long)r;
+                }
+                if (eof[i]) patch_eof(h[i], n[i]);
+            }
+            (void)grew;
+            const bool more = n[0] && n[1];   // no pair can be formed once either file is exhausted
+            if (more && sk_submit(ctx.c, slot_i, 0, n[0], 0, n[1]) != SK_OK) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
+            if (have_prev) {   // previous batch's streams are still in the other slot's pinned buffers
+                if (!write_outputs(prev, outs)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
+                have_prev = false;
+            }
+            if (!more) break;
+            sk_result r;
+            if (sk_wait(ctx.c, slot_i, &r) != SK_OK) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
+            if (r.error.kind) { r.error.record += base[r.error.file]; return report_data_error(r, h[0], h[1]); }
+            add_totals(tot, r);
+            base[0] += (long long)r.records[0]; base[1] += (long long)r.records[1];
+            prev = r;
+            have_prev = true;
+            if (r.consumed[0] == 0 && r.consumed[1] == 0) {
+                if (n[0] == slot || n[1] == slot) { fprintf(stderr, "****Error: a record does not fit in a %llu-byte slot (raise SICKLE_B200_SLOT_MB).\n\n", slot); return EXIT_FAILURE; }
+                break;   // only an incomplete pair is left: dropped, as the reference does at end of file
+            }
+            for (int i = 0; i < 2; ++i) { carry_ptr[i] = h[i] + r.consumed[i]; carry_len[i] = n[i] - r.consumed[i]; }
+            slot_i ^= 1;
+        }
+        if (have_prev && !write_outputs(prev, outs)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
+        return EXIT_SUCCESS;
+    }
+
+    // ---------------------------------------------------------------------------------------
+    // (C) one input stream (se, interleaved pe), pipelined: the bulk of slot k+1 is read at a
+    //     headroom offset and uploaded (sk_upload) while batch k runs; once batch k reports how much
+    //     it consumed, its unconsumed tail is copied in front of that bulk and batch k+1 is submitted;
+    //     only then are batch k's outputs written.
+    // ---------------------------------------------------------------------------------------
+    const unsigned long long H = std::min<unsigned long long>(slot / 4, env_u64("SICKLE_B200_HEADROOM_MB", 8) << 20);
+    const unsigned long long bulk_cap = slot - H;
+    struct Pending { int slot; unsigned long long start, end; } pend = {-1, 0, 0};
+    int cur = 0;
+    bool eof = false;
+    long long base = 0;
+    while (true) {
+        char *h = sk_in_buffer(ctx.c, cur, 0);
+        unsigned long long bulk = 0;
+        if (!eof) {
+            const long long r = in0->read(h + H, bulk_cap);
+            if (r < 0) { fprintf(stderr, "****Error: read failed\n\n"); return EXIT_FAILURE; }
+            bulk = (unsigned long long)r;
+            if (bulk < bulk_cap) eof = true;
+            if (bulk && sk_upload(ctx.c, cur, 0, H, bulk) != SK_OK) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
+        }
+        unsigned long long tail = 0;
+        sk_result prev;
+        bool have_prev = false;
+        if (pend.slot >= 0) {
+            if (sk_wait(ctx.c, pend.slot, &prev) != SK_OK) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
+            char *ph = sk_in_buffer(ctx.c, pend.slot, 0);
+            if (prev.error.kind) { prev.error.record += base; return report_data_error(prev, ph, nullptr); }
+            add_totals(tot, prev);
+            base += (long long)prev.records[0];
+            have_prev = true;
+            tail = pend.end - pend.start - prev.consumed[0];
+            if (tail > H) {
+                fprintf(stderr, "****Error: a record (pair) of more than %llu bytes does not fit the carry area (raise SICKLE_B200_HEADROOM_MB).\n\n", H);
+                return EXIT_FAILURE;
+            }
+            if (tail) memcpy(h + H - tail, ph + pend.start + prev.consumed[0], tail);
+            const bool stuck = prev.consumed[0] == 0 && bulk == 0;
+            pend.slot = -1;
+            if (stuck) {   // nothing new and nothing consumed: an incomplete record (pair) at end of file
+                if (!write_outputs(prev, outs)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
+                break;
+            }
+        }
+        if (bulk + tail > 0) {
+            const unsigned long long start = H - tail, end = H + bulk;
+            if (eof) patch_eof(h, end);
+            if (sk_submit(ctx.c, cur, start, end, 0, 0) != SK_OK) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
+            pend = {cur, start, end};
+            cur = (cur + 1) % nslots;
+        }
+        if (have_prev && !write_outputs(prev, outs)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
+        if (pend.slot < 0) break;
+    }
+    return EXIT_SUCCESS;
+}
+
+// =============================================================================================
+// sickle se      (reference src/trim_single.cpp)
+// =============================================================================================
+static struct option single_long_options[] = {
+    {"fastq-file", required_argument, 0, 'f'}, {"output-file", required_argument, 0, 'o'},
+    {"qual-type", required_argument, 0, 't'},  {"qual-threshold", required_argument, 0, 'q'},
+    {"length-threshold", required_argument, 0, 'l'}, {"no-fiveprime", no_argument, 0, 'x'},
+    {"discard-n", no_argument, 0, 'n'},        {"gzip-output", no_argument, 0, 'g'},
+    {"quiet", no_argument, 0, 'z'},            {"threads", no_argument, 0, 'a'},
+    {"batch", no_argument, 0, 'b'},            {"help", no_argument, 0, CHAR_MIN - 2},
+    {"version", no_argument, 0, CHAR_MIN - 3}, {NULL, 0, NULL, 0}};
+
+static void print_version_and_exit() {
+    fprintf(stdout, "%s version %0.3f\nCopyright (c) 2011 The Regents of University of California, Davis Campus.\n"
+                    "%s is free software and comes with ABSOLUTELY NO WARRANTY.\nDistributed under the MIT License.\n\n"
+                    "Written by %s\n", PROGRAM_NAME, (double)SICKLE_VERSION, PROGRAM_NAME,
+            "Nikhil Joshi, UC Davis Bioinformatics Core\n");
+    exit(EXIT_SUCCESS);
+}
+
+static int parse_qualtype(const char *s) {
+    if (!strcmp(s, "illumina")) return SK_QUAL_ILLUMINA;
+    if (!strcmp(s, "solexa")) return SK_QUAL_SOLEXA;
+    if (!strcmp(s, "sanger")) return SK_QUAL_SANGER;
+    return -1;
+}
+
+void Trim_Single::usage(int status, char const *msg) {
+    fprintf(stderr, "\nUsage: %s se [options] -f <fastq sequence file> -t <quality type> -o <trimmed fastq file>\n\
+\n\
+Options:\n\
+-f, --fastq-file, Input fastq file (required)\n\
+-t, --qual-type, Type of quality values (solexa (CASAVA < 1.3), illumina (CASAVA 1.3 to 1.7), sanger (which is CASAVA >= 1.8)) (required)\n\
+-o, --output-file, Output trimmed fastq file (required)\n", PROGRAM_NAME);
+    fprintf(stderr, "-q, --qual-threshold, Threshold for trimming based on average quality in a window. Default 20.\n\
+-l, --length-threshold, Threshold to keep a read based on length after trimming. Default 20.\n\
+-x, --no-fiveprime, Don't do five prime trimming.\n\
+-n, --trunc-n, Truncate sequences at position of first N.\n\
+-g, --gzip-output, Output gzipped files.\n\
+-a, --threads, Number of threads to use. Default and minimum: Available cores - 1.\n\
+-b, --batch, maximum MB of data to read from the input file at each cycle.\n\
+\tThe greater the value, the greater the memory usage can be. The value, multiplied by 1024^2, must be \n\
+\tbigger than the lenght of the longest read. Minimum 1. Default: 512.\n\
+--quiet, Don't print out any trimming information\n\
+--help, display this help and exit\n\
+--version, output version information and exit\n\n");
+    if (msg) fprintf(stderr, "%s\n\n", msg);
+    exit(status);
+}
+
+int Trim_Single::parse_args(int argc, char *argv[]) {
+    int optc;
+    while (true) {
+        int option_index = 0;
+        optc = getopt_long(argc, argv, "df:t:o:q:a:b:l:zxng", single_long_options, &option_index);
+        if (optc == -1) break;
+        switch (optc) {
+            case 'f': infn = strdup(optarg); break;
+            case 't':
+                qualtype = parse_qualtype(optarg);
+                if (qualtype < 0) { fprintf(stderr, "Error: Quality type '%s' is not a valid type.\n", optarg); return EXIT_FAILURE; }
+                break;
+            case 'o': outfn = strdup(optarg); break;
+            case 'q':
+                qual_threshold = atoi(optarg);
+                if (qual_threshold < 0) { fprintf(stderr, "Quality threshold must be >= 0\n"); return EXIT_FAILURE; }
+                break;
+            case 'l':
+                length_threshold = atoi(optarg);
+                if (length_threshold < 0) { fprintf(stderr, "Length threshold must be >= 0\n"); return EXIT_FAILURE; }
+                break;
+            case 'x': no_fiveprime = 1; break;
+            case 'n': trunc_n = 1; break;
+            case 'g': gzip_output = 1; break;
+            case 'z': quiet = 1; break;
+            case 'd': debug = 1; break;
+            case 'a': threads = atoi(optarg); threads_given = true; break;
+            case 'b': batch_mib = atoi(optarg); break;
+            case CHAR_MIN - 2: usage(EXIT_SUCCESS, NULL); break;
+            case CHAR_MIN - 3: print_version_and_exit(); break;
+            default: usage(EXIT_FAILURE, NULL); break;
+        }
+    }
+    if (qualtype == -1 || !infn || !outfn) usage(EXIT_FAILURE, "****Error: Must have quality type, input file, and output file.");
+    if (!strcmp(infn, outfn)) { fprintf(stderr, "****Error: Input file is same as output file.\n\n"); return EXIT_FAILURE; }
+    return 0;
+}
+
+int Trim_Single::trim_main() {
+    ByteSource in;
+    if (!in.open(infn)) { fprintf(stderr, "****Error: Could not open input file '%s'.\n\n", infn); return EXIT_FAILURE; }
+    ByteSink out;
+    if (!out.open(outfn, gzip_output != 0)) { fprintf(stderr, "****Error: Could not open output file '%s'.\n\n", outfn); return EXIT_FAILURE; }
+    ByteSink *outs[3] = {&out, nullptr, nullptr};
+    Totals t;
+    const int rc = run_device(SK_MODE_SE, &in, nullptr, outs, false, t);
+    out.close();
+    if (rc != EXIT_SUCCESS) return rc;
+    if (!quiet)
+        fprintf(stdout, "\nSE input file: %s\n\nTotal FastQ records: %lld\nFastQ records kept: %lld\nFastQ records discarded: %lld\n\n",
+                infn, t.kept + t.discard, t.kept, t.discard);
+    if (debug) fprintf(stderr, "[sickle_b200] batches %lld (fused %lld), kernel time %.3f ms, gzip inflate %.3f s\n", t.batches,
+                       t.fused_batches, t.kernel_ms, in.inflate_seconds());
+    return EXIT_SUCCESS;
+}
+
+// =============================================================================================
+// sickle pe      (reference src/trim_paired.cpp)
+// =============================================================================================
+static struct option paired_long_options[] = {
+    {"qual-type", required_argument, 0, 't'},     {"pe-file1", required_argument, 0, 'f'},
+    {"pe-file2", required_argument, 0, 'r'},      {"pe-interleaved", required_argument, 0, 'c'},
+    {"output-pe1", required_argument, 0, 'o'},    {"output-pe2", required_argument, 0, 'p'},
+    {"output-single", required_argument, 0, 's'}, {"output-interleaved", required_argument, 0, 'm'},
+    {"output-combo-all", required_argument, 0, 'M'}, {"qual-threshold", required_argument, 0, 'q'},
+    {"length-threshold", required_argument, 0, 'l'}, {"no-fiveprime", no_argument, 0, 'x'},
+    {"truncate-n", no_argument, 0, 'n'},          {"gzip-output", no_argument, 0, 'g'},
+    {"quiet", no_argument, 0, 'z'},               {"threads", no_argument, 0, 'a'},
+    {"batch", no_argument, 0, 'b'},               {"help", no_argument, 0, CHAR_MIN - 2},
+    {"version", no_argument, 0, CHAR_MIN - 3},    {NULL, 0, NULL, 0}};
+
+void Trim_Paired::usage(int status, char const *msg) {
+    fprintf(stderr, "\nIf you have separate files for forward and reverse reads:\n");
+    fprintf(stderr, "Usage: %s pe [options] -f <paired-end forward fastq file> -r <paired-end reverse fastq file> -t <quality type> -o <trimmed PE forward file> -p <trimmed PE reverse file> -s <trimmed singles file>\n\n", PROGRAM_NAME);
+    fprintf(stderr, "If you have one file with interleaved forward and reverse reads:\n");
+    fprintf(stderr, "Usage: %s pe [options] -c <interleaved input file> -t <quality type> -m <interleaved trimmed paired-end output> -s <trimmed singles file>\n\n\
+If you have one file with interleaved reads as input and you want ONLY one interleaved file as output:\n\
+Usage: %s pe [options] -c <interleaved input file> -t <quality type> -M <interleaved trimmed output>\n\n", PROGRAM_NAME, PROGRAM_NAME);
+    fprintf(stderr, "Options:\n\
+Paired-end separated reads\n\
+--------------------------\n\
+-f, --pe-file1, Input paired-end forward fastq file (Input files must have same number of records)\n\
+-r, --pe-file2, Input paired-end reverse fastq file\n\
+-o, --output-pe1, Output trimmed forward fastq file\n\
+-p, --output-pe2, Output trimmed reverse fastq file. Must use -s option.\n\n\
+Paired-end interleaved reads\n\
+----------------------------\n");
+    fprintf(stderr, "-c, --pe-interleaved, Combined (interleaved) input paired-end fastq\n\
+-m, --output-interleaved, Output combined (interleaved) paired-end fastq file. Must use -s option.\n\
+-M, --output-combo-all, Output combined (interleaved) paired-end fastq file with any discarded read written to output file as a single N. Cannot be used with the -s option.\n\
+--------------\n\
+-t, --qual-type, Type of quality values (solexa (CASAVA < 1.3), illumina (CASAVA 1.3 to 1.7), sanger (which is CASAVA >= 1.8)) (required)\n");
+    fprintf(stderr, "-s, --output-single, Output trimmed singles fastq file\n\
+-q, --qual-threshold, Threshold for trimming based on average quality in a window. Default 20.\n\
+-l, --length-threshold, Threshold to keep a read based on length after trimming. Default 20.\n\
+-x, --no-fiveprime, Don't do five prime trimming.\n\
+-n, --truncate-n, Truncate sequences at position of first N.\n\
+-a, --threads, Number of threads to use. Default and minimum: Available cores - 1.\n\
+-b, --batch, maximum MB of data to read from the input file at each cycle.\n\
+\tThe greater the value, the greater the memory usage can be. The value, multiplied by 1024^2, must be \n\
+\tbigger than the lenght of the longest read. Minimum 1. Default: 512.\n");
+    fprintf(stderr, "-g, --gzip-output, Output gzipped files.\n--quiet, do not output trimming info\n\
+--help, display this help and exit\n\
+--version, output version information and exit\n\n");
+    if (msg) fprintf(stderr, "%s\n\n", msg);
+    exit(status);
+}
+
+int Trim_Paired::parse_args(int argc, char *argv[]) {
+    int optc;
+    while (true) {
+        int option_index = 0;
+        optc = getopt_long(argc, argv, "df:r:c:t:o:p:m:M:s:q:a:b:l:xng", paired_long_options, &option_index);
+        if (optc == -1) break;
+        switch (optc) {
+            case 'f': infn = strdup(optarg); break;
+            case 'r': infn2 = strdup(optarg); break;
+            case 'c': infnc = strdup(optarg); break;
+            case 't':
+                qualtype = parse_qualtype(optarg);
+                if (qualtype < 0) { fprintf(stderr, "Error: Quality type '%s' is not a valid type.\n", optarg); return EXIT_FAILURE; }
+                break;
+            case 'o': outfn = strdup(optarg); break;
+            case 'p': outfn2 = strdup(optarg); break;
+            case 'm': outfnc = strdup(optarg); break;
+            case 'M': outfnM = strdup(optarg); break;   // absent from the fork's switch (usage + exit 1 there); README.md:116-120
+            case 's': sfn = strdup(optarg); break;
+            case 'q':
+                qual_threshold = atoi(optarg);
+                if (qual_threshold < 0) { fprintf(stderr, "Quality threshold must be >= 0\n"); return EXIT_FAILURE; }
+                break;
+            case 'l':
+                length_threshold = atoi(optarg);
+                if (length_threshold < 0) { fprintf(stderr, "Length threshold must be >= 0\n"); return EXIT_FAILURE; }
+                break;
+            case 'x': no_fiveprime = 1; break;
+            case 'n': trunc_n = 1; break;
+            case 'g': gzip_output = 1; break;
+            case 'z': quiet = 1; break;
+            case 'd': debug = 1; break;
+            case 'a': threads = atoi(optarg); threads_given = true; break;
+            case 'b': batch_mib = atoi(optarg); break;
+            case CHAR_MIN - 2: usage(EXIT_SUCCESS, NULL); break;
+            case CHAR_MIN - 3: print_version_and_exit(); break;
+            default: usage(EXIT_FAILURE, NULL); break;
+        }
+    }
+    if (qualtype == -1) { usage(EXIT_FAILURE, "****Error: Quality type is required."); return EXIT_FAILURE; }
+    if (!infn && !infnc) { usage(EXIT_FAILURE, "****Error: Must have either -f OR -c argument."); return EXIT_FAILURE; }
+    return 0;
+}
+
+int Trim_Paired::trim_main() {
+    ByteSource in0, in1;
+    ByteSink o_main, o_mate2, o_single;
+    ByteSink *outs[3] = {nullptr, nullptr, nullptr};
+    int mode;
+    const bool gz = gzip_output != 0;
+    if (infnc) {   // interleaved input (reference init_streams, src/trim_paired.cpp:628-658)
+        if (infn || infn2 || outfn || outfn2) { usage(EXIT_FAILURE, "****Error: Cannot have -f, -r, -o, or -p options with -c."); return EXIT_FAILURE; }
+        if (outfnM && (outfnc || sfn)) { usage(EXIT_FAILURE, "****Error: Cannot have -m or -s options with -M."); return EXIT_FAILURE; }
+        if (!outfnM && !outfnc) { usage(EXIT_FAILURE, "****Error: Must have -m or -M with -c."); return EXIT_FAILURE; }
+        if (!in0.open(infnc)) { fprintf(stderr, "****Error: Could not open interleaved input file '%s'.\n\n", infnc); return EXIT_FAILURE; }
+        const char *o = outfnM ? outfnM : outfnc;
+        if (!o_main.open(o, gz)) { fprintf(stderr, "****Error: Could not open interleaved output file '%s'.\n\n", o); return EXIT_FAILURE; }
+        outs[0] = &o_main;
+        mode = outfnM ? SK_MODE_PE_INTER_M : SK_MODE_PE_INTER;
+    } else {       // forward and reverse files (src/trim_paired.cpp:658-709)
+        if (infn && (!infn2 || !outfn || !outfn2 || !sfn)) { usage(EXIT_FAILURE, "****Error: Using the -f option means you must have the -r, -o, -p, and -s options."); return EXIT_FAILURE; }
+        if (infn && (infnc || outfnc || outfnM)) { usage(EXIT_FAILURE, "****Error: The -f option cannot be used in combination with -c, -m, or -M."); return EXIT_FAILURE; }
+        if (!in0.open(infn)) { fprintf(stderr, "****Error: Could not open input file '%s'.\n\n", infn); return EXIT_FAILURE; }
+        if (!in1.open(infn2)) { fprintf(stderr, "****Error: Could not open input file '%s'.\n\n", infn2); return EXIT_FAILURE; }
+        if (!o_main.open(outfn, gz)) { fprintf(stderr, "****Error: Could not open output file '%s'.\n\n", outfn); return EXIT_FAILURE; }
+        if (!o_mate2.open(outfn2, gz)) { fprintf(stderr, "****Error: Could not open output file '%s'.\n\n", outfn2); return EXIT_FAILURE; }
+        outs[0] = &o_main;
+        outs[1] = &o_mate2;
+        mode = SK_MODE_PE_2FILE;
+    }
+    if (sfn) {
+        if (!o_single.open(sfn, gz)) { fprintf(stderr, "****Error: Could not open single output file '%s'.\n\n", sfn); return EXIT_FAILURE; }
+        outs[2] = &o_single;
+    }
+    Totals t;
+    const int rc = run_device(mode, &in0, mode == SK_MODE_PE_2FILE ? &in1 : nullptr, outs, sfn != nullptr, t);
+    o_main.close(); o_mate2.close(); o_single.close();
+    if (rc != EXIT_SUCCESS) return rc;
+    if (!quiet) {   // reference src/trim_paired.cpp:464-476, with the true record total
+        const long long total = t.kept_p + t.kept_s1 + t.kept_s2 + t.discard_p + t.discard_s1 + t.discard_s2;
+        if (infn && infn2) fprintf(stdout, "\nPE forward file: %s\nPE reverse file: %s\n", infn, infn2);
+        if (infnc) fprintf(stdout, "\nPE interleaved file: %s\n", infnc);
+        fprintf(stdout, "\nTotal input FastQ records: %lld (%lld pairs)\n", total, total / 2);
+        fprintf(stdout, "\nFastQ paired records kept: %lld (%lld pairs)\n", t.kept_p, t.kept_p / 2);
+        if (infnc) fprintf(stdout, "FastQ single records kept: %lld\n", t.kept_s1 + t.kept_s2);
+        else fprintf(stdout, "FastQ single records kept: %lld (from PE1: %lld, from PE2: %lld)\n", t.kept_s1 + t.kept_s2, t.kept_s1, t.kept_s2);
+        fprintf(stdout, "FastQ paired records discarded: %lld (%lld pairs)\n", t.discard_p, t.discard_p / 2);
+        if (infnc) fprintf(stdout, "FastQ single records discarded: %lld\n\n", t.discard_s1 + t.discard_s2);
+        else fprintf(stdout, "FastQ single records discarded: %lld (from PE1: %lld, from PE2: %lld)\n\n", t.discard_s1 + t.discard_s2, t.discard_s1, t.discard_s2);
+    }
+    if (debug) fprintf(stderr, "[sickle_b200] batches %lld (fused %lld), kernel time %.3f ms\n", t.batches, t.fused_batches, t.kernel_ms);
+    return EXIT_SUCCESS;
+}

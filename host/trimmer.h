@@ -1,0 +1,119 @@
+// trimmer.h -- host side of the drop-in `sickle se` / `sickle pe` command line.
+//
+// Mirrors the reference's operator interface for this path: Abstract_Trimmer with parse_args(),
+// trim_main() and usage() (reference src/trim.h:8-38), implemented by Trim_Single
+// (src/trim_single.{h,cpp}) and Trim_Paired (src/trim_paired.{h,cpp}).  Same option letters, same
+// defaults, same messages and exit codes; what differs is trim_main(): instead of splitting lines on
+// the host and running sliding_window() in std::threads, it streams whole byte batches through the
+// C ABI of include/sickle_b200.h (one B200 per context, pinned slots, H2D / kernels / D2H overlapped).
+#ifndef SICKLE_B200_HOST_TRIMMER_H
+#define SICKLE_B200_HOST_TRIMMER_H
+
+#include <cstdint>
+#include <string>
+#include <vector>
+
+#include "sickle_b200.h"
+
+#ifndef PROGRAM_NAME
+#define PROGRAM_NAME "sickle"
+#endif
+#ifndef SICKLE_VERSION
+#define SICKLE_VERSION 1.33
+#endif
+
+namespace host {
+
+// Sequential byte reader over a plain or gzip file (the reference reads everything through zlib's
+// gzopen/gzgets, src/GZReader.cpp:13,77; plain files are read with read(2) here).
+class ByteSource {
+public:
+    ~ByteSource();
+    bool open(const char *path);
+    // Read up to n bytes; returns the count (0 at end of file), -1 on error.
+    long long read(char *dst, unsigned long long n);
+    bool gzip() const { return gz_ != nullptr; }
+    unsigned long long file_size() const { return size_; }
+    double inflate_seconds() const { return inflate_s_; }
+
+private:
+    int fd_ = -1;
+    void *gz_ = nullptr;
+    unsigned long long size_ = 0;
+    double inflate_s_ = 0;
+};
+
+// Append-only writer: plain file or gzip (-g).  The reference's -g path is broken (gzprintf with the
+// payload as format string, src/trim_single.cpp:418); this one writes a valid gzip of the same bytes.
+class ByteSink {
+public:
+    ~ByteSink();
+    bool open(const char *path, bool gzip);
+    bool write(const char *src, unsigned long long n);
+    void close();
+    bool is_open() const { return fd_ >= 0 || gz_ != nullptr; }
+
+private:
+    int fd_ = -1;
+    void *gz_ = nullptr;
+};
+
+struct Totals {
+    long long kept = 0, discard = 0;
+    long long kept_p = 0, discard_p = 0, kept_s1 = 0, kept_s2 = 0, discard_s1 = 0, discard_s2 = 0;
+    long long records[2] = {0, 0};
+    double kernel_ms = 0;
+    long long batches = 0, fused_batches = 0;
+};
+
+}  // namespace host
+
+class Abstract_Trimmer {
+public:
+    virtual ~Abstract_Trimmer() {}
+    virtual int parse_args(int argc, char *argv[]) = 0;
+    virtual int trim_main() = 0;
+    virtual void usage(int status, char const *msg) = 0;
+
+protected:
+    // option state, same meaning as the reference members (src/trim.h:18-27)
+    int qualtype = -1;
+    int length_threshold = 20;
+    int qual_threshold = 20;
+    int no_fiveprime = 0;
+    int trunc_n = 0;
+    int debug = 0;
+    int threads = 1;          // -a: reference output order to reproduce (1 = input order)
+    bool threads_given = false;
+    long long batch_mib = 512;   // -b
+    int quiet = 0;
+    int gzip_output = 0;
+    char *infn = nullptr;
+    char *outfn = nullptr;
+
+    // Run one input stream (se, or interleaved pe) / two input streams through the device.
+    // outs[k] may be null (stream not written).  Returns the process exit code.
+    int run_device(int mode, host::ByteSource *in0, host::ByteSource *in1, host::ByteSink *outs[3],
+                   bool has_singles, host::Totals &tot);
+    int report_data_error(const sk_result &r, const char *buf0, const char *buf1);
+};
+
+class Trim_Single : public Abstract_Trimmer {
+public:
+    int parse_args(int argc, char *argv[]) override;
+    int trim_main() override;
+    void usage(int status, char const *msg) override;
+};
+
+class Trim_Paired : public Abstract_Trimmer {
+public:
+    int parse_args(int argc, char *argv[]) override;
+    int trim_main() override;
+    void usage(int status, char const *msg) override;
+
+private:
+    char *infn2 = nullptr, *infnc = nullptr;
+    char *outfn2 = nullptr, *outfnc = nullptr, *sfn = nullptr, *outfnM = nullptr;
+};
+
+#endif
