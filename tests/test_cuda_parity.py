@@ -272,3 +272,24 @@ def test_large_batch_properties(capi):
     # every kept record: len(seq) == len(qual) and starts with '@SRR'
     lines = got.split(b"\n")
     assert all(len(lines[i + 1]) == len(lines[i + 3]) and lines[i].startswith(b"@SRR") for i in range(0, 4000, 4))
+
+
+@pytest.mark.parametrize("world", [2, 5])
+def test_sharded_plan_on_cuda_path(capi, world):
+    """The multi-GPU plan (sickle_b200/sharding.py: counted record phase, rank-ordered concatenation)
+    with every shard run through the CUDA path -- ranks emulated one after the other on one GPU."""
+    from sickle_b200 import sharding, synth
+
+    data = synth.fixed_length_records(30011, 150, "sanger", seed=13).tobytes()
+    data += b"".join(_random_fastq(np.random.default_rng(5), 2000, 300, "sanger"))
+    want = orc.run(orc.MODE_SE, orc.make_params("sanger"), data, batch_len=1 << 40)
+    bounds = sharding.shard_bounds(data, world, 4)
+    flags = dict(qualtype="sanger", q=20, l=20, x=False, n=False)
+    outs, kept = [], 0
+    for r in range(world):
+        got = _run_cuda(capi, capi.MODE_SE, flags, data[bounds[r]:bounds[r + 1]], slot_bytes=1 << 20, pipelined=True,
+                        n_slots=2, headroom=1 << 14)
+        outs.append(got["out"][0])
+        kept += got["counters"]["kept"]
+    assert b"".join(outs) == want["out"][0]
+    assert kept == want["counters"]["kept"]
