@@ -1,0 +1,13 @@
+import sys, os, json
+ROOT=os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT,'tests'))
+import golden_util as gu
+from sickle_b200 import capi, runner
+g=json.load(open(os.path.join(ROOT,'tests/golden/golden.json'))); gdir=os.path.join(ROOT,'tests/golden')
+case=[c for c in g['cases'] if c['id']==sys.argv[1]][0]
+kind,in0,in1=gu.load_inputs(case,gdir); f=gu.parse_flags(case['flags'])
+modes={"se":capi.MODE_SE,"pei":capi.MODE_PE_INTER,"pe2":capi.MODE_PE_2FILE}
+p=capi.make_params(f['qualtype'],f['q'],f['l'],f['x'],f['n'],mode=modes[kind],has_singles='-s' in case['outputs'])
+with capi.Context(p,1<<16,1) as ctx:
+    r=runner.trim_stream(ctx,in0,in1)
+print("ok", r['batches'], r['fused_batches'], gu.md5(r['out'][0])==case['outputs']['-o']['md5'])

@@ -46,6 +46,21 @@ void set_err(const char *fmt, ...) {
         }                                                                                    \
     } while (0)
 
+// SICKLE_B200_DEBUG_SYNC=1: synchronise after every kernel and name the one that faulted
+#define SK_DEBUG_SYNC(st, name)                                                                     \
+    do {                                                                                            \
+        static const bool dbg__ = getenv("SICKLE_B200_DEBUG_SYNC") != nullptr;                      \
+        if (dbg__) {                                                                                \
+            cudaError_t e__ = cudaStreamSynchronize(st);                                            \
+            if (e__ == cudaSuccess) e__ = cudaGetLastError();                                       \
+            if (e__ != cudaSuccess) {                                                               \
+                set_err("kernel %s failed: %s", name, cudaGetErrorString(e__));                     \
+                fprintf(stderr, "[sickle_b200] kernel %s failed: %s\n", name, cudaGetErrorString(e__)); \
+                return SK_E_CUDA;                                                                   \
+            }                                                                                       \
+        }                                                                                           \
+    } while (0)
+
 constexpr uint64_t kPad = 64;           // readable padding after every device input buffer
 constexpr uint64_t kMaxSlotBytes = (1ull << 31) - 4096;
 constexpr int kFusedMinTile = sk::FusedCfg<5>::kTile;   // smallest tile of the instantiated configs
@@ -179,8 +194,8 @@ int alloc_slot(sk_ctx *c, Slot &s, bool host_buffers) {
     SK_CUDA(cudaMalloc((void **)&s.d_status_k2, (size_t)c->k2_tiles_cap * 8 * sk::kMaxStreams));
     SK_CUDA(cudaMemset(s.d_status_k2, 0, (size_t)c->k2_tiles_cap * 8 * sk::kMaxStreams));
     if (c->fused_eligible) {
-        SK_CUDA(cudaMalloc((void **)&s.d_status_f, (size_t)c->fused_tiles_cap * 8 * 3));
-        SK_CUDA(cudaMemset(s.d_status_f, 0, (size_t)c->fused_tiles_cap * 8 * 3));
+        SK_CUDA(cudaMalloc((void **)&s.d_status_f, (size_t)c->fused_tiles_cap * 8 * 3 * sk::kWideStatusStride));
+        SK_CUDA(cudaMemset(s.d_status_f, 0, (size_t)c->fused_tiles_cap * 8 * 3 * sk::kWideStatusStride));
     }
     if (host_buffers) {
         // stream capacities: an output stream never exceeds the bytes of the inputs feeding it
@@ -222,7 +237,7 @@ int next_epoch(sk_ctx *c, Slot &s, cudaStream_t st) {
     if ((s.epoch & (uint32_t)sk::kEpochMask) == 0) {  // epoch tag wrapped: clear the status words once
         for (int i = 0; i < c->n_inputs; ++i) SK_CUDA(cudaMemsetAsync(s.d_status_k1[i], 0, (size_t)c->k1_tiles_cap * 8, st));
         SK_CUDA(cudaMemsetAsync(s.d_status_k2, 0, (size_t)c->k2_tiles_cap * 8 * sk::kMaxStreams, st));
-        if (s.d_status_f) SK_CUDA(cudaMemsetAsync(s.d_status_f, 0, (size_t)c->fused_tiles_cap * 8 * 3, st));
+        if (s.d_status_f) SK_CUDA(cudaMemsetAsync(s.d_status_f, 0, (size_t)c->fused_tiles_cap * 8 * 3 * sk::kWideStatusStride, st));
         s.epoch += 1;
     }
     return SK_OK;
@@ -244,6 +259,7 @@ int launch_general(sk_ctx *c, Slot &s, const BatchArgs &a) {
         const int grid = tiles < (uint32_t)resident ? (int)tiles : resident;
         sk::k1_line_index<<<grid, sk::kK1Threads, 0, st>>>(di[i], s.d_ctl, i, s.d_status_k1[i], tiles, s.epoch);
         s.launches++;
+        SK_DEBUG_SYNC(st, "k1_line_index");
     }
     SK_CUDA(cudaEventRecord(s.ev_stage[0], st));
     // units <= bytes / 4 (a line is at least its '\n'); usually ~bytes/325
@@ -252,11 +268,14 @@ int launch_general(sk_ctx *c, Slot &s, const BatchArgs &a) {
     const int grid = tiles < (uint64_t)resident ? (int)tiles : resident;
     sk::k2_trim_route<<<grid, sk::kK2Threads, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, s.d_desc[0], s.d_desc[1],
                                                        s.d_status_k2, c->k2_tiles_cap, s.epoch);
+    SK_DEBUG_SYNC(st, "k2_trim_route");
     SK_CUDA(cudaEventRecord(s.ev_stage[1], st));
     sk::k3_emit<<<resident, sk::kK3Threads, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, s.d_desc[0], s.d_desc[1], op);
+    SK_DEBUG_SYNC(st, "k3_emit");
     SK_CUDA(cudaEventRecord(s.ev_stage[2], st));
     sk::k_finalize<<<1, 32, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, op, s.d_res);
     s.launches += 3;
+    SK_DEBUG_SYNC(st, "k_finalize");
     SK_CUDA(cudaEventRecord(s.ev_end, st));
     SK_CUDA(cudaGetLastError());
     s.last_fused = false;
@@ -272,9 +291,11 @@ int launch_fused_ch(sk_ctx *c, Slot &s, const BatchArgs &a, const sk::DevInput &
     if (tiles) {
         const int grid = tiles < (uint32_t)c->fused_grid ? (int)tiles : c->fused_grid;
         sk::kf_fused<CH><<<grid, sk::kFThreads, Cfg::kSmem, st>>>(di, c->dev, s.d_ctl, op, s.d_status_f,
-                                                                 s.d_status_f + c->fused_tiles_cap, c->fused_tiles_cap,
+                                                                 s.d_status_f + (size_t)c->fused_tiles_cap * sk::kWideStatusStride,
+                                                                 c->fused_tiles_cap * sk::kWideStatusStride,
                                                                  tiles, s.epoch);
         s.launches++;
+        SK_DEBUG_SYNC(st, "kf_fused");
     }
     return SK_OK;
 }
@@ -596,5 +617,22 @@ int sk_result_device(sk_ctx *ctx, int slot, void *stream, sk_result *res) {
     if (int rc = stage_times(s, res)) return rc;
     return check_capacity(ctx, s);
 }
+
+#ifdef SK_PHASE_TIMING
+// debug build only: cycles per fused-kernel phase, summed over tiles (thread 0 of every CTA)
+int sk_debug_phase_cycles(unsigned long long out[8], int reset) {
+    SK_CUDA(cudaDeviceSynchronize());
+    SK_CUDA(cudaMemcpyFromSymbol(out, sk::g_phase_cycles, sizeof(unsigned long long) * 8));
+    unsigned long long w[4];
+    SK_CUDA(cudaMemcpyFromSymbol(w, sk::g_walk_dbg, sizeof w));
+    fprintf(stderr, "[walk dbg] walks %llu steps %llu threads-that-spun %llu spin-iterations %llu\n", w[0], w[1], w[2], w[3]);
+    if (reset) {
+        unsigned long long z[8] = {0};
+        SK_CUDA(cudaMemcpyToSymbol(sk::g_phase_cycles, z, sizeof z));
+        SK_CUDA(cudaMemcpyToSymbol(sk::g_walk_dbg, z, sizeof(unsigned long long) * 4));
+    }
+    return SK_OK;
+}
+#endif
 
 }  // extern "C"

@@ -22,9 +22,11 @@
 //   S6  validate + sliding window out of shared memory, thread-per-read and branch-free: 32 windows
 //       per step, window totals by dp4a straight from the packed quality words, good/bad windows and
 //       out-of-range bytes collected as bit masks and resolved once per step.
-//   S7  routing, 2-stream block scan, decoupled look-back #2 -> byte offsets in the output streams.
-//   S8  each thread copies its trimmed record into a shared staging buffer laid out like the
-//       destination (same 16-byte phase), then the CTA flushes it with aligned 16-byte stores.
+//   S7  routing, 2-stream block scan; the tile's output sizes are published for look-back #2.
+//   S8a two lanes per record copy the trimmed record into a shared staging buffer.
+//   S8b one tile LATER (after the next tile's S1-S3): look-back #2 -> byte offsets in the output
+//       streams, then the CTA flushes the staged bytes with destination-aligned 16-byte stores
+//       (128-bit funnel shift for the destination's phase).
 // Anything this kernel cannot handle exactly -- a record longer than the halo, more than 128
 // records or 1024 newlines in a tile, or ANY data error -- sets Control::fast_fail; the host then
 // re-runs the batch through the general path, which also produces the reference's error details.
@@ -35,6 +37,21 @@
 #include "sk_device.cuh"
 
 namespace sk {
+
+// Debug only (-DSK_PHASE_TIMING): barrier-to-barrier cycles of thread 0, summed over tiles.
+#ifdef SK_PHASE_TIMING
+__device__ unsigned long long g_phase_cycles[8];
+#define SK_TICK(k)                                                            \
+    do {                                                                      \
+        if (tid == 0) {                                                       \
+            const long long t_now = clock64();                                \
+            atomicAdd(&g_phase_cycles[k], (unsigned long long)(t_now - t_prev)); \
+            t_prev = t_now;                                                   \
+        }                                                                     \
+    } while (0)
+#else
+#define SK_TICK(k) do { } while (0)
+#endif
 
 constexpr int kFThreads = 256;
 constexpr int kFTileThreads = 224;   // 7 warps own tile bytes, the 8th warp scans the halo
@@ -48,8 +65,8 @@ struct FusedCfg {
     static constexpr int kTile = kFTileThreads * kBytesPerThread;
     static constexpr int kInBytes = kRegion + 96;        // the window loop reads up to ~50 bytes past a record
     static constexpr int kOutBytes = kTile + 768 + 96;   // a tile of output + the last record's overhang + phase shifts
-    // CH = 7: 56,896 B -> four CTAs per SM (4 x (56,896 + 144 static + 1,024 reserved) <= 232,448)
-    static constexpr size_t kSmem = (size_t)kInBytes + kOutBytes + kFMaxNl * 2 + 128;
+    // CH = 7: 56,768 B -> four CTAs per SM (4 x (56,768 + 248 static + 1,024 reserved) <= 232,448)
+    static constexpr size_t kSmem = (size_t)kInBytes + kOutBytes + kFMaxNl * 2;
 };
 
 // four successive bytes at a time from an arbitrary shared-memory byte offset
@@ -290,6 +307,52 @@ __device__ __forceinline__ void smem_copy(uint8_t *__restrict__ out, uint32_t ds
         if (j < len) out[dst + j] = in[src + j];
 }
 
+// Flush `tot` staged bytes (shared memory, starting at the 16-byte aligned offset `sb`) to the global
+// address `gdst`, which has an arbitrary 16-byte phase: destination-aligned 16-byte stores fed by a
+// 128-bit funnel shift of two aligned shared-memory chunks; byte stores only on the two ragged ends.
+__device__ __forceinline__ void flush_realigned(uint8_t *__restrict__ gdst, const uint8_t *__restrict__ s_out,
+                                                uint32_t sb, uint32_t tot, int tid) {
+    if (tot == 0) return;
+    const uint32_t ph = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);
+    uint8_t *gal = gdst - ph;                                  // 16-byte aligned
+    const uint32_t nch = (ph + tot + 15u) >> 4;
+    const uint32_t r = (16u - ph) & 15u;                       // byte offset inside the older chunk
+    const uint32_t q = r >> 2, sh = (r & 3u) * 8u;
+    const uint4 *__restrict__ s16 = reinterpret_cast<const uint4 *>(s_out + sb);
+    for (uint32_t c = tid; c < nch; c += kFThreads) {
+        const uint32_t lo = c == 0 ? ph : 0u;
+        const uint32_t hi = min(16u, ph + tot - 16u * c);
+        if (lo == 0 && hi == 16) {
+            uint4 v;
+            if (ph == 0) {
+                v = s16[c];
+            } else {                                           // c >= 1 here (chunk 0 is ragged when ph != 0)
+                const uint4 A = s16[c - 1], B = s16[c];
+                uint32_t w0, w1, w2, w3, w4;
+                switch (q) {
+                    case 0: w0 = A.x; w1 = A.y; w2 = A.z; w3 = A.w; w4 = B.x; break;
+                    case 1: w0 = A.y; w1 = A.z; w2 = A.w; w3 = B.x; w4 = B.y; break;
+                    case 2: w0 = A.z; w1 = A.w; w2 = B.x; w3 = B.y; w4 = B.z; break;
+                    default: w0 = A.w; w1 = B.x; w2 = B.y; w3 = B.z; w4 = B.w; break;
+                }
+                v.x = __funnelshift_r(w0, w1, sh);
+                v.y = __funnelshift_r(w1, w2, sh);
+                v.z = __funnelshift_r(w2, w3, sh);
+                v.w = __funnelshift_r(w3, w4, sh);
+            }
+            __stcs(reinterpret_cast<uint4 *>(gal) + c, v);
+        } else {
+            for (uint32_t b = lo; b < hi; ++b) gal[16u * c + b] = s_out[sb + 16u * c + b - ph];
+        }
+    }
+}
+
+// Software-pipelined over tiles: the output of tile t is staged in shared memory right after it is
+// trimmed, its size is published, and only one tile later -- after the next tile has been loaded and
+// scanned -- does the CTA ask for tile t's output offset and flush.  By then every predecessor has
+// long published its size, so the second look-back does not wait; with hundreds of heavy tiles in
+// flight an immediate look-back makes every tile wait for the slowest predecessor (measured: 22 % of
+// the tile time).
 template <int CH>
 __global__ void __launch_bounds__(kFThreads, 4)
 kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
@@ -304,8 +367,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
     __shared__ uint32_t s_tile;
     __shared__ uint32_t warp_tot[kFThreads / 32];
     __shared__ uint32_t warp_tot2[kFThreads / 32][2];
-    __shared__ unsigned long long s_G;
-    __shared__ unsigned long long s_O[2];
+    __shared__ unsigned long long s_lb[kFThreads / 32][2];   // look-back scratch
     __shared__ uint32_t s_fail;
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -314,67 +376,107 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
     const bool paired = P.mode != 0;
     const bool mmode = P.mode == 3;
     const uint32_t lpu = paired ? 8u : 4u;   // lines per unit
+    const int nstreams = paired ? 2 : 1;
+    unsigned long long *const st_nl[2] = {status_nl, nullptr};
+    unsigned long long *const st_out[2] = {status_out, status_out + status_stride};
     RangeCheck rc;
     rc.init(P);
 
+    // the tile whose output is staged in s_out and not flushed yet
+    bool have_prev = false;
+    uint32_t p_tile = 0, p_tot0 = 0, p_tot1 = 0;
+
+#ifdef SK_PHASE_TIMING
+    long long t_prev = clock64();
+#endif
     while (true) {
         if (tid == 0) { s_tile = atomicAdd(&ctl->tile_counter[3], 1u); s_fail = 0; }
         __syncthreads();
+        SK_TICK(0);   // ticket
         const uint32_t tile = s_tile;
-        if (tile >= num_tiles) break;
+        const bool done = tile >= num_tiles;
         const uint32_t t0 = tile * (uint32_t)Cfg::kTile;
 
-        // ---- S1: region -> shared memory
-#pragma unroll
-        for (int k = 0; k < CH; ++k) {
-            const uint32_t c = k * kFThreads + tid;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            const uint32_t g = (t0 >> 4) + c;
-            if (g < nchunks) v = __ldcs(src + g);
-            reinterpret_cast<uint4 *>(s_in)[c] = v;
-        }
-        __syncthreads();
-
-        // ---- S2: newline masks of this thread's CH*16 contiguous bytes (two 64-bit halves)
-        const uint32_t b0 = tid * Cfg::kBytesPerThread;          // region-relative
         uint32_t mw[(CH + 1) / 2];                               // newline bits, 32 bytes per word
-#pragma unroll
-        for (int k = 0; k < (CH + 1) / 2; ++k) mw[k] = 0;
-        {
-            // only the first tile (bytes before the batch start) and the tiles touching the end of
-            // the batch have bytes to mask off
-            const bool edge = tile == 0 || (unsigned long long)t0 + Cfg::kRegion > in.nbytes;
-            const uint32_t lo = (tile == 0) ? in.first : 0u;
-            const uint32_t hi = in.nbytes > t0 ? in.nbytes - t0 : 0u;
+        uint32_t cnt = 0, incl = 0, wbase = 0, n_all = 0, c_t = 0;
+        const uint32_t b0 = tid * Cfg::kBytesPerThread;          // region-relative
+        bool nl_overflow = false;
+        if (!done) {
+            // ---- S1: region -> shared memory
 #pragma unroll
             for (int k = 0; k < CH; ++k) {
-                const uint4 v = reinterpret_cast<const uint4 *>(s_in)[CH * tid + k];
-                uint32_t mk = newline_mask16(v);
-                if (edge) {
-                    const uint32_t cb = b0 + 16u * k;
-                    if (cb + 16u > hi) mk &= cb >= hi ? 0u : ((1u << (hi - cb)) - 1u);
-                    if (cb < lo) mk &= cb + 16u <= lo ? 0u : (0xffffu << (lo - cb));
+                const uint32_t c = k * kFThreads + tid;
+                uint4 v = make_uint4(0, 0, 0, 0);
+                const uint32_t g = (t0 >> 4) + c;
+                if (g < nchunks) v = __ldcs(src + g);
+                reinterpret_cast<uint4 *>(s_in)[c] = v;
+            }
+            __syncthreads();
+            SK_TICK(1);   // S1 load
+
+            // ---- S2: newline masks of this thread's CH*16 contiguous bytes
+#pragma unroll
+            for (int k = 0; k < (CH + 1) / 2; ++k) mw[k] = 0;
+            {
+                // only the first tile (bytes before the batch start) and the tiles touching the end of
+                // the batch have bytes to mask off
+                const bool edge = tile == 0 || (unsigned long long)t0 + Cfg::kRegion > in.nbytes;
+                const uint32_t lo = (tile == 0) ? in.first : 0u;
+                const uint32_t hi = in.nbytes > t0 ? in.nbytes - t0 : 0u;
+#pragma unroll
+                for (int k = 0; k < CH; ++k) {
+                    const uint4 v = reinterpret_cast<const uint4 *>(s_in)[CH * tid + k];
+                    uint32_t mk = newline_mask16(v);
+                    if (edge) {
+                        const uint32_t cb = b0 + 16u * k;
+                        if (cb + 16u > hi) mk &= cb >= hi ? 0u : ((1u << (hi - cb)) - 1u);
+                        if (cb < lo) mk &= cb + 16u <= lo ? 0u : (0xffffu << (lo - cb));
+                    }
+                    mw[k >> 1] |= mk << (16 * (k & 1));
                 }
-                mw[k >> 1] |= mk << (16 * (k & 1));
+            }
+#pragma unroll
+            for (int k = 0; k < (CH + 1) / 2; ++k) cnt += __popc(mw[k]);
+            // ---- S3: ranks
+            incl = warp_incl_scan(cnt, lane);
+            if (lane == 31) warp_tot[wid] = incl;
+            __syncthreads();
+            SK_TICK(2);   // S2 masks + warp scan
+#pragma unroll
+            for (int w = 0; w < kFThreads / 32; ++w) {
+                const uint32_t t = warp_tot[w];
+                if (w < wid) wbase += t;
+                if (w < kFTileThreads / 32) c_t += t;
+                n_all += t;
+            }
+            nl_overflow = n_all > (uint32_t)kFMaxNl;
+            // the tile's newline count goes out before anything else is done with the tile
+            {
+                const unsigned long long agg[2] = {c_t, 0};
+                block_publish(st_nl, tile, agg, 1, epoch, tid);
             }
         }
-        uint32_t cnt = 0;
-#pragma unroll
-        for (int k = 0; k < (CH + 1) / 2; ++k) cnt += __popc(mw[k]);
-        // ---- S3: ranks
-        const uint32_t incl = warp_incl_scan(cnt, lane);
-        if (lane == 31) warp_tot[wid] = incl;
-        __syncthreads();
-        uint32_t wbase = 0, n_all = 0, c_t = 0;
-#pragma unroll
-        for (int w = 0; w < kFThreads / 32; ++w) {
-            const uint32_t t = warp_tot[w];
-            if (w < wid) wbase += t;
-            if (w < kFTileThreads / 32) c_t += t;
-            n_all += t;
+
+        // ---- deferred S7b/S8b of the previous tile: output offsets, then the flush.  s_desc (which
+        // aliases s_nl) was consumed by the previous tile's S8a, s_out is only read here.
+        if (have_prev) {
+            const unsigned long long agg[2] = {p_tot0, p_tot1};
+            unsigned long long ex[2];
+            block_walk(st_out, p_tile, agg, nstreams, epoch, tid, s_lb, ex);
+            if (tid == 0 && p_tile == num_tiles - 1) { ctl->out_bytes[0] = ex[0] + agg[0]; ctl->out_bytes[2] = ex[1] + agg[1]; }
+            SK_TICK(5);   // look-back #2 of the previous tile
+            const bool cap_ok = ex[0] + p_tot0 <= outs.cap[0] && (p_tot1 == 0 || (outs.p[2] && ex[1] + p_tot1 <= outs.cap[2]));
+            if (!cap_ok) {
+                if (tid == 0) ctl->index_overflow = 2u;
+            } else {
+                flush_realigned(outs.p[0] + ex[0], s_out, 0u, p_tot0, tid);
+                if (p_tot1) flush_realigned(outs.p[2] + ex[1], s_out, (p_tot0 + 15u) & ~15u, p_tot1, tid);
+            }
+            have_prev = false;
+            SK_TICK(7);   // flush of the previous tile
         }
-        const bool nl_overflow = n_all > (uint32_t)kFMaxNl;
-        // publish the tile's newline count as early as possible (S4 part 1 happens inside look-back)
+        if (done) break;
+
         if (!nl_overflow) {
             // a 32-byte word of a FASTQ file holds 0, 1 or (around the '+' line) 2 newlines: two
             // straight-line extractions, a loop only for pathological input
@@ -397,12 +499,15 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             }
         }
         // ---- S4: global line number of the tile
-        if (wid == 0) {
-            const unsigned long long p = lookback_exclusive(status_nl, tile, c_t, epoch, lane);
-            if (lane == 0) s_G = p;
+        uint32_t G;
+        {
+            const unsigned long long agg[2] = {c_t, 0};
+            unsigned long long ex[2];
+            block_walk(st_nl, tile, agg, 1, epoch, tid, s_lb, ex);
+            G = (uint32_t)ex[0];
         }
-        __syncthreads();
-        const uint32_t G = (uint32_t)s_G;
+        __syncthreads();   // newline positions visible to every thread; previous flush finished reading s_out
+        SK_TICK(3);   // S3 positions + S4 look-back #1
 
         // ---- S5: units owned by this tile.  Newline j (j < c_t) is global newline G+j; the line
         // after it is line G+j+1; a unit starts at every line that is a multiple of lpu.  Tile 0
@@ -452,7 +557,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         }
         if (fail) s_fail = 1u;
 
-        // ---- S7: routing + output offsets (lane = record; mates are lanes 2k, 2k+1)
+        // ---- S7: routing + output sizes (lane = record; mates are lanes 2k, 2k+1)
         const bool live = has_rec && complete;
         const bool keep = live && cut.three >= 0;
         const uint32_t nkeep = keep ? (uint32_t)(cut.three - cut.five) : 0u;
@@ -477,6 +582,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         const uint32_t inc1 = paired ? warp_incl_scan(add1, lane) : 0u;
         if (lane == 31) { warp_tot2[wid][0] = inc0; warp_tot2[wid][1] = inc1; }
         __syncthreads();
+        SK_TICK(4);   // S5 + S6 + S7 scan
         uint32_t wb0 = 0, wb1 = 0, tot0 = 0, tot1 = 0;
 #pragma unroll
         for (int w = 0; w < kFThreads / 32; ++w) {
@@ -487,112 +593,78 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         // the staging buffer holds a tile's worth of output; a tile whose (long, untrimmed) records
         // reach far into the halo can exceed it -> general path
         const bool tile_fail = s_fail != 0 || tot0 + tot1 + 64u > (uint32_t)Cfg::kOutBytes;
-        if (wid < 2) {
-            const uint32_t total = tile_fail ? 0u : (wid == 0 ? tot0 : tot1);
-            const unsigned long long pre =
-                lookback_exclusive(status_out + (size_t)wid * status_stride, tile, total, epoch, lane);
-            if (lane == 0) {
-                s_O[wid] = pre;
-                if (tile == num_tiles - 1) ctl->out_bytes[wid == 0 ? 0 : 2] = pre + total;
-            }
+        if (tile_fail) { tot0 = 0; tot1 = 0; if (tid == 0) ctl->fast_fail = 1u; }
+        {   // the tile's output sizes go out now; its own offsets are asked for one tile later
+            const unsigned long long agg[2] = {tot0, tot1};
+            block_publish(st_out, tile, agg, nstreams, epoch, tid);
         }
-        if (tile_fail) {
-            if (tid == 0) ctl->fast_fail = 1u;
-            __syncthreads();
-            continue;
-        }
+        have_prev = true;
+        p_tile = tile; p_tot0 = tot0; p_tot1 = tot1;
+        const uint32_t base1 = (tot0 + 15u) & ~15u;                    // singles staged after the main bytes
+
         // record descriptors for S8a (two lanes per record); they reuse the newline-position array,
         // which nobody reads after S5
         if (has_rec) {   // every slot S8a may look at is rewritten (x == 0: nothing to emit)
             uint4 dsc;
-            dsc.x = stream < 0 ? 0u
-                               : ((stream == 1 ? wb1 + inc1 - add1 : wb0 + inc0 - add0) |
-                                  (stream == 1 ? 0x80000000u : 0u) | (nrec_out ? 0x40000000u : 0u) | 0x20000000u);
+            dsc.x = (stream < 0 || tile_fail)
+                        ? 0u
+                        : ((stream == 1 ? wb1 + inc1 - add1 : wb0 + inc0 - add0) | (stream == 1 ? 0x80000000u : 0u) |
+                           (nrec_out ? 0x40000000u : 0u) | 0x20000000u);
             dsc.y = start | (e0 << 16);
             dsc.z = e1 | (e2 << 16);
             dsc.w = (keep ? (uint32_t)cut.five : 0u) | (nkeep << 16);
             s_desc[tid] = dsc;
         }
         __syncthreads();
-        const unsigned long long O0 = s_O[0], O1 = s_O[1];
-        uint8_t *g0 = outs.p[0] + O0;
-        uint8_t *g1 = outs.p[2] ? outs.p[2] + O1 : nullptr;
-        const uint32_t ph0 = (uint32_t)(reinterpret_cast<uintptr_t>(g0) & 15u);
-        const uint32_t ph1 = (uint32_t)(reinterpret_cast<uintptr_t>(g1) & 15u);
-        const uint32_t base1 = ((ph0 + tot0 + 15u) & ~15u) + ph1;      // singles staged after the main bytes
-        const bool cap_ok = O0 + tot0 <= outs.cap[0] && (tot1 == 0 || (g1 && O1 + tot1 <= outs.cap[2]));
-        if (!cap_ok) {
-            if (tid == 0) ctl->index_overflow = 2u;
-            __syncthreads();
-            continue;
-        }
 
-        // ---- S8a: two lanes per record copy it into the staging buffer (destination-phase aligned):
+        // ---- S8a: two lanes per record copy it into the staging buffer (phase 0; the flush realigns):
         // lane 0 takes [name '\n' seq), lane 1 takes ['\n' line3 '\n' qual '\n')
         {
             const uint32_t r = (uint32_t)tid >> 1, sub = (uint32_t)tid & 1u;
             uint4 dsc = make_uint4(0, 0, 0, 0);
-            if (r < nrec_t) dsc = s_desc[r];
+            if (!tile_fail && r < nrec_t) dsc = s_desc[r];   // a failed tile wrote no descriptors
             if (dsc.x & 0x20000000u) {
                 const uint32_t r_start = dsc.y & 0xffffu, r_e0 = dsc.y >> 16, r_e1 = dsc.z & 0xffffu, r_e2 = dsc.z >> 16;
                 const uint32_t five = dsc.w & 0xffffu, n = dsc.w >> 16;
                 const uint32_t nlen = r_e0 - r_start, plen = r_e2 - r_e1 - 1u;
-                uint32_t d = ((dsc.x & 0x80000000u) ? base1 : ph0) + (dsc.x & 0xffffu);
-                if (dsc.x & 0x40000000u) {                                 // "N record"
-                    if (sub == 0) {
-                        smem_copy(s_out, d, s_in, r_start, nlen + 1u);     // name line and its '\n'
-                        s_out[d + nlen + 1u] = 'N';
-                        s_out[d + nlen + 2u] = '\n';
-                    } else {
-                        d += nlen + 3u;
-                        smem_copy(s_out, d, s_in, r_e1 + 1u, plen + 1u);   // line 3 verbatim
-                        s_out[d + plen + 1u] = (uint8_t)P.qmin;
-                        s_out[d + plen + 2u] = '\n';
-                    }
-                } else if (sub == 0) {
-                    if (five == 0) {
-                        smem_copy(s_out, d, s_in, r_start, nlen + 1u + n); // contiguous in the source
-                    } else {
-                        smem_copy(s_out, d, s_in, r_start, nlen + 1u);
-                        smem_copy(s_out, d + nlen + 1u, s_in, r_e0 + 1u + five, n);
-                    }
-                } else {
-                    d += nlen + 1u + n;
+                const uint32_t d = ((dsc.x & 0x80000000u) ? base1 : 0u) + (dsc.x & 0xffffu);
+                // Both lanes run the same two copies with different arguments (lanes of one warp that
+                // took different branches would serialise).  Run A then run B, B possibly empty:
+                //   lane 0: A = name '\n' [+ seq if nothing is cut at 5']   B = seq[five..) if cut at 5'
+                //   lane 1: A = '\n' line3 '\n' [+ qual '\n' if uncut]      B = qual[five..three)
+                uint32_t a_dst, a_src, a_len, b_dst, b_src, b_len;
+                int nl_at = -1;                       // staging offset of a '\n' to add after the copies
+                const bool nrec = (dsc.x & 0x40000000u) != 0;
+                if (sub == 0) {
+                    a_dst = d; a_src = r_start;
+                    a_len = nlen + 1u + ((five == 0 && !nrec) ? n : 0u);
+                    b_dst = d + nlen + 1u; b_src = r_e0 + 1u + five;
+                    b_len = (five != 0 && !nrec) ? n : 0u;
+                } else if (!nrec) {
                     const uint32_t Lr = r_e1 - r_e0 - 1u;
-                    if (five == 0 && n == Lr) {
-                        smem_copy(s_out, d, s_in, r_e1, plen + 2u + n + 1u);   // rest of the record
-                    } else {
-                        smem_copy(s_out, d, s_in, r_e1, plen + 2u);        // '\n' + line 3 + '\n'
-                        smem_copy(s_out, d + plen + 2u, s_in, r_e2 + 1u + five, n);
-                        s_out[d + plen + 2u + n] = '\n';
-                    }
+                    const bool whole = five == 0 && n == Lr;         // rest of the record is contiguous
+                    a_dst = d + nlen + 1u + n; a_src = r_e1;
+                    a_len = plen + 2u + (whole ? n + 1u : 0u);
+                    b_dst = a_dst + plen + 2u; b_src = r_e2 + 1u + five;
+                    b_len = whole ? 0u : n;
+                    if (!whole) nl_at = (int)(b_dst + n);
+                } else {                                             // "N record": name '\n' N '\n' line3 '\n' Qmin '\n'
+                    a_dst = d + nlen + 3u; a_src = r_e1 + 1u; a_len = plen + 1u;
+                    b_dst = 0; b_src = 0; b_len = 0;
+                }
+                smem_copy(s_out, a_dst, s_in, a_src, a_len);
+                smem_copy(s_out, b_dst, s_in, b_src, b_len);
+                if (nl_at >= 0) s_out[nl_at] = '\n';
+                if (nrec) {
+                    if (sub == 0) { s_out[d + nlen + 1u] = 'N'; s_out[d + nlen + 2u] = '\n'; }
+                    else { s_out[a_dst + plen + 1u] = (uint8_t)P.qmin; s_out[a_dst + plen + 2u] = '\n'; }
                 }
             }
         }
-        __syncthreads();
-
-        // ---- S8b: flush with destination-aligned 16-byte stores (byte stores on the ragged ends)
-#pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            const uint32_t tot = s == 0 ? tot0 : tot1;
-            if (tot == 0) continue;
-            const uint32_t ph = s == 0 ? ph0 : ph1;
-            const uint32_t sb = s == 0 ? 0u : base1 - ph1;             // staging offset of the 16-byte grid
-            uint8_t *gal = (s == 0 ? g0 : g1) - ph;                    // 16-byte aligned
-            const uint32_t nch = (ph + tot + 15u) >> 4;
-            for (uint32_t c = tid; c < nch; c += kFThreads) {
-                const uint32_t lo = c == 0 ? ph : 0u;
-                const uint32_t hi = min(16u, ph + tot - 16u * c);
-                if (lo == 0 && hi == 16) {
-                    __stcs(reinterpret_cast<uint4 *>(gal) + c, *reinterpret_cast<const uint4 *>(s_out + sb + 16u * c));
-                } else {
-                    for (uint32_t b = lo; b < hi; ++b) gal[16u * c + b] = s_out[sb + 16u * c + b];
-                }
-            }
-        }
+        SK_TICK(6);   // descriptors + S8a
 
         // ---- bookkeeping: consumed bytes, record count, counters
-        {
+        if (!tile_fail) {
             // end of the last complete record of this tile (absolute offset in the input buffer)
             uint32_t end = live ? t0 + e3 + 1u : 0u;
 #pragma unroll
@@ -622,7 +694,8 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 }
             }
         }
-        __syncthreads();   // staging buffers and scan scratch are reused by the next tile
+        // the ticket barrier at the top of the loop orders S8a (reads s_in, writes s_out) before the
+        // next tile's load (writes s_in) and flush (reads s_out)
     }
 }
 

@@ -7,6 +7,10 @@
 
 namespace sk {
 
+#ifdef SK_PHASE_TIMING
+__device__ unsigned long long g_walk_dbg[4];   // debug: walks, steps, threads that had to spin, spin iterations
+#endif
+
 constexpr int kMaxStreams = 3;
 
 // Trimming parameters in the form the kernels want (built from sk_params on the host).
@@ -140,6 +144,94 @@ __device__ __forceinline__ unsigned long long lookback_exclusive(unsigned long l
     }
     if (lane == 0) st_status(&status[tile], pack_status(kFlagInclusive, epoch, exclusive + aggregate));
     return exclusive;
+}
+
+// Wide-window look-back for heavy tiles, called by ALL threads of a 256-thread CTA (contains
+// __syncthreads).  With hundreds of tiles in flight and tiles that take tens of microseconds, the
+// nearest predecessor that already knows its inclusive prefix is hundreds of tiles back; a 32-wide
+// window would need ~20 dependent L2 round trips to get there.  Here every thread inspects one
+// predecessor per step: `nstreams` (1 or 2) independent prefixes are walked at once, each by
+// 256/nstreams threads.  `scratch` needs 8 x 2 x 8 bytes of shared memory.
+// aggregate[s] must be block-uniform.  Returns the exclusive prefix of stream s in excl[s].
+//
+// Status words of the wide look-back are padded to one 128-byte line each: hundreds of CTAs poll the
+// same few hundred words at the same time, and 16 words per line would funnel all of that into a
+// handful of L2 slices.
+constexpr int kWideStatusStride = 16;   // in 8-byte words
+//
+// The two halves can be called apart: block_publish makes the tile's aggregate visible (successors
+// can already add it), block_walk -- possibly much later, after other work -- finds the exclusive
+// prefix and upgrades the status to "inclusive".  The later the walk, the less it waits.
+__device__ __forceinline__ void block_publish(unsigned long long *const status[2], uint32_t tile,
+                                              const unsigned long long aggregate[2], int nstreams, uint32_t epoch,
+                                              int tid) {
+    if (tid < nstreams)
+        st_status(&status[tid][(size_t)tile * kWideStatusStride],
+                  pack_status(tile == 0 ? kFlagInclusive : kFlagAggregate, epoch, aggregate[tid]));
+}
+
+__device__ __forceinline__ void block_walk(unsigned long long *const status[2], uint32_t tile,
+                                           const unsigned long long aggregate[2], int nstreams, uint32_t epoch,
+                                           int tid, unsigned long long (*scratch)[2], unsigned long long excl[2]) {
+    const int lane = tid & 31, wid = tid >> 5;
+    const int wps = 8 / nstreams;                 // warps per stream
+    const int sid = wid / wps;                    // the stream this warp works on
+    const int width = wps * 32;
+    const int lt = tid - sid * width;             // distance slot inside the stream's window
+    excl[0] = excl[1] = 0;
+    if (tile == 0) return;                        // published as inclusive already
+    bool done[2] = {false, nstreams < 2};
+    int64_t idx = (int64_t)tile - 1;
+#ifdef SK_PHASE_TIMING
+    bool spun = false;
+    if (tid == 0) atomicAdd(&g_walk_dbg[0], 1ull);
+#endif
+    while (!(done[0] && done[1])) {
+        // ---- every thread: one predecessor of its stream (or nothing if that stream is finished)
+        uint32_t flag = 2;
+        unsigned long long v = 0;
+        const int64_t my = idx - lt;
+        if (!done[sid] && my >= 0) {
+            unsigned long long w;
+            while (true) {
+                w = ld_status(&status[sid][(size_t)my * kWideStatusStride]);
+                flag = status_flag(w, epoch);
+                if (flag) break;
+#ifdef SK_PHASE_TIMING
+                atomicAdd(&g_walk_dbg[3], 1ull);
+                if (!spun) { spun = true; atomicAdd(&g_walk_dbg[2], 1ull); }
+#endif
+                __nanosleep(40);
+            }
+            v = w & kValueMask;
+        }
+#ifdef SK_PHASE_TIMING
+        if (tid == 0) atomicAdd(&g_walk_dbg[1], 1ull);
+#endif
+        const uint32_t incl = __ballot_sync(0xffffffffu, flag == 2);
+        if (incl) {
+            const int first = __ffs(incl) - 1;
+            if (lane > first) v = 0;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+        if (lane == 0) { scratch[wid][0] = v; scratch[wid][1] = incl ? 1ull : 0ull; }
+        __syncthreads();
+        // ---- combine the warps of each stream in distance order, stop at the first inclusive one
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+            if (s < nstreams && !done[s]) {
+                for (int w = 0; w < wps; ++w) {
+                    excl[s] += scratch[s * wps + w][0];
+                    if (scratch[s * wps + w][1]) { done[s] = true; break; }
+                }
+            }
+        }
+        __syncthreads();
+        idx -= width;
+    }
+    if (tid < nstreams)
+        st_status(&status[tid][(size_t)tile * kWideStatusStride], pack_status(kFlagInclusive, epoch, excl[tid] + aggregate[tid]));
 }
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
