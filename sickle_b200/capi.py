@@ -10,7 +10,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsickle_b200.so")
+LIB_PATH = os.environ.get("SICKLE_B200_LIB", os.path.join(_HERE, "libsickle_b200.so"))   # override: A/B builds
 
 QUAL_SANGER, QUAL_SOLEXA, QUAL_ILLUMINA = 1, 2, 3
 QUALTYPE = {"sanger": QUAL_SANGER, "solexa": QUAL_SOLEXA, "illumina": QUAL_ILLUMINA}

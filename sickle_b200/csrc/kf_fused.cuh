@@ -310,40 +310,55 @@ __device__ __forceinline__ void smem_copy(uint8_t *__restrict__ out, uint32_t ds
 // Flush `tot` staged bytes (shared memory, starting at the 16-byte aligned offset `sb`) to the global
 // address `gdst`, which has an arbitrary 16-byte phase: destination-aligned 16-byte stores fed by a
 // 128-bit funnel shift of two aligned shared-memory chunks; byte stores only on the two ragged ends.
-__device__ __forceinline__ void flush_realigned(uint8_t *__restrict__ gdst, const uint8_t *__restrict__ s_out,
+// Q = word part of the shift (block-uniform, so the four variants never diverge).
+template <int Q>
+__device__ __forceinline__ void flush_full_chunks(uint4 *__restrict__ gal16, const uint4 *__restrict__ s16, uint32_t c_lo,
+                                                  uint32_t c_hi, uint32_t sh, int tid) {
+    for (uint32_t c = c_lo + tid; c < c_hi; c += kFThreads) {
+        const uint4 A = s16[c - 1], B = s16[c];
+        const uint32_t w0 = Q == 0 ? A.x : Q == 1 ? A.y : Q == 2 ? A.z : A.w;
+        const uint32_t w1 = Q == 0 ? A.y : Q == 1 ? A.z : Q == 2 ? A.w : B.x;
+        const uint32_t w2 = Q == 0 ? A.z : Q == 1 ? A.w : Q == 2 ? B.x : B.y;
+        const uint32_t w3 = Q == 0 ? A.w : Q == 1 ? B.x : Q == 2 ? B.y : B.z;
+        const uint32_t w4 = Q == 0 ? B.x : Q == 1 ? B.y : Q == 2 ? B.z : B.w;
+        uint4 v;
+        v.x = __funnelshift_r(w0, w1, sh);
+        v.y = __funnelshift_r(w1, w2, sh);
+        v.z = __funnelshift_r(w2, w3, sh);
+        v.w = __funnelshift_r(w3, w4, sh);
+        __stcs(gal16 + c, v);
+    }
+}
+
+__device__ __noinline__ void flush_realigned(uint8_t *__restrict__ gdst, const uint8_t *__restrict__ s_out,
                                                 uint32_t sb, uint32_t tot, int tid) {
     if (tot == 0) return;
     const uint32_t ph = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);
     uint8_t *gal = gdst - ph;                                  // 16-byte aligned
-    const uint32_t nch = (ph + tot + 15u) >> 4;
-    const uint32_t r = (16u - ph) & 15u;                       // byte offset inside the older chunk
-    const uint32_t q = r >> 2, sh = (r & 3u) * 8u;
+    const uint32_t end = ph + tot;                             // in bytes from gal
+    const uint32_t c_lo = ph ? 1u : 0u;                        // first chunk that is written in full
+    const uint32_t c_hi = end >> 4;                            // one past the last full chunk
     const uint4 *__restrict__ s16 = reinterpret_cast<const uint4 *>(s_out + sb);
-    for (uint32_t c = tid; c < nch; c += kFThreads) {
-        const uint32_t lo = c == 0 ? ph : 0u;
-        const uint32_t hi = min(16u, ph + tot - 16u * c);
-        if (lo == 0 && hi == 16) {
-            uint4 v;
-            if (ph == 0) {
-                v = s16[c];
-            } else {                                           // c >= 1 here (chunk 0 is ragged when ph != 0)
-                const uint4 A = s16[c - 1], B = s16[c];
-                uint32_t w0, w1, w2, w3, w4;
-                switch (q) {
-                    case 0: w0 = A.x; w1 = A.y; w2 = A.z; w3 = A.w; w4 = B.x; break;
-                    case 1: w0 = A.y; w1 = A.z; w2 = A.w; w3 = B.x; w4 = B.y; break;
-                    case 2: w0 = A.z; w1 = A.w; w2 = B.x; w3 = B.y; w4 = B.z; break;
-                    default: w0 = A.w; w1 = B.x; w2 = B.y; w3 = B.z; w4 = B.w; break;
-                }
-                v.x = __funnelshift_r(w0, w1, sh);
-                v.y = __funnelshift_r(w1, w2, sh);
-                v.z = __funnelshift_r(w2, w3, sh);
-                v.w = __funnelshift_r(w3, w4, sh);
-            }
-            __stcs(reinterpret_cast<uint4 *>(gal) + c, v);
-        } else {
-            for (uint32_t b = lo; b < hi; ++b) gal[16u * c + b] = s_out[sb + 16u * c + b - ph];
+    if (ph == 0) {
+        for (uint32_t c = tid; c < c_hi; c += kFThreads) __stcs(reinterpret_cast<uint4 *>(gal) + c, s16[c]);
+    } else {
+        const uint32_t r = 16u - ph;                           // byte offset inside the older chunk
+        const uint32_t sh = (r & 3u) * 8u;
+        switch (r >> 2) {
+            case 0: flush_full_chunks<0>(reinterpret_cast<uint4 *>(gal), s16, c_lo, c_hi, sh, tid); break;
+            case 1: flush_full_chunks<1>(reinterpret_cast<uint4 *>(gal), s16, c_lo, c_hi, sh, tid); break;
+            case 2: flush_full_chunks<2>(reinterpret_cast<uint4 *>(gal), s16, c_lo, c_hi, sh, tid); break;
+            default: flush_full_chunks<3>(reinterpret_cast<uint4 *>(gal), s16, c_lo, c_hi, sh, tid); break;
         }
+    }
+    // ragged head (bytes [ph, 16) of chunk 0) and tail (bytes of the last, partial chunk): one byte per thread
+    if (ph && tid < 16) {
+        const uint32_t b = (uint32_t)tid;
+        if (b >= ph && b < end) gal[b] = s_out[sb + b - ph];
+    }
+    if ((end & 15u) && c_hi >= c_lo && tid >= 32 && tid < 48) {
+        const uint32_t b = 16u * c_hi + (uint32_t)(tid - 32);
+        if (b < end && (c_hi > 0 || ph == 0)) gal[b] = s_out[sb + b - ph];
     }
 }
 
@@ -459,9 +474,11 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
 
         // ---- deferred S7b/S8b of the previous tile: output offsets, then the flush.  s_desc (which
         // aliases s_nl) was consumed by the previous tile's S8a, s_out is only read here.
+        SK_TICK(2);   // (+ newline-count publish)
         if (have_prev) {
             const unsigned long long agg[2] = {p_tot0, p_tot1};
             unsigned long long ex[2];
+            // (prefetching the status words earlier was measured: no gain, and the extra live registers spill)
             block_walk(st_out, p_tile, agg, nstreams, epoch, tid, s_lb, ex);
             if (tid == 0 && p_tile == num_tiles - 1) { ctl->out_bytes[0] = ex[0] + agg[0]; ctl->out_bytes[2] = ex[1] + agg[1]; }
             SK_TICK(5);   // look-back #2 of the previous tile

@@ -170,31 +170,47 @@ __device__ __forceinline__ void block_publish(unsigned long long *const status[2
                   pack_status(tile == 0 ? kFlagInclusive : kFlagAggregate, epoch, aggregate[tid]));
 }
 
+// block_walk_prefetch issues this thread's status load of the FIRST window step and returns the raw
+// word; handing it to block_walk later (after unrelated work) hides the L2 round trip of the walk.
+__device__ __forceinline__ unsigned long long block_walk_prefetch(unsigned long long *const status[2], uint32_t tile,
+                                                                  int nstreams, int tid) {
+    const int wps = 8 / nstreams;
+    const int sid = (tid >> 5) / wps;
+    const int lt = tid - sid * wps * 32;
+    const int64_t my = (int64_t)tile - 1 - lt;
+    if (tile == 0 || my < 0) return 0ull;
+    return ld_status(&status[sid][(size_t)my * kWideStatusStride]);
+}
+
 __device__ __forceinline__ void block_walk(unsigned long long *const status[2], uint32_t tile,
                                            const unsigned long long aggregate[2], int nstreams, uint32_t epoch,
-                                           int tid, unsigned long long (*scratch)[2], unsigned long long excl[2]) {
+                                           int tid, unsigned long long (*scratch)[2], unsigned long long excl[2],
+                                           bool have_prefetch = false, unsigned long long prefetched = 0ull) {
     const int lane = tid & 31, wid = tid >> 5;
     const int wps = 8 / nstreams;                 // warps per stream
     const int sid = wid / wps;                    // the stream this warp works on
     const int width = wps * 32;
     const int lt = tid - sid * width;             // distance slot inside the stream's window
+    unsigned long long *const my_status = sid ? status[1] : status[0];
+    uint32_t ex0 = 0, ex1 = 0;                    // values of one batch fit 32 bits (see pack_status)
     excl[0] = excl[1] = 0;
     if (tile == 0) return;                        // published as inclusive already
-    bool done[2] = {false, nstreams < 2};
+    bool done0 = false, done1 = nstreams < 2;
     int64_t idx = (int64_t)tile - 1;
+    uint2 *const sc = reinterpret_cast<uint2 *>(scratch);   // one (sum, has-inclusive) pair per warp
 #ifdef SK_PHASE_TIMING
     bool spun = false;
     if (tid == 0) atomicAdd(&g_walk_dbg[0], 1ull);
 #endif
-    while (!(done[0] && done[1])) {
+    while (!(done0 && done1)) {
         // ---- every thread: one predecessor of its stream (or nothing if that stream is finished)
-        uint32_t flag = 2;
-        unsigned long long v = 0;
+        uint32_t flag = 2, v = 0;
         const int64_t my = idx - lt;
-        if (!done[sid] && my >= 0) {
+        if (!(sid ? done1 : done0) && my >= 0) {
             unsigned long long w;
             while (true) {
-                w = ld_status(&status[sid][(size_t)my * kWideStatusStride]);
+                if (have_prefetch) { w = prefetched; have_prefetch = false; }   // first step only
+                else w = ld_status(&my_status[(size_t)my * kWideStatusStride]);
                 flag = status_flag(w, epoch);
                 if (flag) break;
 #ifdef SK_PHASE_TIMING
@@ -203,35 +219,38 @@ __device__ __forceinline__ void block_walk(unsigned long long *const status[2], 
 #endif
                 __nanosleep(40);
             }
-            v = w & kValueMask;
+            v = (uint32_t)w;
         }
+        have_prefetch = false;
 #ifdef SK_PHASE_TIMING
         if (tid == 0) atomicAdd(&g_walk_dbg[1], 1ull);
 #endif
         const uint32_t incl = __ballot_sync(0xffffffffu, flag == 2);
-        if (incl) {
-            const int first = __ffs(incl) - 1;
-            if (lane > first) v = 0;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-        if (lane == 0) { scratch[wid][0] = v; scratch[wid][1] = incl ? 1ull : 0ull; }
+        if (incl && lane > __ffs(incl) - 1) v = 0;            // nothing beyond the first inclusive prefix
+        v = __reduce_add_sync(0xffffffffu, v);
+        if (lane == 0) sc[wid] = make_uint2(v, incl ? 1u : 0u);
         __syncthreads();
         // ---- combine the warps of each stream in distance order, stop at the first inclusive one
+        if (!done0) {
 #pragma unroll
-        for (int s = 0; s < 2; ++s) {
-            if (s < nstreams && !done[s]) {
-                for (int w = 0; w < wps; ++w) {
-                    excl[s] += scratch[s * wps + w][0];
-                    if (scratch[s * wps + w][1]) { done[s] = true; break; }
-                }
+            for (int w = 0; w < 8; ++w) {
+                if (w < wps && !done0) { const uint2 e = sc[w]; ex0 += e.x; done0 = e.y != 0; }
+            }
+        }
+        if (!done1) {
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                if (!done1) { const uint2 e = sc[4 + w]; ex1 += e.x; done1 = e.y != 0; }
             }
         }
         __syncthreads();
         idx -= width;
     }
+    excl[0] = ex0;
+    excl[1] = ex1;
     if (tid < nstreams)
-        st_status(&status[tid][(size_t)tile * kWideStatusStride], pack_status(kFlagInclusive, epoch, excl[tid] + aggregate[tid]));
+        st_status(&status[tid][(size_t)tile * kWideStatusStride],
+                  pack_status(kFlagInclusive, epoch, (tid ? ex1 : ex0) + aggregate[tid]));
 }
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
