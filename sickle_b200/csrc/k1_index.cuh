@@ -24,6 +24,23 @@ constexpr int kK1TileBytes = kK1Threads * kK1BytesPerThread;  // 16384
 // 0x80 in every byte of w that equals '\n' (exact, no false positives).
 // Three ALU ops per word: the low 7 bits of (w ^ 0x0A..) are zero iff +0x7F leaves bit 7 clear, and
 // the byte's own bit 7 (unchanged by the xor) must be clear as well.
+//
+// A LOP3 takes one immediate, so "(w ^ 0x0A..) & 0x7F.." with two literals costs two instructions;
+// SwarConsts keeps the two patterns in registers (made opaque to constant folding) so that the xor-and
+// is a single three-register LOP3 (LUT 0x28 = (a ^ b) & c).
+struct SwarConsts {
+    uint32_t nl, low7;
+    __device__ __forceinline__ void init() {
+        asm volatile("mov.u32 %0, 0x0A0A0A0A;" : "=r"(nl));
+        asm volatile("mov.u32 %0, 0x7F7F7F7F;" : "=r"(low7));
+    }
+};
+__device__ __forceinline__ uint32_t newline_flags(uint32_t w, const SwarConsts &k) {
+    uint32_t t;
+    asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(t) : "r"(w), "r"(k.nl), "r"(k.low7));
+    t += 0x7F7F7F7Fu;
+    return ~(t | w) & 0x80808080u;
+}
 __device__ __forceinline__ uint32_t newline_flags(uint32_t w) {
     const uint32_t t = ((w ^ 0x0A0A0A0Au) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
     return ~(t | w) & 0x80808080u;
@@ -34,6 +51,10 @@ __device__ __forceinline__ uint32_t flags_to_nibble(uint32_t f) { return (f * 0x
 __device__ __forceinline__ uint32_t newline_mask16(const uint4 v) {
     return flags_to_nibble(newline_flags(v.x)) + (flags_to_nibble(newline_flags(v.y)) << 4) +
            (flags_to_nibble(newline_flags(v.z)) << 8) + (flags_to_nibble(newline_flags(v.w)) << 12);
+}
+__device__ __forceinline__ uint32_t newline_mask16(const uint4 v, const SwarConsts &k) {
+    return flags_to_nibble(newline_flags(v.x, k)) + (flags_to_nibble(newline_flags(v.y, k)) << 4) +
+           (flags_to_nibble(newline_flags(v.z, k)) << 8) + (flags_to_nibble(newline_flags(v.w, k)) << 12);
 }
 
 // swizzled position (in 16-byte chunks) of logical chunk c inside the staging tile
@@ -50,6 +71,8 @@ k1_line_index(DevInput in, Control *__restrict__ ctl, int which, unsigned long l
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint4 *__restrict__ src = reinterpret_cast<const uint4 *>(in.data);
     const uint32_t nchunks = (in.nbytes + 15u) >> 4;  // padding bytes are masked below
+    SwarConsts swar;
+    swar.init();
 
     while (true) {
         if (tid == 0) s_tile = atomicAdd(&ctl->tile_counter[which], 1u);
@@ -74,7 +97,7 @@ k1_line_index(DevInput in, Control *__restrict__ ctl, int which, unsigned long l
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
             const uint4 v = stage[swz(4 * tid + k)];
-            mask |= (unsigned long long)newline_mask16(v) << (16 * k);
+            mask |= (unsigned long long)newline_mask16(v, swar) << (16 * k);
         }
         // mask off bytes at or beyond nbytes (zero padding cannot be '\n', but the caller's buffer
         // beyond nbytes inside the last 16-byte chunk may hold stale data)

@@ -396,6 +396,8 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
     unsigned long long *const st_out[2] = {status_out, status_out + status_stride};
     RangeCheck rc;
     rc.init(P);
+    SwarConsts swar;
+    swar.init();
 
     // the tile whose output is staged in s_out and not flushed yet
     bool have_prev = false;
@@ -441,7 +443,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
 #pragma unroll
                 for (int k = 0; k < CH; ++k) {
                     const uint4 v = reinterpret_cast<const uint4 *>(s_in)[CH * tid + k];
-                    uint32_t mk = newline_mask16(v);
+                    uint32_t mk = newline_mask16(v, swar);
                     if (edge) {
                         const uint32_t cb = b0 + 16u * k;
                         if (cb + 16u > hi) mk &= cb >= hi ? 0u : ((1u << (hi - cb)) - 1u);
