@@ -498,22 +498,20 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
 
         if (!nl_overflow) {
             // a 32-byte word of a FASTQ file holds 0, 1 or (around the '+' line) 2 newlines: two
-            // straight-line extractions, a loop only for pathological input
+            // predicated (branch-free) extractions keep the warp converged, a loop only for more
             uint32_t rank = wbase + incl - cnt;
 #pragma unroll
             for (int k = 0; k < (CH + 1) / 2; ++k) {
-                uint32_t m = mw[k];
-                if (m) {
-                    s_nl[rank++] = (uint16_t)(b0 + 32u * k + (uint32_t)__ffs(m) - 1u);
-                    m &= m - 1;
-                    if (m) {
-                        s_nl[rank++] = (uint16_t)(b0 + 32u * k + (uint32_t)__ffs(m) - 1u);
-                        m &= m - 1;
-                        while (m) {
-                            s_nl[rank++] = (uint16_t)(b0 + 32u * k + (uint32_t)__ffs(m) - 1u);
-                            m &= m - 1;
-                        }
-                    }
+                const uint32_t m = mw[k];
+                const uint32_t m2 = m & (m - 1u);
+                if (m) s_nl[rank] = (uint16_t)(b0 + 32u * k + (uint32_t)__ffs(m) - 1u);
+                rank += m ? 1u : 0u;
+                if (m2) s_nl[rank] = (uint16_t)(b0 + 32u * k + (uint32_t)__ffs(m2) - 1u);
+                rank += m2 ? 1u : 0u;
+                uint32_t m3 = m2 & (m2 - 1u);
+                while (m3) {
+                    s_nl[rank++] = (uint16_t)(b0 + 32u * k + (uint32_t)__ffs(m3) - 1u);
+                    m3 &= m3 - 1;
                 }
             }
         }

@@ -198,6 +198,7 @@ __device__ __forceinline__ void block_walk(unsigned long long *const status[2], 
     bool done0 = false, done1 = nstreams < 2;
     int64_t idx = (int64_t)tile - 1;
     uint2 *const sc = reinterpret_cast<uint2 *>(scratch);   // one (sum, has-inclusive) pair per warp
+    uint2 *const res = sc + 8;                               // combined (sum, done) per stream
 #ifdef SK_PHASE_TIMING
     bool spun = false;
     if (tid == 0) atomicAdd(&g_walk_dbg[0], 1ull);
@@ -230,20 +231,25 @@ __device__ __forceinline__ void block_walk(unsigned long long *const status[2], 
         v = __reduce_add_sync(0xffffffffu, v);
         if (lane == 0) sc[wid] = make_uint2(v, incl ? 1u : 0u);
         __syncthreads();
-        // ---- combine the warps of each stream in distance order, stop at the first inclusive one
-        if (!done0) {
-#pragma unroll
-            for (int w = 0; w < 8; ++w) {
-                if (w < wps && !done0) { const uint2 e = sc[w]; ex0 += e.x; done0 = e.y != 0; }
-            }
-        }
-        if (!done1) {
-#pragma unroll
-            for (int w = 0; w < 4; ++w) {
-                if (!done1) { const uint2 e = sc[4 + w]; ex1 += e.x; done1 = e.y != 0; }
+        // ---- warp 0 combines the warps of each stream in distance order, up to the first one that
+        // met an inclusive prefix; everybody else only reads the two results after the barrier
+        if (wid == 0) {
+            const uint2 e = lane < 8 ? sc[lane] : make_uint2(0u, 0u);
+            const uint32_t has = __ballot_sync(0xffffffffu, e.y != 0);
+            const uint32_t m0 = (1u << wps) - 1u;                       // lanes of stream 0
+            const uint32_t h0 = has & m0, h1 = (has >> 4) & 0xfu;       // stream 1 only exists with wps == 4
+            const uint32_t take0 = h0 ? ((2u << (__ffs(h0) - 1)) - 1u) : m0;
+            const uint32_t take1 = h1 ? ((2u << (__ffs(h1) - 1)) - 1u) : 0xfu;
+            const uint32_t s0 = __reduce_add_sync(0xffffffffu, ((take0 >> lane) & 1u) && !done0 ? e.x : 0u);
+            const uint32_t s1 = __reduce_add_sync(0xffffffffu, (lane >= 4 && lane < 8 && ((take1 >> (lane - 4)) & 1u) && !done1) ? e.x : 0u);
+            if (lane == 0) {
+                res[0] = make_uint2(s0, h0 ? 1u : 0u);
+                res[1] = make_uint2(s1, h1 ? 1u : 0u);
             }
         }
         __syncthreads();
+        if (!done0) { const uint2 r0 = res[0]; ex0 += r0.x; done0 = r0.y != 0; }
+        if (!done1) { const uint2 r1 = res[1]; ex1 += r1.x; done1 = r1.y != 0; }
         idx -= width;
     }
     excl[0] = ex0;
