@@ -17,10 +17,14 @@ $(LIB): $(CSRC)/capi.cu $(KERNELS)
 	$(NVCC) $(NVFLAGS) -shared $(CSRC)/capi.cu -o $@ 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; exit 1)
 	@grep -E "error|warning: v|spill" $(CSRC)/ptxas.log | grep -v "0 bytes spill" || true
 
-cli: bin/sickle
-bin/sickle: host/sickle_main.cpp host/trimmer.cpp host/trimmer.h include/sickle_b200.h $(LIB)
+cli: bin/sickle bin/io_tool
+# the CLI's I/O stages alone (no CUDA): used by tests/test_host_io.py
+bin/io_tool: host/io_tool.cpp host/io.cpp host/io.h
 	@mkdir -p bin
-	g++ -O2 -std=c++17 -Wall -Iinclude host/sickle_main.cpp host/trimmer.cpp -o $@ \
+	g++ -O2 -std=c++17 -Wall host/io_tool.cpp host/io.cpp -o $@ -lz -lpthread
+bin/sickle: host/sickle_main.cpp host/trimmer.cpp host/io.cpp host/trimmer.h host/io.h include/sickle_b200.h $(LIB)
+	@mkdir -p bin
+	g++ -O2 -std=c++17 -Wall -Iinclude host/sickle_main.cpp host/trimmer.cpp host/io.cpp -o $@ \
 	    -Lsickle_b200 -lsickle_b200 -lz -lpthread -Wl,-rpath,'$$ORIGIN/../sickle_b200'
 
 oracle:

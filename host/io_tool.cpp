@@ -1,0 +1,32 @@
+// io_tool.cpp -- copies a file through the CLI's I/O stages (ByteSource -> ByteSink), for the CPU
+// tests of host/io.{h,cpp}:   io_tool <src> <dst> <read_chunk_bytes> <gzip_output 0|1>
+// Prints "bgzf=<0|1> gzip=<0|1> bytes=<n>" on success; exit 1 on any read/write error.
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+#include "io.h"
+
+int main(int argc, char **argv) {
+    if (argc != 5) { fprintf(stderr, "usage: io_tool <src> <dst> <chunk> <gzip 0|1>\n"); return 2; }
+    const unsigned long long chunk = strtoull(argv[3], nullptr, 10);
+    host::ByteSource in;
+    if (!in.open(argv[1])) { fprintf(stderr, "cannot open %s\n", argv[1]); return 1; }
+    host::ByteSink out;
+    if (!out.open(argv[2], atoi(argv[4]) != 0)) { fprintf(stderr, "cannot open %s\n", argv[2]); return 1; }
+    // two buffers in flight, like the slots of the trimmer
+    std::vector<char> buf[2] = {std::vector<char>(chunk), std::vector<char>(chunk)};
+    unsigned long long ticket[2] = {0, 0}, total = 0;
+    for (int k = 0;; k ^= 1) {
+        if (ticket[k] && !out.wait(ticket[k])) { fprintf(stderr, "write failed\n"); return 1; }
+        const long long r = in.read(buf[k].data(), chunk);
+        if (r < 0) { fprintf(stderr, "read failed\n"); return 1; }
+        if (r == 0) break;
+        ticket[k] = out.write_async(buf[k].data(), (unsigned long long)r);
+        total += (unsigned long long)r;
+        if ((unsigned long long)r < chunk) break;
+    }
+    if (!out.close()) { fprintf(stderr, "write failed\n"); return 1; }
+    printf("bgzf=%d gzip=%d bytes=%llu\n", in.bgzf() ? 1 : 0, in.gzip() ? 1 : 0, total);
+    return 0;
+}

@@ -18,96 +18,6 @@
 
 namespace host {
 
-static double now_s() {
-    return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
-}
-
-// ---------------------------------------------------------------------------------------------
-ByteSource::~ByteSource() {
-    if (gz_) gzclose((gzFile)gz_);
-    if (fd_ >= 0) ::close(fd_);
-}
-
-bool ByteSource::open(const char *path) {
-    int fd = ::open(path, O_RDONLY);
-    if (fd < 0) return false;
-    struct stat st;
-    if (fstat(fd, &st) == 0) size_ = (unsigned long long)st.st_size;
-    unsigned char magic[2] = {0, 0};
-    const ssize_t got = ::pread(fd, magic, 2, 0);
-    if (got == 2 && magic[0] == 0x1f && magic[1] == 0x8b) {
-        gzFile g = gzdopen(fd, "rb");
-        if (!g) { ::close(fd); return false; }
-        gzbuffer(g, 1u << 20);
-        gz_ = g;
-    } else {
-        fd_ = fd;
-#ifdef POSIX_FADV_SEQUENTIAL
-        posix_fadvise(fd, 0, 0, POSIX_FADV_SEQUENTIAL);
-#endif
-    }
-    return true;
-}
-
-long long ByteSource::read(char *dst, unsigned long long n) {
-    unsigned long long done = 0;
-    if (gz_) {
-        const double t0 = now_s();
-        while (done < n) {
-            const unsigned want = (unsigned)std::min<unsigned long long>(n - done, 1u << 30);
-            const int r = gzread((gzFile)gz_, dst + done, want);
-            if (r < 0) return -1;
-            if (r == 0) break;
-            done += (unsigned long long)r;
-        }
-        inflate_s_ += now_s() - t0;
-        return (long long)done;
-    }
-    while (done < n) {
-        const ssize_t r = ::read(fd_, dst + done, (size_t)std::min<unsigned long long>(n - done, 1ull << 30));
-        if (r < 0) return -1;
-        if (r == 0) break;
-        done += (unsigned long long)r;
-    }
-    return (long long)done;
-}
-
-ByteSink::~ByteSink() { close(); }
-
-bool ByteSink::open(const char *path, bool gzip) {
-    if (gzip) {
-        gzFile g = gzopen(path, "wb");
-        if (!g) return false;
-        gzbuffer(g, 1u << 20);
-        gz_ = g;
-        return true;
-    }
-    fd_ = ::open(path, O_WRONLY | O_CREAT | O_TRUNC, 0644);
-    return fd_ >= 0;
-}
-
-bool ByteSink::write(const char *src, unsigned long long n) {
-    unsigned long long done = 0;
-    while (done < n) {
-        if (gz_) {
-            const unsigned want = (unsigned)std::min<unsigned long long>(n - done, 1u << 30);
-            const int r = gzwrite((gzFile)gz_, src + done, want);
-            if (r <= 0) return false;
-            done += (unsigned long long)r;
-        } else {
-            const ssize_t r = ::write(fd_, src + done, (size_t)std::min<unsigned long long>(n - done, 1ull << 30));
-            if (r < 0) return false;
-            done += (unsigned long long)r;
-        }
-    }
-    return true;
-}
-
-void ByteSink::close() {
-    if (gz_) { gzclose((gzFile)gz_); gz_ = nullptr; }
-    if (fd_ >= 0) { ::close(fd_); fd_ = -1; }
-}
-
 // Trim_Single::recommended_batch_len / Trim_Paired::recommended_batch_len
 // (reference src/trim_single.cpp:194-211, src/trim_paired.cpp:246-263)
 static long long recommended_batch_len(unsigned long long file_size, long long b_mib, bool paired) {
@@ -247,14 +157,38 @@ namespace {
 
 struct Ctx {
     sk_ctx *c = nullptr;
-    ~Ctx() { if (c) sk_destroy(c); }
+    Totals *tot = nullptr;
+    ~Ctx() {
+        // SICKLE_B200_KEEP_CONTEXT=1: leave buffers and context to process exit (the CLI exits right after)
+        static const bool keep = getenv("SICKLE_B200_KEEP_CONTEXT") && atoi(getenv("SICKLE_B200_KEEP_CONTEXT")) != 0;
+        const double t0 = host::now_s();
+        if (c && !keep) sk_destroy(c);
+        if (tot) tot->t_teardown += host::now_s() - t0;
+    }
 };
 
-bool write_outputs(const sk_result &r, ByteSink *outs[3]) {
-    for (int k = 0; k < 3; ++k)
-        if (r.out_bytes[k] && outs[k] && outs[k]->is_open())
-            if (!outs[k]->write(r.out[k], r.out_bytes[k])) return false;
-    return true;
+// Output of one batch: queued on the (asynchronous, ordered) sinks straight out of the slot's pinned
+// result buffers.  The tickets are waited for before that slot is submitted again.
+struct Tickets {
+    unsigned long long t[3] = {0, 0, 0};
+};
+Tickets queue_outputs(const sk_result &r, ByteSink *outs[3]) {
+    Tickets k;
+    for (int i = 0; i < 3; ++i)
+        if (r.out_bytes[i] && outs[i] && outs[i]->is_open()) k.t[i] = outs[i]->write_async(r.out[i], r.out_bytes[i]);
+    return k;
+}
+bool wait_outputs(Tickets &k, ByteSink *outs[3], Totals &tot) {
+    const double t0 = host::now_s();
+    bool ok = true;
+    for (int i = 0; i < 3; ++i)
+        if (k.t[i]) { ok = outs[i]->wait(k.t[i]) && ok; k.t[i] = 0; }
+    tot.t_write_wait += host::now_s() - t0;
+    return ok;
+}
+bool write_outputs(const sk_result &r, ByteSink *outs[3], Totals &tot) {
+    Tickets k = queue_outputs(r, outs);
+    return wait_outputs(k, outs, tot);
 }
 
 void add_totals(Totals &t, const sk_result &r) {
@@ -297,6 +231,7 @@ int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, Byt
     const int device = (int)env_u64("SICKLE_B200_DEVICE", 0);
     const bool two = mode == SK_MODE_PE_2FILE;
     const bool paired = mode != SK_MODE_SE;
+    const double t_begin = host::now_s();
 
     if (sk_device_count() <= 0) {
         fprintf(stderr, "****Error: no usable CUDA device (%s). This build has no CPU path.\n\n", sk_last_error());
@@ -331,18 +266,35 @@ int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, Byt
             sk_result r;
             if (sk_wait(ctx.c, 0, &r) != SK_OK) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
             if (r.error.kind) { r.error.record += base[r.error.file]; return report_data_error(r, h0, h1); }
-            if (!write_outputs(r, outs)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
+            if (!write_outputs(r, outs, tot)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
             add_totals(tot, r);
             base[0] += (long long)r.records[0]; base[1] += (long long)r.records[1];
         }
         return EXIT_SUCCESS;
     }
 
-    const unsigned long long slot = env_u64("SICKLE_B200_SLOT_MB", 256) << 20;
+    // Slot size: 64 MiB keeps PCIe and the kernels efficient (a batch is ~1 ms of either) while the
+    // pinned buffers stay cheap to allocate (~0.4 s per GiB); small plain files get one small slot's worth.
+    unsigned long long slot = env_u64("SICKLE_B200_SLOT_MB", 0) << 20;
+    if (!slot) {
+        slot = 64ull << 20;
+        unsigned long long sz = in0->gzip() ? ~0ull : in0->file_size();
+        if (in1) sz = in1->gzip() ? ~0ull : std::max(sz, in1->file_size());
+        if (sz < (40ull << 20)) slot = ((sz + sz / 2) | 0xfffffull) + 1;   // >= 4/3 of the file, whole MiB
+    }
     const int nslots = two ? 2 : 3;
     Ctx ctx;
+    ctx.tot = &tot;
     ctx.c = sk_create(device, slot, nslots, &p);
     if (!ctx.c) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
+    tot.t_init = host::now_s() - t_begin;
+    std::vector<Tickets> tickets((size_t)nslots);
+    auto timed_wait = [&](int s_, sk_result *r_) {
+        const double t0 = host::now_s();
+        const int rc_ = sk_wait(ctx.c, s_, r_);
+        tot.t_wait += host::now_s() - t0;
+        return rc_;
+    };
 
     // ---------------------------------------------------------------------------------------
     // (B) two input files: pairs are matched by record number.  Each batch is the carried tail of
@@ -376,14 +328,16 @@ int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, Byt
             }
             (void)grew;
             const bool more = n[0] && n[1];   // no pair can be formed once either file is exhausted
+            // this slot's previous outputs must have left its pinned result buffers
+            if (more && !wait_outputs(tickets[(size_t)slot_i], outs, tot)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
             if (more && sk_submit(ctx.c, slot_i, 0, n[0], 0, n[1]) != SK_OK) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
             if (have_prev) {   // previous batch's streams are still in the other slot's pinned buffers
-                if (!write_outputs(prev, outs)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
+                tickets[(size_t)(slot_i ^ 1)] = queue_outputs(prev, outs);
                 have_prev = false;
             }
             if (!more) break;
             sk_result r;
-            if (sk_wait(ctx.c, slot_i, &r) != SK_OK) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
+            if (timed_wait(slot_i, &r) != SK_OK) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
             if (r.error.kind) { r.error.record += base[r.error.file]; return report_data_error(r, h[0], h[1]); }
             add_totals(tot, r);
             base[0] += (long long)r.records[0]; base[1] += (long long)r.records[1];
@@ -396,7 +350,9 @@ int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, Byt
             for (int i = 0; i < 2; ++i) { carry_ptr[i] = h[i] + r.consumed[i]; carry_len[i] = n[i] - r.consumed[i]; }
             slot_i ^= 1;
         }
-        if (have_prev && !write_outputs(prev, outs)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
+        if (have_prev) tickets[(size_t)slot_i] = queue_outputs(prev, outs);   // (slot_i is the slot `prev` ran in)
+        for (auto &k : tickets)
+            if (!wait_outputs(k, outs, tot)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
         return EXIT_SUCCESS;
     }
 
@@ -425,8 +381,9 @@ int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, Byt
         unsigned long long tail = 0;
         sk_result prev;
         bool have_prev = false;
+        int prev_slot = -1;
         if (pend.slot >= 0) {
-            if (sk_wait(ctx.c, pend.slot, &prev) != SK_OK) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
+            if (timed_wait(pend.slot, &prev) != SK_OK) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
             char *ph = sk_in_buffer(ctx.c, pend.slot, 0);
             if (prev.error.kind) { prev.error.record += base; return report_data_error(prev, ph, nullptr); }
             add_totals(tot, prev);
@@ -439,22 +396,28 @@ int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, Byt
             }
             if (tail) memcpy(h + H - tail, ph + pend.start + prev.consumed[0], tail);
             const bool stuck = prev.consumed[0] == 0 && bulk == 0;
+            prev_slot = pend.slot;
             pend.slot = -1;
             if (stuck) {   // nothing new and nothing consumed: an incomplete record (pair) at end of file
-                if (!write_outputs(prev, outs)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
+                tickets[(size_t)prev_slot] = queue_outputs(prev, outs);
                 break;
             }
         }
         if (bulk + tail > 0) {
             const unsigned long long start = H - tail, end = H + bulk;
             if (eof) patch_eof(h, end);
+            // the outputs this slot produced nslots batches ago must have left its pinned result buffers
+            if (!wait_outputs(tickets[(size_t)cur], outs, tot)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
             if (sk_submit(ctx.c, cur, start, end, 0, 0) != SK_OK) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
             pend = {cur, start, end};
             cur = (cur + 1) % nslots;
         }
-        if (have_prev && !write_outputs(prev, outs)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
+        // batch k's output is handed to the writer threads only after batch k+1 is on the device
+        if (have_prev) tickets[(size_t)prev_slot] = queue_outputs(prev, outs);
         if (pend.slot < 0) break;
     }
+    for (auto &k : tickets)
+        if (!wait_outputs(k, outs, tot)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
     return EXIT_SUCCESS;
 }
 
@@ -547,6 +510,7 @@ int Trim_Single::parse_args(int argc, char *argv[]) {
 }
 
 int Trim_Single::trim_main() {
+    const double t_start = host::now_s();
     ByteSource in;
     if (!in.open(infn)) { fprintf(stderr, "****Error: Could not open input file '%s'.\n\n", infn); return EXIT_FAILURE; }
     ByteSink out;
@@ -554,13 +518,17 @@ int Trim_Single::trim_main() {
     ByteSink *outs[3] = {&out, nullptr, nullptr};
     Totals t;
     const int rc = run_device(SK_MODE_SE, &in, nullptr, outs, false, t);
-    out.close();
+    const bool closed = out.close();
     if (rc != EXIT_SUCCESS) return rc;
+    if (!closed) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
     if (!quiet)
         fprintf(stdout, "\nSE input file: %s\n\nTotal FastQ records: %lld\nFastQ records kept: %lld\nFastQ records discarded: %lld\n\n",
                 infn, t.kept + t.discard, t.kept, t.discard);
-    if (debug) fprintf(stderr, "[sickle_b200] batches %lld (fused %lld), kernel time %.3f ms, gzip inflate %.3f s\n", t.batches,
-                       t.fused_batches, t.kernel_ms, in.inflate_seconds());
+    if (debug)
+        fprintf(stderr, "[sickle_b200] batches %lld (fused %lld), kernel %.3f ms | host: init %.3f s, read %.3f s%s, device wait %.3f s, "
+                        "write wait %.3f s (writer busy %.3f s), teardown %.3f s, total %.3f s\n",
+                t.batches, t.fused_batches, t.kernel_ms, t.t_init, in.read_seconds(), in.gzip() ? " (gzip)" : "", t.t_wait,
+                t.t_write_wait, out.busy_seconds(), t.t_teardown, host::now_s() - t_start);
     return EXIT_SUCCESS;
 }
 
@@ -692,8 +660,9 @@ int Trim_Paired::trim_main() {
     }
     Totals t;
     const int rc = run_device(mode, &in0, mode == SK_MODE_PE_2FILE ? &in1 : nullptr, outs, sfn != nullptr, t);
-    o_main.close(); o_mate2.close(); o_single.close();
+    const bool c0 = o_main.close(), c1 = o_mate2.close(), c2 = o_single.close();
     if (rc != EXIT_SUCCESS) return rc;
+    if (!(c0 && c1 && c2)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
     if (!quiet) {   // reference src/trim_paired.cpp:464-476, with the true record total
         const long long total = t.kept_p + t.kept_s1 + t.kept_s2 + t.discard_p + t.discard_s1 + t.discard_s2;
         if (infn && infn2) fprintf(stdout, "\nPE forward file: %s\nPE reverse file: %s\n", infn, infn2);
@@ -706,6 +675,10 @@ int Trim_Paired::trim_main() {
         if (infnc) fprintf(stdout, "FastQ single records discarded: %lld\n\n", t.discard_s1 + t.discard_s2);
         else fprintf(stdout, "FastQ single records discarded: %lld (from PE1: %lld, from PE2: %lld)\n\n", t.discard_s1 + t.discard_s2, t.discard_s1, t.discard_s2);
     }
-    if (debug) fprintf(stderr, "[sickle_b200] batches %lld (fused %lld), kernel time %.3f ms\n", t.batches, t.fused_batches, t.kernel_ms);
+    if (debug)
+        fprintf(stderr, "[sickle_b200] batches %lld (fused %lld), kernel %.3f ms | host: init %.3f s, read %.3f s, device wait %.3f s, "
+                        "write wait %.3f s (writers busy %.3f s)\n",
+                t.batches, t.fused_batches, t.kernel_ms, t.t_init, in0.read_seconds() + in1.read_seconds(), t.t_wait, t.t_write_wait,
+                o_main.busy_seconds() + o_mate2.busy_seconds() + o_single.busy_seconds());
     return EXIT_SUCCESS;
 }

@@ -13,6 +13,7 @@
 #include <string>
 #include <vector>
 
+#include "io.h"
 #include "sickle_b200.h"
 
 #ifndef PROGRAM_NAME
@@ -24,45 +25,12 @@
 
 namespace host {
 
-// Sequential byte reader over a plain or gzip file (the reference reads everything through zlib's
-// gzopen/gzgets, src/GZReader.cpp:13,77; plain files are read with read(2) here).
-class ByteSource {
-public:
-    ~ByteSource();
-    bool open(const char *path);
-    // Read up to n bytes; returns the count (0 at end of file), -1 on error.
-    long long read(char *dst, unsigned long long n);
-    bool gzip() const { return gz_ != nullptr; }
-    unsigned long long file_size() const { return size_; }
-    double inflate_seconds() const { return inflate_s_; }
-
-private:
-    int fd_ = -1;
-    void *gz_ = nullptr;
-    unsigned long long size_ = 0;
-    double inflate_s_ = 0;
-};
-
-// Append-only writer: plain file or gzip (-g).  The reference's -g path is broken (gzprintf with the
-// payload as format string, src/trim_single.cpp:418); this one writes a valid gzip of the same bytes.
-class ByteSink {
-public:
-    ~ByteSink();
-    bool open(const char *path, bool gzip);
-    bool write(const char *src, unsigned long long n);
-    void close();
-    bool is_open() const { return fd_ >= 0 || gz_ != nullptr; }
-
-private:
-    int fd_ = -1;
-    void *gz_ = nullptr;
-};
-
 struct Totals {
     long long kept = 0, discard = 0;
     long long kept_p = 0, discard_p = 0, kept_s1 = 0, kept_s2 = 0, discard_s1 = 0, discard_s2 = 0;
     long long records[2] = {0, 0};
     double kernel_ms = 0;
+    double t_init = 0, t_wait = 0, t_write_wait = 0, t_teardown = 0;   // host stage times (-d)
     long long batches = 0, fused_batches = 0;
 };
 

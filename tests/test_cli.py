@@ -98,6 +98,19 @@ def test_gzip_input_and_output(sickle, golden, tmp_path):
     assert hashlib.md5(want).hexdigest() == case["outputs"]["-o"]["md5"]
     assert gzip.open(gz_out, "rb").read() == want
     assert gzip.open(gz_out2, "rb").read() == want
+    # blocked gzip (BGZF, what -g writes and what bgzip / Illumina's converters produce) as input:
+    # blocks are inflated in parallel; the records come out the same
+    from sickle_b200 import synth
+
+    big = synth.fixed_length_records(60000, 150, "sanger", seed=21).tobytes()
+    big_plain, big_gz, o1, o2 = (str(tmp_path / n) for n in ("big.fq", "big.fq.gz", "big1.fq", "big2.fq"))
+    open(big_plain, "wb").write(big)
+    subprocess.run([os.path.join(os.path.dirname(sickle), "io_tool"), big_plain, big_gz, str(1 << 22), "1"], check=True,
+                   capture_output=True)
+    subprocess.run([sickle, "se", "-f", big_plain, "-t", "sanger", "-o", o1], check=True, capture_output=True)
+    p = subprocess.run([sickle, "se", "-f", big_gz, "-t", "sanger", "-o", o2, "-d"], check=True, capture_output=True)
+    assert open(o1, "rb").read() == open(o2, "rb").read()
+    assert b"(gzip)" in p.stderr
 
 
 def test_M_mode_matches_oracle(sickle, golden, tmp_path):

@@ -216,6 +216,41 @@ def test_batch_size_invariance_and_pipelined_upload(capi):
     assert ref["records"][0] == 20000
 
 
+def test_lines_that_look_like_other_lines(capi):
+    """Record boundaries come from counting newlines, never from what a line starts with ('@' and '+'
+    are valid quality characters, line 3 is not checked for '+').  Inputs whose
+    sequence / quality lines look like headers must come out right, on the single-pass kernel."""
+    rng = np.random.default_rng(77)
+    flags = dict(qualtype="sanger", q=20, l=20, x=False, n=False)
+
+    def recs(n, seq0, line3, qual0, tag):
+        out = []
+        for i in range(n):
+            L = int(rng.integers(100, 250))   # < 128 records per 25 KB tile, the single-pass kernel's limit
+            seq = seq0 + bytes(rng.choice(list(b"ACGT"), L - 1).astype(np.uint8))
+            q = qual0 + bytes((rng.integers(2, 41, L - 1) + 33).astype(np.uint8))
+            out.append(b"@%s%d\n" % (tag, i) + seq + b"\n" + line3 + b"\n" + q + b"\n")
+        return b"".join(out)
+
+    normal = recs(4000, b"A", b"+", b"I", b"n")
+    ambiguous = recs(4000, b"+", b"+", b"@", b"a")       # two classes look like record starts
+    no_plus = recs(4000, b"A", b"-", b"I", b"m")         # line 3 without '+': no class qualifies
+    fooling = recs(4000, b"+", b"x", b"@", b"f")         # only the quality-line class qualifies: wrong
+    for name, data, all_fused in (("normal", normal, True), ("ambiguous", ambiguous, True), ("no_plus", no_plus, True),
+                                  ("fooling", fooling, True), ("normal+fooling", normal + fooling, True),
+                                  ("fooling+normal+ambiguous", fooling + normal + ambiguous, True)):
+        want = orc.run(orc.MODE_SE, orc.make_params("sanger"), data, batch_len=1 << 40)
+        assert want["rc"] == 0
+        got = _run_cuda(capi, capi.MODE_SE, flags, data, slot_bytes=1 << 18)
+        assert got["out"][0] == want["out"][0], name
+        assert got["counters"]["kept"] == want["counters"]["kept"], name
+        assert got["batches"] > 1
+        if all_fused:
+            assert got["fused_batches"] == got["batches"], name
+        else:
+            assert got["fused_batches"] < got["batches"], name
+
+
 def test_edge_inputs(capi):
     flags = dict(qualtype="sanger", q=20, l=20, x=False, n=False)
     # empty input, a single record, a record without final newline, trailing partial record, lone newlines

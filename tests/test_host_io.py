@@ -1,0 +1,144 @@
+"""Host I/O stages of the CLI (host/io.{h,cpp}) -- CPU only, no CUDA.
+
+bin/io_tool copies a file through ByteSource -> ByteSink exactly as the trimmer's batch loop does
+(bounded reads, two buffers in flight, ordered asynchronous writes).  Python's gzip module is the
+independent check of the `-g` output (BGZF = ordinary multi-member gzip) and the producer of plain
+single-member .gz inputs.
+"""
+import gzip
+import os
+import struct
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+TOOL = os.path.join(ROOT, "bin", "io_tool")
+
+
+@pytest.fixture(scope="module")
+def tool():
+    subprocess.run(["make", "-s", "bin/io_tool"], cwd=ROOT, check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert os.path.exists(TOOL)
+    return TOOL
+
+
+def _fastq_like(nbytes, seed=5):
+    rng = np.random.default_rng(seed)
+    rec = []
+    size = 0
+    i = 0
+    while size < nbytes:
+        L = int(rng.integers(30, 300))
+        r = b"@r%d\n" % i + bytes(rng.choice(list(b"ACGTN"), L).astype(np.uint8)) + b"\n+\n" + \
+            bytes((rng.integers(2, 41, L) + 33).astype(np.uint8)) + b"\n"
+        rec.append(r)
+        size += len(r)
+        i += 1
+    return b"".join(rec)[:nbytes]
+
+
+def _run(tool, src, dst, chunk, gz, env=None):
+    e = dict(os.environ)
+    e.update(env or {})
+    p = subprocess.run([tool, src, dst, str(chunk), "1" if gz else "0"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e)
+    return p.returncode, p.stdout.decode().strip(), p.stderr.decode()
+
+
+@pytest.mark.parametrize("chunk", [1 << 22, 999_983, 4096])
+@pytest.mark.parametrize("threads", ["1", "8"])
+def test_plain_copy_is_identical(tool, tmp_path, chunk, threads):
+    data = _fastq_like(9_000_001)
+    src, dst = tmp_path / "a.fastq", tmp_path / "b.fastq"
+    src.write_bytes(data)
+    rc, out, err = _run(tool, str(src), str(dst), chunk, False, {"SICKLE_B200_IO_THREADS": threads})
+    assert rc == 0, err
+    assert out == "bgzf=0 gzip=0 bytes=%d" % len(data)
+    assert dst.read_bytes() == data
+
+
+def test_mapped_output_is_identical(tool, tmp_path):
+    """SICKLE_B200_MMAP_OUT=1: large writes go through ftruncate + shared mapping + parallel memcpy,
+    small ones through pwrite at the same running offset."""
+    data = _fastq_like(30_000_007, seed=9)
+    src, dst = tmp_path / "a.fastq", tmp_path / "b.fastq"
+    src.write_bytes(data)
+    for chunk in (12_000_001, 9_000_000, 100_000):   # mapped + pwrite tail, unaligned offsets, pwrite only
+        rc, out, err = _run(tool, str(src), str(dst), chunk, False, {"SICKLE_B200_MMAP_OUT": "1"})
+        assert rc == 0, err
+        assert dst.read_bytes() == data, chunk
+
+
+def _bgzf_blocks(raw):
+    """Walk BGZF blocks; returns [(compressed_size, uncompressed_size)]."""
+    out, o = [], 0
+    while o < len(raw):
+        assert raw[o:o + 4] == b"\x1f\x8b\x08\x04", o
+        xlen = struct.unpack_from("<H", raw, o + 10)[0]
+        extra = raw[o + 12:o + 12 + xlen]
+        assert extra[:4] == b"BC\x02\x00"
+        bsize = struct.unpack_from("<H", extra, 4)[0] + 1
+        out.append((bsize, struct.unpack_from("<I", raw, o + bsize - 4)[0]))
+        o += bsize
+    assert o == len(raw)
+    return out
+
+
+@pytest.mark.parametrize("threads", ["1", "8"])
+def test_gzip_output_is_valid_bgzf_and_reads_back_in_parallel(tool, tmp_path, threads):
+    data = _fastq_like(21_000_003, seed=6)
+    src, gzf, back = tmp_path / "a.fastq", tmp_path / "a.fastq.gz", tmp_path / "back.fastq"
+    src.write_bytes(data)
+    env = {"SICKLE_B200_IO_THREADS": threads}
+    rc, out, err = _run(tool, str(src), str(gzf), 5_000_000, True, env)
+    assert rc == 0, err
+    raw = gzf.read_bytes()
+    assert gzip.decompress(raw) == data                 # any gunzip reads it
+    blocks = _bgzf_blocks(raw)
+    assert blocks[-1] == (28, 0)                        # BGZF end-of-file marker
+    assert sum(u for _, u in blocks) == len(data) and max(u for _, u in blocks) <= 0xff00
+    assert len(raw) < 0.6 * len(data)
+    # ... and back through the parallel block reader, with read sizes that split blocks
+    for chunk in (1 << 22, 1_000_003, 1000):
+        rc, out, err = _run(tool, str(gzf), str(back), chunk, False, env)
+        assert rc == 0, err
+        assert out == "bgzf=1 gzip=1 bytes=%d" % len(data)
+        assert back.read_bytes() == data
+    # the same file through the generic single-stream zlib reader
+    rc, out, err = _run(tool, str(gzf), str(back), 1 << 20, False, dict(env, SICKLE_B200_NO_BGZF="1"))
+    assert rc == 0 and out == "bgzf=0 gzip=1 bytes=%d" % len(data) and back.read_bytes() == data
+
+
+def test_plain_gzip_and_concatenated_members(tool, tmp_path):
+    data = _fastq_like(3_000_000, seed=7)
+    gzf, back = tmp_path / "p.gz", tmp_path / "p.fastq"
+    gzf.write_bytes(gzip.compress(data[:1_000_000]) + gzip.compress(data[1_000_000:]))   # cat a.gz b.gz
+    rc, out, err = _run(tool, str(gzf), str(back), 700_001, False)
+    assert rc == 0, err
+    assert out == "bgzf=0 gzip=1 bytes=%d" % len(data)
+    assert back.read_bytes() == data
+
+
+def test_empty_and_damaged_inputs(tool, tmp_path):
+    empty, gzf, back = tmp_path / "e.fastq", tmp_path / "e.gz", tmp_path / "e.back"
+    empty.write_bytes(b"")
+    rc, out, err = _run(tool, str(empty), str(gzf), 4096, True)
+    assert rc == 0 and out.endswith("bytes=0")
+    assert gzip.decompress(gzf.read_bytes()) == b""
+    rc, out, err = _run(tool, str(gzf), str(back), 4096, False)
+    assert rc == 0 and out == "bgzf=1 gzip=1 bytes=0" and back.read_bytes() == b""
+    # a BGZF file cut in the middle of a block, and one with a flipped payload bit: read errors
+    data = _fastq_like(400_000, seed=8)
+    src, good = tmp_path / "d.fastq", tmp_path / "d.gz"
+    src.write_bytes(data)
+    assert _run(tool, str(src), str(good), 1 << 20, True)[0] == 0
+    raw = bytearray(good.read_bytes())
+    cut = tmp_path / "cut.gz"
+    cut.write_bytes(bytes(raw[:len(raw) // 2]))
+    assert _run(tool, str(cut), str(back), 1 << 20, False)[0] == 1
+    raw[len(raw) // 3] ^= 0x10
+    bad = tmp_path / "bad.gz"
+    bad.write_bytes(bytes(raw))
+    assert _run(tool, str(bad), str(back), 1 << 20, False)[0] == 1
+    assert _run(tool, str(tmp_path / "missing"), str(back), 4096, False)[0] == 1
