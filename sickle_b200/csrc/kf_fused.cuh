@@ -313,8 +313,8 @@ __device__ __forceinline__ void smem_copy(uint8_t *__restrict__ out, uint32_t ds
 // Q = word part of the shift (block-uniform, so the four variants never diverge).
 template <int Q>
 __device__ __forceinline__ void flush_full_chunks(uint4 *__restrict__ gal16, const uint4 *__restrict__ s16, uint32_t c_lo,
-                                                  uint32_t c_hi, uint32_t sh, int tid) {
-    for (uint32_t c = c_lo + tid; c < c_hi; c += kFThreads) {
+                                                  uint32_t c_hi, uint32_t sh, int tid, int nthreads) {
+    for (uint32_t c = c_lo + tid; c < c_hi; c += nthreads) {
         const uint4 A = s16[c - 1], B = s16[c];
         const uint32_t w0 = Q == 0 ? A.x : Q == 1 ? A.y : Q == 2 ? A.z : A.w;
         const uint32_t w1 = Q == 0 ? A.y : Q == 1 ? A.z : Q == 2 ? A.w : B.x;
@@ -331,7 +331,7 @@ __device__ __forceinline__ void flush_full_chunks(uint4 *__restrict__ gal16, con
 }
 
 __device__ __noinline__ void flush_realigned(uint8_t *__restrict__ gdst, const uint8_t *__restrict__ s_out,
-                                                uint32_t sb, uint32_t tot, int tid) {
+                                                uint32_t sb, uint32_t tot, int tid, int nthreads) {
     if (tot == 0) return;
     const uint32_t ph = (uint32_t)(reinterpret_cast<uintptr_t>(gdst) & 15u);
     uint8_t *gal = gdst - ph;                                  // 16-byte aligned
@@ -340,15 +340,15 @@ __device__ __noinline__ void flush_realigned(uint8_t *__restrict__ gdst, const u
     const uint32_t c_hi = end >> 4;                            // one past the last full chunk
     const uint4 *__restrict__ s16 = reinterpret_cast<const uint4 *>(s_out + sb);
     if (ph == 0) {
-        for (uint32_t c = tid; c < c_hi; c += kFThreads) __stcs(reinterpret_cast<uint4 *>(gal) + c, s16[c]);
+        for (uint32_t c = tid; c < c_hi; c += nthreads) __stcs(reinterpret_cast<uint4 *>(gal) + c, s16[c]);
     } else {
         const uint32_t r = 16u - ph;                           // byte offset inside the older chunk
         const uint32_t sh = (r & 3u) * 8u;
         switch (r >> 2) {
-            case 0: flush_full_chunks<0>(reinterpret_cast<uint4 *>(gal), s16, c_lo, c_hi, sh, tid); break;
-            case 1: flush_full_chunks<1>(reinterpret_cast<uint4 *>(gal), s16, c_lo, c_hi, sh, tid); break;
-            case 2: flush_full_chunks<2>(reinterpret_cast<uint4 *>(gal), s16, c_lo, c_hi, sh, tid); break;
-            default: flush_full_chunks<3>(reinterpret_cast<uint4 *>(gal), s16, c_lo, c_hi, sh, tid); break;
+            case 0: flush_full_chunks<0>(reinterpret_cast<uint4 *>(gal), s16, c_lo, c_hi, sh, tid, nthreads); break;
+            case 1: flush_full_chunks<1>(reinterpret_cast<uint4 *>(gal), s16, c_lo, c_hi, sh, tid, nthreads); break;
+            case 2: flush_full_chunks<2>(reinterpret_cast<uint4 *>(gal), s16, c_lo, c_hi, sh, tid, nthreads); break;
+            default: flush_full_chunks<3>(reinterpret_cast<uint4 *>(gal), s16, c_lo, c_hi, sh, tid, nthreads); break;
         }
     }
     // ragged head (bytes [ph, 16) of chunk 0) and tail (bytes of the last, partial chunk): one byte per thread
@@ -360,6 +360,27 @@ __device__ __noinline__ void flush_realigned(uint8_t *__restrict__ gdst, const u
         const uint32_t b = 16u * c_hi + (uint32_t)(tid - 32);
         if (b < end && (c_hi > 0 || ph == 0)) gal[b] = s_out[sb + b - ph];
     }
+}
+
+// The deferred half of a tile (S7b + S8b), run by the "flush group" -- warps 4..7, which never own a
+// record -- while warps 0..3 validate and trim the next tile: look-back #2 over the output sizes,
+// then the staged bytes go out.  gtid = thread index inside the group (0..127), named barrier 1.
+constexpr int kFlushWarps = 4, kFlushThreads = kFlushWarps * 32, kFlushBarrier = 1;
+__device__ __forceinline__ void flush_previous_tile(unsigned long long *const st_out[2], uint32_t p_tile, uint32_t p_tot0,
+                                                    uint32_t p_tot1, int nstreams, uint32_t epoch, int gtid,
+                                                    unsigned long long (*s_lb)[2], Control *__restrict__ ctl,
+                                                    const OutPtrs &outs, const uint8_t *__restrict__ s_out, uint32_t num_tiles) {
+    const unsigned long long agg[2] = {p_tot0, p_tot1};
+    unsigned long long ex[2];
+    block_walk(st_out, p_tile, agg, nstreams, epoch, gtid, s_lb, ex, kFlushWarps, kFlushBarrier);
+    if (gtid == 0 && p_tile == num_tiles - 1) { ctl->out_bytes[0] = ex[0] + agg[0]; ctl->out_bytes[2] = ex[1] + agg[1]; }
+    const bool cap_ok = ex[0] + p_tot0 <= outs.cap[0] && (p_tot1 == 0 || (outs.p[2] && ex[1] + p_tot1 <= outs.cap[2]));
+    if (!cap_ok) {
+        if (gtid == 0) ctl->index_overflow = 2u;
+        return;
+    }
+    flush_realigned(outs.p[0] + ex[0], s_out, 0u, p_tot0, gtid, kFlushThreads);
+    if (p_tot1) flush_realigned(outs.p[2] + ex[1], s_out, (p_tot0 + 15u) & ~15u, p_tot1, gtid, kFlushThreads);
 }
 
 // Software-pipelined over tiles: the output of tile t is staged in shared memory right after it is
@@ -474,27 +495,13 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             }
         }
 
-        // ---- deferred S7b/S8b of the previous tile: output offsets, then the flush.  s_desc (which
-        // aliases s_nl) was consumed by the previous tile's S8a, s_out is only read here.
         SK_TICK(2);   // (+ newline-count publish)
-        if (have_prev) {
-            const unsigned long long agg[2] = {p_tot0, p_tot1};
-            unsigned long long ex[2];
-            // (prefetching the status words earlier was measured: no gain, and the extra live registers spill)
-            block_walk(st_out, p_tile, agg, nstreams, epoch, tid, s_lb, ex);
-            if (tid == 0 && p_tile == num_tiles - 1) { ctl->out_bytes[0] = ex[0] + agg[0]; ctl->out_bytes[2] = ex[1] + agg[1]; }
-            SK_TICK(5);   // look-back #2 of the previous tile
-            const bool cap_ok = ex[0] + p_tot0 <= outs.cap[0] && (p_tot1 == 0 || (outs.p[2] && ex[1] + p_tot1 <= outs.cap[2]));
-            if (!cap_ok) {
-                if (tid == 0) ctl->index_overflow = 2u;
-            } else {
-                flush_realigned(outs.p[0] + ex[0], s_out, 0u, p_tot0, tid);
-                if (p_tot1) flush_realigned(outs.p[2] + ex[1], s_out, (p_tot0 + 15u) & ~15u, p_tot1, tid);
-            }
-            have_prev = false;
-            SK_TICK(7);   // flush of the previous tile
+        if (done) {   // no tile left: only the last staged tile remains to be flushed
+            if (have_prev && wid >= kFThreads / 32 - kFlushWarps)
+                flush_previous_tile(st_out, p_tile, p_tot0, p_tot1, nstreams, epoch, tid - (kFThreads - kFlushThreads), s_lb, ctl,
+                                    outs, s_out, num_tiles);
+            break;
         }
-        if (done) break;
 
         if (!nl_overflow) {
             // a 32-byte word of a FASTQ file holds 0, 1 or (around the '+' line) 2 newlines: two
@@ -523,8 +530,19 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             block_walk(st_nl, tile, agg, 1, epoch, tid, s_lb, ex);
             G = (uint32_t)ex[0];
         }
-        __syncthreads();   // newline positions visible to every thread; previous flush finished reading s_out
+        __syncthreads();   // newline positions visible to every thread
         SK_TICK(3);   // S3 positions + S4 look-back #1
+
+        // ---- deferred S7b/S8b of the PREVIOUS tile, by the flush group, overlapped with S5-S7 of this
+        // tile on the record warps: output offsets (look-back #2), then the flush.  s_desc (which aliases
+        // s_nl) was consumed by the previous tile's S8a; s_out is only read here and is not written
+        // again before the barrier in front of this tile's S8a.  (A tile has at most 128 records, so
+        // warps 4..7 have nothing else to do until that barrier: measured, 22 % of all warp time was
+        // spent waiting there.)
+        if (have_prev && wid >= kFThreads / 32 - kFlushWarps)
+            flush_previous_tile(st_out, p_tile, p_tot0, p_tot1, nstreams, epoch, tid - (kFThreads - kFlushThreads), s_lb, ctl, outs,
+                                s_out, num_tiles);
+        have_prev = false;
 
         // ---- S5: units owned by this tile.  Newline j (j < c_t) is global newline G+j; the line
         // after it is line G+j+1; a unit starts at every line that is a multiple of lpu.  Tile 0

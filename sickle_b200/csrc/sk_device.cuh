@@ -170,27 +170,24 @@ __device__ __forceinline__ void block_publish(unsigned long long *const status[2
                   pack_status(tile == 0 ? kFlagInclusive : kFlagAggregate, epoch, aggregate[tid]));
 }
 
-// block_walk_prefetch issues this thread's status load of the FIRST window step and returns the raw
-// word; handing it to block_walk later (after unrelated work) hides the L2 round trip of the walk.
-__device__ __forceinline__ unsigned long long block_walk_prefetch(unsigned long long *const status[2], uint32_t tile,
-                                                                  int nstreams, int tid) {
-    const int wps = 8 / nstreams;
-    const int sid = (tid >> 5) / wps;
-    const int lt = tid - sid * wps * 32;
-    const int64_t my = (int64_t)tile - 1 - lt;
-    if (tile == 0 || my < 0) return 0ull;
-    return ld_status(&status[sid][(size_t)my * kWideStatusStride]);
+// Barrier over a subset of the CTA's warps (named barrier `id` > 0, `nthreads` a multiple of 32);
+// id 0 is __syncthreads().
+__device__ __forceinline__ void group_sync(int id, int nthreads) {
+    if (id == 0) __syncthreads();
+    else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// Called by a group of `gwarps` (8, 4 or 2; 2 * nstreams at least) whole warps, `gtid` = thread index
+// inside the group, `bar` = the group's barrier (0: the whole 256-thread CTA).
 __device__ __forceinline__ void block_walk(unsigned long long *const status[2], uint32_t tile,
                                            const unsigned long long aggregate[2], int nstreams, uint32_t epoch,
-                                           int tid, unsigned long long (*scratch)[2], unsigned long long excl[2],
-                                           bool have_prefetch = false, unsigned long long prefetched = 0ull) {
-    const int lane = tid & 31, wid = tid >> 5;
-    const int wps = 8 / nstreams;                 // warps per stream
+                                           int gtid, unsigned long long (*scratch)[2], unsigned long long excl[2],
+                                           int gwarps = 8, int bar = 0) {
+    const int lane = gtid & 31, wid = gtid >> 5;
+    const int wps = gwarps / nstreams;            // warps per stream
     const int sid = wid / wps;                    // the stream this warp works on
     const int width = wps * 32;
-    const int lt = tid - sid * width;             // distance slot inside the stream's window
+    const int lt = gtid - sid * width;            // distance slot inside the stream's window
     unsigned long long *const my_status = sid ? status[1] : status[0];
     uint32_t ex0 = 0, ex1 = 0;                    // values of one batch fit 32 bits (see pack_status)
     excl[0] = excl[1] = 0;
@@ -201,7 +198,7 @@ __device__ __forceinline__ void block_walk(unsigned long long *const status[2], 
     uint2 *const res = sc + 8;                               // combined (sum, done) per stream
 #ifdef SK_PHASE_TIMING
     bool spun = false;
-    if (tid == 0) atomicAdd(&g_walk_dbg[0], 1ull);
+    if (gtid == 0) atomicAdd(&g_walk_dbg[0], 1ull);
 #endif
     while (!(done0 && done1)) {
         // ---- every thread: one predecessor of its stream (or nothing if that stream is finished)
@@ -210,8 +207,7 @@ __device__ __forceinline__ void block_walk(unsigned long long *const status[2], 
         if (!(sid ? done1 : done0) && my >= 0) {
             unsigned long long w;
             while (true) {
-                if (have_prefetch) { w = prefetched; have_prefetch = false; }   // first step only
-                else w = ld_status(&my_status[(size_t)my * kWideStatusStride]);
+                w = ld_status(&my_status[(size_t)my * kWideStatusStride]);
                 flag = status_flag(w, epoch);
                 if (flag) break;
 #ifdef SK_PHASE_TIMING
@@ -222,41 +218,41 @@ __device__ __forceinline__ void block_walk(unsigned long long *const status[2], 
             }
             v = (uint32_t)w;
         }
-        have_prefetch = false;
 #ifdef SK_PHASE_TIMING
-        if (tid == 0) atomicAdd(&g_walk_dbg[1], 1ull);
+        if (gtid == 0) atomicAdd(&g_walk_dbg[1], 1ull);
 #endif
         const uint32_t incl = __ballot_sync(0xffffffffu, flag == 2);
         if (incl && lane > __ffs(incl) - 1) v = 0;            // nothing beyond the first inclusive prefix
         v = __reduce_add_sync(0xffffffffu, v);
         if (lane == 0) sc[wid] = make_uint2(v, incl ? 1u : 0u);
-        __syncthreads();
-        // ---- warp 0 combines the warps of each stream in distance order, up to the first one that
-        // met an inclusive prefix; everybody else only reads the two results after the barrier
+        group_sync(bar, gwarps * 32);
+        // ---- warp 0 of the group combines the warps of each stream in distance order, up to the first
+        // one that met an inclusive prefix; everybody else only reads the two results after the barrier
         if (wid == 0) {
-            const uint2 e = lane < 8 ? sc[lane] : make_uint2(0u, 0u);
+            const uint2 e = lane < gwarps ? sc[lane] : make_uint2(0u, 0u);
             const uint32_t has = __ballot_sync(0xffffffffu, e.y != 0);
-            const uint32_t m0 = (1u << wps) - 1u;                       // lanes of stream 0
-            const uint32_t h0 = has & m0, h1 = (has >> 4) & 0xfu;       // stream 1 only exists with wps == 4
+            const uint32_t m0 = (1u << wps) - 1u;                       // lanes of stream 0; stream 1 follows
+            const uint32_t h0 = has & m0, h1 = (has >> wps) & m0;
             const uint32_t take0 = h0 ? ((2u << (__ffs(h0) - 1)) - 1u) : m0;
-            const uint32_t take1 = h1 ? ((2u << (__ffs(h1) - 1)) - 1u) : 0xfu;
-            const uint32_t s0 = __reduce_add_sync(0xffffffffu, ((take0 >> lane) & 1u) && !done0 ? e.x : 0u);
-            const uint32_t s1 = __reduce_add_sync(0xffffffffu, (lane >= 4 && lane < 8 && ((take1 >> (lane - 4)) & 1u) && !done1) ? e.x : 0u);
+            const uint32_t take1 = h1 ? ((2u << (__ffs(h1) - 1)) - 1u) : m0;
+            const uint32_t s0 = __reduce_add_sync(0xffffffffu, (lane < wps && ((take0 >> lane) & 1u) && !done0) ? e.x : 0u);
+            const uint32_t s1 = __reduce_add_sync(0xffffffffu, (nstreams > 1 && lane >= wps && lane < 2 * wps &&
+                                                                ((take1 >> (lane - wps)) & 1u) && !done1) ? e.x : 0u);
             if (lane == 0) {
                 res[0] = make_uint2(s0, h0 ? 1u : 0u);
                 res[1] = make_uint2(s1, h1 ? 1u : 0u);
             }
         }
-        __syncthreads();
+        group_sync(bar, gwarps * 32);
         if (!done0) { const uint2 r0 = res[0]; ex0 += r0.x; done0 = r0.y != 0; }
         if (!done1) { const uint2 r1 = res[1]; ex1 += r1.x; done1 = r1.y != 0; }
         idx -= width;
     }
     excl[0] = ex0;
     excl[1] = ex1;
-    if (tid < nstreams)
-        st_status(&status[tid][(size_t)tile * kWideStatusStride],
-                  pack_status(kFlagInclusive, epoch, (tid ? ex1 : ex0) + aggregate[tid]));
+    if (gtid < nstreams)
+        st_status(&status[gtid][(size_t)tile * kWideStatusStride],
+                  pack_status(kFlagInclusive, epoch, (gtid ? ex1 : ex0) + aggregate[gtid]));
 }
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
