@@ -114,52 +114,70 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
     return d;
 }
 
-// Thread-per-read sliding window over shared memory.  Same decisions as warp_sliding_window.
-// Window i is "good" iff total(i) >= qthr*ws (trim.cpp:36,42,61).  Let i5 = first good window,
-// i3 = first bad window after it (or the first bad window at all with -x).  Quality bytes are range-
-// checked exactly where the reference's scalar loop touches them: the first window always, and the
-// byte entering window i+1 iff the loop gets past window i (i < i3 and i+1 < nwin).
-__device__ __forceinline__ TrimOut thread_sliding_window(const uint8_t *__restrict__ sm, uint32_t seq_off, uint32_t L,
-                                                         uint32_t qual_off, const DevParams &P, const RangeCheck &rc) {
+// Sliding window over shared memory by ONE or TWO lanes per read.  Same decisions as
+// warp_sliding_window.  Window i is "good" iff total(i) >= qthr*ws (trim.cpp:36,42,61).  Let i5 = first
+// good window, i3 = first bad window after it (or the first bad window at all with -x).  Quality bytes
+// are range-checked exactly where the reference's scalar loop touches them: the first window always,
+// and the byte entering window w+1 iff the loop gets past window w (w < i3 and w+1 < nwin).
+//
+// With nsub == 2 the windows are cut into two contiguous halves (whole 32-window steps); lane `sub`
+// scans its half without knowing what the other finds, and records what either outcome needs: its
+// first good window, its first bad window, its first bad window after its first good one, and the
+// first window whose entering byte is out of range.  The pair then exchanges these four numbers
+// (shuffles inside the pair only: both lanes of a read take the same branches up to there) and
+// both derive i5 / i3 / the error exactly as the sequential loop would have.  After that lane 0
+// looks for the 5' cut inside window i5 while lane 1 looks for the 3' cut inside window i3.
+struct HalfScan {
+    int g, b_any, b_after, o_first;
+};
+__device__ __forceinline__ TrimOut lane_sliding_window(const uint8_t *__restrict__ sm, uint32_t seq_off, uint32_t L,
+                                                       uint32_t qual_off, const DevParams &P, const RangeCheck &rc,
+                                                       uint32_t sub, uint32_t nsub, int lane) {
     TrimOut o;
     o.five = -1; o.three = -1; o.error = false;
-    if (L < (uint32_t)P.lthr) return o;                                  // trim.cpp:21-26
-    const uint8_t *__restrict__ q = sm + qual_off;
+    if (L < (uint32_t)P.lthr) return o;                                  // trim.cpp:21-26 (same for both lanes)
     uint32_t ws = L / 10u;                                               // trim.cpp:8
     if (ws == 0) ws = L;                                                 // trim.cpp:30
     const long long thr_ll = (long long)P.qthr * (long long)ws;
     // window totals of a record that fits a tile are < 2^23; clamp so that T - thr cannot overflow
     const int thr = thr_ll > 0x3fffffffLL ? 0x3fffffff : (int)thr_ll;
+    const uint32_t nwin = L - ws + 1u;                                   // trim.cpp:34
+    const uint32_t nseg = (nwin + 31u) >> 5;
+    const uint32_t half = nsub == 2u ? (nseg + 1u) >> 1 : nseg;
+    const uint32_t w_lo = sub ? half * 32u : 0u;                         // first window of this lane
+    const uint32_t w_hi = sub ? nwin : min(nwin, half * 32u);            // one past its last window
+    const bool x = P.no_fiveprime != 0;                                  // -x: as if the 5' end was already found
 
-    // ---- first window (trim.cpp:31-33): dp4a sums + SWAR range check, 4 bytes at a time
+    // ---- total of this lane's first window: dp4a sums, 4 bytes at a time.  Window 0 is also range
+    // checked here (trim.cpp:31-33); the bytes of lane 1's first window are entering bytes of lane 0's.
     int T = 0;
-    {
+    uint32_t bad = 0;
+    if (w_lo < w_hi) {
         Stream4 s;
-        s.init(sm, qual_off);
+        s.init(sm, qual_off + w_lo);
         uint32_t j = 0;
-        uint32_t bad = 0;
         for (; j + 4 <= ws; j += 4) {
-            const uint32_t x = s.next();
-            bad |= rc.bad4(x);
-            T = (int)__dp4a(x, 0x01010101u, (uint32_t)T);
+            const uint32_t v = s.next();
+            bad |= rc.bad4(v);
+            T = (int)__dp4a(v, 0x01010101u, (uint32_t)T);
         }
+        const uint8_t *__restrict__ q = sm + qual_off + w_lo;
         for (; j < ws; ++j) {
             const int b = q[j];
             bad |= (uint32_t)((b < P.qmin) | (b > P.qmax));
             T += b;
         }
-        if (bad) { o.error = true; return o; }
         T -= (int)ws * P.qoff;
     }
+    if (sub) bad = 0;
     int Tm = T - thr;                          // sign bit set <=> window is bad
-    const uint32_t nwin = L - ws + 1u;         // trim.cpp:34
-    bool found = P.no_fiveprime != 0;          // -x: behave as if the 5' end was already found
-    int i5 = -1, i3 = -1;
+    HalfScan me;
+    me.g = -1; me.b_any = -1; me.b_after = -1; me.o_first = 0x7fffffff;
 
     Stream4 lead, trail;
-    lead.init(sm, qual_off + ws);
-    trail.init(sm, qual_off);
-    for (uint32_t base = 0; base < nwin && i3 < 0; base += 32) {
+    lead.init(sm, qual_off + w_lo + ws);
+    trail.init(sm, qual_off + w_lo);
+    for (uint32_t base = w_lo; base < w_hi && bad == 0 && (x ? me.b_any : me.b_after) < 0; base += 32) {
         uint32_t negw = 0;   // bit k: window base+k is bad
         uint32_t oorw = 0;   // bit k: the byte entering window base+k+1 is outside the encoding's range
 #pragma unroll
@@ -178,37 +196,56 @@ __device__ __forceinline__ TrimOut thread_sliding_window(const uint8_t *__restri
             oorw += flags_to_nibble(rc.bad4(lw)) << (4 * g);
             Tm = T4;
         }
-        // ---- resolve the 32 windows of this step
+        // ---- what the 32 windows of this step contribute
         const uint32_t left = nwin - base;                               // windows from base on (>= 1)
         const uint32_t vmask = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
-        const uint32_t goodw = ~negw & vmask;
+        const uint32_t goodw = ~negw & vmask, badw = negw & vmask;
+        // the last window of the read has no entering byte
+        const uint32_t oo = oorw & (left > 32 ? 0xffffffffu : ((1u << (left - 1u)) - 1u));
+        if (oo && me.o_first == 0x7fffffff) me.o_first = (int)base + __ffs(oo) - 1;
+        if (badw && me.b_any < 0) me.b_any = (int)base + __ffs(badw) - 1;
         uint32_t after = 0xffffffffu;
-        if (!found) {                                                    // first good window: trim.cpp:42
+        if (me.g < 0) {                                                  // first good window: trim.cpp:42
             if (goodw) {
                 const int k = __ffs(goodw) - 1;
-                i5 = (int)base + k;
-                found = true;
+                me.g = (int)base + k;
                 after = 0xffffffffu << k;
             } else after = 0;
         }
-        const uint32_t cand = negw & vmask & after;                      // first bad window after it: trim.cpp:61
-        uint32_t visited;                                                // which entering bytes were really fetched
-        if (cand) {
-            const int k3 = __ffs(cand) - 1;
-            i3 = (int)base + k3;
-            visited = (1u << k3) - 1u;                                   // windows before the break
-        } else {
-            visited = left > 32 ? 0xffffffffu : ((1u << (left - 1u)) - 1u);   // all but the last window
-        }
-        if (oorw & visited) { o.error = true; return o; }
+        const uint32_t cand = badw & after;                              // first bad window after it: trim.cpp:61
+        if (cand && me.b_after < 0) me.b_after = (int)base + __ffs(cand) - 1;
     }
+
+    // ---- the two halves in order (A = windows from 0, B = the rest)
+    HalfScan A = me, B;
+    B.g = -1; B.b_any = -1; B.b_after = -1; B.o_first = 0x7fffffff;
+    if (nsub == 2u) {
+        const uint32_t pm = 3u << (lane & 30);
+        HalfScan ot;
+        ot.g = __shfl_xor_sync(pm, me.g, 1);
+        ot.b_any = __shfl_xor_sync(pm, me.b_any, 1);
+        ot.b_after = __shfl_xor_sync(pm, me.b_after, 1);
+        ot.o_first = __shfl_xor_sync(pm, me.o_first, 1);
+        bad |= __shfl_xor_sync(pm, bad, 1);
+        if (sub) { A = ot; B = me; } else B = ot;
+    }
+    if (bad) { o.error = true; return o; }
+    int i5 = x ? -1 : A.g;
+    int i3 = x ? A.b_any : A.b_after;
+    if (i3 < 0) {                                   // the loop runs on into the second half
+        if (x || A.g >= 0) i3 = B.b_any;
+        else { i5 = B.g; i3 = B.b_after; }
+    }
+    // entering bytes are fetched for the windows before the break (or before the last window)
+    const int fetched = i3 >= 0 ? i3 : (int)nwin - 1;
+    if (min(A.o_first, B.o_first) < fetched) { o.error = true; return o; }
 
     // The two in-window scans only touch bytes the loop above has range-checked (all < 128), so
     // "q - qoff >= qthr" is the SWAR test "(b | 0x80) - c has bit 7 set" with c = qthr + qoff.
     int five = 0, three = (int)L;
     const int cthr = P.qthr + P.qoff;
     const uint32_t c4 = (uint32_t)(cthr < 1 ? 0 : (cthr > 128 ? 128 : cthr)) * 0x01010101u;
-    if (i5 >= 0) {                                                       // trim.cpp:46-51
+    if (i5 >= 0 && (nsub == 1u || sub == 0u)) {                          // trim.cpp:46-51
         Stream4 s;
         s.init(sm, qual_off + (uint32_t)i5);
         for (uint32_t j = 0; j < ws; j += 4) {
@@ -218,7 +255,7 @@ __device__ __forceinline__ TrimOut thread_sliding_window(const uint8_t *__restri
             if (nib) { five = i5 + (int)j + __ffs(nib) - 1; break; }
         }
     }
-    if (i3 >= 0) {                                                       // trim.cpp:65-70
+    if (i3 >= 0 && (nsub == 1u || sub == 1u)) {                          // trim.cpp:65-70
         Stream4 s;
         s.init(sm, qual_off + (uint32_t)i3);
         for (uint32_t j = 0; j < ws; j += 4) {
@@ -228,26 +265,44 @@ __device__ __forceinline__ TrimOut thread_sliding_window(const uint8_t *__restri
             if (nib) { three = i3 + (int)j + __ffs(nib) - 1; break; }
         }
     }
-    if (P.trunc_n) {                                                     // trim.cpp:86-98
+    int pn = -1;
+    uint32_t anyN = 0;
+    if (P.trunc_n) {                                                     // trim.cpp:86-98; each lane one half of the bases
+        const uint32_t mid = nsub == 2u ? ((L / 2u + 3u) & ~3u) : L;
+        const uint32_t j0 = sub ? mid : 0u, j1 = sub ? L : min(mid, L);
         Stream4 s;
-        s.init(sm, seq_off);
-        int pn = -1;
-        uint32_t anyN = 0;
-        for (uint32_t j = 0; j < L; j += 4) {
-            const uint32_t x = s.next();
-            // exact zero-byte tests of x ^ 'n' and x ^ 'N' (same trick as newline_flags)
-            const uint32_t tn = ((x ^ 0x6E6E6E6Eu) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
-            const uint32_t tN = ((x ^ 0x4E4E4E4Eu) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
-            uint32_t fn = flags_to_nibble(~(tn | x) & 0x80808080u);
-            uint32_t fN = flags_to_nibble(~(tN | x) & 0x80808080u);
-            if (L - j < 4) { const uint32_t m = (1u << (L - j)) - 1u; fn &= m; fN &= m; }
+        s.init(sm, seq_off + j0);
+        for (uint32_t j = j0; j < j1; j += 4) {
+            const uint32_t v = s.next();
+            // exact zero-byte tests of v ^ 'n' and v ^ 'N' (same trick as newline_flags)
+            const uint32_t tn = ((v ^ 0x6E6E6E6Eu) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+            const uint32_t tN = ((v ^ 0x4E4E4E4Eu) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+            uint32_t fn = flags_to_nibble(~(tn | v) & 0x80808080u);
+            uint32_t fN = flags_to_nibble(~(tN | v) & 0x80808080u);
+            if (j1 - j < 4) { const uint32_t m = (1u << (j1 - j)) - 1u; fn &= m; fN &= m; }
             if (fn) { pn = (int)j + __ffs(fn) - 1; break; }
             anyN |= fN;
         }
+    }
+    if (nsub == 2u) {
+        const uint32_t pm = 3u << (lane & 30);
+        const int o_cut = __shfl_xor_sync(pm, sub ? three : five, 1);    // lane 0 sends five, lane 1 sends three
+        if (sub) five = o_cut; else three = o_cut;
+        if (P.trunc_n) {
+            const int o_pn = __shfl_xor_sync(pm, pn, 1);
+            const uint32_t o_any = __shfl_xor_sync(pm, anyN, 1);
+            // the scan stops at the first lowercase n: an uppercase N only counts if it comes before it
+            const int pn_a = sub ? o_pn : pn, pn_b = sub ? pn : o_pn;
+            const uint32_t any_a = sub ? o_any : anyN, any_b = sub ? anyN : o_any;
+            pn = pn_a >= 0 ? pn_a : pn_b;
+            anyN = any_a | (pn_a >= 0 ? 0u : any_b);
+        }
+    }
+    if (P.trunc_n) {
         if (pn >= 0) three = pn - 1;
         else if (anyN) three = -2;
     }
-    const bool have5 = (i5 >= 0) || P.no_fiveprime;
+    const bool have5 = (i5 >= 0) || x;
     if (!have5 || (three - five < P.lthr)) return o;                     // trim.cpp:103
     o.five = five;
     o.three = three;
@@ -365,22 +420,31 @@ __device__ __noinline__ void flush_realigned(uint8_t *__restrict__ gdst, const u
 // The deferred half of a tile (S7b + S8b), run by the "flush group" -- warps 4..7, which never own a
 // record -- while warps 0..3 validate and trim the next tile: look-back #2 over the output sizes,
 // then the staged bytes go out.  gtid = thread index inside the group (0..127), named barrier 1.
-constexpr int kFlushWarps = 4, kFlushThreads = kFlushWarps * 32, kFlushBarrier = 1;
+constexpr int kFlushBarrier = 1;
 __device__ __forceinline__ void flush_previous_tile(unsigned long long *const st_out[2], uint32_t p_tile, uint32_t p_tot0,
-                                                    uint32_t p_tot1, int nstreams, uint32_t epoch, int gtid,
+                                                    uint32_t p_tot1, int nstreams, uint32_t epoch, int gtid, int gwarps,
                                                     unsigned long long (*s_lb)[2], Control *__restrict__ ctl,
                                                     const OutPtrs &outs, const uint8_t *__restrict__ s_out, uint32_t num_tiles) {
     const unsigned long long agg[2] = {p_tot0, p_tot1};
     unsigned long long ex[2];
-    block_walk(st_out, p_tile, agg, nstreams, epoch, gtid, s_lb, ex, kFlushWarps, kFlushBarrier);
+#ifdef SK_PHASE_TIMING
+    const long long t_in = clock64();
+#endif
+    block_walk(st_out, p_tile, agg, nstreams, epoch, gtid, s_lb, ex, gwarps, kFlushBarrier);
+#ifdef SK_PHASE_TIMING
+    if (gtid == 0) atomicAdd(&g_phase_cycles[5], (unsigned long long)(clock64() - t_in));   // look-back #2 (flush group)
+#endif
     if (gtid == 0 && p_tile == num_tiles - 1) { ctl->out_bytes[0] = ex[0] + agg[0]; ctl->out_bytes[2] = ex[1] + agg[1]; }
     const bool cap_ok = ex[0] + p_tot0 <= outs.cap[0] && (p_tot1 == 0 || (outs.p[2] && ex[1] + p_tot1 <= outs.cap[2]));
     if (!cap_ok) {
         if (gtid == 0) ctl->index_overflow = 2u;
         return;
     }
-    flush_realigned(outs.p[0] + ex[0], s_out, 0u, p_tot0, gtid, kFlushThreads);
-    if (p_tot1) flush_realigned(outs.p[2] + ex[1], s_out, (p_tot0 + 15u) & ~15u, p_tot1, gtid, kFlushThreads);
+    flush_realigned(outs.p[0] + ex[0], s_out, 0u, p_tot0, gtid, gwarps * 32);
+    if (p_tot1) flush_realigned(outs.p[2] + ex[1], s_out, (p_tot0 + 15u) & ~15u, p_tot1, gtid, gwarps * 32);
+#ifdef SK_PHASE_TIMING
+    if (gtid == 0) atomicAdd(&g_phase_cycles[7], (unsigned long long)(clock64() - t_in));   // look-back #2 + flush (flush group)
+#endif
 }
 
 // Software-pipelined over tiles: the output of tile t is staged in shared memory right after it is
@@ -433,7 +497,6 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         // stalls every look-back behind it; a ticket must be drawn only when its tile starts at once.)
         if (tid == 0) { s_tile = atomicAdd(&ctl->tile_counter[3], 1u); s_fail = 0; }
         __syncthreads();
-        SK_TICK(0);   // ticket
         const uint32_t tile = s_tile;
         const bool done = tile >= num_tiles;
         const uint32_t t0 = tile * (uint32_t)Cfg::kTile;
@@ -505,9 +568,8 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
 
         SK_TICK(2);   // (+ newline-count publish)
         if (done) {   // no tile left: only the last staged tile remains to be flushed
-            if (have_prev && wid >= kFThreads / 32 - kFlushWarps)
-                flush_previous_tile(st_out, p_tile, p_tot0, p_tot1, nstreams, epoch, tid - (kFThreads - kFlushThreads), s_lb, ctl,
-                                    outs, s_out, num_tiles);
+            if (have_prev && wid >= 4)
+                flush_previous_tile(st_out, p_tile, p_tot0, p_tot1, nstreams, epoch, tid - 128, 4, s_lb, ctl, outs, s_out, num_tiles);
             break;
         }
 
@@ -541,17 +603,6 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         __syncthreads();   // newline positions visible to every thread
         SK_TICK(3);   // S3 positions + S4 look-back #1
 
-        // ---- deferred S7b/S8b of the PREVIOUS tile, by the flush group, overlapped with S5-S7 of this
-        // tile on the record warps: output offsets (look-back #2), then the flush.  s_desc (which aliases
-        // s_nl) was consumed by the previous tile's S8a; s_out is only read here and is not written
-        // again before the barrier in front of this tile's S8a.  (A tile has at most 128 records, so
-        // warps 4..7 have nothing else to do until that barrier: measured, 22 % of all warp time was
-        // spent waiting there.)
-        if (have_prev && wid >= kFThreads / 32 - kFlushWarps)
-            flush_previous_tile(st_out, p_tile, p_tot0, p_tot1, nstreams, epoch, tid - (kFThreads - kFlushThreads), s_lb, ctl, outs,
-                                s_out, num_tiles);
-        have_prev = false;
-
         // ---- S5: units owned by this tile.  Newline j (j < c_t) is global newline G+j; the line
         // after it is line G+j+1; a unit starts at every line that is a multiple of lpu.  Tile 0
         // also owns the unit starting at the batch's first byte ("newline -1").
@@ -561,13 +612,30 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         const uint32_t rpu = paired ? 2u : 1u;
         const uint32_t nrec_t = n_units * rpu;
         bool fail = nl_overflow || nrec_t > (uint32_t)kFThreads / 2u;   // S8a gives every record two lanes
+        // Lanes per record in S6: two while the records then still leave three warps for the flush group
+        // (150-base reads: 77 records -> 154 lanes = warps 0..4), else one (warps 0..3, flush group 4..7).
+        const uint32_t nsub = nrec_t <= 80u ? 2u : 1u;
+        const int flush_warp0 = nsub == 2u ? 5 : 4;
 
-        // per-record state (thread = record)
-        const bool has_rec = !fail && (uint32_t)tid < nrec_t;
+        // ---- deferred S7b/S8b of the PREVIOUS tile, by the flush group, overlapped with S5-S7 of this
+        // tile on the record warps: output offsets (look-back #2), then the flush.  s_desc (which aliases
+        // s_nl) was consumed by the previous tile's S8a; s_out is only read here and is not written
+        // again before the barrier in front of this tile's S8a.  (The flush group's warps never own a
+        // record, so they have nothing else to do until that barrier: measured, 22 % of all warp time
+        // was spent waiting there.)
+        if (have_prev && wid >= flush_warp0)
+            flush_previous_tile(st_out, p_tile, p_tot0, p_tot1, nstreams, epoch, tid - flush_warp0 * 32, kFThreads / 32 - flush_warp0,
+                                s_lb, ctl, outs, s_out, num_tiles);
+        have_prev = false;
+
+        // per-record state (nsub adjacent lanes = one record; mates of a pair are nsub lanes apart)
+        const uint32_t rec = (uint32_t)tid / nsub, sub = (uint32_t)tid % nsub;
+        const bool has_rec = !fail && rec < nrec_t;
+        const bool owner = sub == 0u;
         bool complete = false;
         uint32_t start = 0, e0 = 0, e1 = 0, e2 = 0, e3 = 0;
         if (has_rec) {
-            const int j = j_s + (int)(lpu * ((uint32_t)tid / rpu)) + 4 * (int)((uint32_t)tid % rpu);
+            const int j = j_s + (int)(lpu * (rec / rpu)) + 4 * (int)(rec % rpu);
             if ((uint32_t)(j + 4) < n_all) {
                 complete = true;
                 start = j < 0 ? in.first : (uint32_t)s_nl[j] + 1u;
@@ -575,7 +643,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             }
         }
         if (paired) {   // a pair is complete only if both mates are (all lanes take part in the shuffle)
-            const int mate_complete = __shfl_xor_sync(0xffffffffu, (int)complete, 1);
+            const int mate_complete = __shfl_xor_sync(0xffffffffu, (int)complete, (int)nsub);
             complete = complete && mate_complete != 0;
         }
         // an incomplete unit is fine only as the unfinished tail of the batch
@@ -594,21 +662,21 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             // FQEntry::validate (src/FQEntry.cpp:53-97): any violation is a data error
             if (name_len <= 1u || s_in[start] != '@' || L < 1u || qlen < 1u || qlen != L) fail = true;
             else {
-                cut = thread_sliding_window(s_in, e0 + 1u, L, e2 + 1u, P, rc);
+                cut = lane_sliding_window(s_in, e0 + 1u, L, e2 + 1u, P, rc, sub, nsub, lane);
                 if (cut.error) fail = true;
             }
         }
         if (fail) s_fail = 1u;
 
-        // ---- S7: routing + output sizes (lane = record; mates are lanes 2k, 2k+1)
-        const bool live = has_rec && complete;
+        // ---- S7: routing + output sizes (the record's first lane speaks for it)
+        const bool live = has_rec && complete && owner;
         const bool keep = live && cut.three >= 0;
         const uint32_t nkeep = keep ? (uint32_t)(cut.three - cut.five) : 0u;
         const uint32_t fixed = name_len + plus_len + 4u;
         uint32_t add0 = 0, add1 = 0;        // bytes for the main stream / the singles stream
         bool nrec_out = false;              // emit as an "N record" (-M)
         int stream = -1;
-        const bool other = paired && __shfl_xor_sync(0xffffffffu, (int)keep, 1) != 0;   // mate's keep flag
+        const bool other = paired && __shfl_xor_sync(0xffffffffu, (int)keep, (int)nsub) != 0;   // mate's keep flag
         if (live) {
             if (!paired) {
                 if (keep) { stream = 0; add0 = fixed + 2u * nkeep; }
@@ -624,8 +692,11 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         const uint32_t inc0 = warp_incl_scan(add0, lane);
         const uint32_t inc1 = paired ? warp_incl_scan(add1, lane) : 0u;
         if (lane == 31) { warp_tot2[wid][0] = inc0; warp_tot2[wid][1] = inc1; }
+#ifdef SK_PHASE_TIMING
+        if (tid == 0) atomicAdd(&g_phase_cycles[0], (unsigned long long)(clock64() - t_prev));   // warp 0's own S5-S7 time
+#endif
         __syncthreads();
-        SK_TICK(4);   // S5 + S6 + S7 scan
+        SK_TICK(4);   // S5 + S6 + S7 scan (incl. waiting for the other warps)
         uint32_t wb0 = 0, wb1 = 0, tot0 = 0, tot1 = 0;
 #pragma unroll
         for (int w = 0; w < kFThreads / 32; ++w) {
@@ -647,7 +718,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
 
         // record descriptors for S8a (two lanes per record); they reuse the newline-position array,
         // which nobody reads after S5
-        if (has_rec) {   // every slot S8a may look at is rewritten (x == 0: nothing to emit)
+        if (has_rec && owner) {   // every slot S8a may look at is rewritten (x == 0: nothing to emit)
             uint4 dsc;
             dsc.x = (stream < 0 || tile_fail)
                         ? 0u
@@ -656,7 +727,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             dsc.y = start | (e0 << 16);
             dsc.z = e1 | (e2 << 16);
             dsc.w = (keep ? (uint32_t)cut.five : 0u) | (nkeep << 16);
-            s_desc[tid] = dsc;
+            s_desc[rec] = dsc;
         }
         __syncthreads();
 
@@ -717,7 +788,8 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             uint32_t m_other = 0;
             if (paired) {
                 // bit k = keep flag of lane k's mate
-                m_other = ((m_keep & 0x55555555u) << 1) | ((m_keep & 0xAAAAAAAAu) >> 1);
+                const uint32_t m1 = nsub == 2u ? 0x11111111u : 0x55555555u;   // owner lanes of first mates
+                m_other = ((m_keep & m1) << nsub) | ((m_keep & (m1 << nsub)) >> nsub);
             }
             if (lane == 0 && m_live) {
                 atomicMax(&ctl->fast_consumed, end);
@@ -726,7 +798,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                     atomicAdd(&ctl->counters[0], (unsigned long long)__popc(m_keep));
                     atomicAdd(&ctl->counters[1], (unsigned long long)__popc(m_live & ~m_keep));
                 } else {
-                    const uint32_t even = 0x55555555u & m_live;          // one bit per pair (mate 1's lane)
+                    const uint32_t even = (nsub == 2u ? 0x11111111u : 0x55555555u) & m_live;   // one bit per pair (mate 1's lane)
                     const uint32_t k1 = m_keep & even, k2 = m_other & even;
                     atomicAdd(&ctl->counters[2], 2ull * __popc(k1 & k2));           // kept_p
                     atomicAdd(&ctl->counters[3], 2ull * __popc(even & ~k1 & ~k2));  // discard_p

@@ -177,7 +177,7 @@ __device__ __forceinline__ void group_sync(int id, int nthreads) {
     else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-// Called by a group of `gwarps` (8, 4 or 2; 2 * nstreams at least) whole warps, `gtid` = thread index
+// Called by a group of `gwarps` (nstreams .. 8) whole warps, `gtid` = thread index
 // inside the group, `bar` = the group's barrier (0: the whole 256-thread CTA).
 __device__ __forceinline__ void block_walk(unsigned long long *const status[2], uint32_t tile,
                                            const unsigned long long aggregate[2], int nstreams, uint32_t epoch,
@@ -204,7 +204,7 @@ __device__ __forceinline__ void block_walk(unsigned long long *const status[2], 
         // ---- every thread: one predecessor of its stream (or nothing if that stream is finished)
         uint32_t flag = 2, v = 0;
         const int64_t my = idx - lt;
-        if (!(sid ? done1 : done0) && my >= 0) {
+        if (sid < nstreams && !(sid ? done1 : done0) && my >= 0) {   // (a third warp of a 2-stream group idles)
             unsigned long long w;
             while (true) {
                 w = ld_status(&my_status[(size_t)my * kWideStatusStride]);
