@@ -67,6 +67,8 @@ struct FusedCfg {
     static constexpr int kOutBytes = kTile + 768 + 96;   // a tile of output + the last record's overhang + phase shifts
     // CH = 7: 56,768 B -> four CTAs per SM (4 x (56,768 + 248 static + 1,024 reserved) <= 232,448)
     static constexpr size_t kSmem = (size_t)kInBytes + kOutBytes + kFMaxNl * 2;
+    // CTAs per SM by shared memory (232,448 B per SM, 1,024 B reserved per CTA); also the register budget
+    static constexpr int kCtasPerSm = (int)(232448 / (kSmem + 1024 + 256)) > 4 ? 4 : (int)(232448 / (kSmem + 1024 + 256));
 };
 
 // four successive bytes at a time from an arbitrary shared-memory byte offset
@@ -90,10 +92,22 @@ struct Stream4 {
 
 struct RangeCheck {
     uint32_t kmin, kmax;   // qmin * 0x01010101, (qmax | 0x80) * 0x01010101
+    uint32_t add_hi, add_lo;   // (0x7f - qmax) * 0x01010101, (0x80 - qmin) * 0x01010101
     __device__ __forceinline__ void init(const DevParams &P) {
         kmin = (uint32_t)P.qmin * 0x01010101u;
         kmax = ((uint32_t)P.qmax | 0x80u) * 0x01010101u;
+        add_hi = (0x7fu - (uint32_t)P.qmax) * 0x01010101u;
+        add_lo = (0x80u - (uint32_t)P.qmin) * 0x01010101u;
     }
+    // Cheap screen for many words: fold every word into (hi, lo) with screen(), then suspicious() says
+    // whether ANY byte seen may be out of range.  No false negatives (a carry out of a byte >= 0x80
+    // can only disturb its neighbour, and that byte is flagged through `x` itself); callers re-check
+    // the words exactly with bad4() when it fires.
+    __device__ __forceinline__ void screen(uint32_t x, uint32_t &hi, uint32_t &lo) const {
+        hi |= (x + add_hi) | x;      // bit 7: byte > qmax, or >= 0x80
+        lo &= x + add_lo;            // bit 7 cleared: byte < qmin
+    }
+    __device__ __forceinline__ bool suspicious(uint32_t hi, uint32_t lo) const { return ((hi | ~lo) & 0x80808080u) != 0; }
     // 0x80 in every byte of x that is outside [qmin, qmax] (qmax <= 126)
     __device__ __forceinline__ uint32_t bad4(uint32_t x) const {
         const uint32_t lo = (x | 0x80808080u) - kmin;          // bit 7 set iff (b & 0x7f) >= qmin
@@ -178,8 +192,10 @@ __device__ __forceinline__ TrimOut lane_sliding_window(const uint8_t *__restrict
     lead.init(sm, qual_off + w_lo + ws);
     trail.init(sm, qual_off + w_lo);
     for (uint32_t base = w_lo; base < w_hi && bad == 0 && (x ? me.b_any : me.b_after) < 0; base += 32) {
-        uint32_t negw = 0;   // bit k: window base+k is bad
-        uint32_t oorw = 0;   // bit k: the byte entering window base+k+1 is outside the encoding's range
+        // bit 31-k: window base+k is bad.  Each total's sign bit is shifted in from the right by one
+        // funnel shift, so the step's first window ends up in the top bit (first = __clz).
+        uint32_t negr = 0;
+        uint32_t r_hi = 0, r_lo = 0xffffffffu;   // range screen of the 32 entering bytes
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
             const uint32_t lw = lead.next(), tw = trail.next();
@@ -188,32 +204,41 @@ __device__ __forceinline__ TrimOut lane_sliding_window(const uint8_t *__restrict
             const int T2 = dp4a_us(lw, 0x00000101, dp4a_us(tw, 0x0000FFFF, Tm));
             const int T3 = dp4a_us(lw, 0x00010101, dp4a_us(tw, 0x00FFFFFF, Tm));
             const int T4 = dp4a_us(lw, 0x01010101, dp4a_us(tw, (int)0xFFFFFFFF, Tm));
-            // sign bytes of windows base+4g .. +3 -> 4 flag bits
-            const uint32_t s01 = __byte_perm((uint32_t)Tm, (uint32_t)T1, 0x0073);
-            const uint32_t s23 = __byte_perm((uint32_t)T2, (uint32_t)T3, 0x0073);
-            const uint32_t sg = __byte_perm(s01, s23, 0x5410) & 0x80808080u;
-            negw += flags_to_nibble(sg) << (4 * g);
-            oorw += flags_to_nibble(rc.bad4(lw)) << (4 * g);
+            negr = __funnelshift_l((uint32_t)Tm, negr, 1);
+            negr = __funnelshift_l((uint32_t)T1, negr, 1);
+            negr = __funnelshift_l((uint32_t)T2, negr, 1);
+            negr = __funnelshift_l((uint32_t)T3, negr, 1);
+            rc.screen(lw, r_hi, r_lo);
             Tm = T4;
         }
         // ---- what the 32 windows of this step contribute
         const uint32_t left = nwin - base;                               // windows from base on (>= 1)
-        const uint32_t vmask = left >= 32 ? 0xffffffffu : ((1u << left) - 1u);
-        const uint32_t goodw = ~negw & vmask, badw = negw & vmask;
-        // the last window of the read has no entering byte
-        const uint32_t oo = oorw & (left > 32 ? 0xffffffffu : ((1u << (left - 1u)) - 1u));
-        if (oo && me.o_first == 0x7fffffff) me.o_first = (int)base + __ffs(oo) - 1;
-        if (badw && me.b_any < 0) me.b_any = (int)base + __ffs(badw) - 1;
+        if ((left <= 32u || rc.suspicious(r_hi, r_lo)) && me.o_first == 0x7fffffff) {
+            // the read's last step (its words run past the quality line) or, rarely, a suspect byte:
+            // find the first window of this step whose entering byte is out of range, exactly
+            // (bit k of oorw: the byte entering window base+k+1)
+            Stream4 again;
+            again.init(sm, qual_off + base + ws);
+            uint32_t oorw = 0;
+#pragma unroll 1
+            for (int g = 0; g < 8; ++g) oorw += flags_to_nibble(rc.bad4(again.next())) << (4 * g);
+            // the last window of the read has no entering byte
+            const uint32_t oo = oorw & (left > 32 ? 0xffffffffu : ((1u << (left - 1u)) - 1u));
+            if (oo) me.o_first = (int)base + __ffs(oo) - 1;
+        }
+        const uint32_t vmask = left >= 32 ? 0xffffffffu : ~(0xffffffffu >> left);   // top `left` bits
+        const uint32_t goodw = ~negr & vmask, badw = negr & vmask;
+        if (badw && me.b_any < 0) me.b_any = (int)base + __clz(badw);
         uint32_t after = 0xffffffffu;
         if (me.g < 0) {                                                  // first good window: trim.cpp:42
             if (goodw) {
-                const int k = __ffs(goodw) - 1;
+                const int k = __clz(goodw);
                 me.g = (int)base + k;
-                after = 0xffffffffu << k;
+                after = 0xffffffffu >> k;
             } else after = 0;
         }
         const uint32_t cand = badw & after;                              // first bad window after it: trim.cpp:61
-        if (cand && me.b_after < 0) me.b_after = (int)base + __ffs(cand) - 1;
+        if (cand && me.b_after < 0) me.b_after = (int)base + __clz(cand);
     }
 
     // ---- the two halves in order (A = windows from 0, B = the rest)
@@ -454,7 +479,7 @@ __device__ __forceinline__ void flush_previous_tile(unsigned long long *const st
 // flight an immediate look-back makes every tile wait for the slowest predecessor (measured: 22 % of
 // the tile time).
 template <int CH>
-__global__ void __launch_bounds__(kFThreads, 4)
+__global__ void __launch_bounds__(kFThreads, FusedCfg<CH>::kCtasPerSm)
 kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
          unsigned long long *__restrict__ status_nl, unsigned long long *__restrict__ status_out /* [2][stride] */,
          uint32_t status_stride, uint32_t num_tiles, uint32_t epoch) {
@@ -492,9 +517,9 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
     long long t_prev = clock64();
 #endif
     while (true) {
-        // (Drawing the ticket one tile ahead -- to hide the atomic and to know what to prefetch -- was
-        // measured: 0.38 -> 0.56 ms.  A ticket held by a CTA that is still busy with its previous tile
-        // stalls every look-back behind it; a ticket must be drawn only when its tile starts at once.)
+        // (Drawing the ticket ahead of time to hide the atomic's round trip was measured.  A whole tile
+        // ahead: 0.38 -> 0.56 ms -- a ticket held by a CTA that is still busy stalls every look-back
+        // behind it.  During S8a of the previous tile: no change.  So: drawn when the tile starts.)
         if (tid == 0) { s_tile = atomicAdd(&ctl->tile_counter[3], 1u); s_fail = 0; }
         __syncthreads();
         const uint32_t tile = s_tile;
@@ -707,7 +732,10 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         // the staging buffer holds a tile's worth of output; a tile whose (long, untrimmed) records
         // reach far into the halo can exceed it -> general path
         const bool tile_fail = s_fail != 0 || tot0 + tot1 + 64u > (uint32_t)Cfg::kOutBytes;
-        if (tile_fail) { tot0 = 0; tot1 = 0; if (tid == 0) ctl->fast_fail = 1u; }
+        if (tile_fail) {   // bit 1: the tile simply holds too many records (the host then picks smaller tiles)
+            tot0 = 0; tot1 = 0;
+            if (tid == 0) atomicOr(&ctl->fast_fail, (nl_overflow || nrec_t > (uint32_t)kFThreads / 2u) ? 3u : 1u);
+        }
         {   // the tile's output sizes go out now; its own offsets are asked for one tile later
             const unsigned long long agg[2] = {tot0, tot1};
             block_publish(st_out, tile, agg, nstreams, epoch, tid);
@@ -737,42 +765,43 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             const uint32_t r = (uint32_t)tid >> 1, sub = (uint32_t)tid & 1u;
             uint4 dsc = make_uint4(0, 0, 0, 0);
             if (!tile_fail && r < nrec_t) dsc = s_desc[r];   // a failed tile wrote no descriptors
-            if (dsc.x & 0x20000000u) {
-                const uint32_t r_start = dsc.y & 0xffffu, r_e0 = dsc.y >> 16, r_e1 = dsc.z & 0xffffu, r_e2 = dsc.z >> 16;
-                const uint32_t five = dsc.w & 0xffffu, n = dsc.w >> 16;
-                const uint32_t nlen = r_e0 - r_start, plen = r_e2 - r_e1 - 1u;
-                const uint32_t d = ((dsc.x & 0x80000000u) ? base1 : 0u) + (dsc.x & 0xffffu);
-                // Both lanes run the same two copies with different arguments (lanes of one warp that
-                // took different branches would serialise).  Run A then run B, B possibly empty:
-                //   lane 0: A = name '\n' [+ seq if nothing is cut at 5']   B = seq[five..) if cut at 5'
-                //   lane 1: A = '\n' line3 '\n' [+ qual '\n' if uncut]      B = qual[five..three)
-                uint32_t a_dst, a_src, a_len, b_dst, b_src, b_len;
-                int nl_at = -1;                       // staging offset of a '\n' to add after the copies
-                const bool nrec = (dsc.x & 0x40000000u) != 0;
+            // Both lanes run the same copies with different arguments (lanes of one warp that took
+            // different branches would serialise).  Run A, then -- only in warps where some read is cut
+            // at its 5' end -- run B:
+            //   lane 0: A = name '\n' [+ seq[0..n) if nothing is cut at 5']      B = seq[five..five+n)
+            //   lane 1: A = '\n' line3 '\n' [+ qual[0..n) if nothing is cut at 5']  B = qual[five..five+n)
+            // (with five == 0 the kept quality prefix follows line 3 in the input as well); the record's
+            // last '\n' is stored separately.
+            uint32_t a_dst = 0, a_src = 0, a_len = 0, b_dst = 0, b_src = 0, b_len = 0;
+            int nl_at = -1;                       // staging offset of a '\n' to add after the copies
+            const bool emit = (dsc.x & 0x20000000u) != 0;
+            const bool nrec = (dsc.x & 0x40000000u) != 0;
+            const uint32_t r_start = dsc.y & 0xffffu, r_e0 = dsc.y >> 16, r_e1 = dsc.z & 0xffffu, r_e2 = dsc.z >> 16;
+            const uint32_t five = dsc.w & 0xffffu, n = dsc.w >> 16;
+            const uint32_t nlen = r_e0 - r_start, plen = r_e2 - r_e1 - 1u;
+            const uint32_t d = ((dsc.x & 0x80000000u) ? base1 : 0u) + (dsc.x & 0xffffu);
+            if (emit) {
                 if (sub == 0) {
                     a_dst = d; a_src = r_start;
                     a_len = nlen + 1u + ((five == 0 && !nrec) ? n : 0u);
                     b_dst = d + nlen + 1u; b_src = r_e0 + 1u + five;
                     b_len = (five != 0 && !nrec) ? n : 0u;
                 } else if (!nrec) {
-                    const uint32_t Lr = r_e1 - r_e0 - 1u;
-                    const bool whole = five == 0 && n == Lr;         // rest of the record is contiguous
                     a_dst = d + nlen + 1u + n; a_src = r_e1;
-                    a_len = plen + 2u + (whole ? n + 1u : 0u);
+                    a_len = plen + 2u + (five == 0 ? n : 0u);
                     b_dst = a_dst + plen + 2u; b_src = r_e2 + 1u + five;
-                    b_len = whole ? 0u : n;
-                    if (!whole) nl_at = (int)(b_dst + n);
+                    b_len = five != 0 ? n : 0u;
+                    nl_at = (int)(b_dst + n);
                 } else {                                             // "N record": name '\n' N '\n' line3 '\n' Qmin '\n'
                     a_dst = d + nlen + 3u; a_src = r_e1 + 1u; a_len = plen + 1u;
-                    b_dst = 0; b_src = 0; b_len = 0;
                 }
-                smem_copy(s_out, a_dst, s_in, a_src, a_len);
-                smem_copy(s_out, b_dst, s_in, b_src, b_len);
-                if (nl_at >= 0) s_out[nl_at] = '\n';
-                if (nrec) {
-                    if (sub == 0) { s_out[d + nlen + 1u] = 'N'; s_out[d + nlen + 2u] = '\n'; }
-                    else { s_out[a_dst + plen + 1u] = (uint8_t)P.qmin; s_out[a_dst + plen + 2u] = '\n'; }
-                }
+            }
+            smem_copy(s_out, a_dst, s_in, a_src, a_len);
+            if (__any_sync(0xffffffffu, b_len != 0)) smem_copy(s_out, b_dst, s_in, b_src, b_len);
+            if (nl_at >= 0) s_out[nl_at] = '\n';
+            if (emit && nrec) {
+                if (sub == 0) { s_out[d + nlen + 1u] = 'N'; s_out[d + nlen + 2u] = '\n'; }
+                else { s_out[a_dst + plen + 1u] = (uint8_t)P.qmin; s_out[a_dst + plen + 2u] = '\n'; }
             }
         }
         SK_TICK(6);   // descriptors + S8a
@@ -823,7 +852,7 @@ __global__ void kf_finalize(DevInput in, DevParams P, Control *__restrict__ ctl,
     r.records[0] = ctl->fast_records;
     r.consumed[0] = ctl->fast_consumed;
     for (int k = 0; k < 8; ++k) r.counters[k] = (long long)ctl->counters[k];
-    r.index_overflow = (ctl->index_overflow & 2u) | (ctl->fast_fail ? 4u : 0u);
+    r.index_overflow = (ctl->index_overflow & 2u) | (ctl->fast_fail ? 4u : 0u) | ((ctl->fast_fail & 2u) ? 8u : 0u);
     *res = r;
     Control z;
     memset(&z, 0, sizeof z);

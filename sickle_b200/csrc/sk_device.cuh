@@ -53,7 +53,7 @@ struct Control {
     uint32_t tile_counter[4];     // dynamic tile tickets: K1 input 0, K1 input 1, K2, K3
     uint32_t nlines[2];           // written by K1's last tile
     uint32_t index_overflow;      // bit 0: a line index ran out of capacity; bit 1: an output buffer did
-    uint32_t fast_fail;           // fused path met something it does not handle: re-run on the general path
+    uint32_t fast_fail;           // fused path met something it does not handle (bit 0; bit 1: too many records in a tile): re-run on the general path
     uint32_t fast_consumed;       // fused path: end of the last complete unit (max over tiles)
     uint32_t fast_records;        // fused path: complete records
     unsigned long long err_key;   // min over offending (class, unit, mate, position); ~0 = none
@@ -171,14 +171,17 @@ __device__ __forceinline__ void block_publish(unsigned long long *const status[2
 }
 
 // Barrier over a subset of the CTA's warps (named barrier `id` > 0, `nthreads` a multiple of 32);
-// id 0 is __syncthreads().
+// id 0 with all threads is __syncthreads().  Only ids 0 and 1 are used.
 __device__ __forceinline__ void group_sync(int id, int nthreads) {
-    if (id == 0) __syncthreads();
-    else asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+    // literal barrier numbers: with a register operand ptxas reserves all 16 barriers for the CTA
+    if (id == 0) asm volatile("bar.sync 0, %0;" ::"r"(nthreads) : "memory");
+    else asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
 
 // Called by a group of `gwarps` (nstreams .. 8) whole warps, `gtid` = thread index
 // inside the group, `bar` = the group's barrier (0: the whole 256-thread CTA).
+// (De-inlining this and flush_previous_tile to shrink the kernel -- instruction fetch shows up as a
+// stall -- was measured: 0.356 -> 0.391 ms; the by-pointer arguments go through local memory.)
 __device__ __forceinline__ void block_walk(unsigned long long *const status[2], uint32_t tile,
                                            const unsigned long long aggregate[2], int nstreams, uint32_t epoch,
                                            int gtid, unsigned long long (*scratch)[2], unsigned long long excl[2],

@@ -216,6 +216,24 @@ def test_batch_size_invariance_and_pipelined_upload(capi):
     assert ref["records"][0] == 20000
 
 
+@pytest.mark.parametrize("L,min_fused_frac", [(250, 0.9), (150, 0.9), (100, 0.85), (75, 0.85), (50, 0.0), (36, 0.0)])
+def test_tile_size_follows_record_size(capi, L, min_fused_frac):
+    """The single-pass kernel holds at most 128 records per tile; the runtime picks the tile size from
+    the record size it sees (and sends very short reads to the general path).  Same bytes either way."""
+    from sickle_b200 import synth
+
+    data = synth.fixed_length_records(30000, L, "sanger", seed=31).tobytes()
+    flags = dict(qualtype="sanger", q=20, l=20, x=False, n=False)
+    want = orc.run(orc.MODE_SE, orc.make_params("sanger"), data)
+    got = _run_cuda(capi, capi.MODE_SE, flags, data, slot_bytes=1 << 18)
+    assert got["out"][0] == want["out"][0]
+    assert got["counters"]["kept"] == want["counters"]["kept"]
+    assert got["batches"] >= 10
+    assert got["fused_batches"] >= min_fused_frac * got["batches"], (got["fused_batches"], got["batches"])
+    if min_fused_frac == 0.0:
+        assert got["fused_batches"] <= 3, "short reads must settle on the general path"
+
+
 def test_lines_that_look_like_other_lines(capi):
     """Record boundaries come from counting newlines, never from what a line starts with ('@' and '+'
     are valid quality characters, line 3 is not checked for '+').  Inputs whose
