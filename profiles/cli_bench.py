@@ -72,7 +72,10 @@ def main():
     outs = {}
     tools = [("b200", os.path.join(ROOT, "bin", "sickle"), ["-d"])]
     if not a.skip_ref:
-        tools.append(("reference", os.path.join(ROOT, "oracle", "_ref", "sickle"), ["-a", str(os.cpu_count())]))
+        # se: the reference sources with synchronous output (oracle/Makefile) -- the unpatched binary's
+        # detached writer thread races and crashes on large inputs
+        ref = "sickle" if a.paired else "sickle_sync"
+        tools.append(("reference", os.path.join(ROOT, "oracle", "_ref", ref), ["-a", str(os.cpu_count())]))
     env = dict(os.environ)
     for kv in a.env:
         k, v = kv.split("=", 1)
