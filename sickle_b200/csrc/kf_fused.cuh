@@ -12,24 +12,27 @@
 //
 // Tile structure (256 threads, persistent CTAs, tiles handed out by an atomic ticket):
 //   S1  region = tile (224 threads x CH x 16 B) + halo (32 threads x CH x 16 B) -> shared memory,
-//       coalesced 16-byte loads.  The halo lets a record that starts in the tile finish.
+//       coalesced 16-byte loads.  The halo lets a record that starts in the tile finish.  The tile one
+//       grid-width ahead is prefetched into L2.
 //   S2  each thread scans its CH*16 contiguous bytes (odd CH => conflict-free LDS.128): SWAR newline
 //       test (3 ALU ops / word) -> bit masks -> popc.
 //   S3  block scan -> rank of every newline; positions to shared memory (u16).
 //   S4  decoupled look-back #1 over the tiles' newline counts -> global line number of the tile.
 //   S5  records are lines 4r..4r+3; a record (pair) belongs to the tile holding the newline in
-//       front of it.  One thread per record from here on.
-//   S6  validate + sliding window out of shared memory, thread-per-read and branch-free: 32 windows
-//       per step, window totals by dp4a straight from the packed quality words, good/bad windows and
-//       out-of-range bytes collected as bit masks and resolved once per step.
+//       front of it.
+//   S6  validate + sliding window out of shared memory, one or two lanes per read and branch-free:
+//       32 windows per step, window totals by dp4a straight from the packed quality words, the sign
+//       of every total shifted into a bit mask, a cheap range screen per word; resolved once per step.
 //   S7  routing, 2-stream block scan; the tile's output sizes are published for look-back #2.
 //   S8a two lanes per record copy the trimmed record into a shared staging buffer.
-//   S8b one tile LATER (after the next tile's S1-S3): look-back #2 -> byte offsets in the output
-//       streams, then the CTA flushes the staged bytes with destination-aligned 16-byte stores
-//       (128-bit funnel shift for the destination's phase).
-// Anything this kernel cannot handle exactly -- a record longer than the halo, more than 128
-// records or 1024 newlines in a tile, or ANY data error -- sets Control::fast_fail; the host then
-// re-runs the batch through the general path, which also produces the reference's error details.
+//   S8b one tile LATER, by the "flush group" -- the 3 or 4 warps that never own a record -- while the
+//       record warps run S5-S7 of the next tile: look-back #2 -> byte offsets in the output streams,
+//       then the staged bytes go out with destination-aligned 16-byte stores (128-bit funnel shift
+//       for the destination's phase).
+// CH (5, 7 or 9: 18 / 25 / 32 KB tiles) is chosen by the host per batch so that a tile holds at most
+// ~112 records.  Anything this kernel cannot handle exactly -- a record longer than the halo, more
+// than 128 records or 1024 newlines in a tile, or ANY data error -- sets Control::fast_fail; the host
+// then re-runs the batch through the general path, which also produces the reference's error details.
 #pragma once
 
 #include "k1_index.cuh"
