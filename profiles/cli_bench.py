@@ -47,11 +47,21 @@ def main():
     ap.add_argument("--input-format", default="plain", choices=["plain", "bgzf", "gzip"])
     ap.add_argument("--gzip-out", action="store_true", help="-g (b200 only: the reference's -g is broken)")
     ap.add_argument("--paired", action="store_true", help="interleaved pairs (pe -c) instead of se")
+    ap.add_argument("--two-files", action="store_true", help="pe -f -r -o -p -s (forward / reverse files)")
     a = ap.parse_args()
     src = os.path.join(a.dir, "cli_bench_in.fastq")
+    src2 = os.path.join(a.dir, "cli_bench_in2.fastq")
     chunk = 1_000_000
-    with open(src, "wb") as f:
-        for s in range(0, a.reads, chunk):
+    if a.two_files:
+        a.paired = True
+        with open(src, "wb") as f, open(src2, "wb") as f2:
+            for s in range(0, a.reads, chunk):
+                n = min(chunk, a.reads - s)
+                fw, rv, _ = synth.paired_records(n // 2, 150, "sanger", seed=3, start=s // 2)
+                fw.tofile(f)
+                rv.tofile(f2)
+    with open(src, "ab" if a.two_files else "wb") as f:
+        for s in range(0, 0 if a.two_files else a.reads, chunk):
             n = min(chunk, a.reads - s)
             if a.paired:
                 synth.paired_records(n // 2, 150, "sanger", seed=3, start=s // 2)[2].tofile(f)
@@ -68,7 +78,7 @@ def main():
                           "ratio": round(os.path.getsize(src) / os.path.getsize(gz), 2)}))
         os.unlink(src)
         src = gz
-    size = os.path.getsize(src)
+    size = os.path.getsize(src) + (os.path.getsize(src2) if a.two_files else 0)
     outs = {}
     tools = [("b200", os.path.join(ROOT, "bin", "sickle"), ["-d"])]
     if not a.skip_ref:
@@ -83,7 +93,9 @@ def main():
     for name, exe, extra in tools:
         out = os.path.join(a.dir, "cli_bench_out_%s.fastq" % name)
         sng = os.path.join(a.dir, "cli_bench_sng_%s.fastq" % name)
-        if a.paired:
+        if a.two_files:
+            cmd = [exe, "pe", "-f", src, "-r", src2, "-t", "sanger", "-o", out, "-p", out + ".2", "-s", sng] + extra
+        elif a.paired:
             cmd = [exe, "pe", "-c", src, "-t", "sanger", "-m", out, "-s", sng] + extra
         else:
             cmd = [exe, "se", "-f", src, "-t", "sanger", "-o", out] + extra

@@ -76,14 +76,50 @@ k3_emit(DevInput in0, DevInput in1, DevParams P, const Control *__restrict__ ctl
 #pragma unroll
     for (int s = 0; s < kMaxStreams; ++s)
         if (ctl->out_bytes[s] > outs.cap[s]) return;  // reported by finalize as a capacity error
-    const uint32_t total = g.nrec0 + g.nrec1;
+    // A warp takes 32 consecutive records at a time.  First every lane fetches the descriptor and the
+    // line ends of ITS record (coalesced, and the three dependent loads happen once per 32 records
+    // instead of once per record); then the warp copies the records one after the other, the copy
+    // parameters coming from the owning lane by shuffle.  Records cut at the 5' end and -M "N records"
+    // (rare) take the four-piece path.
     const uint32_t nwarps = gridDim.x * (kK3Threads / 32);
-    for (uint32_t w = blockIdx.x * (kK3Threads / 32) + (threadIdx.x >> 5); w < total; w += nwarps) {
-        const bool second = w >= g.nrec0;
-        const uint32_t rec = second ? w - g.nrec0 : w;
-        const RecDesc d = second ? desc1[rec] : desc0[rec];
-        if (!(d.route & kRouteEmit)) continue;
-        emit_record(second ? in1 : in0, rec, d, outs.p, P, lane);
+    const uint32_t chunks0 = (g.nrec0 + 31u) / 32u, chunks1 = (g.nrec1 + 31u) / 32u;
+    for (uint32_t c = blockIdx.x * (kK3Threads / 32) + (threadIdx.x >> 5); c < chunks0 + chunks1; c += nwarps) {
+        const bool second = c >= chunks0;
+        const DevInput &in = second ? in1 : in0;
+        const uint32_t nrec = second ? g.nrec1 : g.nrec0;
+        const uint32_t rec = (second ? c - chunks0 : c) * 32u + (uint32_t)lane;
+        RecDesc d;
+        d.route = 0; d.dst_off = 0; d.five = 0; d.nkeep = 0;
+        if (rec < nrec) d = (second ? desc1 : desc0)[rec];
+        const bool emit = (d.route & kRouteEmit) != 0;
+        const bool slow = emit && (d.five != 0 || (d.route & kRouteNRec));
+        uint32_t a_src = 0, a_len = 0, b_src = 0, b_len = 0;
+        if (emit && !slow) {
+            const RecLines r = record_lines(in, rec);
+            a_src = r.start[0]; a_len = r.len[0] + 1u + d.nkeep;          // name '\n' seq[0:three]
+            b_src = r.start[2] - 1u; b_len = r.len[2] + 2u + d.nkeep;    // '\n' line3 '\n' qual[0:three]
+        }
+        for (uint32_t todo = __ballot_sync(0xffffffffu, emit); todo; todo &= todo - 1) {
+            const int k = __ffs(todo) - 1;
+            const uint32_t route = __shfl_sync(0xffffffffu, d.route, k);
+            const uint32_t off = __shfl_sync(0xffffffffu, d.dst_off, k);
+            if (__shfl_sync(0xffffffffu, (int)slow, k)) {
+                RecDesc dk;
+                dk.route = route; dk.dst_off = off;
+                dk.five = __shfl_sync(0xffffffffu, d.five, k);
+                dk.nkeep = __shfl_sync(0xffffffffu, d.nkeep, k);
+                emit_record(in, rec - (uint32_t)lane + (uint32_t)k, dk, outs.p, P, lane);
+                continue;
+            }
+            const uint32_t sa = __shfl_sync(0xffffffffu, a_src, k), la = __shfl_sync(0xffffffffu, a_len, k);
+            const uint32_t sb = __shfl_sync(0xffffffffu, b_src, k), lb = __shfl_sync(0xffffffffu, b_len, k);
+            uint8_t *dst = outs.p[route & 3u] + off;
+            // (issuing all loads of both runs before the first store was measured: no faster -- the
+            // kernel is bound by instructions per byte of this 4-byte-per-lane copy, not by latency)
+            warp_copy(dst, in.data + sa, la, lane);
+            warp_copy(dst + la, in.data + sb, lb, lane);
+            if (lane == 0) dst[la + lb] = '\n';
+        }
     }
 }
 
