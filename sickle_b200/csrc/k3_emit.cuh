@@ -36,6 +36,28 @@ __device__ __forceinline__ void warp_copy(uint8_t *__restrict__ dst, const uint8
     if ((uint32_t)lane < tail) dst[4 * nw + lane] = src[4 * nw + lane];
 }
 
+// Quarter-warp copy (8 lanes, `gl` = lane inside the group), 16 bytes per lane and step: destination
+// chunks are written 16-byte aligned, source words fetched aligned and funnel-shifted.  Four records
+// are copied side by side by the four quarters of a warp.  May read up to 7 bytes past src+n.
+__device__ __forceinline__ void quarter_copy16(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, uint32_t n, int gl) {
+    uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;
+    if (head > n) head = n;
+    for (uint32_t j = gl; j < head; j += 8) dst[j] = src[j];
+    dst += head; src += head; n -= head;
+    const uint32_t nq = n >> 4;
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
+    const uint32_t *__restrict__ s32 = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
+    uint4 *__restrict__ d128 = reinterpret_cast<uint4 *>(dst);
+    for (uint32_t k = gl; k < nq; k += 8) {
+        const uint32_t a = s32[4 * k], b = s32[4 * k + 1], c = s32[4 * k + 2], e = s32[4 * k + 3];
+        const uint32_t f = sh ? s32[4 * k + 4] : 0u;
+        d128[k] = make_uint4(__funnelshift_r(a, b, sh), __funnelshift_r(b, c, sh), __funnelshift_r(c, e, sh),
+                             __funnelshift_r(e, f, sh));
+    }
+    const uint32_t tail = n & 15u;
+    for (uint32_t j = gl; j < tail; j += 8) dst[16 * nq + j] = src[16 * nq + j];
+}
+
 __device__ __forceinline__ void emit_record(const DevInput &in, uint32_t rec, const RecDesc d, uint8_t *const *outs,
                                             const DevParams &P, int lane) {
     const RecLines r = record_lines(in, rec);
@@ -99,26 +121,37 @@ k3_emit(DevInput in0, DevInput in1, DevParams P, const Control *__restrict__ ctl
             a_src = r.start[0]; a_len = r.len[0] + 1u + d.nkeep;          // name '\n' seq[0:three]
             b_src = r.start[2] - 1u; b_len = r.len[2] + 2u + d.nkeep;    // '\n' line3 '\n' qual[0:three]
         }
-        for (uint32_t todo = __ballot_sync(0xffffffffu, emit); todo; todo &= todo - 1) {
-            const int k = __ffs(todo) - 1;
-            const uint32_t route = __shfl_sync(0xffffffffu, d.route, k);
-            const uint32_t off = __shfl_sync(0xffffffffu, d.dst_off, k);
-            if (__shfl_sync(0xffffffffu, (int)slow, k)) {
-                RecDesc dk;
-                dk.route = route; dk.dst_off = off;
-                dk.five = __shfl_sync(0xffffffffu, d.five, k);
-                dk.nkeep = __shfl_sync(0xffffffffu, d.nkeep, k);
-                emit_record(in, rec - (uint32_t)lane + (uint32_t)k, dk, outs.p, P, lane);
-                continue;
+        // the four quarters of the warp copy four records at a time
+        const int quarter = lane >> 3, gl = lane & 7;
+        for (uint32_t todo = __ballot_sync(0xffffffffu, emit && !slow); todo;) {
+            int k = -1, k0 = __ffs(todo) - 1;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                if (todo) {
+                    if (q == quarter) k = __ffs(todo) - 1;
+                    todo &= todo - 1;
+                }
             }
-            const uint32_t sa = __shfl_sync(0xffffffffu, a_src, k), la = __shfl_sync(0xffffffffu, a_len, k);
-            const uint32_t sb = __shfl_sync(0xffffffffu, b_src, k), lb = __shfl_sync(0xffffffffu, b_len, k);
+            const int from = k < 0 ? k0 : k;                      // (-1: fewer than four records left, this quarter idles)
+            const uint32_t route = __shfl_sync(0xffffffffu, d.route, from);
+            const uint32_t off = __shfl_sync(0xffffffffu, d.dst_off, from);
+            const uint32_t sa = __shfl_sync(0xffffffffu, a_src, from);
+            const uint32_t sb = __shfl_sync(0xffffffffu, b_src, from);
+            const uint32_t la = __shfl_sync(0xffffffffu, a_len, from), lb = __shfl_sync(0xffffffffu, b_len, from);
+            if (k < 0) continue;
             uint8_t *dst = outs.p[route & 3u] + off;
-            // (issuing all loads of both runs before the first store was measured: no faster -- the
-            // kernel is bound by instructions per byte of this 4-byte-per-lane copy, not by latency)
-            warp_copy(dst, in.data + sa, la, lane);
-            warp_copy(dst + la, in.data + sb, lb, lane);
-            if (lane == 0) dst[la + lb] = '\n';
+            quarter_copy16(dst, in.data + sa, la, gl);
+            quarter_copy16(dst + la, in.data + sb, lb, gl);
+            if (gl == 0) dst[la + lb] = '\n';
+        }
+        for (uint32_t todo = __ballot_sync(0xffffffffu, slow); todo; todo &= todo - 1) {
+            const int k = __ffs(todo) - 1;
+            RecDesc dk;
+            dk.route = __shfl_sync(0xffffffffu, d.route, k);
+            dk.dst_off = __shfl_sync(0xffffffffu, d.dst_off, k);
+            dk.five = __shfl_sync(0xffffffffu, d.five, k);
+            dk.nkeep = __shfl_sync(0xffffffffu, d.nkeep, k);
+            emit_record(in, rec - (uint32_t)lane + (uint32_t)k, dk, outs.p, P, lane);
         }
     }
 }
