@@ -3,7 +3,10 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <string>
+#include <vector>
 
+#include <getopt.h>
 #include <unistd.h>
 
 #include "trimmer.h"
@@ -20,7 +23,56 @@ se\tsingle-end sequence trimming\n\
     exit(status);
 }
 
+static int run_command(int argc, char *argv[]) {
+    if (strcmp(argv[1], "pe") == 0) {
+        Trim_Paired trimmer;
+        const int rc = trimmer.parse_args(argc, argv);
+        return rc != 0 ? rc : trimmer.trim_main();
+    }
+    Trim_Single trimmer;
+    const int rc = trimmer.parse_args(argc, argv);
+    return rc != 0 ? rc : trimmer.trim_main();
+}
+
+// `sickle batch` (not in the reference): one `se ...` / `pe ...` command per line on stdin, run one
+// after the other in this process, so that CUDA start-up and the pinned buffers are paid once per
+// process instead of once per file.  After every command a line `##rc <exit code>` goes to stdout.
+// Arguments are split at blanks; double quotes keep blanks.  A usage error ends the whole batch, as
+// it would end `sickle` itself.
+static int run_batch() {
+    host::batch_mode = true;
+    int worst = EXIT_SUCCESS;
+    char *line = nullptr;
+    size_t cap = 0;
+    while (getline(&line, &cap, stdin) > 0) {
+        std::vector<std::string> tok;
+        std::string cur;
+        bool quoted = false, any = false;
+        for (const char *p = line; *p && *p != '\n'; ++p) {
+            if (*p == '"') { quoted = !quoted; any = true; }
+            else if ((*p == ' ' || *p == '\t') && !quoted) { if (any) tok.push_back(cur); cur.clear(); any = false; }
+            else { cur += *p; any = true; }
+        }
+        if (any) tok.push_back(cur);
+        if (tok.empty()) continue;
+        if (tok[0] != "se" && tok[0] != "pe") { fprintf(stderr, "****Error: batch lines start with se or pe\n\n"); worst = EXIT_FAILURE; continue; }
+        std::vector<char *> av;
+        std::string prog = PROGRAM_NAME;
+        av.push_back(&prog[0]);
+        for (auto &t : tok) av.push_back(&t[0]);
+        av.push_back(nullptr);
+        optind = 0;   // glibc: restart getopt_long from scratch
+        const int rc = run_command((int)av.size() - 1, av.data());
+        fprintf(stdout, "##rc %d\n", rc);
+        fflush(stdout);
+        if (rc != EXIT_SUCCESS) worst = rc;
+    }
+    fflush(NULL);
+    _exit(worst);
+}
+
 int main(int argc, char *argv[]) {
+    if (argc >= 2 && strcmp(argv[1], "batch") == 0) return run_batch();
     if (argc < 2 || (strcmp(argv[1], "pe") != 0 && strcmp(argv[1], "se") != 0 && strcmp(argv[1], "--version") != 0 &&
                      strcmp(argv[1], "--help") != 0))
         main_usage(EXIT_FAILURE);
@@ -33,18 +85,7 @@ int main(int argc, char *argv[]) {
     }
     if (strcmp(argv[1], "--help") == 0) main_usage(EXIT_SUCCESS);
 
-    int retval;
-    if (strcmp(argv[1], "pe") == 0) {
-        Trim_Paired trimmer;
-        retval = trimmer.parse_args(argc, argv);
-        if (retval != 0) return retval;
-        retval = trimmer.trim_main();
-    } else {
-        Trim_Single trimmer;
-        retval = trimmer.parse_args(argc, argv);
-        if (retval != 0) return retval;
-        retval = trimmer.trim_main();
-    }
+    const int retval = run_command(argc, argv);
     // Every output file is closed by now.  Leave without the CUDA runtime's exit handlers: tearing the
     // context down call by call costs several hundred milliseconds that the kernel's cleanup does not.
     fflush(NULL);

@@ -18,6 +18,8 @@
 
 namespace host {
 
+bool batch_mode = false;
+
 // Trim_Single::recommended_batch_len / Trim_Paired::recommended_batch_len
 // (reference src/trim_single.cpp:194-211, src/trim_paired.cpp:246-263)
 static long long recommended_batch_len(unsigned long long file_size, long long b_mib, bool paired) {
@@ -155,14 +157,43 @@ int Abstract_Trimmer::report_data_error(const sk_result &r, const char *buf0, co
 
 namespace {
 
+// `sickle batch` runs many commands in one process: the context (CUDA start-up, pinned slots, device
+// buffers) of the previous command is kept and reused when the next one asks for the same thing.
+struct CachedCtx {
+    sk_ctx *c = nullptr;
+    sk_params p{};
+    int device = -1, nslots = 0;
+    unsigned long long slot = 0;
+} g_cache;
+
 struct Ctx {
     sk_ctx *c = nullptr;
     Totals *tot = nullptr;
+    bool reusable = false;   // set once the run finished with every slot idle
+    sk_params p{};
+    int device = 0, nslots = 0;
+    unsigned long long slot = 0;
+    bool acquire(int device_, unsigned long long slot_, int nslots_, const sk_params &p_) {
+        device = device_; slot = slot_; nslots = nslots_; p = p_;
+        if (g_cache.c && g_cache.device == device && g_cache.slot == slot && g_cache.nslots == nslots &&
+            memcmp(&g_cache.p, &p, sizeof p) == 0) {
+            c = g_cache.c;
+            g_cache.c = nullptr;
+            return true;
+        }
+        if (g_cache.c) { sk_destroy(g_cache.c); g_cache.c = nullptr; }
+        c = sk_create(device, slot, nslots, &p);
+        return c != nullptr;
+    }
     ~Ctx() {
         // SICKLE_B200_KEEP_CONTEXT=1: leave buffers and context to process exit (the CLI exits right after)
         static const bool keep = getenv("SICKLE_B200_KEEP_CONTEXT") && atoi(getenv("SICKLE_B200_KEEP_CONTEXT")) != 0;
         const double t0 = host::now_s();
-        if (c && !keep) sk_destroy(c);
+        if (c && host::batch_mode && reusable) {
+            g_cache.c = c; g_cache.p = p; g_cache.device = device; g_cache.nslots = nslots; g_cache.slot = slot;
+        } else if (c && !keep) {
+            sk_destroy(c);
+        }
         if (tot) tot->t_teardown += host::now_s() - t0;
     }
 };
@@ -280,13 +311,12 @@ int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, Byt
         slot = 64ull << 20;
         unsigned long long sz = in0->gzip() ? ~0ull : in0->file_size();
         if (in1) sz = in1->gzip() ? ~0ull : std::max(sz, in1->file_size());
-        if (sz < (40ull << 20)) slot = ((sz + sz / 2) | 0xfffffull) + 1;   // >= 4/3 of the file, whole MiB
+        if (sz < (40ull << 20) && !host::batch_mode) slot = ((sz + sz / 2) | 0xfffffull) + 1;   // >= 4/3 of the file, whole MiB
     }
     const int nslots = two ? 2 : 3;
     Ctx ctx;
     ctx.tot = &tot;
-    ctx.c = sk_create(device, slot, nslots, &p);
-    if (!ctx.c) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
+    if (!ctx.acquire(device, slot, nslots, p)) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
     tot.t_init = host::now_s() - t_begin;
     std::vector<Tickets> tickets((size_t)nslots);
     auto timed_wait = [&](int s_, sk_result *r_) {
@@ -353,6 +383,7 @@ int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, Byt
         if (have_prev) tickets[(size_t)slot_i] = queue_outputs(prev, outs);   // (slot_i is the slot `prev` ran in)
         for (auto &k : tickets)
             if (!wait_outputs(k, outs, tot)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
+        ctx.reusable = true;
         return EXIT_SUCCESS;
     }
 
@@ -418,6 +449,7 @@ int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, Byt
     }
     for (auto &k : tickets)
         if (!wait_outputs(k, outs, tot)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
+    ctx.reusable = true;
     return EXIT_SUCCESS;
 }
 

@@ -25,6 +25,9 @@
 
 namespace host {
 
+// Set by `sickle batch`: several commands run in this process, contexts are kept between them.
+extern bool batch_mode;
+
 struct Totals {
     long long kept = 0, discard = 0;
     long long kept_p = 0, discard_p = 0, kept_s1 = 0, kept_s2 = 0, discard_s1 = 0, discard_s2 = 0;

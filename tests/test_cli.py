@@ -146,3 +146,36 @@ def test_usage_and_argument_errors(sickle, tmp_path):
     assert p.returncode == 1 and b"you must have the -r, -o, -p, and -s options" in p.stderr
     p = subprocess.run([sickle, "--version"], capture_output=True)
     assert p.returncode == 0 and b"sickle version 1.33" in p.stdout
+
+
+def test_batch_mode_runs_commands_in_one_process(sickle, golden, tmp_path):
+    """`sickle batch`: one command per stdin line, context reused; outputs equal those of separate
+    processes, a data error in one command is reported and does not disturb the next ones."""
+    g = golden["dir"]
+    se, inter, bad = (os.path.join(g, n) for n in ("se_r150.fastq", "pe_r150_inter.fastq", "err_len_mismatch.fastq"))
+    f, r = os.path.join(g, "pe_r150_f.fastq"), os.path.join(g, "pe_r150_r.fastq")
+    spaced = tmp_path / "with space"
+    spaced.mkdir()
+    o = {k: str(tmp_path / k) for k in ("a", "b", "bs", "c", "d", "e1", "e2", "es")}
+    o["sp"] = str(spaced / "out file.fq")
+    lines = ["se -f %s -t sanger -o %s" % (se, o["a"]),
+             "pe -c %s -t sanger -m %s -s %s" % (inter, o["b"], o["bs"]),
+             "se -f %s -t sanger -o %s" % (bad, o["c"]),
+             "se -f %s -t sanger -o %s -q 30" % (se, o["d"]),
+             "pe -f %s -r %s -t sanger -o %s -p %s -s %s" % (f, r, o["e1"], o["e2"], o["es"]),
+             'se -f %s -t sanger -o "%s"' % (se, o["sp"])]
+    p = subprocess.run([sickle, "batch"], input="\n".join(lines) + "\n", capture_output=True, text=True, timeout=300)
+    rcs = [int(l.split()[1]) for l in p.stdout.splitlines() if l.startswith("##rc ")]
+    assert rcs == [0, 0, 1, 0, 0, 0], (rcs, p.stderr[-500:])
+    assert p.returncode == 1 and "different lengths" in p.stderr
+    singles = {"a": ["se", "-f", se, "-t", "sanger", "-o"], "d": ["se", "-f", se, "-t", "sanger", "-q", "30", "-o"]}
+    for k, cmd in singles.items():
+        ref = str(tmp_path / ("ref_" + k))
+        subprocess.run([sickle] + cmd + [ref], check=True, capture_output=True)
+        assert md5(o[k]) == md5(ref), k
+    assert md5(o["sp"]) == md5(o["a"])
+    ref = [str(tmp_path / n) for n in ("rb", "rbs", "r1", "r2", "rs")]
+    subprocess.run([sickle, "pe", "-c", inter, "-t", "sanger", "-m", ref[0], "-s", ref[1]], check=True, capture_output=True)
+    subprocess.run([sickle, "pe", "-f", f, "-r", r, "-t", "sanger", "-o", ref[2], "-p", ref[3], "-s", ref[4]], check=True,
+                   capture_output=True)
+    assert [md5(o[k]) for k in ("b", "bs", "e1", "e2", "es")] == [md5(x) for x in ref]
