@@ -191,8 +191,8 @@ int alloc_slot(sk_ctx *c, Slot &s, bool host_buffers) {
         }
         SK_CUDA(cudaMalloc((void **)&s.d_line_end[i], (size_t)c->line_cap * sizeof(uint32_t) + 64));
         SK_CUDA(cudaMalloc((void **)&s.d_desc[i], ((size_t)c->line_cap / 4 + 1) * sizeof(sk::RecDesc)));
-        SK_CUDA(cudaMalloc((void **)&s.d_status_k1[i], (size_t)c->k1_tiles_cap * 8));
-        SK_CUDA(cudaMemset(s.d_status_k1[i], 0, (size_t)c->k1_tiles_cap * 8));
+        SK_CUDA(cudaMalloc((void **)&s.d_status_k1[i], (size_t)c->k1_tiles_cap * 8 * sk::kWideStatusStride));
+        SK_CUDA(cudaMemset(s.d_status_k1[i], 0, (size_t)c->k1_tiles_cap * 8 * sk::kWideStatusStride));
     }
     SK_CUDA(cudaMalloc((void **)&s.d_status_k2, (size_t)c->k2_tiles_cap * 8 * sk::kMaxStreams));
     SK_CUDA(cudaMemset(s.d_status_k2, 0, (size_t)c->k2_tiles_cap * 8 * sk::kMaxStreams));
@@ -238,7 +238,7 @@ void make_inputs(const sk_ctx *c, const Slot &s, const BatchArgs &a, sk::DevInpu
 int next_epoch(sk_ctx *c, Slot &s, cudaStream_t st) {
     s.epoch += 1;
     if ((s.epoch & (uint32_t)sk::kEpochMask) == 0) {  // epoch tag wrapped: clear the status words once
-        for (int i = 0; i < c->n_inputs; ++i) SK_CUDA(cudaMemsetAsync(s.d_status_k1[i], 0, (size_t)c->k1_tiles_cap * 8, st));
+        for (int i = 0; i < c->n_inputs; ++i) SK_CUDA(cudaMemsetAsync(s.d_status_k1[i], 0, (size_t)c->k1_tiles_cap * 8 * sk::kWideStatusStride, st));
         SK_CUDA(cudaMemsetAsync(s.d_status_k2, 0, (size_t)c->k2_tiles_cap * 8 * sk::kMaxStreams, st));
         if (s.d_status_f) SK_CUDA(cudaMemsetAsync(s.d_status_f, 0, (size_t)c->fused_tiles_cap * 8 * 3 * sk::kWideStatusStride, st));
         s.epoch += 1;

@@ -10,7 +10,7 @@
 // contiguous bytes per instruction), staged through XOR-swizzled shared memory so that each thread
 // then owns 64 *contiguous* bytes (bank-conflict free both ways).  Newlines are found with a SWAR
 // zero-byte test, counted with popc, ranked with a warp-shuffle + cross-warp prefix scan, and the tile
-// prefix comes from a decoupled look-back over 8-byte status words.  Bytes are read once.
+// prefix comes from a decoupled look-back over (padded) 8-byte status words.  Bytes are read once.
 #pragma once
 
 #include "sk_device.cuh"
@@ -66,7 +66,7 @@ k1_line_index(DevInput in, Control *__restrict__ ctl, int which, unsigned long l
     __shared__ uint4 stage[kK1TileBytes / 16];
     __shared__ uint32_t warp_tot[kK1Threads / 32];
     __shared__ uint32_t s_tile;
-    __shared__ unsigned long long s_prefix;
+    __shared__ unsigned long long s_lb[kK1Threads / 32][2];   // look-back scratch
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint4 *__restrict__ src = reinterpret_cast<const uint4 *>(in.data);
@@ -117,15 +117,15 @@ k1_line_index(DevInput in, Control *__restrict__ ctl, int which, unsigned long l
             if (w < wid) wbase += t;
             total += t;
         }
-        if (wid == 0) {
-            const unsigned long long p = lookback_exclusive(tile_status, tile, total, epoch, lane);
-            if (lane == 0) {
-                s_prefix = p;
-                if (tile == num_tiles - 1) ctl->nlines[which] = (uint32_t)(p + total);
-            }
-        }
-        __syncthreads();
-        uint32_t rank = (uint32_t)s_prefix + wbase + incl - cnt;
+        // wide look-back (one predecessor per thread, 128-byte padded status words): with ~16 K tiles
+        // per batch and a thousand CTAs in flight the 32-wide, unpadded walk was most of this kernel
+        unsigned long long *const st[2] = {tile_status, nullptr};
+        const unsigned long long agg[2] = {total, 0};
+        unsigned long long ex[2];
+        block_publish(st, tile, agg, 1, epoch, tid);
+        block_walk(st, tile, agg, 1, epoch, tid, s_lb, ex);
+        if (tid == 0 && tile == num_tiles - 1) ctl->nlines[which] = (uint32_t)(ex[0] + total);
+        uint32_t rank = (uint32_t)ex[0] + wbase + incl - cnt;
         while (mask) {
             const int b = __ffsll((long long)mask) - 1;
             mask &= mask - 1;
