@@ -73,6 +73,11 @@ def measure(name, mode, inputs, n_records, env=None, emulate_threads=1, steps=10
 def main():
     dev = torch.device("cuda:0")
     target = 300_000_000
+    if len(sys.argv) > 1 and sys.argv[1] == "--general-only":   # short run for profiling K1/K2/K3 under ncu
+        m = synth.fixed_length_records(200_000, 150, "sanger", seed=190)
+        buf, n, recs = device_bytes(m, target, dev)
+        measure("se R150, general path (K1/K2/K3)", capi.MODE_SE, [(buf, n)], recs, env={"SICKLE_B200_PATH": "general"}, steps=3)
+        return
     for L in (50, 75, 100, 150, 250):
         m = synth.fixed_length_records(200_000, L, "sanger", seed=40 + L)
         buf, n, recs = device_bytes(m, target, dev)
