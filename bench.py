@@ -45,6 +45,24 @@ def hbm_peak():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
+def ncu_traffic():
+    """DRAM bytes (read + write) of one kf_fused launch over the same 1 M-read batch, from the committed
+    `ncu --set full` capture (profiles/r1_fused_v6_ncu_full_summary.csv); None if the file is missing."""
+    import csv
+
+    p = os.path.join(ROOT, "profiles", "r1_fused_v6_ncu_full_summary.csv")
+    try:
+        rows = list(csv.reader(open(p)))
+        h, units, r = rows[0], rows[1], rows[2]
+        tot = 0.0
+        for k in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = h.index(k)
+            tot += float(r[i]) * {"Mbyte": 1e6, "Gbyte": 1e9, "Kbyte": 1e3, "byte": 1.0}[units[i]]
+        return tot
+    except Exception:  # noqa: BLE001
+        return None
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons during the timed region."""
 
@@ -278,7 +296,7 @@ def run_cuda_arm(args):
                    "reads_per_gpu_timed": B * args.steps, "kept_fraction": kept / (nb * B)},
         "fastq_gb_s": value * RECORD_BYTES / 1e9,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src,
+                     "traffic": ncu_traffic() if fused == nb else None, "peak_source": peak_src,
                      "kernel": ("kf_fused (parse+trim+route+emit, single pass) + summary, per step" if fused == nb else
                                 "K1 line index + K2 trim/route + K3 emit + summary, per step"),
                      "algorithmic_bytes_per_step": alg_bytes,
