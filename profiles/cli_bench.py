@@ -47,6 +47,7 @@ def main():
     ap.add_argument("--input-format", default="plain", choices=["plain", "bgzf", "gzip"])
     ap.add_argument("--gzip-out", action="store_true", help="-g (b200 only: the reference's -g is broken)")
     ap.add_argument("--paired", action="store_true", help="interleaved pairs (pe -c) instead of se")
+    ap.add_argument("--threads", type=int, default=0, help="pass -a N to bin/sickle too (reference output order)")
     ap.add_argument("--two-files", action="store_true", help="pe -f -r -o -p -s (forward / reverse files)")
     a = ap.parse_args()
     src = os.path.join(a.dir, "cli_bench_in.fastq")
@@ -101,6 +102,8 @@ def main():
             cmd = [exe, "se", "-f", src, "-t", "sanger", "-o", out] + extra
         if a.gzip_out and name == "b200":
             cmd.append("-g")
+        if a.threads and name == "b200":
+            cmd += ["-a", str(a.threads)]
         best = None
         for _ in range(a.repeat if name == "b200" else 1):
             for p_ in (out, sng):
