@@ -269,6 +269,85 @@ def test_lines_that_look_like_other_lines(capi):
             assert got["fused_batches"] < got["batches"], name
 
 
+def _mutate(rng, data):
+    """One random edit of the kind real files suffer: a dropped / doubled / blank line, a flipped,
+    deleted or inserted byte, a cut-off tail, CRLF line ends."""
+    b = bytearray(data)
+    if not b:
+        return bytes(b)
+    kind = int(rng.integers(0, 9))
+    lines = bytes(b).split(b"\n")
+    if kind == 0:
+        return bytes(b[:-1])                                   # no final newline
+    if kind == 1 and len(lines) > 2:
+        k = int(rng.integers(0, len(lines) - 1))
+        return b"\n".join(lines[:k] + lines[k + 1:])           # a line is missing
+    if kind == 2:
+        k = int(rng.integers(0, len(lines)))
+        return b"\n".join(lines[:k] + [b""] + lines[k:])       # a blank line
+    if kind == 3:
+        k = int(rng.integers(0, len(lines) - 1))
+        return b"\n".join(lines[:k] + [lines[k]] + lines[k:])  # a doubled line
+    if kind == 4:
+        k = int(rng.integers(0, len(b)))
+        b[k] = int(rng.choice([10, 13, 0, 32, 64, 43, 127, 200, 255, int(rng.integers(33, 127))]))
+        return bytes(b)                                        # a flipped byte
+    if kind == 5:
+        k = int(rng.integers(0, len(b)))
+        del b[k]
+        return bytes(b)                                        # a deleted byte
+    if kind == 6:
+        k = int(rng.integers(0, len(b) + 1))
+        b[k:k] = bytes([int(rng.choice([10, 64, 43, 65, 73, 33]))])
+        return bytes(b)                                        # an inserted byte
+    if kind == 7:
+        return bytes(b[:int(rng.integers(0, len(b)))])         # cut off
+    return bytes(b).replace(b"\n", b"\r\n")                   # CRLF
+
+
+def test_fuzzed_inputs_vs_oracle(capi, kernel_path):
+    """Small random inputs, most of them damaged, single-end and interleaved: the same bytes and
+    counters as the oracle, or the same first data error (kind, record, position, byte)."""
+    from sickle_b200 import runner
+
+    rng = np.random.default_rng(20260101)
+    n_ok = n_err = 0
+    for case in range(600):
+        qualtype = ["sanger", "illumina", "solexa"][case % 3]
+        recs = _random_fastq(rng, int(rng.integers(1, 30)), int(rng.choice([3, 12, 40, 90])), qualtype)
+        data = b"".join(recs)
+        for _ in range(int(rng.integers(0, 3))):
+            data = _mutate(rng, data)
+        fl = dict(FLAGSETS[case % len(FLAGSETS)])
+        if case % 5 == 0:
+            fl["q"], fl["l"] = int(rng.integers(0, 45)), int(rng.integers(0, 30))
+        inter = case % 4 == 3
+        omode, cmode = (orc.MODE_PE_INTER, capi.MODE_PE_INTER) if inter else (orc.MODE_SE, capi.MODE_SE)
+        want = orc.run(omode, orc.make_params(qualtype, fl["q"], fl["l"], fl["x"], fl["n"]), data, batch_len=1 << 40)
+        flags = dict(qualtype=qualtype, **fl)
+        for slot in ((1 << 16,) if want["rc"] else (1 << 16, 2048)):
+            got = err = None
+            try:
+                got = _run_cuda(capi, cmode, flags, data, slot_bytes=slot)
+            except runner.DataError as e:
+                err = e
+            ctx_ = (case, qualtype, fl, inter, slot, data[:200])
+            if want["rc"] == 0:
+                assert err is None, ctx_
+                for s_ in (0, 2):
+                    assert got["out"][s_] == want["out"][s_], ctx_
+                for k in ("kept", "discard", "kept_p", "discard_p"):
+                    assert got["counters"][k] == want["counters"][k], ctx_
+                n_ok += 1
+            else:
+                assert err is not None and err.kind == want["rc"], (ctx_, None if err is None else err.kind, want["rc"])
+                assert err.record == want["err"]["record"], (ctx_, err.record, want["err"])
+                if want["rc"] == 6:
+                    assert (err.position, err.byte) == (want["err"]["position"], want["err"]["byte"]), ctx_
+                n_err += 1
+    assert n_ok > 250 and n_err > 150, (n_ok, n_err)
+
+
 def test_edge_inputs(capi):
     flags = dict(qualtype="sanger", q=20, l=20, x=False, n=False)
     # empty input, a single record, a record without final newline, trailing partial record, lone newlines
