@@ -1,0 +1,96 @@
+"""The oracle against the reference binary itself on damaged inputs (CPU only).
+
+tests/golden pins the oracle on fixed fixtures; here a few hundred seeded random files, most with one
+random defect (missing / blank / doubled line, flipped / deleted / inserted byte, cut-off tail, CRLF),
+go through `oracle/_ref/sickle_sync` (the reference's sources, built by oracle/Makefile where
+/root/reference exists; the binary travels with the repository) and through the oracle with the
+reference's own batch geometry.  Same exit status, same output bytes, same error message class.
+Skipped where the reference binary is absent.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_py as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = os.path.join(ROOT, "oracle", "_ref", "sickle_sync")
+ERRKIND = {"Sequence ID is to short.": 1, "Invalid char at the beggining of ID.": 2,
+           "Sequence line is empty": 3, "Quality line is empty.": 4,
+           "Sequence and quality lines have different lengths:": 5, "ERROR: Quality value": 6}
+FLAGSETS = [dict(q=20, l=20, x=False, n=False), dict(q=30, l=5, x=True, n=False), dict(q=10, l=0, x=False, n=True),
+            dict(q=25, l=1, x=True, n=True)]
+
+
+def _records(rng, n, lmax, qualtype):
+    off = {"sanger": 33, "illumina": 64, "solexa": 64}[qualtype]
+    lo, hi = {"sanger": (0, 60), "illumina": (0, 46), "solexa": (-6, 48)}[qualtype]
+    out = []
+    for i in range(n):
+        L = int(rng.integers(1, lmax + 1))
+        seq = np.frombuffer(b"ACGTNn", dtype=np.uint8)[rng.choice(6, L, p=[.245, .245, .245, .245, .015, .005])]
+        q = np.clip(np.sort(rng.integers(lo, hi + 1, L))[::-1] + rng.integers(-6, 7, L), lo, hi) if i % 2 else rng.integers(lo, hi + 1, L)
+        plus = b"+r%d" % i if i % 4 == 0 else b"+"
+        out.append(b"@r%d\n" % i + seq.tobytes() + b"\n" + plus + b"\n" + (q + off).astype(np.uint8).tobytes() + b"\n")
+    return b"".join(out)
+
+
+def _damage(rng, data):
+    b = bytearray(data)
+    lines = data.split(b"\n")
+    kind = int(rng.integers(0, 8))
+    k = int(rng.integers(0, len(lines) - 1))
+    if kind == 0:
+        return data[:-1]
+    if kind == 1:
+        return b"\n".join(lines[:k] + lines[k + 1:])
+    if kind == 2:
+        return b"\n".join(lines[:k] + [b""] + lines[k:])
+    if kind == 3:
+        return b"\n".join(lines[:k] + [lines[k]] + lines[k:])
+    p = int(rng.integers(0, len(b)))
+    if kind == 4:
+        b[p] = int(rng.choice([10, 13, 32, 64, 43, 127, 200, 255, int(rng.integers(33, 127))]))
+        return bytes(b)
+    if kind == 5:
+        del b[p]
+        return bytes(b)
+    if kind == 6:
+        b[p:p] = bytes([int(rng.choice([10, 64, 43, 65, 73, 33]))])
+        return bytes(b)
+    return data[:p]
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference binary not built (oracle/Makefile target `ref`)")
+def test_oracle_equals_reference_on_damaged_files(tmp_path):
+    rng = np.random.default_rng(777)
+    n_ok = n_err = 0
+    src, out = str(tmp_path / "in.fastq"), str(tmp_path / "out.fastq")
+    for case in range(600):
+        qualtype = ["sanger", "illumina", "solexa"][case % 3]
+        # >= 8 x the longest line, or the reference mis-cuts its batches
+        data = _records(rng, int(rng.integers(120, 400)), int(rng.choice([12, 40, 90])), qualtype)
+        if case % 4:
+            data = _damage(rng, data)
+        fl = FLAGSETS[case % len(FLAGSETS)]
+        open(src, "wb").write(data)
+        if os.path.exists(out):
+            os.unlink(out)
+        cmd = [REF, "se", "-f", src, "-t", qualtype, "-o", out, "-a", "1", "-q", str(fl["q"]), "-l", str(fl["l"])]
+        cmd += (["-x"] if fl["x"] else []) + (["-n"] if fl["n"] else [])
+        p = subprocess.run(cmd, capture_output=True, timeout=60)
+        want = orc.run(orc.MODE_SE, orc.make_params(qualtype, fl["q"], fl["l"], fl["x"], fl["n"]), data)
+        tag = (case, qualtype, fl, len(data))
+        if p.returncode < 0:
+            continue   # the reference itself crashed (it does on some inputs): nothing to compare
+        assert (p.returncode != 0) == (want["rc"] != 0), (tag, p.returncode, want["rc"], p.stderr[-200:])
+        if want["rc"] == 0:
+            assert open(out, "rb").read() == want["out"][0], tag
+            n_ok += 1
+        else:
+            kinds = [k for msg, k in ERRKIND.items() if msg.encode() in p.stderr]
+            assert kinds and kinds[0] == want["rc"], (tag, p.stderr[-300:], want["rc"])
+            n_err += 1
+    assert n_ok > 200 and n_err > 150, (n_ok, n_err)
