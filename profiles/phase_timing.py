@@ -25,15 +25,16 @@ st = torch.cuda.Stream()
 for it in range(3):
     ctx.trim_device(inp.data_ptr(), n, 0, 0, [out.data_ptr(), 0, 0], [n + 64, 0, 0], st.cuda_stream)
     r = ctx.result_device(st.cuda_stream)
-buf = (C.c_ulonglong * 8)()
+buf = (C.c_ulonglong * 12)()
 lib.sk_debug_phase_cycles(buf, 1)
 ctx.trim_device(inp.data_ptr(), n, 0, 0, [out.data_ptr(), 0, 0], [n + 64, 0, 0], st.cuda_stream)
 r = ctx.result_device(st.cuda_stream)
 lib.sk_debug_phase_cycles(buf, 0)
 names = ["(warp 0's own S5-S7 work, part of the S5-S7 line)", "ticket + S1 load", "S2 masks+scan", "S3 pos + S4 look-back#1",
-         "S5+S6 trim + S7 scan, to barrier", "(flush group: look-back#2)", "S7 publish + desc + S8a staging copy",
-         "(flush group: look-back#2 + flush, overlaps S5-S7)"]
-tot = buf[1] + buf[2] + buf[3] + buf[4] + buf[6]
+         "S5+S6 trim + S7 scan, to barrier", "(flush group: look-back#2)", "S8a staging copy (warp 0)",
+         "(flush group: look-back#2 + flush, overlaps S5-S7)", "S7b totals + publish + descriptors", "S8a: wait for the slowest warp",
+         "-", "-"]
+tot = buf[1] + buf[2] + buf[3] + buf[4] + buf[6] + buf[8] + buf[9]
 print("kernel %.3f ms, fused=%d; cycles summed over CTAs' thread 0:" % (r.kernel_ms, r.fused))
 for k, v in zip(names, buf):
     print("  %-28s %6.2f%%" % (k, 100.0 * v / tot))

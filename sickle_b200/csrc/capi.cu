@@ -655,14 +655,14 @@ int sk_result_device(sk_ctx *ctx, int slot, void *stream, sk_result *res) {
 
 #ifdef SK_PHASE_TIMING
 // debug build only: cycles per fused-kernel phase, summed over tiles (thread 0 of every CTA)
-int sk_debug_phase_cycles(unsigned long long out[8], int reset) {
+int sk_debug_phase_cycles(unsigned long long out[12], int reset) {
     SK_CUDA(cudaDeviceSynchronize());
-    SK_CUDA(cudaMemcpyFromSymbol(out, sk::g_phase_cycles, sizeof(unsigned long long) * 8));
+    SK_CUDA(cudaMemcpyFromSymbol(out, sk::g_phase_cycles, sizeof(unsigned long long) * 12));
     unsigned long long w[4];
     SK_CUDA(cudaMemcpyFromSymbol(w, sk::g_walk_dbg, sizeof w));
     fprintf(stderr, "[walk dbg] walks %llu steps %llu threads-that-spun %llu spin-iterations %llu\n", w[0], w[1], w[2], w[3]);
     if (reset) {
-        unsigned long long z[8] = {0};
+        unsigned long long z[12] = {0};
         SK_CUDA(cudaMemcpyToSymbol(sk::g_phase_cycles, z, sizeof z));
         SK_CUDA(cudaMemcpyToSymbol(sk::g_walk_dbg, z, sizeof(unsigned long long) * 4));
     }

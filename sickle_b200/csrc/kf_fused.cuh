@@ -44,7 +44,7 @@ namespace sk {
 
 // Debug only (-DSK_PHASE_TIMING): barrier-to-barrier cycles of thread 0, summed over tiles.
 #ifdef SK_PHASE_TIMING
-__device__ unsigned long long g_phase_cycles[8];
+__device__ unsigned long long g_phase_cycles[12];
 #define SK_TICK(k)                                                            \
     do {                                                                      \
         if (tid == 0) {                                                       \
@@ -103,6 +103,8 @@ __device__ __forceinline__ void smem_copy(uint8_t *__restrict__ out, uint32_t ds
         }
     }
     uint32_t k = pre;
+    // (unrolling this loop was measured: no gain -- the copy is bound by shared-memory bank conflicts
+    // of 32 lanes walking 32 unrelated records, ~3 wavefronts per access, not by the loop's latency)
     for (; k + 4 <= nw; k += 4) {
         const uint32_t a = w[k + 1], b = w[k + 2], c = w[k + 3], e = w[k + 4];
         uint4 v;
@@ -499,6 +501,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             s_desc[rec] = dsc;
         }
         __syncthreads();
+        SK_TICK(8);   // S7b: totals, publish, descriptors, barrier
 
         // ---- S8a: two lanes per record copy it into the staging buffer (phase 0; the flush realigns):
         // lane 0 takes [name '\n' seq), lane 1 takes ['\n' line3 '\n' qual '\n')
@@ -545,7 +548,9 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 else { s_out[a_dst + plen + 1u] = (uint8_t)P.qmin; s_out[a_dst + plen + 2u] = '\n'; }
             }
         }
-        SK_TICK(6);   // descriptors + S8a
+        SK_TICK(6);   // S8a (thread 0's own copies)
+        __syncthreads();
+        SK_TICK(9);   // S8a: waiting for the slowest warp (timing build only: an extra barrier)
 
         // ---- bookkeeping: consumed bytes, record count, counters
         if (!tile_fail) {
