@@ -549,8 +549,10 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             }
         }
         SK_TICK(6);   // S8a (thread 0's own copies)
-        __syncthreads();
-        SK_TICK(9);   // S8a: waiting for the slowest warp (timing build only: an extra barrier)
+#ifdef SK_PHASE_TIMING
+        __syncthreads();   // timing build only: how long the slowest warp takes beyond thread 0
+        SK_TICK(9);
+#endif
 
         // ---- bookkeeping: consumed bytes, record count, counters
         if (!tile_fail) {
