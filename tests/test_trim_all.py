@@ -75,3 +75,25 @@ def test_directory_run_matches_single_runs(tmp_path, golden):
     want = single.read_bytes()
     for k in range(3):
         assert (o / ("lane%d.trim.fastq" % k)).read_bytes() == want
+
+
+@pytest.mark.gpu
+def test_directory_run_paired(tmp_path, golden):
+    import shutil
+
+    i, o = tmp_path / "in", tmp_path / "out"
+    i.mkdir()
+    for k in ("a", "b"):
+        shutil.copy(os.path.join(golden["dir"], "pe_r150_f.fastq"), i / ("%s_1.fastq" % k))
+        shutil.copy(os.path.join(golden["dir"], "pe_r150_r.fastq"), i / ("%s_2.fastq" % k))
+    assert subprocess.call([sys.executable, os.path.join(ROOT, "trim_all.py"), "pe", "sanger", str(i), str(o), "--procs-per-gpu", "2"]) == 0
+    case = [c for c in golden["cases"] if c["id"] == "pe2.pe_r150.sanger.default"]
+    import hashlib
+
+    for k in ("a", "b"):
+        got = [hashlib.md5((o / ("%s_%s.trim.fastq" % (k, x))).read_bytes()).hexdigest() for x in ("1", "2", "s")]
+        if case:
+            assert got == [case[0]["outputs"][f]["md5"] for f in ("-o", "-p", "-s")]
+    # a second run finds every output in place and does nothing
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "trim_all.py"), "pe", "sanger", str(i), str(o)], capture_output=True, text=True)
+    assert p.returncode == 0 and p.stdout.count("already exists") == 2 and "> " not in p.stdout
