@@ -114,17 +114,25 @@ k3_emit(DevInput in0, DevInput in1, DevParams P, const Control *__restrict__ ctl
         d.route = 0; d.dst_off = 0; d.five = 0; d.nkeep = 0;
         if (rec < nrec) d = (second ? desc1 : desc0)[rec];
         const bool emit = (d.route & kRouteEmit) != 0;
-        const bool slow = emit && (d.five != 0 || (d.route & kRouteNRec));
-        uint32_t a_src = 0, a_len = 0, b_src = 0, b_len = 0;
+        const bool slow = emit && (d.route & kRouteNRec);              // -M "N records": four-piece path
+        // Runs of a kept record, in output order: name '\n' | seq[five:three] | '\n' line3 '\n' | qual[five:three]
+        // | '\n'.  With nothing cut at the 5' end (most reads) the bases follow the name line in the input
+        // and the qualities follow line 3, so runs 1+2 and 3+4 are one run each.
+        uint32_t s1 = 0, l1 = 0, s2 = 0, l2 = 0, s3 = 0, l3 = 0, s4 = 0, l4 = 0;
         if (emit && !slow) {
             const RecLines r = record_lines(in, rec);
-            a_src = r.start[0]; a_len = r.len[0] + 1u + d.nkeep;          // name '\n' seq[0:three]
-            b_src = r.start[2] - 1u; b_len = r.len[2] + 2u + d.nkeep;    // '\n' line3 '\n' qual[0:three]
+            const bool cut5 = d.five != 0;
+            s1 = r.start[0]; l1 = r.len[0] + 1u + (cut5 ? 0u : d.nkeep);
+            s2 = r.start[1] + d.five; l2 = cut5 ? d.nkeep : 0u;
+            s3 = r.start[2] - 1u; l3 = r.len[2] + 2u + (cut5 ? 0u : d.nkeep);
+            s4 = r.start[3] + d.five; l4 = cut5 ? d.nkeep : 0u;
         }
-        // the four quarters of the warp copy four records at a time
+        // the four quarters of the warp copy four records at a time (a quarter without a record runs
+        // the same code with empty runs: the shuffles and votes below are warp-wide)
         const int quarter = lane >> 3, gl = lane & 7;
         for (uint32_t todo = __ballot_sync(0xffffffffu, emit && !slow); todo;) {
-            int k = -1, k0 = __ffs(todo) - 1;
+            int k = -1;
+            const int k0 = __ffs(todo) - 1;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 if (todo) {
@@ -132,17 +140,23 @@ k3_emit(DevInput in0, DevInput in1, DevParams P, const Control *__restrict__ ctl
                     todo &= todo - 1;
                 }
             }
-            const int from = k < 0 ? k0 : k;                      // (-1: fewer than four records left, this quarter idles)
+            const int from = k < 0 ? k0 : k;
+            const bool have = k >= 0;
             const uint32_t route = __shfl_sync(0xffffffffu, d.route, from);
             const uint32_t off = __shfl_sync(0xffffffffu, d.dst_off, from);
-            const uint32_t sa = __shfl_sync(0xffffffffu, a_src, from);
-            const uint32_t sb = __shfl_sync(0xffffffffu, b_src, from);
-            const uint32_t la = __shfl_sync(0xffffffffu, a_len, from), lb = __shfl_sync(0xffffffffu, b_len, from);
-            if (k < 0) continue;
+            const uint32_t a1 = __shfl_sync(0xffffffffu, s1, from), a3 = __shfl_sync(0xffffffffu, s3, from);
+            uint32_t n1 = __shfl_sync(0xffffffffu, l1, from), n3 = __shfl_sync(0xffffffffu, l3, from);
+            uint32_t n2 = __shfl_sync(0xffffffffu, l2, from), n4 = __shfl_sync(0xffffffffu, l4, from);
+            if (!have) { n1 = 0; n2 = 0; n3 = 0; n4 = 0; }
             uint8_t *dst = outs.p[route & 3u] + off;
-            quarter_copy16(dst, in.data + sa, la, gl);
-            quarter_copy16(dst + la, in.data + sb, lb, gl);
-            if (gl == 0) dst[la + lb] = '\n';
+            quarter_copy16(dst, in.data + a1, n1, gl);
+            if (__any_sync(0xffffffffu, (n2 | n4) != 0)) {            // some read of the four is cut at its 5' end
+                const uint32_t a2 = __shfl_sync(0xffffffffu, s2, from), a4 = __shfl_sync(0xffffffffu, s4, from);
+                quarter_copy16(dst + n1, in.data + a2, n2, gl);
+                quarter_copy16(dst + n1 + n2 + n3, in.data + a4, n4, gl);
+            }
+            quarter_copy16(dst + n1 + n2, in.data + a3, n3, gl);
+            if (have && gl == 0) dst[n1 + n2 + n3 + n4] = '\n';
         }
         for (uint32_t todo = __ballot_sync(0xffffffffu, slow); todo; todo &= todo - 1) {
             const int k = __ffs(todo) - 1;
