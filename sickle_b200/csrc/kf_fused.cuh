@@ -237,6 +237,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
     __shared__ uint32_t warp_tot2[kFThreads / 32][2];
     __shared__ unsigned long long s_lb[kFThreads / 32][2];   // look-back scratch
     __shared__ uint32_t s_fail;
+    __shared__ __align__(8) unsigned long long s_mbar;   // completion of the S1 bulk copy
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const uint4 *__restrict__ src = reinterpret_cast<const uint4 *>(in.data);
@@ -251,6 +252,13 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
     rc.init(P);
     SwarConsts swar;
     swar.init();
+
+    uint32_t mbar_phase = 0;
+    if (threadIdx.x == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_mbar)) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
 
     // the tile whose output is staged in s_out and not flushed yet
     bool have_prev = false;
@@ -274,19 +282,32 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         const uint32_t b0 = tid * Cfg::kBytesPerThread;          // region-relative
         bool nl_overflow = false;
         if (!done) {
-            // ---- S1: region -> shared memory
-#pragma unroll
-            for (int k = 0; k < CH; ++k) {
-                const uint32_t c = k * kFThreads + tid;
-                uint4 v = make_uint4(0, 0, 0, 0);
-                const uint32_t g = (t0 >> 4) + c;
-                if (g < nchunks) v = __ldcs(src + g);
-                reinterpret_cast<uint4 *>(s_in)[c] = v;
+            // ---- S1: region -> shared memory, one bulk copy (TMA) issued by thread 0 and signalled on an
+            // mbarrier; the threads only zero what lies beyond the end of the batch (last tiles)
+            const uint32_t have = nchunks - (t0 >> 4);                              // 16-byte chunks from t0 on (>= 1)
+            const uint32_t cp_chunks = have < (uint32_t)(Cfg::kRegion / 16) ? have : (uint32_t)(Cfg::kRegion / 16);
+            if (tid == 0) {
+                const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+                const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_in);
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // S8a's reads of s_in come first
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(cp_chunks * 16u) : "memory");
+                asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                             ::"r"(dst), "l"(in.data + t0), "r"(cp_chunks * 16u), "r"(mb) : "memory");
             }
+            for (uint32_t c = cp_chunks + tid; c < (uint32_t)(Cfg::kRegion / 16); c += kFThreads)
+                reinterpret_cast<uint4 *>(s_in)[c] = make_uint4(0, 0, 0, 0);
             {   // L2 prefetch, one 128-byte line per thread, of the tile one grid-width ahead: in steady
                 // state some CTA (this one, most likely) draws that ticket one tile time from now
                 const unsigned long long nb = ((unsigned long long)tile + gridDim.x) * Cfg::kTile + (unsigned long long)tid * 128u;
                 if (tid < Cfg::kTile / 128 && nb < in.nbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(in.data + nb));
+            }
+            {   // wait for the bulk copy (hardware sleep, not a spin), then for the zero fill
+                const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+                uint32_t ok = 0;
+                while (!ok)
+                    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                                 : "=r"(ok) : "r"(mb), "r"(mbar_phase) : "memory");
+                mbar_phase ^= 1u;
             }
             __syncthreads();
             SK_TICK(1);   // S1 load
