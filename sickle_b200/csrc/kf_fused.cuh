@@ -253,6 +253,8 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
     SwarConsts swar;
     swar.init();
 
+    uint32_t held = 0;   // thread 0: the next ticket (drawn while the previous tile is being staged)
+    if (threadIdx.x == 0) held = atomicAdd(&ctl->tile_counter[3], 1u);
     uint32_t mbar_phase = 0;
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_mbar)) : "memory");
@@ -268,10 +270,11 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
     long long t_prev = clock64();
 #endif
     while (true) {
-        // (Drawing the ticket ahead of time to hide the atomic's round trip was measured.  A whole tile
-        // ahead: 0.38 -> 0.56 ms -- a ticket held by a CTA that is still busy stalls every look-back
-        // behind it.  During S8a of the previous tile: no change.  So: drawn when the tile starts.)
-        if (tid == 0) { s_tile = atomicAdd(&ctl->tile_counter[3], 1u); s_fail = 0; }
+        // The ticket was drawn while the previous tile was being staged (S8a), so the bulk copy below goes
+        // out without waiting for the atomic's round trip (-2 %).  Not earlier than that: a ticket held a
+        // whole tile ahead was measured at 0.38 -> 0.56 ms, because a ticket in the hands of a CTA that
+        // is still busy stalls every look-back behind it.
+        if (tid == 0) { s_tile = held; s_fail = 0; }
         __syncthreads();
         const uint32_t tile = s_tile;
         const bool done = tile >= num_tiles;
@@ -504,6 +507,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             const unsigned long long agg[2] = {tot0, tot1};
             block_publish(st_out, tile, agg, nstreams, epoch, tid);
         }
+        if (tid == 0) held = atomicAdd(&ctl->tile_counter[3], 1u);   // looked at after S8a
         have_prev = true;
         p_tile = tile; p_tot0 = tot0; p_tot1 = tot1;
         const uint32_t base1 = (tot0 + 15u) & ~15u;                    // singles staged after the main bytes
