@@ -47,10 +47,10 @@ def hbm_peak():
 
 def ncu_traffic():
     """DRAM bytes (read + write) of one kf_fused launch over the same 1 M-read batch, from the committed
-    `ncu --set full` capture (profiles/r1_fused_v6_ncu_full_summary.csv); None if the file is missing."""
+    `ncu --set full` capture (profiles/r1_fused_v7_ncu_full_summary.csv); None if the file is missing."""
     import csv
 
-    p = os.path.join(ROOT, "profiles", "r1_fused_v6_ncu_full_summary.csv")
+    p = os.path.join(ROOT, "profiles", "r1_fused_v7_ncu_full_summary.csv")
     try:
         rows = list(csv.reader(open(p)))
         h, units, r = rows[0], rows[1], rows[2]

@@ -11,9 +11,9 @@
 // for SK_MODE_SE, SK_MODE_PE_INTER and SK_MODE_PE_INTER_M in input order (emulate_threads == 1).
 //
 // Tile structure (256 threads, persistent CTAs, tiles handed out by an atomic ticket):
-//   S1  region = tile (224 threads x CH x 16 B) + halo (32 threads x CH x 16 B) -> shared memory,
-//       coalesced 16-byte loads.  The halo lets a record that starts in the tile finish.  The tile one
-//       grid-width ahead is prefetched into L2.
+//   S1  region = tile (224 threads x CH x 16 B) + halo (32 threads x CH x 16 B) -> shared memory by
+//       one TMA bulk copy (cp.async.bulk + mbarrier).  The halo lets a record that starts in the tile
+//       finish.  The tile one grid-width ahead is prefetched into L2.
 //   S2  each thread scans its CH*16 contiguous bytes (odd CH => conflict-free LDS.128): SWAR newline
 //       test (3 ALU ops / word) -> bit masks -> popc.
 //   S3  block scan -> rank of every newline; positions to shared memory (u16).
