@@ -1,7 +1,7 @@
 """Kernel-path throughput of the other rows of the hot path (device-resident input, library events):
 read lengths 50-250, interleaved and two-file paired end, the general (K1/K2/K3) path and `-a N`
 order emulation.  bench.py measures the headline configuration only; this is the table behind
-DESIGN.md section 6.   python profiles/workloads.py > profiles/r1_workloads_v6.jsonl
+DESIGN.md section 6.   python profiles/workloads.py > profiles/r1_workloads_v7.jsonl
 """
 import json
 import os
