@@ -217,11 +217,6 @@ bool wait_outputs(Tickets &k, ByteSink *outs[3], Totals &tot) {
     tot.t_write_wait += host::now_s() - t0;
     return ok;
 }
-bool write_outputs(const sk_result &r, ByteSink *outs[3], Totals &tot) {
-    Tickets k = queue_outputs(r, outs);
-    return wait_outputs(k, outs, tot);
-}
-
 void add_totals(Totals &t, const sk_result &r) {
     t.kept += r.kept; t.discard += r.discard;
     t.kept_p += r.kept_p; t.discard_p += r.discard_p;
@@ -271,7 +266,8 @@ int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, Byt
 
     // ---------------------------------------------------------------------------------------
     // (A) reference output order requested (-a N, N > 1): batches follow the reference's batch
-    //     geometry (src/GZReader.cpp:59-132); one slot, synchronous.
+    //     geometry (src/GZReader.cpp:59-132); one slot.  The output of batch k is written by the
+    //     sinks' threads while the host cuts batch k+1 (the cutting is per-line host work).
     // ---------------------------------------------------------------------------------------
     if (p.emulate_threads > 1) {
         const long long bl = host::recommended_batch_len(in0->file_size(), batch_mib, paired);
@@ -284,6 +280,7 @@ int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, Byt
         host::RefBatcher b1(in1 ? in1 : in0, bl, 4);
         char *h0 = sk_in_buffer(ctx.c, 0, 0), *h1 = two ? sk_in_buffer(ctx.c, 0, 1) : nullptr;
         long long base[2] = {0, 0};
+        Tickets pending;   // writes of the previous batch, out of the slot's pinned result buffers
         while (true) {
             const long long n0 = b0.next(h0, slot);
             if (n0 < 0) { fprintf(stderr, "****Error: a reference batch does not fit in a %llu-byte slot.\n\n", slot); return EXIT_FAILURE; }
@@ -293,14 +290,16 @@ int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, Byt
                 n1 = b1.next(h1, slot);
                 if (n1 <= 0) break;
             }
+            if (!wait_outputs(pending, outs, tot)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
             if (sk_submit(ctx.c, 0, 0, (uint64_t)n0, 0, (uint64_t)n1) != SK_OK) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
             sk_result r;
             if (sk_wait(ctx.c, 0, &r) != SK_OK) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
             if (r.error.kind) { r.error.record += base[r.error.file]; return report_data_error(r, h0, h1); }
-            if (!write_outputs(r, outs, tot)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
+            pending = queue_outputs(r, outs);
             add_totals(tot, r);
             base[0] += (long long)r.records[0]; base[1] += (long long)r.records[1];
         }
+        if (!wait_outputs(pending, outs, tot)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
         return EXIT_SUCCESS;
     }
 
