@@ -3,11 +3,34 @@
 // Prints "bgzf=<0|1> gzip=<0|1> bytes=<n>" on success; exit 1 on any read/write error.
 #include <cstdio>
 #include <cstdlib>
+#include <string>
 #include <vector>
 
 #include "io.h"
+#include "ref_batcher.h"
+
+// io_tool refbatch <src> <batch_len> <minlines> <cap>: prints the size of every reference batch
+static int refbatch(int argc, char **argv) {
+    if (argc != 6) { fprintf(stderr, "usage: io_tool refbatch <src> <batch_len> <minlines> <cap>\n"); return 2; }
+    host::ByteSource in;
+    if (!in.open(argv[2])) { fprintf(stderr, "cannot open %s\n", argv[2]); return 1; }
+    host::RefBatcher b(&in, atoll(argv[3]), atoi(argv[4]));
+    std::vector<char> buf((size_t)strtoull(argv[5], nullptr, 10));
+    const double t0 = host::now_s();
+    unsigned long long total = 0;
+    while (true) {
+        const long long n = b.next(buf.data(), buf.size());
+        if (n < 0) { printf("-1\n"); return 1; }
+        if (n == 0) break;
+        printf("%lld\n", n);
+        total += (unsigned long long)n;
+    }
+    fprintf(stderr, "refbatch: %llu bytes in %.3f s\n", total, host::now_s() - t0);
+    return 0;
+}
 
 int main(int argc, char **argv) {
+    if (argc >= 2 && std::string(argv[1]) == "refbatch") return refbatch(argc, argv);
     if (argc != 5) { fprintf(stderr, "usage: io_tool <src> <dst> <chunk> <gzip 0|1>\n"); return 2; }
     const unsigned long long chunk = strtoull(argv[3], nullptr, 10);
     host::ByteSource in;

@@ -3,6 +3,8 @@
 // All per-read work happens on the GPU behind include/sickle_b200.h; there is no CPU trimming here.
 #include "trimmer.h"
 
+#include "ref_batcher.h"
+
 #include <fcntl.h>
 #include <getopt.h>
 #include <sys/stat.h>
@@ -30,81 +32,6 @@ static long long recommended_batch_len(unsigned long long file_size, long long b
     if (rec > mx) return (long long)mx;
     return (long long)rec;
 }
-
-// Cuts a byte stream into the batches GZReader::read_lines would form (reference
-// src/GZReader.cpp:59-132): lines are added until the sum of their lengths (without '\n') reaches
-// batch_len, a multiple of `minlines` lines is kept and the rest carried.  Only needed to reproduce
-// the reference's `-a N` output order, which is defined per reference batch.
-class RefBatcher {
-public:
-    RefBatcher(ByteSource *src, long long batch_len, int minlines) : src_(src), batch_len_(batch_len), minlines_(minlines) {}
-    // Fills dst (capacity cap) with the next batch; returns its size, 0 at the end, -1 if it does not fit.
-    long long next(char *dst, unsigned long long cap) {
-        if (eof_) return 0;
-        unsigned long long n = 0;
-        std::vector<unsigned long long> ends;   // end offset (after '\n') of every line in dst
-        long long remaining = batch_len_;
-        // carried lines first
-        if (!carry_.empty()) {
-            if (carry_.size() > cap) return -1;
-            memcpy(dst, carry_.data(), carry_.size());
-            unsigned long long p = 0;
-            while (p < carry_.size()) {
-                const char *nl = (const char *)memchr(carry_.data() + p, '\n', carry_.size() - p);
-                const unsigned long long e = nl ? (unsigned long long)(nl - carry_.data()) + 1 : carry_.size();
-                remaining -= (long long)(e - p - 1);
-                ends.push_back(e);
-                p = e;
-            }
-            n = carry_.size();
-            carry_.clear();
-        }
-        do {
-            const char *line;
-            unsigned long long len;
-            if (!next_line(&line, &len)) { eof_ = true; break; }
-            if (n + len > cap) return -1;
-            memcpy(dst + n, line, len);
-            if (dst[n + len - 1] != '\n') dst[n + len - 1] = '\n';   // unterminated last line: GZReader.cpp:81-88
-            n += len;
-            ends.push_back(n);
-            remaining -= (long long)(len - 1);
-        } while (remaining > 0);
-        const size_t extra = ends.size() % (size_t)minlines_;
-        const size_t keep = ends.size() - extra;
-        if (keep == 0) return 0;
-        const unsigned long long end = ends[keep - 1];
-        carry_.assign(dst + end, dst + n);
-        return (long long)end;
-    }
-
-private:
-    bool next_line(const char **line, unsigned long long *len) {
-        while (true) {
-            if (pos_ < buf_.size()) {
-                const char *p = buf_.data() + pos_;
-                const char *nl = (const char *)memchr(p, '\n', buf_.size() - pos_);
-                if (nl) { *line = p; *len = (unsigned long long)(nl - p) + 1; pos_ += *len; return true; }
-                if (src_done_) { *line = p; *len = buf_.size() - pos_; pos_ = buf_.size(); return *len > 0; }
-            } else if (src_done_) return false;
-            // refill, keeping the unfinished line
-            std::vector<char> nb(buf_.begin() + (long)pos_, buf_.end());
-            const size_t keep = nb.size();
-            nb.resize(keep + (8u << 20));
-            const long long r = src_->read(nb.data() + keep, 8u << 20);
-            nb.resize(keep + (size_t)std::max<long long>(r, 0));
-            if (r <= 0) src_done_ = true;
-            buf_.swap(nb);
-            pos_ = 0;
-        }
-    }
-    ByteSource *src_;
-    long long batch_len_;
-    int minlines_;
-    bool eof_ = false, src_done_ = false;
-    std::vector<char> buf_, carry_;
-    size_t pos_ = 0;
-};
 
 }  // namespace host
 

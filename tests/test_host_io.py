@@ -142,3 +142,36 @@ def test_empty_and_damaged_inputs(tool, tmp_path):
     bad.write_bytes(bytes(raw))
     assert _run(tool, str(bad), str(back), 1 << 20, False)[0] == 1
     assert _run(tool, str(tmp_path / "missing"), str(back), 4096, False)[0] == 1
+
+
+def test_reference_batch_cutter_matches_the_python_model(tool, tmp_path):
+    """host/ref_batcher.h (block-wise newline counting) cuts exactly the batches of
+    runner.reference_batches (the line-by-line model of GZReader::read_lines, itself checked against the
+    reference's -a N outputs by the golden tests)."""
+    import sys
+
+    sys.path.insert(0, ROOT)
+    from sickle_b200 import runner
+
+    rng = np.random.default_rng(12)
+    datas = [_fastq_like(300_000, seed=20), _fastq_like(300_001, seed=21)[:-7],        # cut mid-line, no final newline
+             b"".join(b"@r%d\n%s\n+\n%s\n" % (i, b"A" * 3, b"I" * 3) for i in range(5000)),   # tiny records
+             b"@only\nACGT\n+\nIIII\n", b"", b"\n\n\n\n\n", b"@x\n" + b"A" * 200_000 + b"\n+\n" + b"I" * 200_000 + b"\n"]
+    big = _fastq_like(2_000_000, seed=22) * 7              # > 8 MB: the multi-threaded pre-scan takes part
+    src = tmp_path / "big.fastq"
+    src.write_bytes(big)
+    for batch_len, minlines in ((9_000_000, 4), (3_100_000, 8), (20_000_000, 4)):
+        want = [b - a for a, b in runner.reference_batches(big, batch_len, minlines)]
+        p = subprocess.run([tool, "refbatch", str(src), str(batch_len), str(minlines), str(32_000_000)],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert p.returncode == 0 and [int(x) for x in p.stdout.split()] == want, (batch_len, minlines)
+    for di, data in enumerate(datas):
+        src = tmp_path / ("d%d.fastq" % di)
+        src.write_bytes(data)
+        for batch_len in (20, 777, 70_000, int(rng.integers(1000, 50_000)), 10_000_000):
+            for minlines in (4, 8):
+                want = [b - a for a, b in runner.reference_batches(data, batch_len, minlines)]
+                p = subprocess.run([tool, "refbatch", str(src), str(batch_len), str(minlines), str(2_000_000)],
+                                   stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+                got = [int(x) for x in p.stdout.split()]
+                assert p.returncode == 0 and got == want, (di, batch_len, minlines, got[:5], want[:5], len(got), len(want))
