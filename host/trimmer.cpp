@@ -201,8 +201,10 @@ int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, Byt
         unsigned long long slot = (unsigned long long)bl + (unsigned long long)bl / 16 + (4ull << 20);
         slot = std::min<unsigned long long>(slot, (1ull << 31) - 8192);
         Ctx ctx;
+        ctx.tot = &tot;
         ctx.c = sk_create(device, slot, 1, &p);
         if (!ctx.c) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
+        tot.t_init = host::now_s() - t_begin;
         host::RefBatcher b0(in0, bl, (mode == SK_MODE_PE_INTER || mode == SK_MODE_PE_INTER_M) ? 8 : 4);
         host::RefBatcher b1(in1 ? in1 : in0, bl, 4);
         char *h0 = sk_in_buffer(ctx.c, 0, 0), *h1 = two ? sk_in_buffer(ctx.c, 0, 1) : nullptr;
@@ -220,7 +222,10 @@ int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, Byt
             if (!wait_outputs(pending, outs, tot)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
             if (sk_submit(ctx.c, 0, 0, (uint64_t)n0, 0, (uint64_t)n1) != SK_OK) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
             sk_result r;
-            if (sk_wait(ctx.c, 0, &r) != SK_OK) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
+            const double t_w = host::now_s();
+            const int wrc = sk_wait(ctx.c, 0, &r);
+            tot.t_wait += host::now_s() - t_w;
+            if (wrc != SK_OK) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
             if (r.error.kind) { r.error.record += base[r.error.file]; return report_data_error(r, h0, h1); }
             pending = queue_outputs(r, outs);
             add_totals(tot, r);
