@@ -103,7 +103,16 @@ REF_PE = os.path.join(ROOT, "oracle", "_ref", "sickle")
 def test_oracle_equals_reference_on_damaged_interleaved_files(tmp_path):
     """Same for `sickle pe -c -m -s` (unpatched reference binary).  Its output threads occasionally
     write the batches of a multi-batch run in another order ("differed in batch order
-    only"), so a byte mismatch is retried; the oracle must equal one of three runs."""
+    only"), so a byte mismatch is retried, and after three tries the comparison falls back to the
+    multiset of pairs / single records (order is what tests/golden pins)."""
+
+    def units(b, lines_per_unit):
+        ls = b.split(b"\n")
+        assert ls[-1] == b""
+        ls = ls[:-1]
+        assert len(ls) % lines_per_unit == 0
+        return sorted(b"\n".join(ls[i:i + lines_per_unit]) for i in range(0, len(ls), lines_per_unit))
+
     rng = np.random.default_rng(4242)
     n_ok = n_err = 0
     src, out, sng = (str(tmp_path / n) for n in ("in.fastq", "m.fastq", "s.fastq"))
@@ -119,27 +128,39 @@ def test_oracle_equals_reference_on_damaged_interleaved_files(tmp_path):
         want = orc.run(orc.MODE_PE_INTER, orc.make_params(qualtype, fl["q"], fl["l"], fl["x"], fl["n"]), data)
         tag = (case, qualtype, fl, len(data))
         matched = crashed = False
-        for _ in range(3):
+        why = None
+        for _ in range(3):          # the unpatched reference races now and then: any agreeing run counts
             for f_ in (out, sng):
                 if os.path.exists(f_):
                     os.unlink(f_)
             p = subprocess.run(cmd, capture_output=True, timeout=60)
             if p.returncode < 0:
                 crashed = True
-                break
-            assert (p.returncode != 0) == (want["rc"] != 0), (tag, p.returncode, want["rc"], p.stderr[-200:])
+                continue
+            if (p.returncode != 0) != (want["rc"] != 0):
+                why = ("rc", p.returncode, want["rc"], p.stderr[-200:])
+                continue
             if want["rc"]:
                 kinds = [k for msg, k in ERRKIND.items() if msg.encode() in p.stderr]
-                assert kinds and kinds[0] == want["rc"], (tag, p.stderr[-300:], want["rc"])
-                matched = True
-                break
+                if kinds and kinds[0] == want["rc"]:
+                    matched = True
+                    break
+                why = ("kind", p.stderr[-300:], want["rc"])
+                continue
             got = [open(f_, "rb").read() if os.path.exists(f_) else b"" for f_ in (out, sng)]
             if got == [want["out"][0], want["out"][2]]:
                 matched = True
                 break
-        if crashed:
-            continue
-        assert matched, tag
+            try:
+                if units(got[0], 8) == units(want["out"][0], 8) and units(got[1], 4) == units(want["out"][2], 4):
+                    matched = True      # same pairs and singles, batches written in another order
+                    break
+            except AssertionError:
+                pass
+            why = ("bytes", len(got[0]), len(want["out"][0]), len(got[1]), len(want["out"][2]))
+        if not matched and crashed and why is None:
+            continue                # the reference only ever crashed on this input
+        assert matched, (tag, why)
         n_ok += want["rc"] == 0
         n_err += want["rc"] != 0
     assert n_ok > 50 and n_err > 50, (n_ok, n_err)
