@@ -9,11 +9,14 @@
 // that is exactly  total >= qthr*ws  (IEEE division is correctly rounded and monotone; SURVEY.md
 // section 8-a2), and (int)(0.1*L) == L/10 for every L < 5e6.
 //
-// This is the general ("any read length") formulation: one warp walks one read, 32 window
-// positions per step, window totals from a warp-shuffle prefix scan of q[i+ws]-q[i].  A warp
-// handles 32 consecutive units (reads, or pairs) so that lane k ends up holding unit k's result;
-// routing, the 3-stream output-length scan (warp scan + decoupled look-back) and the per-record
-// descriptors are then lane-parallel.
+// This is the general ("any read length") path.  A warp handles 32 consecutive units (reads, or
+// pairs) and lane k ends up holding unit k's result; routing, the 3-stream output-length scan (warp
+// scan + decoupled look-back) and the per-record descriptors are then lane-parallel.  Reads of up to
+// 600 bases are trimmed by their own lane (lane_sliding_window, shared with the single-pass kernel);
+// whatever that declines -- longer reads, malformed records, quality bytes out of range, the last
+// record before the end of the buffer -- is walked by the whole warp, 32 window positions per step,
+// window totals from a warp-shuffle prefix scan of q[i+ws]-q[i]; that path also finds the position
+// the reference reports for a bad quality byte.
 #pragma once
 
 #include "sk_device.cuh"
