@@ -38,6 +38,30 @@ def test_python_binding_lists_every_export():
     assert sorted(capi.EXPORTS) == declared_functions()
 
 
+def test_header_is_plain_c(tmp_path):
+    """The boundary is a C ABI: the header compiles as C99 and as C++, and a C program using every entry
+    point links against the library (nothing runs: no GPU here)."""
+    for std, lang in (("c99", "c"), ("c++17", "c++")):
+        subprocess.run(["gcc", "-std=" + std, "-Wall", "-Werror", "-fsyntax-only", "-x", lang, HEADER], check=True)
+    src = tmp_path / "use.c"
+    src.write_text(
+        '#include "sickle_b200.h"\n#include <stdio.h>\n'
+        "int main(int argc, char **argv) {\n"
+        "  if (argc < 99) { printf(\"%d\\n\", sk_abi_version()); return 0; }\n"
+        "  sk_params p = {0}; sk_result r; void *o[3] = {0}; uint64_t c[3] = {0};\n"
+        "  sk_ctx *x = sk_create(0, 1u << 20, 2, &p);\n"
+        "  char *b = sk_in_buffer(x, 0, 0); (void)b; (void)sk_slot_bytes(x); (void)sk_device_count();\n"
+        "  sk_upload(x, 0, 0, 0, 16); sk_submit(x, 0, 0, 16, 0, 0); sk_wait(x, 0, &r);\n"
+        "  sk_trim_device(x, 0, 0, 0, 0, 0, o, c, 0); sk_result_device(x, 0, 0, &r);\n"
+        "  puts(sk_last_error()); sk_destroy(x); return 0; }\n")
+    exe = tmp_path / "use"
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", os.path.join(ROOT, "sickle_b200"), "-lsickle_b200", "-Wl,-rpath," + os.path.join(ROOT, "sickle_b200")],
+                   check=True)
+    out = subprocess.run([str(exe)], capture_output=True, check=True).stdout
+    assert int(out) >= 1
+
+
 def test_abi_version(lib):
     lib.sk_abi_version.restype = ctypes.c_int
     assert lib.sk_abi_version() == 1
