@@ -19,10 +19,10 @@ $(LIB): $(CSRC)/capi.cu $(KERNELS)
 
 cli: bin/sickle bin/io_tool
 # the CLI's I/O stages alone (no CUDA): used by tests/test_host_io.py
-bin/io_tool: host/io_tool.cpp host/io.cpp host/io.h host/ref_batcher.h
+bin/io_tool: host/io_tool.cpp host/io.cpp host/io.h host/ref_batcher.h host/unit_cutter.h
 	@mkdir -p bin
 	g++ -O2 -std=c++17 -Wall host/io_tool.cpp host/io.cpp -o $@ -lz -lpthread
-bin/sickle: host/sickle_main.cpp host/trimmer.cpp host/io.cpp host/trimmer.h host/io.h host/ref_batcher.h include/sickle_b200.h $(LIB)
+bin/sickle: host/sickle_main.cpp host/trimmer.cpp host/io.cpp host/trimmer.h host/io.h host/ref_batcher.h host/unit_cutter.h include/sickle_b200.h $(LIB)
 	@mkdir -p bin
 	g++ -O2 -std=c++17 -Wall -Iinclude host/sickle_main.cpp host/trimmer.cpp host/io.cpp -o $@ \
 	    -Lsickle_b200 -lsickle_b200 -lz -lpthread -Wl,-rpath,'$$ORIGIN/../sickle_b200'

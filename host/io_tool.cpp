@@ -8,6 +8,7 @@
 
 #include "io.h"
 #include "ref_batcher.h"
+#include "unit_cutter.h"
 
 // io_tool refbatch <src> <batch_len> <minlines> <cap>: prints the size of every reference batch
 static int refbatch(int argc, char **argv) {
@@ -29,8 +30,36 @@ static int refbatch(int argc, char **argv) {
     return 0;
 }
 
+// io_tool units <cap> <lines_per_unit> <src0> [<src1>]: the whole-unit batches the multi-GPU driver
+// would dispatch (host/unit_cutter.h), one line "<bytes0> <bytes1> <units>" per batch.  With two sources
+// (paired files) a batch holds the same number of records of each, lines_per_unit applies to src0
+// (src1 is always 4).  Exit 3: a full buffer without a complete unit.
+static int units(int argc, char **argv) {
+    if (argc != 5 && argc != 6) { fprintf(stderr, "usage: io_tool units <cap> <lines_per_unit> <src0> [<src1>]\n"); return 2; }
+    const unsigned long long cap = strtoull(argv[2], nullptr, 10);
+    const bool two = argc == 6;
+    host::ByteSource in0, in1;
+    if (!in0.open(argv[4]) || (two && !in1.open(argv[5]))) { fprintf(stderr, "cannot open input\n"); return 1; }
+    host::UnitStream s0(&in0, atoi(argv[3])), s1(two ? &in1 : &in0, 4);
+    // two buffers per input: the carried bytes stay in the previous buffer until the next fill()
+    std::vector<char> buf[2][2];
+    for (auto &a : buf) for (auto &b : a) b.resize((size_t)cap);
+    for (int k = 0;; k ^= 1) {
+        if (!s0.fill(buf[0][k].data(), cap) || (two && !s1.fill(buf[1][k].data(), cap))) { fprintf(stderr, "read failed\n"); return 1; }
+        const unsigned long long u = two ? std::min(s0.units(), s1.units()) : s0.units();
+        if (u == 0) {
+            if ((s0.units() == 0 && s0.full() && !s0.eof()) || (two && s1.units() == 0 && s1.full() && !s1.eof())) return 3;
+            break;
+        }
+        const unsigned long long n0 = s0.cut(u), n1 = two ? s1.cut(u) : 0;
+        printf("%llu %llu %llu\n", n0, n1, u);
+    }
+    return 0;
+}
+
 int main(int argc, char **argv) {
     if (argc >= 2 && std::string(argv[1]) == "refbatch") return refbatch(argc, argv);
+    if (argc >= 2 && std::string(argv[1]) == "units") return units(argc, argv);
     if (argc != 5) { fprintf(stderr, "usage: io_tool <src> <dst> <chunk> <gzip 0|1>\n"); return 2; }
     const unsigned long long chunk = strtoull(argv[3], nullptr, 10);
     host::ByteSource in;

@@ -4,6 +4,7 @@
 #include "trimmer.h"
 
 #include "ref_batcher.h"
+#include "unit_cutter.h"
 
 #include <fcntl.h>
 #include <getopt.h>
@@ -17,6 +18,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <memory>
+#include <string>
 
 namespace host {
 
@@ -167,6 +170,165 @@ inline void patch_eof(char *buf, unsigned long long end) {
     if (end > 0 && buf[end - 1] != '\n') buf[end - 1] = '\n';
 }
 
+
+// Devices to use: SICKLE_B200_DEVICES = comma-separated CUDA device numbers (a number may repeat: two
+// contexts on one GPU), or SICKLE_B200_GPUS = N (devices 0..N-1; "all" = every device).  Default: one
+// context on device SICKLE_B200_DEVICE (0).
+std::vector<int> device_list() {
+    std::vector<int> d;
+    if (const char *e = getenv("SICKLE_B200_DEVICES")) {
+        for (const char *p = e; *p;) {
+            char *end = nullptr;
+            const long v = strtol(p, &end, 10);
+            if (end == p) break;
+            d.push_back((int)v);
+            p = *end == ',' ? end + 1 : end;
+            if (*end && *end != ',') break;
+        }
+    } else if (const char *g = getenv("SICKLE_B200_GPUS")) {
+        const int n = !strcmp(g, "all") ? sk_device_count() : atoi(g);
+        for (int i = 0; i < n; ++i) d.push_back(i);
+    }
+    if (d.empty()) d.push_back((int)env_u64("SICKLE_B200_DEVICE", 0));
+    return d;
+}
+
+// Several contexts (one per listed device) fed with independent batches.  Batch k runs on context
+// k mod G in slot (k / G) mod S.  Every context is driven by its own host thread (the C ABI's rule:
+// one thread per context), which submits what is queued for it and waits for its oldest batch; the
+// caller fills input buffers, hands batches over with dispatch() and collects results in batch order
+// with result().  No data moves between the devices: reads are independent.
+class DeviceFarm {
+public:
+    struct Job {
+        long long k = -1;
+        uint64_t r[4] = {0, 0, 0, 0};   // start0, end0, start1, end1
+    };
+    struct Done {
+        bool ready = false;
+        int rc = SK_OK;
+        std::string err;
+        sk_result res{};
+    };
+
+    ~DeviceFarm() {
+        for (auto &w : workers_) {
+            { std::lock_guard<std::mutex> l(w->mu); w->stop = true; }
+            w->cv.notify_all();
+        }
+        for (auto &w : workers_)
+            if (w->th.joinable()) w->th.join();
+        static const bool keep = getenv("SICKLE_B200_KEEP_CONTEXT") && atoi(getenv("SICKLE_B200_KEEP_CONTEXT")) != 0;
+        if (!keep)
+            for (auto &w : workers_)
+                if (w->c) sk_destroy(w->c);
+    }
+
+    // Contexts are created side by side (pinned allocations dominate: ~0.4 s per GiB each).
+    bool create(const std::vector<int> &devices, unsigned long long slot_bytes, int nslots, const sk_params &p, std::string &err) {
+        G_ = (int)devices.size();
+        S_ = nslots;
+        done_.resize((size_t)(G_ * S_));
+        std::vector<std::string> errs((size_t)G_);
+        std::vector<std::thread> th;
+        for (int g = 0; g < G_; ++g) workers_.emplace_back(new Worker());
+        for (int g = 0; g < G_; ++g)
+            th.emplace_back([&, g] {
+                workers_[(size_t)g]->c = sk_create(devices[(size_t)g], slot_bytes, nslots, &p);
+                if (!workers_[(size_t)g]->c) errs[(size_t)g] = sk_last_error();
+            });
+        for (auto &t : th) t.join();
+        for (int g = 0; g < G_; ++g)
+            if (!workers_[(size_t)g]->c) { err = errs[(size_t)g]; return false; }
+        const int n_in = p.mode == SK_MODE_PE_2FILE ? 2 : 1;
+        in_.assign((size_t)(G_ * S_ * 2), nullptr);
+        for (int g = 0; g < G_; ++g)
+            for (int s = 0; s < S_; ++s)
+                for (int i = 0; i < n_in; ++i) in_[(size_t)((g * S_ + s) * 2 + i)] = sk_in_buffer(workers_[(size_t)g]->c, s, i);
+        for (int g = 0; g < G_; ++g) workers_[(size_t)g]->th = std::thread([this, g] { run(g); });
+        return true;
+    }
+
+    int depth() const { return G_ * S_; }                       // batches that can be in flight
+    int ring(long long k) const { return (int)(k % depth()); }  // index of batch k's slot among all slots
+    char *in_buffer(long long k, int which) const { return in_[(size_t)((dev(k) * S_ + slot(k)) * 2 + which)]; }
+
+    void dispatch(long long k, uint64_t s0, uint64_t e0, uint64_t s1, uint64_t e1) {
+        { std::lock_guard<std::mutex> l(mu_done_); done_[(size_t)ring(k)] = Done(); }
+        Worker &w = *workers_[(size_t)dev(k)];
+        Job j;
+        j.k = k; j.r[0] = s0; j.r[1] = e0; j.r[2] = s1; j.r[3] = e1;
+        { std::lock_guard<std::mutex> l(w.mu); w.jobs.push_back(j); }
+        w.cv.notify_all();
+    }
+
+    // Result of batch k (valid until its slot is dispatched again); with block == false returns null
+    // when the batch is still running.
+    const Done *result(long long k, bool block) {
+        std::unique_lock<std::mutex> l(mu_done_);
+        Done &d = done_[(size_t)ring(k)];
+        if (!block && !d.ready) return nullptr;
+        cv_done_.wait(l, [&] { return d.ready; });
+        return &d;
+    }
+
+private:
+    struct Worker {
+        sk_ctx *c = nullptr;
+        std::thread th;
+        std::mutex mu;
+        std::condition_variable cv;
+        std::deque<Job> jobs;
+        bool stop = false;
+    };
+    int dev(long long k) const { return (int)(k % G_); }
+    int slot(long long k) const { return (int)((k / G_) % S_); }
+
+    void publish(long long k, int rc, const sk_result *res) {
+        std::lock_guard<std::mutex> l(mu_done_);
+        Done &d = done_[(size_t)ring(k)];
+        d.rc = rc;
+        if (rc != SK_OK) d.err = sk_last_error();
+        if (res) d.res = *res;
+        d.ready = true;
+        cv_done_.notify_all();
+    }
+
+    void run(int g) {
+        Worker &w = *workers_[(size_t)g];
+        std::deque<Job> inflight;
+        while (true) {
+            Job j;
+            bool submit = false;
+            {
+                std::unique_lock<std::mutex> l(w.mu);
+                w.cv.wait(l, [&] { return !w.jobs.empty() || !inflight.empty() || w.stop; });
+                if (!w.jobs.empty() && (int)inflight.size() < S_) { j = w.jobs.front(); w.jobs.pop_front(); submit = true; }
+                else if (inflight.empty()) return;   // stop requested, nothing left
+            }
+            if (submit) {   // keep the device supplied first ...
+                const int rc = sk_submit(w.c, slot(j.k), j.r[0], j.r[1], j.r[2], j.r[3]);
+                if (rc != SK_OK) publish(j.k, rc, nullptr);
+                else inflight.push_back(j);
+                continue;
+            }
+            // ... then wait for the oldest batch of this device
+            j = inflight.front();
+            inflight.pop_front();
+            sk_result r;
+            const int rc = sk_wait(w.c, slot(j.k), &r);
+            publish(j.k, rc, rc == SK_OK ? &r : nullptr);
+        }
+    }
+
+    int G_ = 0, S_ = 0;
+    std::vector<std::unique_ptr<Worker>> workers_;
+    std::vector<char *> in_;
+    std::mutex mu_done_;
+    std::condition_variable cv_done_;
+    std::vector<Done> done_;
+};
+
 }  // namespace
 
 int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, ByteSink *outs[3], bool has_singles,
@@ -181,7 +343,8 @@ int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, Byt
     p.mode = mode;
     p.emulate_threads = threads > 1 ? threads : 1;
     p.has_singles = has_singles ? 1 : 0;
-    const int device = (int)env_u64("SICKLE_B200_DEVICE", 0);
+    const std::vector<int> devices = device_list();
+    const int device = devices[0];
     const bool two = mode == SK_MODE_PE_2FILE;
     const bool paired = mode != SK_MODE_SE;
     const double t_begin = host::now_s();
@@ -190,6 +353,7 @@ int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, Byt
         fprintf(stderr, "****Error: no usable CUDA device (%s). This build has no CPU path.\n\n", sk_last_error());
         return EXIT_FAILURE;
     }
+    if (devices.size() > 1) return run_devices(devices, p, in0, in1, outs, tot);
 
     // ---------------------------------------------------------------------------------------
     // (A) reference output order requested (-a N, N > 1): batches follow the reference's batch
@@ -383,6 +547,140 @@ int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, Byt
     ctx.reusable = true;
     return EXIT_SUCCESS;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Several GPUs (SICKLE_B200_DEVICES / SICKLE_B200_GPUS): the input is cut on the host into
+// independent batches of whole records (pairs) -- contiguous byte ranges, SURVEY.md 8-e --, batch k
+// runs on device k mod G, and the outputs are appended in batch order, so the files are the same
+// bytes as with one GPU.  With -a N (N > 1) the batches are the reference's own batches
+// (host/ref_batcher.h), which keeps the reference's output order across any number of devices.
+// ---------------------------------------------------------------------------------------------
+int Abstract_Trimmer::run_devices(const std::vector<int> &devices, const sk_params &p, ByteSource *in0, ByteSource *in1,
+                                  ByteSink *outs[3], Totals &tot) {
+    const double t_begin = host::now_s();
+    const bool two = p.mode == SK_MODE_PE_2FILE;
+    const bool inter = p.mode == SK_MODE_PE_INTER || p.mode == SK_MODE_PE_INTER_M;
+    const bool ref_order = p.emulate_threads > 1;
+    unsigned long long slot;
+    long long ref_batch_len = 0;
+    if (ref_order) {
+        ref_batch_len = host::recommended_batch_len(in0->file_size(), batch_mib, p.mode != SK_MODE_SE);
+        slot = (unsigned long long)ref_batch_len + (unsigned long long)ref_batch_len / 16 + (4ull << 20);
+        slot = std::min<unsigned long long>(slot, (1ull << 31) - 8192);
+    } else {
+        slot = env_u64("SICKLE_B200_SLOT_KB", 0) << 10;   // (small slots: tests)
+        if (!slot) slot = env_u64("SICKLE_B200_SLOT_MB", 64) << 20;
+        slot = std::min<unsigned long long>(std::max<unsigned long long>(slot, 4096), (1ull << 31) - 8192);
+    }
+    const int nslots = ref_order && slot > (256ull << 20) ? 1 : 2;
+    DeviceFarm farm;
+    {
+        std::string err;
+        if (!farm.create(devices, slot, nslots, p, err)) { fprintf(stderr, "****Error: %s\n\n", err.c_str()); return EXIT_FAILURE; }
+    }
+    tot.t_init = host::now_s() - t_begin;
+
+    const int depth = farm.depth();
+    std::vector<Tickets> tickets((size_t)depth);
+    std::vector<uint64_t> cut0((size_t)depth, 0), cut1((size_t)depth, 0);   // submitted sizes, checked against `consumed`
+    long long dispatched = 0, retired = 0;
+    long long base[2] = {0, 0};
+
+    // Take the result of the oldest batch not yet collected: errors first, then its streams go to the
+    // writers (in batch order).  0 = done, 1 = nothing ready (only when !block), -1 = failed (exit code in rc).
+    int rc = EXIT_SUCCESS;
+    auto retire = [&](bool block) -> int {
+        const double t0 = host::now_s();
+        const DeviceFarm::Done *d = farm.result(retired, block);
+        if (block) tot.t_wait += host::now_s() - t0;
+        if (!d) return 1;
+        const int ring = farm.ring(retired);
+        if (d->rc != SK_OK) { fprintf(stderr, "****Error: %s\n\n", d->err.c_str()); rc = EXIT_FAILURE; return -1; }
+        sk_result r = d->res;
+        if (r.error.kind) {
+            r.error.record += base[r.error.file];
+            rc = report_data_error(r, farm.in_buffer(retired, 0), two ? farm.in_buffer(retired, 1) : nullptr);
+            return -1;
+        }
+        if (r.consumed[0] != cut0[(size_t)ring] || (two && r.consumed[1] != cut1[(size_t)ring])) {
+            fprintf(stderr, "****Error: internal: batch %lld was cut at %llu / %llu bytes but the device consumed %llu / %llu.\n\n", retired,
+                    (unsigned long long)cut0[(size_t)ring], (unsigned long long)cut1[(size_t)ring],
+                    (unsigned long long)r.consumed[0], (unsigned long long)r.consumed[1]);
+            rc = EXIT_FAILURE;
+            return -1;
+        }
+        tickets[(size_t)ring] = queue_outputs(r, outs);
+        add_totals(tot, r);
+        base[0] += (long long)r.records[0]; base[1] += (long long)r.records[1];
+        ++retired;
+        return 0;
+    };
+    // Make batch k's slot usable: the batch that ran in it `depth` batches ago has been collected and
+    // its output has left the slot's pinned result buffers.
+    auto claim = [&](long long k) -> bool {
+        while (retired + depth <= k)
+            if (retire(true) != 0) return false;
+        if (!wait_outputs(tickets[(size_t)farm.ring(k)], outs, tot)) { fprintf(stderr, "****Error: write failed\n\n"); rc = EXIT_FAILURE; return false; }
+        return true;
+    };
+    auto dispatch = [&](long long k, uint64_t n0, uint64_t n1) {
+        cut0[(size_t)farm.ring(k)] = n0; cut1[(size_t)farm.ring(k)] = n1;
+        farm.dispatch(k, 0, n0, 0, n1);
+        dispatched = k + 1;
+    };
+    auto collect_ready = [&]() -> bool {
+        while (retired < dispatched) {
+            const int s = retire(false);
+            if (s < 0) return false;
+            if (s > 0) break;
+        }
+        return true;
+    };
+
+    if (ref_order) {
+        host::RefBatcher b0(in0, ref_batch_len, inter ? 8 : 4);
+        host::RefBatcher b1(in1 ? in1 : in0, ref_batch_len, 4);
+        for (long long k = 0;; ++k) {
+            if (!claim(k)) return rc;
+            const long long n0 = b0.next(farm.in_buffer(k, 0), slot);
+            if (n0 < 0) { fprintf(stderr, "****Error: a reference batch does not fit in a %llu-byte slot.\n\n", slot); return EXIT_FAILURE; }
+            if (n0 == 0) break;
+            long long n1 = 0;
+            if (two) {
+                n1 = b1.next(farm.in_buffer(k, 1), slot);
+                if (n1 <= 0) break;
+            }
+            dispatch(k, (uint64_t)n0, (uint64_t)n1);
+            if (!collect_ready()) return rc;
+        }
+    } else {
+        host::UnitStream s0(in0, inter ? 8 : 4), s1(in1 ? in1 : in0, 4);
+        for (long long k = 0;; ++k) {
+            if (!claim(k)) return rc;
+            if (!s0.fill(farm.in_buffer(k, 0), slot) || (two && !s1.fill(farm.in_buffer(k, 1), slot))) {
+                fprintf(stderr, "****Error: read failed\n\n");
+                return EXIT_FAILURE;
+            }
+            const unsigned long long units = two ? std::min(s0.units(), s1.units()) : s0.units();
+            if (units == 0) {
+                // nothing whole is left (what remains is dropped, as the reference does at end of file),
+                // unless a full buffer holds no complete record (pair)
+                const bool starved = (s0.units() == 0 && s0.full() && !s0.eof()) || (two && s1.units() == 0 && s1.full() && !s1.eof());
+                if (starved) { fprintf(stderr, "****Error: a record does not fit in a %llu-byte slot (raise SICKLE_B200_SLOT_MB).\n\n", slot); return EXIT_FAILURE; }
+                break;
+            }
+            const unsigned long long n0 = s0.cut(units), n1 = two ? s1.cut(units) : 0;
+            dispatch(k, n0, n1);
+            if (!collect_ready()) return rc;
+        }
+    }
+    while (retired < dispatched)
+        if (retire(true) != 0) return rc;
+    for (auto &k : tickets)
+        if (!wait_outputs(k, outs, tot)) { fprintf(stderr, "****Error: write failed\n\n"); return EXIT_FAILURE; }
+    return EXIT_SUCCESS;
+}
+
 
 // =============================================================================================
 // sickle se      (reference src/trim_single.cpp)

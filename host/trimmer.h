@@ -66,6 +66,9 @@ protected:
     // outs[k] may be null (stream not written).  Returns the process exit code.
     int run_device(int mode, host::ByteSource *in0, host::ByteSource *in1, host::ByteSink *outs[3],
                    bool has_singles, host::Totals &tot);
+    // The same over several GPUs (independent whole-record batches dealt to one context per device).
+    int run_devices(const std::vector<int> &devices, const sk_params &p, host::ByteSource *in0, host::ByteSource *in1,
+                    host::ByteSink *outs[3], host::Totals &tot);
     int report_data_error(const sk_result &r, const char *buf0, const char *buf1);
 };
 

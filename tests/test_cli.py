@@ -179,3 +179,124 @@ def test_batch_mode_runs_commands_in_one_process(sickle, golden, tmp_path):
     subprocess.run([sickle, "pe", "-f", f, "-r", r, "-t", "sanger", "-o", ref[2], "-p", ref[3], "-s", ref[4]], check=True,
                    capture_output=True)
     assert [md5(o[k]) for k in ("b", "bs", "e1", "e2", "es")] == [md5(x) for x in ref]
+
+
+# ---------------------------------------------------------------------------------------------
+# several devices (SICKLE_B200_DEVICES): independent whole-record batches dealt to one context per
+# device, outputs appended in batch order.  "0,0" = two contexts on one GPU, so the dealing, the
+# host-side cutting (host/unit_cutter.h) and the ordered collection are covered on a one-GPU box;
+# real device pairs are added when the box has them.
+# ---------------------------------------------------------------------------------------------
+def _device_lists():
+    import ctypes
+
+    lib = ctypes.CDLL(os.path.join(ROOT, "sickle_b200", "libsickle_b200.so"))
+    n = lib.sk_device_count()
+    lists = ["0,0", "0,0,0"]
+    if n >= 2:
+        lists.append("0,1")
+    if n >= 4:
+        lists.append("0,1,2,3")
+    return lists
+
+
+def test_several_devices_golden_cases(sickle, golden, tmp_path):
+    """Golden cases (all -a N ones, all error fixtures, a sample of the rest) with the input cut into
+    64 KiB batches over two contexts: same files, counters, exit codes and messages as the reference."""
+    bad = []
+    n = 0
+    for i, case in enumerate(golden["cases"]):
+        edge = "err_" in case["id"] or "ok_" in case["id"]
+        if not (i % 16 == 0 or case["threads"] > 1 or edge):
+            continue
+        n += 1
+        env = {"SICKLE_B200_DEVICES": "0,0", "SICKLE_B200_SLOT_KB": "64"}
+        p, outs = run_case(sickle, case, golden["dir"], str(tmp_path), extra_env=env)
+        if p.returncode != case["rc"]:
+            bad.append((case["id"], "rc", p.returncode, p.stderr[-300:]))
+            continue
+        if case["rc"] == 0:
+            for k, o in case["outputs"].items():
+                if md5(outs[k]) != o["md5"]:
+                    bad.append((case["id"], "md5", k, os.path.getsize(outs[k]), o["bytes"]))
+            got = counts(p.stdout.decode())
+            for k, v in case["counts"].items():
+                if k in got and k != "total" and got[k] != v:
+                    bad.append((case["id"], "count", k, got[k], v))
+        elif p.stderr.decode("latin-1") != case["stderr"]:
+            bad.append((case["id"], "stderr", p.stderr.decode("latin-1")[:400], case["stderr"][:400]))
+    assert not bad, bad[:6]
+    assert n > 30
+
+
+def test_several_devices_many_batches(sickle, tmp_path):
+    """Larger synthetic inputs, tens of batches in flight over 2-4 contexts: single end, interleaved
+    pairs (+ singles, and -M), two files whose mates differ in length; against the CPU oracle."""
+    import oracle_py as orc
+    from sickle_b200 import synth
+
+    se = synth.fixed_length_records(30000, 150, "sanger", seed=41).tobytes()
+    f1, f2, inter = (a.tobytes() for a in synth.paired_records(12000, 150, "sanger", seed=42))
+    # mate 2 cut to 90 bases: the two files then hold different numbers of records per megabyte
+    recs = f2.split(b"\n")
+    short = []
+    for r in range(0, len(recs) - 1, 4):
+        short += [recs[r], recs[r + 1][:90], recs[r + 2], recs[r + 3][:90]]
+    f2s = b"\n".join(short) + b"\n"
+    paths = {k: str(tmp_path / (k + ".fq")) for k in ("se", "f1", "f2s", "inter")}
+    for k, d in (("se", se), ("f1", f1), ("f2s", f2s), ("inter", inter)):
+        open(paths[k], "wb").write(d)
+    pr = orc.make_params("sanger")
+    want_se = orc.run(orc.MODE_SE, pr, se)
+    want_il = orc.run(orc.MODE_PE_INTER, pr, inter, batch_len=1 << 40)
+    want_m = orc.run(orc.MODE_PE_INTER_M, pr, inter, batch_len=1 << 40)
+    want_2f = orc.run(orc.MODE_PE_2FILE, pr, f1, f2s, batch_len=1 << 40)
+    assert want_2f["rc"] == 0 and want_il["rc"] == 0 and want_se["rc"] == 0
+    o = lambda name: str(tmp_path / name)
+    for devs in _device_lists():
+        for slot_kb in ("256", "1000"):
+            env = dict(os.environ, SICKLE_B200_DEVICES=devs, SICKLE_B200_SLOT_KB=slot_kb)
+            tag = (devs, slot_kb)
+            p = subprocess.run([sickle, "se", "-f", paths["se"], "-t", "sanger", "-o", o("se.out"), "-d"], capture_output=True, env=env, timeout=120)
+            assert p.returncode == 0, (tag, p.stderr)
+            assert open(o("se.out"), "rb").read() == want_se["out"][0], tag
+            assert counts(p.stdout.decode())["kept"] == want_se["counters"]["kept"]
+            nb = int(re.search(rb"batches (\d+)", p.stderr).group(1))
+            assert nb >= len(se) // (int(slot_kb) << 10), (tag, nb)
+            p = subprocess.run([sickle, "pe", "-c", paths["inter"], "-t", "sanger", "-m", o("il.out"), "-s", o("il.s")], capture_output=True, env=env, timeout=120)
+            assert p.returncode == 0, (tag, p.stderr)
+            assert open(o("il.out"), "rb").read() == want_il["out"][0] and open(o("il.s"), "rb").read() == want_il["out"][2], tag
+            p = subprocess.run([sickle, "pe", "-f", paths["f1"], "-r", paths["f2s"], "-t", "sanger", "-o", o("p1"), "-p", o("p2"), "-s", o("ps")],
+                               capture_output=True, env=env, timeout=120)
+            assert p.returncode == 0, (tag, p.stderr)
+            for k, name in ((0, "p1"), (1, "p2"), (2, "ps")):
+                assert open(o(name), "rb").read() == want_2f["out"][k], (tag, name)
+        p = subprocess.run([sickle, "pe", "-c", paths["inter"], "-t", "sanger", "-M", o("m.out")], capture_output=True,
+                           env=dict(os.environ, SICKLE_B200_DEVICES=devs, SICKLE_B200_SLOT_KB="300"), timeout=120)
+        assert p.returncode == 0 and open(o("m.out"), "rb").read() == want_m["out"][0], devs
+
+
+def test_several_devices_errors(sickle, tmp_path):
+    """A data error in a late batch: exit 1 with the reference's message and the record's true number;
+    a record that does not fit a slot; an unusable device number."""
+    from sickle_b200 import synth
+
+    data = bytearray(synth.fixed_length_records(6000, 150, "sanger", seed=43).tobytes())
+    lines = bytes(data).split(b"\n")
+    rec = 5000
+    lines[4 * rec + 3] = b"\x7f" + lines[4 * rec + 3][1:]   # 127 > Sanger's maximum (126)
+    src = str(tmp_path / "bad.fq")
+    open(src, "wb").write(b"\n".join(lines))
+    env = dict(os.environ, SICKLE_B200_DEVICES="0,0", SICKLE_B200_SLOT_KB="128")
+    p = subprocess.run([sickle, "se", "-f", src, "-t", "sanger", "-o", str(tmp_path / "o.fq")], capture_output=True, env=env, timeout=120)
+    single = subprocess.run([sickle, "se", "-f", src, "-t", "sanger", "-o", str(tmp_path / "o1.fq")], capture_output=True, timeout=120)
+    assert p.returncode == 1 and single.returncode == 1
+    assert p.stderr == single.stderr and b"Quality value (127)" in p.stderr and lines[4 * rec] in p.stderr
+    long_rec = b"@x\n" + b"A" * 70000 + b"\n+\n" + b"I" * 70000 + b"\n"
+    open(src, "wb").write(long_rec * 4)
+    p = subprocess.run([sickle, "se", "-f", src, "-t", "sanger", "-o", str(tmp_path / "o.fq")], capture_output=True,
+                       env=dict(os.environ, SICKLE_B200_DEVICES="0,0", SICKLE_B200_SLOT_KB="64"), timeout=120)
+    assert p.returncode == 1 and b"does not fit" in p.stderr
+    p = subprocess.run([sickle, "se", "-f", src, "-t", "sanger", "-o", str(tmp_path / "o.fq")], capture_output=True,
+                       env=dict(os.environ, SICKLE_B200_DEVICES="0,99"), timeout=120)
+    assert p.returncode == 1 and b"not available" in p.stderr

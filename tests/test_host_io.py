@@ -175,3 +175,83 @@ def test_reference_batch_cutter_matches_the_python_model(tool, tmp_path):
                                    stdout=subprocess.PIPE, stderr=subprocess.PIPE)
                 got = [int(x) for x in p.stdout.split()]
                 assert p.returncode == 0 and got == want, (di, batch_len, minlines, got[:5], want[:5], len(got), len(want))
+
+
+def _unit_batches_model(datas, cap, lpu):
+    """Plain-Python model of host/unit_cutter.h's UnitStream loop: returns ([(bytes0, bytes1, units)], starved)."""
+    st = [dict(data=d, pos=0, carry=b"", eof=False) for d in datas]
+    per_unit = [lpu] + [4] * (len(datas) - 1)
+    out = []
+    while True:
+        bufs = []
+        for s in st:
+            buf = s["carry"]
+            want = cap - len(buf)
+            if not s["eof"] and want > 0:
+                got = s["data"][s["pos"]:s["pos"] + want]
+                s["pos"] += len(got)
+                if len(got) < want:
+                    s["eof"] = True
+                buf += got
+            if s["eof"] and buf and buf[-1:] != b"\n":
+                buf = buf[:-1] + b"\n"
+            bufs.append(buf)
+        units = [b.count(b"\n") // u for b, u in zip(bufs, per_unit)]
+        u = min(units)
+        if u == 0:
+            starved = any(n == 0 and len(b) == cap and not s["eof"] for n, b, s in zip(units, bufs, st))
+            return out, starved
+        cuts = []
+        for s, b, per in zip(st, bufs, per_unit):
+            p = 0
+            for _ in range(u * per):
+                p = b.index(b"\n", p) + 1
+            s["carry"] = b[p:]
+            cuts.append(p)
+        out.append((cuts[0], cuts[1] if len(cuts) > 1 else 0, u))
+
+
+def test_unit_cutter_matches_the_python_model(tool, tmp_path):
+    """host/unit_cutter.h: the multi-GPU driver's batches hold whole records (pairs), cover the input
+    without gaps, and pair two files by record number even when their records differ in size."""
+    def run(cap, lpu, *paths):
+        p = subprocess.run([tool, "units", str(cap), str(lpu)] + [str(x) for x in paths], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        return p.returncode, [tuple(int(v) for v in ln.split()) for ln in p.stdout.decode().splitlines()]
+
+    big = _fastq_like(3_000_000, seed=31) * 4                      # > 4 MiB buffers: several counting threads
+    big = big[:big.rfind(b"\n@r") + 1]
+    datas = [_fastq_like(300_000, seed=30), _fastq_like(300_001, seed=32)[:-7],   # cut mid-line, no final newline
+             b"".join(b"@r%d\nACG\n+\nIII\n" % i for i in range(5000)), b"@only\nACGT\n+\nIIII\n", b"", b"\n\n\n\n\n", big]
+    for di, data in enumerate(datas):
+        src = tmp_path / ("u%d.fastq" % di)
+        src.write_bytes(data)
+        for cap in ((6 << 20, 2_500_000) if data is big else (1_000_000, 65_536, 4_099, 700)):
+            for lpu in (4, 8):
+                want, starved = _unit_batches_model([data], cap, lpu)
+                rc, got = run(cap, lpu, src)
+                assert rc == (3 if starved else 0) and got == want, (di, cap, lpu)
+                # whole units, no gaps: the batches are a prefix of the input, line count a multiple of lpu
+                if not starved and data.endswith(b"\n"):         # (an unterminated last line gets patched)
+                    covered = sum(g[0] for g in got)
+                    assert data[:covered].count(b"\n") == sum(g[2] for g in got) * lpu
+                    assert covered == 0 or data[covered - 1:covered] == b"\n"
+                    assert data[covered:].count(b"\n") < lpu        # only an incomplete unit is left over
+    # two files whose records differ in size (mate 2 reads are shorter): same record count per batch
+    rng = np.random.default_rng(33)
+    n = 6000
+    f1 = b"".join(b"@p%d/1\n%s\n+\n%s\n" % (i, b"A" * L, b"I" * L) for i, L in enumerate(rng.integers(50, 250, n)))
+    f2 = b"".join(b"@p%d/2\n%s\n+\n%s\n" % (i, b"C" * L, b"5" * L) for i, L in enumerate(rng.integers(20, 90, n)))
+    p1, p2 = tmp_path / "m1.fastq", tmp_path / "m2.fastq"
+    p1.write_bytes(f1)
+    p2.write_bytes(f2 + b"@extra\nAC\n+\nII\n")               # one record too many in file 2: dropped
+    for cap in (300_000, 70_000, 1 << 20):
+        want, starved = _unit_batches_model([f1, p2.read_bytes()], cap, 4)
+        rc, got = run(cap, 4, p1, p2)
+        assert rc == 0 and not starved and got == want
+        assert sum(g[2] for g in got) == n and sum(g[0] for g in got) == len(f1) and sum(g[1] for g in got) == len(f2)
+    # a record longer than the buffer
+    long_rec = b"@x\n" + b"A" * 5000 + b"\n+\n" + b"I" * 5000 + b"\n"
+    src = tmp_path / "long.fastq"
+    src.write_bytes(long_rec * 3)
+    assert run(4096, 4, src)[0] == 3
+    assert run(20_000, 4, src) == (0, [(len(long_rec), 0, 1)] * 3)
