@@ -29,17 +29,24 @@ def md5(path):
     return hashlib.md5(open(path, "rb").read()).hexdigest() if os.path.exists(path) else None
 
 
-def run_case(sickle, case, gdir, tmp, extra_env=None):
-    cmd = [sickle, case["mode"]]
+def case_args(case, gdir, tmp, tag=""):
+    """Arguments of one golden case (after the program name) and its output paths."""
+    args = [case["mode"]]
     for k, v in case["inputs"].items():
-        cmd += [k, os.path.join(gdir, v)]
+        args += [k, os.path.join(gdir, v)]
     outs = {}
     for k in case["outputs"]:
-        outs[k] = os.path.join(tmp, "out" + k.strip("-"))
-        cmd += [k, outs[k]]
-    cmd += case["flags"]
+        outs[k] = os.path.join(tmp, "out" + tag + k.strip("-"))
+        args += [k, outs[k]]
+    args += case["flags"]
     if case["threads"] > 1:
-        cmd += ["-a", str(case["threads"])]
+        args += ["-a", str(case["threads"])]
+    return args, outs
+
+
+def run_case(sickle, case, gdir, tmp, extra_env=None):
+    args, outs = case_args(case, gdir, tmp)
+    cmd = [sickle] + args
     env = dict(os.environ, SICKLE_B200_SLOT_MB="1", SICKLE_B200_HEADROOM_MB="1")
     env.update(extra_env or {})
     p = subprocess.run(cmd, capture_output=True, timeout=120, env=env)
@@ -184,54 +191,71 @@ def test_batch_mode_runs_commands_in_one_process(sickle, golden, tmp_path):
 # ---------------------------------------------------------------------------------------------
 # several devices (SICKLE_B200_DEVICES): independent whole-record batches dealt to one context per
 # device, outputs appended in batch order.  "0,0" = two contexts on one GPU, so the dealing, the
-# host-side cutting (host/unit_cutter.h) and the ordered collection are covered on a one-GPU box;
-# real device pairs are added when the box has them.
+# host-side cutting (host/unit_cutter.h) and the ordered collection run against the real library on
+# a one-GPU box; real device pairs are added when the box has them.  Every process pays 2-3 s of CUDA
+# start-up, so the commands of one configuration go through one `sickle batch` process.  (The host
+# logic itself is covered case by case on CPU in tests/test_host_logic.py.)
 # ---------------------------------------------------------------------------------------------
+def run_batch(sickle, commands, env):
+    """Run argument lists through one `sickle batch` process.  Returns ([(rc, stdout of the command)], stderr)."""
+    text = "".join(" ".join('"%s"' % a for a in args) + "\n" for args in commands)
+    p = subprocess.run([sickle, "batch"], input=text.encode(), capture_output=True, timeout=600, env=dict(os.environ, **env))
+    res, cur = [], []
+    for line in p.stdout.decode().splitlines():
+        if line.startswith("##rc "):
+            res.append((int(line.split()[1]), "\n".join(cur)))
+            cur = []
+        else:
+            cur.append(line)
+    assert len(res) == len(commands), (len(res), len(commands), p.stderr[-600:])
+    return res, p.stderr
+
+
 def _device_lists():
     import ctypes
 
     lib = ctypes.CDLL(os.path.join(ROOT, "sickle_b200", "libsickle_b200.so"))
     n = lib.sk_device_count()
-    lists = ["0,0", "0,0,0"]
+    lists = [("0,0", "256"), ("0,0,0", "1000")]
     if n >= 2:
-        lists.append("0,1")
+        lists.append(("0,1", "256"))
     if n >= 4:
-        lists.append("0,1,2,3")
+        lists.append(("3,1,0,2", "512"))
     return lists
 
 
 def test_several_devices_golden_cases(sickle, golden, tmp_path):
-    """Golden cases (all -a N ones, all error fixtures, a sample of the rest) with the input cut into
+    """Golden cases (all -a N ones, all error fixtures, every fourth of the rest) with the input cut into
     64 KiB batches over two contexts: same files, counters, exit codes and messages as the reference."""
+    picked = [c for i, c in enumerate(golden["cases"]) if i % 4 == 0 or c["threads"] > 1 or "err_" in c["id"] or "ok_" in c["id"]]
+    assert len(picked) > 70
+    cmds, outs = [], []
+    for i, case in enumerate(picked):
+        a, o = case_args(case, golden["dir"], str(tmp_path), tag="%d" % i)
+        cmds.append(a)
+        outs.append(o)
+    res, stderr = run_batch(sickle, cmds, {"SICKLE_B200_DEVICES": "0,0", "SICKLE_B200_SLOT_KB": "64"})
     bad = []
-    n = 0
-    for i, case in enumerate(golden["cases"]):
-        edge = "err_" in case["id"] or "ok_" in case["id"]
-        if not (i % 16 == 0 or case["threads"] > 1 or edge):
-            continue
-        n += 1
-        env = {"SICKLE_B200_DEVICES": "0,0", "SICKLE_B200_SLOT_KB": "64"}
-        p, outs = run_case(sickle, case, golden["dir"], str(tmp_path), extra_env=env)
-        if p.returncode != case["rc"]:
-            bad.append((case["id"], "rc", p.returncode, p.stderr[-300:]))
-            continue
-        if case["rc"] == 0:
-            for k, o in case["outputs"].items():
-                if md5(outs[k]) != o["md5"]:
-                    bad.append((case["id"], "md5", k, os.path.getsize(outs[k]), o["bytes"]))
-            got = counts(p.stdout.decode())
+    for case, o, (rc, out) in zip(picked, outs, res):
+        if rc != case["rc"]:
+            bad.append((case["id"], "rc", rc))
+        elif rc == 0:
+            for k, want in case["outputs"].items():
+                if md5(o[k]) != want["md5"]:
+                    bad.append((case["id"], "md5", k, os.path.getsize(o[k]), want["bytes"]))
+            got = counts(out)
             for k, v in case["counts"].items():
                 if k in got and k != "total" and got[k] != v:
                     bad.append((case["id"], "count", k, got[k], v))
-        elif p.stderr.decode("latin-1") != case["stderr"]:
-            bad.append((case["id"], "stderr", p.stderr.decode("latin-1")[:400], case["stderr"][:400]))
-    assert not bad, bad[:6]
-    assert n > 30
+    assert not bad, (bad[:6], stderr[-400:])
+    # the error fixtures' messages, in the order the commands ran
+    assert stderr.decode("latin-1") == "".join(c["stderr"] for c in picked if c["rc"] != 0)
 
 
 def test_several_devices_many_batches(sickle, tmp_path):
     """Larger synthetic inputs, tens of batches in flight over 2-4 contexts: single end, interleaved
-    pairs (+ singles, and -M), two files whose mates differ in length; against the CPU oracle."""
+    pairs (+ singles, and -M), two files whose mates differ in length, -a 3 with the reference's
+    batches; against whole-input runs of the CPU oracle."""
     import oracle_py as orc
     from sickle_b200 import synth
 
@@ -251,52 +275,51 @@ def test_several_devices_many_batches(sickle, tmp_path):
     want_il = orc.run(orc.MODE_PE_INTER, pr, inter, batch_len=1 << 40)
     want_m = orc.run(orc.MODE_PE_INTER_M, pr, inter, batch_len=1 << 40)
     want_2f = orc.run(orc.MODE_PE_2FILE, pr, f1, f2s, batch_len=1 << 40)
-    assert want_2f["rc"] == 0 and want_il["rc"] == 0 and want_se["rc"] == 0
+    want_a3 = orc.run(orc.MODE_SE, pr, se, threads=3, b_mib=1)
+    assert want_2f["rc"] == 0 and want_il["rc"] == 0 and want_se["rc"] == 0 and want_a3["counters"]["n_batches"] > 5
     o = lambda name: str(tmp_path / name)
-    for devs in _device_lists():
-        for slot_kb in ("256", "1000"):
-            env = dict(os.environ, SICKLE_B200_DEVICES=devs, SICKLE_B200_SLOT_KB=slot_kb)
-            tag = (devs, slot_kb)
-            p = subprocess.run([sickle, "se", "-f", paths["se"], "-t", "sanger", "-o", o("se.out"), "-d"], capture_output=True, env=env, timeout=120)
-            assert p.returncode == 0, (tag, p.stderr)
-            assert open(o("se.out"), "rb").read() == want_se["out"][0], tag
-            assert counts(p.stdout.decode())["kept"] == want_se["counters"]["kept"]
-            nb = int(re.search(rb"batches (\d+)", p.stderr).group(1))
-            assert nb >= len(se) // (int(slot_kb) << 10), (tag, nb)
-            p = subprocess.run([sickle, "pe", "-c", paths["inter"], "-t", "sanger", "-m", o("il.out"), "-s", o("il.s")], capture_output=True, env=env, timeout=120)
-            assert p.returncode == 0, (tag, p.stderr)
-            assert open(o("il.out"), "rb").read() == want_il["out"][0] and open(o("il.s"), "rb").read() == want_il["out"][2], tag
-            p = subprocess.run([sickle, "pe", "-f", paths["f1"], "-r", paths["f2s"], "-t", "sanger", "-o", o("p1"), "-p", o("p2"), "-s", o("ps")],
-                               capture_output=True, env=env, timeout=120)
-            assert p.returncode == 0, (tag, p.stderr)
-            for k, name in ((0, "p1"), (1, "p2"), (2, "ps")):
-                assert open(o(name), "rb").read() == want_2f["out"][k], (tag, name)
-        p = subprocess.run([sickle, "pe", "-c", paths["inter"], "-t", "sanger", "-M", o("m.out")], capture_output=True,
-                           env=dict(os.environ, SICKLE_B200_DEVICES=devs, SICKLE_B200_SLOT_KB="300"), timeout=120)
-        assert p.returncode == 0 and open(o("m.out"), "rb").read() == want_m["out"][0], devs
+    cmds = [["se", "-f", paths["se"], "-t", "sanger", "-o", o("se.out"), "-d"],
+            ["pe", "-c", paths["inter"], "-t", "sanger", "-m", o("il.out"), "-s", o("il.s")],
+            ["pe", "-f", paths["f1"], "-r", paths["f2s"], "-t", "sanger", "-o", o("p1"), "-p", o("p2"), "-s", o("ps")],
+            ["pe", "-c", paths["inter"], "-t", "sanger", "-M", o("m.out")],
+            ["se", "-f", paths["se"], "-t", "sanger", "-o", o("a3.out"), "-a", "3", "-b", "1", "-d"]]
+    want = {"se.out": want_se["out"][0], "il.out": want_il["out"][0], "il.s": want_il["out"][2], "p1": want_2f["out"][0],
+            "p2": want_2f["out"][1], "ps": want_2f["out"][2], "m.out": want_m["out"][0], "a3.out": want_a3["out"][0]}
+    for devs, slot_kb in _device_lists():
+        for name in want:
+            if os.path.exists(o(name)):
+                os.remove(o(name))
+        res, stderr = run_batch(sickle, cmds, {"SICKLE_B200_DEVICES": devs, "SICKLE_B200_SLOT_KB": slot_kb})
+        assert [rc for rc, _ in res] == [0] * len(cmds), (devs, stderr[-600:])
+        for name, data in want.items():
+            assert open(o(name), "rb").read() == data, (devs, slot_kb, name)
+        assert counts(res[0][1])["kept"] == want_se["counters"]["kept"]
+        assert counts(res[2][1])["kept_p"] == want_2f["counters"]["kept_p"]
+        nb = [int(x) for x in re.findall(rb"batches (\d+)", stderr)]
+        assert nb[0] >= len(se) // (int(slot_kb) << 10) and nb[1] == want_a3["counters"]["n_batches"], (devs, nb)
 
 
 def test_several_devices_errors(sickle, tmp_path):
-    """A data error in a late batch: exit 1 with the reference's message and the record's true number;
-    a record that does not fit a slot; an unusable device number."""
+    """A data error in a late batch: exit 1 with the reference's message and the record's true number
+    (same text as with one context); a record that does not fit a slot; an unusable device number."""
     from sickle_b200 import synth
 
-    data = bytearray(synth.fixed_length_records(6000, 150, "sanger", seed=43).tobytes())
-    lines = bytes(data).split(b"\n")
+    lines = synth.fixed_length_records(6000, 150, "sanger", seed=43).tobytes().split(b"\n")
     rec = 5000
     lines[4 * rec + 3] = b"\x7f" + lines[4 * rec + 3][1:]   # 127 > Sanger's maximum (126)
-    src = str(tmp_path / "bad.fq")
+    src, src2, src3 = (str(tmp_path / n) for n in ("bad.fq", "bad2.fq", "long.fq"))
     open(src, "wb").write(b"\n".join(lines))
-    env = dict(os.environ, SICKLE_B200_DEVICES="0,0", SICKLE_B200_SLOT_KB="128")
-    p = subprocess.run([sickle, "se", "-f", src, "-t", "sanger", "-o", str(tmp_path / "o.fq")], capture_output=True, env=env, timeout=120)
-    single = subprocess.run([sickle, "se", "-f", src, "-t", "sanger", "-o", str(tmp_path / "o1.fq")], capture_output=True, timeout=120)
-    assert p.returncode == 1 and single.returncode == 1
-    assert p.stderr == single.stderr and b"Quality value (127)" in p.stderr and lines[4 * rec] in p.stderr
+    lines[4 * rec + 3] = lines[4 * rec + 3][:100]            # and a quality line shorter than its sequence
+    open(src2, "wb").write(b"\n".join(lines))
     long_rec = b"@x\n" + b"A" * 70000 + b"\n+\n" + b"I" * 70000 + b"\n"
-    open(src, "wb").write(long_rec * 4)
-    p = subprocess.run([sickle, "se", "-f", src, "-t", "sanger", "-o", str(tmp_path / "o.fq")], capture_output=True,
-                       env=dict(os.environ, SICKLE_B200_DEVICES="0,0", SICKLE_B200_SLOT_KB="64"), timeout=120)
+    open(src3, "wb").write(long_rec * 4)
+    cmds = [["se", "-f", f, "-t", "sanger", "-o", str(tmp_path / "o.fq")] for f in (src, src2)]
+    res, stderr = run_batch(sickle, cmds, {"SICKLE_B200_DEVICES": "0,0", "SICKLE_B200_SLOT_KB": "128"})
+    res1, stderr1 = run_batch(sickle, cmds, {})
+    assert [rc for rc, _ in res] == [1, 1] and [rc for rc, _ in res1] == [1, 1]
+    assert stderr == stderr1 and b"Quality value (127)" in stderr and lines[4 * rec] in stderr and b"different lengths" in stderr
+    cmd = [sickle, "se", "-f", src3, "-t", "sanger", "-o", str(tmp_path / "o.fq")]
+    p = subprocess.run(cmd, capture_output=True, env=dict(os.environ, SICKLE_B200_DEVICES="0,0", SICKLE_B200_SLOT_KB="64"), timeout=120)
     assert p.returncode == 1 and b"does not fit" in p.stderr
-    p = subprocess.run([sickle, "se", "-f", src, "-t", "sanger", "-o", str(tmp_path / "o.fq")], capture_output=True,
-                       env=dict(os.environ, SICKLE_B200_DEVICES="0,99"), timeout=120)
+    p = subprocess.run(cmd, capture_output=True, env=dict(os.environ, SICKLE_B200_DEVICES="0,99"), timeout=120)
     assert p.returncode == 1 and b"not available" in p.stderr
