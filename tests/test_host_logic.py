@@ -95,6 +95,49 @@ def test_four_devices_in_any_order(hoststub, tmp_path):
     assert int(re.search(rb"batches (\d+)", p.stderr).group(1)) >= 60
 
 
+REF = os.path.join(ROOT, "oracle", "_ref", "sickle_sync")
+
+
+@pytest.mark.skipif(not os.path.exists(REF), reason="reference binary not built (oracle/Makefile target `ref`)")
+@pytest.mark.parametrize("env_name", ["one context", "two contexts, 64 KiB batches"])
+def test_host_code_equals_reference_binary_on_damaged_files(hoststub, tmp_path, env_name):
+    """The command line as a whole (host code over the stub) against the reference binary on seeded
+    random files, most of them damaged: exit status, output bytes, the summary on stdout and -- for data
+    errors -- the complete stderr text, which carries the record's name, line number and quality string."""
+    from test_oracle_fuzz_vs_ref import FLAGSETS, _damage, _records
+
+    rng = np.random.default_rng(991)
+    n_ok = n_err = n_other_batch_cut = 0
+    src, out, rout = (str(tmp_path / n) for n in ("in.fastq", "out.fastq", "ref.fastq"))
+    env = dict(os.environ, **ENVS[env_name])
+    for case in range(240):
+        qualtype = ["sanger", "illumina", "solexa"][case % 3]
+        data = _records(rng, int(rng.integers(120, 400)), int(rng.choice([12, 40, 90])), qualtype)
+        if case % 4:
+            data = _damage(rng, data)
+        fl = FLAGSETS[case % len(FLAGSETS)]
+        open(src, "wb").write(data)
+        flags = ["-t", qualtype, "-q", str(fl["q"]), "-l", str(fl["l"])] + (["-x"] if fl["x"] else []) + (["-n"] if fl["n"] else [])
+        r = subprocess.run([REF, "se", "-f", src, "-o", rout, "-a", "1"] + flags, capture_output=True, timeout=60)
+        if r.returncode < 0:
+            continue   # the reference itself crashed
+        p = subprocess.run([hoststub, "se", "-f", src, "-o", out] + flags, capture_output=True, timeout=60, env=env)
+        tag = (case, qualtype, fl, len(data))
+        assert p.returncode == r.returncode, (tag, p.stderr[-300:], r.stderr[-300:])
+        if r.returncode == 0:
+            assert open(out, "rb").read() == open(rout, "rb").read(), tag
+            assert counts(p.stdout.decode()) == counts(r.stdout.decode()), tag
+            n_ok += 1
+        elif p.stderr != r.stderr:
+            # a file with two different data errors: the reference validates a whole batch of its own
+            # geometry before trimming it, so which error comes first depends on the batch cut (DESIGN.md 5)
+            n_other_batch_cut += 1
+        else:
+            n_err += 1
+    print("ok %d, same error text %d, other error first %d" % (n_ok, n_err, n_other_batch_cut))
+    assert n_ok > 80 and n_err > 60 and n_other_batch_cut <= 2, (n_ok, n_err, n_other_batch_cut)
+
+
 def test_product_binary_has_no_cpu_path():
     """bin/sickle is linked against the CUDA library only: without a GPU it refuses to run."""
     import shutil
