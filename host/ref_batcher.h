@@ -16,6 +16,9 @@
 #include <cstdint>
 #include <cstring>
 #include <vector>
+#if defined(__SSE2__)
+#include <emmintrin.h>
+#endif
 
 #include "io.h"
 
@@ -23,6 +26,22 @@ namespace host {
 
 inline unsigned long long count_newlines(const char *p, unsigned long long n) {
     unsigned long long c = 0, i = 0;
+#if defined(__SSE2__)
+    // 16 bytes per compare; per-byte counters (0xFF = -1 per hit) summed every 255 steps by psadbw
+    const __m128i nl = _mm_set1_epi8('\n'), zero = _mm_setzero_si128();
+    while (i + 64 <= n) {
+        __m128i acc0 = zero, acc1 = zero;
+        const unsigned long long stop = std::min<unsigned long long>(n - 63, i + 64ull * 127ull);
+        for (; i < stop; i += 64) {
+            const __m128i a = _mm_loadu_si128((const __m128i *)(p + i)), b = _mm_loadu_si128((const __m128i *)(p + i + 16));
+            const __m128i d = _mm_loadu_si128((const __m128i *)(p + i + 32)), e = _mm_loadu_si128((const __m128i *)(p + i + 48));
+            acc0 = _mm_sub_epi8(acc0, _mm_add_epi8(_mm_cmpeq_epi8(a, nl), _mm_cmpeq_epi8(b, nl)));
+            acc1 = _mm_sub_epi8(acc1, _mm_add_epi8(_mm_cmpeq_epi8(d, nl), _mm_cmpeq_epi8(e, nl)));
+        }
+        const __m128i s = _mm_add_epi64(_mm_sad_epu8(acc0, zero), _mm_sad_epu8(acc1, zero));
+        c += (unsigned long long)_mm_cvtsi128_si64(s) + (unsigned long long)_mm_cvtsi128_si64(_mm_unpackhi_epi64(s, s));
+    }
+#endif
     while (i + 8 <= n) {
         // per-byte counters in one 64-bit word, summed every 255 steps (no popcount instruction needed)
         uint64_t lanes = 0;
