@@ -61,9 +61,14 @@ struct TrimOut {
 
 // dp4a with unsigned bytes in a and signed bytes in b
 __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
+#if defined(__CUDA_ARCH__)
     int d;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;
+#else   // host build of this header (tests/test_lane_logic.py): the same sum, spelled out
+    for (int k = 0; k < 4; ++k) c += (int)((a >> (8 * k)) & 255u) * (int)(int8_t)((uint32_t)b >> (8 * k));
+    return c;
+#endif
 }
 
 // Sliding window over shared memory by ONE or TWO lanes per read.  Same decisions as

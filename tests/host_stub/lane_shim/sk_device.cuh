@@ -1,0 +1,86 @@
+// TEST INFRASTRUCTURE ONLY -- host stand-in for sickle_b200/csrc/sk_device.cuh.
+//
+// tests/test_lane_logic.py copies sickle_b200/csrc/trim_lane.cuh (the device function that trims one
+// read with one or two lanes, shared by the fused kernel and K2) next to this file and k1_index.cuh,
+// and compiles it with g++: the CUDA qualifiers become empty macros, the integer intrinsics are
+// restated here, and the two lanes of a read are two host threads whose __shfl_xor_sync is a
+// rendezvous.  The integer logic that decides the cut points is then checked against the oracle on
+// CPU.  Nothing here is used by the product.
+#pragma once
+
+#include <algorithm>
+#include <atomic>
+#include <cstdint>
+#include <cstring>
+
+#define __device__
+#define __forceinline__ inline
+#define __restrict__
+
+using std::max;
+using std::min;
+
+namespace sk {
+
+// same members as the real DevParams (only names matter here)
+struct DevParams {
+    int32_t qoff, qmin, qmax;
+    int32_t qthr;
+    int32_t lthr;
+    int32_t no_fiveprime;
+    int32_t trunc_n;
+    int32_t mode;
+    int32_t emu_threads;
+    int32_t has_singles;
+};
+
+}  // namespace sk
+
+inline uint32_t __funnelshift_r(uint32_t lo, uint32_t hi, uint32_t sh) {
+    sh &= 31u;
+    return (uint32_t)((((uint64_t)hi << 32) | lo) >> sh);
+}
+inline uint32_t __funnelshift_l(uint32_t lo, uint32_t hi, uint32_t sh) {
+    sh &= 31u;
+    return (uint32_t)(((((uint64_t)hi << 32) | lo) << sh) >> 32);
+}
+inline int __clz(uint32_t x) { return x ? __builtin_clz(x) : 32; }
+inline int __ffs(uint32_t x) { return __builtin_ffs((int)x); }
+inline uint32_t __dp4a(uint32_t a, uint32_t b, uint32_t c) {
+    for (int k = 0; k < 4; ++k) c += ((a >> (8 * k)) & 255u) * ((b >> (8 * k)) & 255u);
+    return c;
+}
+
+// ---- the pair of lanes that shares one read: two host threads, shuffles meet at a rendezvous
+struct LanePair {
+    std::atomic<int> arrived{0};
+    std::atomic<int> generation{0};
+    int slot[2] = {0, 0};
+    std::atomic<bool> broken{false};   // set by the harness when one lane returned early (a logic error)
+};
+extern thread_local LanePair *tl_pair;
+extern thread_local int tl_sub;
+
+inline void lane_rendezvous(LanePair *p) {
+    const int g = p->generation.load(std::memory_order_acquire);
+    if (p->arrived.fetch_add(1, std::memory_order_acq_rel) == 1) {
+        p->arrived.store(0, std::memory_order_relaxed);
+        p->generation.store(g + 1, std::memory_order_release);
+    } else {
+        long spins = 0;
+        while (p->generation.load(std::memory_order_acquire) == g) {
+            if (++spins > 2000000000L || p->broken.load(std::memory_order_relaxed)) { p->broken = true; return; }
+        }
+    }
+}
+template <class T>
+inline T __shfl_xor_sync(uint32_t, T v, int) {
+    static_assert(sizeof(T) == 4, "32-bit shuffles only");
+    LanePair *p = tl_pair;
+    memcpy(&p->slot[tl_sub], &v, 4);
+    lane_rendezvous(p);
+    T r;
+    memcpy(&r, &p->slot[tl_sub ^ 1], 4);
+    lane_rendezvous(p);
+    return r;
+}
