@@ -9,13 +9,19 @@ CSRC      := sickle_b200/csrc
 LIB       := sickle_b200/libsickle_b200.so
 KERNELS   := $(wildcard $(CSRC)/*.cuh) include/sickle_b200.h
 
-.PHONY: all lib cli oracle clean
+.PHONY: all lib cli oracle clean variant
 all: lib cli oracle
 
 lib: $(LIB)
 $(LIB): $(CSRC)/capi.cu $(KERNELS)
 	$(NVCC) $(NVFLAGS) -shared $(CSRC)/capi.cu -o $@ 2> $(CSRC)/ptxas.log || (cat $(CSRC)/ptxas.log; exit 1)
 	@grep -E "error|warning: v|spill" $(CSRC)/ptxas.log | grep -v "0 bytes spill" || true
+
+# experimental build variants for same-GPU A/B runs (profiles/ab.sh): make variant V=SK_LANE_SPLIT4
+#   -> sickle_b200/libsickle_b200_SK_LANE_SPLIT4.so   (select with SICKLE_B200_LIB=...)
+variant:
+	$(NVCC) $(NVFLAGS) -D$(V) -shared $(CSRC)/capi.cu -o sickle_b200/libsickle_b200_$(V).so 2> $(CSRC)/ptxas_$(V).log || (cat $(CSRC)/ptxas_$(V).log; exit 1)
+	@grep -E "spill" $(CSRC)/ptxas_$(V).log | grep -v "0 bytes spill stores, 0 bytes spill loads" || true
 
 cli: bin/sickle bin/io_tool
 # the CLI's I/O stages alone (no CUDA): used by tests/test_host_io.py

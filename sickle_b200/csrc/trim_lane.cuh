@@ -99,10 +99,19 @@ __device__ __forceinline__ TrimOut lane_sliding_window(const uint8_t *__restrict
     // window totals of a record that fits a tile are < 2^23; clamp so that T - thr cannot overflow
     const int thr = thr_ll > 0x3fffffffLL ? 0x3fffffff : (int)thr_ll;
     const uint32_t nwin = L - ws + 1u;                                   // trim.cpp:34
+#ifdef SK_LANE_SPLIT4
+    // Experimental (off by default; next round's A/B): the two lanes get equal shares, cut at a multiple
+    // of 4 windows, and the last step of a share only runs the groups it needs -- instead of whole
+    // 32-window steps (136 windows = 96 + 40 becomes 68 + 68: 17 groups per lane instead of 24).
+    const uint32_t split = nsub == 2u ? min(nwin, (((nwin + 1u) >> 1) + 3u) & ~3u) : nwin;
+    const uint32_t w_lo = sub ? split : 0u;                              // first window of this lane
+    const uint32_t w_hi = sub ? nwin : split;                            // one past its last window
+#else
     const uint32_t nseg = (nwin + 31u) >> 5;
     const uint32_t half = nsub == 2u ? (nseg + 1u) >> 1 : nseg;
     const uint32_t w_lo = sub ? half * 32u : 0u;                         // first window of this lane
     const uint32_t w_hi = sub ? nwin : min(nwin, half * 32u);            // one past its last window
+#endif
     const bool x = P.no_fiveprime != 0;                                  // -x: as if the 5' end was already found
 
     // ---- total of this lane's first window: dp4a sums, 4 bytes at a time.  Window 0 is also range
@@ -139,6 +148,48 @@ __device__ __forceinline__ TrimOut lane_sliding_window(const uint8_t *__restrict
         // funnel shift, so the step's first window ends up in the top bit (first = __clz).
         uint32_t negr = 0;
         uint32_t r_hi = 0, r_lo = 0xffffffffu;   // range screen of the 32 entering bytes
+#ifdef SK_LANE_SPLIT4
+        const uint32_t span = min(32u, w_hi - base);                     // windows of this step (>= 1)
+        auto group = [&]() {
+            const uint32_t lw = lead.next(), tw = trail.next();
+            const int T1 = dp4a_us(lw, 0x00000001, dp4a_us(tw, 0x000000FF, Tm));
+            const int T2 = dp4a_us(lw, 0x00000101, dp4a_us(tw, 0x0000FFFF, Tm));
+            const int T3 = dp4a_us(lw, 0x00010101, dp4a_us(tw, 0x00FFFFFF, Tm));
+            const int T4 = dp4a_us(lw, 0x01010101, dp4a_us(tw, (int)0xFFFFFFFF, Tm));
+            negr = __funnelshift_l((uint32_t)Tm, negr, 1);
+            negr = __funnelshift_l((uint32_t)T1, negr, 1);
+            negr = __funnelshift_l((uint32_t)T2, negr, 1);
+            negr = __funnelshift_l((uint32_t)T3, negr, 1);
+            rc.screen(lw, r_hi, r_lo);
+            Tm = T4;
+        };
+        if (span == 32u) {
+#pragma unroll
+            for (int g = 0; g < 8; ++g) group();
+        } else {                                 // the share's last step: only the groups that hold its windows
+            const uint32_t ng = (span + 3u) >> 2;
+#pragma unroll 1
+            for (uint32_t g = 0; g < ng; ++g) group();
+            negr <<= 32u - 4u * ng;              // first window of the step back in the top bit
+        }
+        // ---- what the windows of this step contribute
+        const uint32_t left = nwin - base;                               // windows of the READ from base on (>= 1)
+        if ((left <= 32u || rc.suspicious(r_hi, r_lo)) && me.o_first == 0x7fffffff) {
+            // the read's last step (its words run past the quality line) or, rarely, a suspect byte:
+            // find the first window of this step whose entering byte is out of range, exactly
+            // (bit k of oorw: the byte entering window base+k+1)
+            Stream4 again;
+            again.init(sm, qual_off + base + ws);
+            uint32_t oorw = 0;
+#pragma unroll 1
+            for (int g = 0; g < 8; ++g) oorw += flags_to_nibble(rc.bad4(again.next())) << (4 * g);
+            // only this step's windows count, and the last window of the read has no entering byte
+            const uint32_t lim = min(span, left - 1u);
+            const uint32_t oo = oorw & (lim >= 32u ? 0xffffffffu : ((1u << lim) - 1u));
+            if (oo) me.o_first = (int)base + __ffs(oo) - 1;
+        }
+        const uint32_t vmask = span >= 32u ? 0xffffffffu : ~(0xffffffffu >> span);   // top `span` bits
+#else
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
             const uint32_t lw = lead.next(), tw = trail.next();
@@ -170,6 +221,7 @@ __device__ __forceinline__ TrimOut lane_sliding_window(const uint8_t *__restrict
             if (oo) me.o_first = (int)base + __ffs(oo) - 1;
         }
         const uint32_t vmask = left >= 32 ? 0xffffffffu : ~(0xffffffffu >> left);   // top `left` bits
+#endif
         const uint32_t goodw = ~negr & vmask, badw = negr & vmask;
         if (badw && me.b_any < 0) me.b_any = (int)base + __clz(badw);
         uint32_t after = 0xffffffffu;

@@ -23,12 +23,12 @@ BUILD = os.path.join(ROOT, "tests", "_build", "lane")
 HARNESS = os.path.join(ROOT, "tests", "_build", "lane_harness")
 
 
-def build_harness(src_header, build_dir, out):
+def build_harness(src_header, build_dir, out, defines=()):
     os.makedirs(build_dir, exist_ok=True)
     shutil.copy(src_header, os.path.join(build_dir, "trim_lane.cuh"))
     for name in ("sk_device.cuh", "k1_index.cuh"):
         shutil.copy(os.path.join(ROOT, "tests", "host_stub", "lane_shim", name), build_dir)
-    subprocess.check_call(["g++", "-O2", "-std=c++17", "-w", "-I" + build_dir, "-I" + os.path.join(ROOT, "oracle"),
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-w"] + ["-D" + d for d in defines] + ["-I" + build_dir, "-I" + os.path.join(ROOT, "oracle"),
                            "-x", "c++", os.path.join(ROOT, "tests", "host_stub", "lane_harness.cpp"),
                            "-x", "c", os.path.join(ROOT, "oracle", "sickle_oracle.c"), "-o", out, "-lpthread"])
     return out
@@ -46,6 +46,18 @@ def test_lane_sliding_window_equals_oracle(harness, seed):
     words = p.stdout.split()
     assert words[0] == "checked" and int(words[1]) == 40000 and int(words[7]) == 0
     assert int(words[3]) > 10000 and int(words[5]) > 500          # plenty of kept reads and of range errors
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_balanced_lane_split_variant_equals_oracle(tmp_path_factory, seed):
+    """-DSK_LANE_SPLIT4 (experimental, off in the shipped build: the two lanes of a read get equal shares
+    cut at a multiple of four windows, partial last step) takes the same decisions."""
+    d = tmp_path_factory.getbasetemp() / "lane_split4"
+    exe = str(d / "lane_harness")
+    if not os.path.exists(exe):
+        build_harness(os.path.join(ROOT, "sickle_b200", "csrc", "trim_lane.cuh"), str(d), exe, defines=("SK_LANE_SPLIT4",))
+    p = subprocess.run([exe, str(seed), "40000"], capture_output=True, text=True, timeout=600)
+    assert p.returncode == 0 and "mismatches 0" in p.stdout, p.stderr[-2000:]
 
 
 def test_harness_notices_a_wrong_kernel(tmp_path):
