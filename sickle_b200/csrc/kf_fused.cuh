@@ -565,6 +565,18 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                     a_dst = d + nlen + 3u; a_src = r_e1 + 1u; a_len = plen + 1u;
                 }
             }
+#ifdef SK_STAGE_LONG_FIRST
+            // Experimental (off by default; next round's A/B): the two runs write disjoint bytes, so a lane
+            // whose read is cut at the 5' end swaps them -- every lane then moves its LONG piece in the first
+            // run and only the short one (name / line 3) in the second, instead of both runs being as long
+            // as the longest piece in the warp.
+            if (b_len != 0) {
+                uint32_t t;
+                t = a_dst; a_dst = b_dst; b_dst = t;
+                t = a_src; a_src = b_src; b_src = t;
+                t = a_len; a_len = b_len; b_len = t;
+            }
+#endif
             smem_copy(s_out, a_dst, s_in, a_src, a_len);
             if (__any_sync(0xffffffffu, b_len != 0)) smem_copy(s_out, b_dst, s_in, b_src, b_len);
             if (nl_at >= 0) s_out[nl_at] = '\n';
