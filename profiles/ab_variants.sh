@@ -1,0 +1,29 @@
+#!/bin/bash
+# Same-GPU A/B of the experimental build variants against the shipped library.
+#   usage (on the GPU box, from the repo root):  profiles/ab_variants.sh [rounds] [VARIANT ...]
+# For every variant (default: all of the list below, plus their combination): build it with
+# `make variant V=<macro>`, run the CUDA parity tests against it (SICKLE_B200_LIB), then alternate
+# kernel-only bench runs of the shipped library and the variant `rounds` times (default 3) and print
+# ms per 1M-read step and the roofline fraction of each run.  A variant that fails parity is not timed.
+set -u
+ROUNDS=${1:-3}
+shift || true
+VARIANTS=("$@")
+[ ${#VARIANTS[@]} -eq 0 ] && VARIANTS=(SK_LANE_SPLIT4 SK_STAGE_LONG_FIRST "SK_LANE_SPLIT4 -DSK_STAGE_LONG_FIRST")
+BASE=sickle_b200/libsickle_b200.so
+one() {   # lib label
+  SICKLE_B200_LIB=$PWD/$1 python bench.py --steps 30 --warmup 3 --kernel-only 2>&1 | tail -1 |
+    python -c "import sys,json; d=json.loads(sys.stdin.read()); print('$2', round(d['ms_per_step'],4), round(d['roofline']['frac'],4))"
+}
+for V in "${VARIANTS[@]}"; do
+  NAME=$(echo "$V" | tr -d ' ' | sed 's/-D/+/g')
+  LIB=sickle_b200/libsickle_b200_${NAME}.so
+  echo "=== $V"
+  /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function \
+      -D$V -shared sickle_b200/csrc/capi.cu -o $LIB 2> /dev/null || { echo "build failed"; continue; }
+  SICKLE_B200_LIB=$PWD/$LIB python -m pytest tests/test_cuda_parity.py -m gpu -x -q > /tmp/ab_parity.log 2>&1
+  RC=$?
+  tail -2 /tmp/ab_parity.log
+  [ $RC -ne 0 ] && { echo "PARITY FAILED: not timed"; continue; }
+  for r in $(seq 1 $ROUNDS); do one $BASE shipped; one $LIB "$NAME"; done
+done
