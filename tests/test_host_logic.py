@@ -95,6 +95,46 @@ def test_four_devices_in_any_order(hoststub, tmp_path):
     assert int(re.search(rb"batches (\d+)", p.stderr).group(1)) >= 60
 
 
+def test_directory_driver_over_batch_workers(hoststub, golden, tmp_path):
+    """trim_all.py (long-lived `sickle batch` workers whose context is reused from file to file) on CPU:
+    single-end and paired directories, two workers per "GPU", outputs equal the reference's."""
+    import hashlib
+    import shutil
+    import sys
+
+    env = dict(os.environ, SICKLE_B200_BIN=hoststub)
+    i, o = tmp_path / "in", tmp_path / "out"
+    i.mkdir()
+    for k in range(5):
+        shutil.copy(os.path.join(golden["dir"], "se_r150.fastq"), i / ("lane%d.fastq" % k))
+    assert subprocess.call([sys.executable, os.path.join(ROOT, "trim_all.py"), "se", "sanger", str(i), str(o), "--gpus", "1"], env=env) == 0
+    case = [c for c in golden["cases"] if c["id"] == "se.se_r150.sanger.default"][0]
+    for k in range(5):
+        assert md5(str(o / ("lane%d.trim.fastq" % k))) == case["outputs"]["-o"]["md5"]
+    i2, o2 = tmp_path / "in2", tmp_path / "out2"
+    i2.mkdir()
+    for k in ("a", "b", "c"):
+        shutil.copy(os.path.join(golden["dir"], "pe_r150_f.fastq"), i2 / ("%s_1.fastq" % k))
+        shutil.copy(os.path.join(golden["dir"], "pe_r150_r.fastq"), i2 / ("%s_2.fastq" % k))
+    assert subprocess.call([sys.executable, os.path.join(ROOT, "trim_all.py"), "pe", "sanger", str(i2), str(o2), "--gpus", "1",
+                            "--procs-per-gpu", "2"], env=env) == 0
+    case = [c for c in golden["cases"] if c["id"] == "pe2.pe_r150.sanger.default"][0]
+    for k in ("a", "b", "c"):
+        got = [hashlib.md5((o2 / ("%s_%s.trim.fastq" % (k, x))).read_bytes()).hexdigest() for x in ("1", "2", "s")]
+        assert got == [case["outputs"][f]["md5"] for f in ("-o", "-p", "-s")]
+    # a damaged file among good ones: reported as failed, the others are still trimmed
+    i3, o3 = tmp_path / "in3", tmp_path / "out3"
+    i3.mkdir()
+    shutil.copy(os.path.join(golden["dir"], "se_r150.fastq"), i3 / "good1.fastq")
+    shutil.copy(os.path.join(golden["dir"], "err_len_mismatch.fastq"), i3 / "bad.fastq")
+    shutil.copy(os.path.join(golden["dir"], "se_r150.fastq"), i3 / "good2.fastq")
+    p = subprocess.run([sys.executable, os.path.join(ROOT, "trim_all.py"), "se", "sanger", str(i3), str(o3), "--gpus", "1", "--procs-per-gpu", "1"],
+                       env=env, capture_output=True, text=True)
+    assert p.returncode == 1 and "FAILED (1): bad.fastq" in p.stderr
+    case = [c for c in golden["cases"] if c["id"] == "se.se_r150.sanger.default"][0]
+    assert md5(str(o3 / "good1.trim.fastq")) == md5(str(o3 / "good2.trim.fastq")) == case["outputs"]["-o"]["md5"]
+
+
 REF = os.path.join(ROOT, "oracle", "_ref", "sickle_sync")
 
 

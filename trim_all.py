@@ -86,7 +86,7 @@ def main(argv=None):
     ap.add_argument("--dry-run", action="store_true", help="print the commands, run nothing")
     a = ap.parse_args(argv)
     here = os.path.dirname(os.path.abspath(__file__))
-    sickle = os.path.join(here, "bin", "sickle")
+    sickle = os.environ.get("SICKLE_B200_BIN") or os.path.join(here, "bin", "sickle")   # (override: an installed binary)
     jobs = plan(a.mode, a.qual_type, a.input_dir, a.output_dir, a.threads, a.max_batch, sickle)
     todo = []
     for label, cmd, outs in jobs:
