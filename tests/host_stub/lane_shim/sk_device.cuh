@@ -1,6 +1,6 @@
 // TEST INFRASTRUCTURE ONLY -- host stand-in for sickle_b200/csrc/sk_device.cuh.
 //
-// tests/test_lane_logic.py copies sickle_b200/csrc/trim_lane.cuh (the device function that trims one
+// tests/test_lane_logic.py (and test_copy_logic.py, for sk_copy.cuh) copies sickle_b200/csrc/trim_lane.cuh (the device function that trims one
 // read with one or two lanes, shared by the fused kernel and K2) next to this file and k1_index.cuh,
 // and compiles it with g++: the CUDA qualifiers become empty macros, the integer intrinsics are
 // restated here, and the two lanes of a read are two host threads whose __shfl_xor_sync is a
@@ -15,7 +15,14 @@
 
 #define __device__
 #define __forceinline__ inline
+#define __noinline__
 #define __restrict__
+
+struct alignas(16) uint4 {
+    uint32_t x, y, z, w;
+};
+inline uint4 make_uint4(uint32_t x, uint32_t y, uint32_t z, uint32_t w) { return uint4{x, y, z, w}; }
+inline void __stcs(uint4 *p, uint4 v) { *p = v; }
 
 using std::max;
 using std::min;
