@@ -34,7 +34,7 @@ def test_copies_equal_memcpy(tmp_path_factory, seed):
 
 
 @pytest.mark.parametrize("old,new", [("const uint32_t sh = (src & 3u) * 8u;", "const uint32_t sh = (src & 3u) * 8u + (len == 77u ? 8u : 0u);"),
-                                     ("const uint32_t c_hi = end >> 4;", "const uint32_t c_hi = (end >> 4) - (tot % 64u == 3u ? 1u : 0u);")])
+                                     ("const uint32_t c_hi = end >> 4;", "const uint32_t c_hi = (end >> 4) - (tot > 100u && tot % 64u == 3u ? 1u : 0u);")])
 def test_harness_notices_a_wrong_copy(tmp_path, old, new):
     src = open(os.path.join(ROOT, "sickle_b200", "csrc", "sk_copy.cuh")).read()
     assert src.count(old) == 1
@@ -42,4 +42,4 @@ def test_harness_notices_a_wrong_copy(tmp_path, old, new):
     mutated.write_text(src.replace(old, new))
     exe = build(str(mutated), str(tmp_path / "b"), str(tmp_path / "h"))
     p = subprocess.run([exe, "1", "400000"], capture_output=True, text=True, timeout=600)
-    assert p.returncode == 1 and "MISMATCH" in p.stderr
+    assert p.returncode != 0 and "MISMATCH" in p.stderr
