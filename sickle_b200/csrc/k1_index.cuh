@@ -31,13 +31,22 @@ constexpr int kK1TileBytes = kK1Threads * kK1BytesPerThread;  // 16384
 struct SwarConsts {
     uint32_t nl, low7;
     __device__ __forceinline__ void init() {
+#if defined(__CUDACC__)
         asm volatile("mov.u32 %0, 0x0A0A0A0A;" : "=r"(nl));
         asm volatile("mov.u32 %0, 0x7F7F7F7F;" : "=r"(low7));
+#else   // host build of the kernels (tests/host_stub/simt)
+        nl = 0x0A0A0A0Au;
+        low7 = 0x7F7F7F7Fu;
+#endif
     }
 };
 __device__ __forceinline__ uint32_t newline_flags(uint32_t w, const SwarConsts &k) {
     uint32_t t;
+#if defined(__CUDACC__)
     asm("lop3.b32 %0, %1, %2, %3, 0x28;" : "=r"(t) : "r"(w), "r"(k.nl), "r"(k.low7));
+#else
+    t = (w ^ k.nl) & k.low7;
+#endif
     t += 0x7F7F7F7Fu;
     return ~(t | w) & 0x80808080u;
 }

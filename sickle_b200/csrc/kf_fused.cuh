@@ -147,10 +147,12 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
     uint32_t held = 0;   // thread 0: the next ticket (drawn while the previous tile is being staged)
     if (threadIdx.x == 0) held = atomicAdd(&ctl->tile_counter[3], 1u);
     uint32_t mbar_phase = 0;
+#if defined(__CUDACC__)
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_mbar)) : "memory");
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+#endif
     __syncthreads();
 
     // the tile whose output is staged in s_out and not flushed yet
@@ -180,6 +182,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             // mbarrier; the threads only zero what lies beyond the end of the batch (last tiles)
             const uint32_t have = nchunks - (t0 >> 4);                              // 16-byte chunks from t0 on (>= 1)
             const uint32_t cp_chunks = have < (uint32_t)(Cfg::kRegion / 16) ? have : (uint32_t)(Cfg::kRegion / 16);
+#if defined(__CUDACC__)
             if (tid == 0) {
                 const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&s_mbar);
                 const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_in);
@@ -188,13 +191,21 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"(dst), "l"(in.data + t0), "r"(cp_chunks * 16u), "r"(mb) : "memory");
             }
+#else   // host build of the kernels (tests/host_stub/simt): the bulk copy is a memcpy by thread 0
+            if (tid == 0) memcpy(s_in, in.data + t0, (size_t)cp_chunks * 16u);
+#endif
             for (uint32_t c = cp_chunks + tid; c < (uint32_t)(Cfg::kRegion / 16); c += kFThreads)
                 reinterpret_cast<uint4 *>(s_in)[c] = make_uint4(0, 0, 0, 0);
             {   // L2 prefetch, one 128-byte line per thread, of the tile one grid-width ahead: in steady
                 // state some CTA (this one, most likely) draws that ticket one tile time from now
                 const unsigned long long nb = ((unsigned long long)tile + gridDim.x) * Cfg::kTile + (unsigned long long)tid * 128u;
+#if defined(__CUDACC__)
                 if (tid < Cfg::kTile / 128 && nb < in.nbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(in.data + nb));
+#else
+                (void)nb;
+#endif
             }
+#if defined(__CUDACC__)
             {   // wait for the bulk copy (hardware sleep, not a spin), then for the zero fill
                 const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&s_mbar);
                 uint32_t ok = 0;
@@ -203,6 +214,9 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                                  : "=r"(ok) : "r"(mb), "r"(mbar_phase) : "memory");
                 mbar_phase ^= 1u;
             }
+#else
+            (void)mbar_phase;
+#endif
             __syncthreads();
             SK_TICK(1);   // S1 load
 

@@ -97,11 +97,19 @@ __device__ __forceinline__ uint32_t status_flag(unsigned long long w, uint32_t e
 }
 __device__ __forceinline__ unsigned long long ld_status(const unsigned long long *p) {
     unsigned long long v;
+#if defined(__CUDACC__)
     asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+#else   // host build of the kernels (tests/host_stub/simt): the same relaxed load
+    v = __atomic_load_n(p, __ATOMIC_RELAXED);
+#endif
     return v;
 }
 __device__ __forceinline__ void st_status(unsigned long long *p, unsigned long long v) {
+#if defined(__CUDACC__)
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+#else
+    __atomic_store_n(p, v, __ATOMIC_RELEASE);
+#endif
 }
 
 // Called by all 32 lanes of ONE warp.  Publishes this tile's aggregate, walks back over the
@@ -174,8 +182,12 @@ __device__ __forceinline__ void block_publish(unsigned long long *const status[2
 // id 0 with all threads is __syncthreads().  Only ids 0 and 1 are used.
 __device__ __forceinline__ void group_sync(int id, int nthreads) {
     // literal barrier numbers: with a register operand ptxas reserves all 16 barriers for the CTA
+#if defined(__CUDACC__)
     if (id == 0) asm volatile("bar.sync 0, %0;" ::"r"(nthreads) : "memory");
     else asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+#else
+    simt::bar_sync(id, nthreads);
+#endif
 }
 
 // Called by a group of `gwarps` (nstreams .. 8) whole warps, `gtid` = thread index

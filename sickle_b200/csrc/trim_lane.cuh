@@ -61,7 +61,7 @@ struct TrimOut {
 
 // dp4a with unsigned bytes in a and signed bytes in b
 __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
-#if defined(__CUDA_ARCH__)
+#if defined(__CUDACC__)
     int d;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
     return d;

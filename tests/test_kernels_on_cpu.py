@@ -1,0 +1,189 @@
+"""The CUDA kernels themselves -- sickle_b200/csrc/kf_fused.cuh (single pass, four tile sizes) and the
+general path k1_index / k2_trim / k3_emit -- compiled for the HOST and run on CPU against the oracle.
+
+tests/host_stub/simt/simt_host.h supplies just enough of the CUDA execution model: a CTA is an OS
+thread, its threads are fibers, barriers and warp collectives are rendezvous, global atomics are the
+host's, and the CTAs of a grid run concurrently (the decoupled look-backs spin on their predecessors).
+The few PTX statements in the kernels have a plain C++ spelling beside them (`#if defined(__CUDACC__)`);
+the SASS nvcc produces is unchanged by that.  tests/host_stub/kernels_harness.cpp launches the kernels
+the way capi.cu does and compares output streams, counters, consumed bytes, record counts and the first
+data error with so_run on the same bytes.
+
+What this pins without a GPU: the parsing, the record / tile ownership rules, look-backs, the window
+arithmetic, routing, scans and every byte the kernels write -- i.e. the logic.  What it cannot show:
+timing, memory-model races that need real parallel warps, the TMA / mbarrier path (a memcpy here).  The
+`-m gpu` tests run the same comparisons on the device.  Test infrastructure only.
+"""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BUILD = os.path.join(ROOT, "tests", "_build")
+QT = {"sanger": 1, "solexa": 2, "illumina": 3}
+MODES = {"se": 0, "pe2": 1, "pei": 2, "peM": 3}
+
+
+def build_harness(name, defines=()):
+    os.makedirs(BUILD, exist_ok=True)
+    out = os.path.join(BUILD, name)
+    stub = os.path.join(ROOT, "tests", "host_stub")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-w", "-fno-extern-tls-init"] + ["-D" + d for d in defines] +
+                          ["-I" + os.path.join(stub, "simt"), "-I" + os.path.join(stub, "simt", "include"),
+                           "-I" + os.path.join(ROOT, "sickle_b200", "csrc"), "-I" + os.path.join(ROOT, "oracle"),
+                           "-x", "c++", os.path.join(stub, "kernels_harness.cpp"), "-x", "c", os.path.join(ROOT, "oracle", "sickle_oracle.c"),
+                           "-o", out, "-lpthread"])
+    return out
+
+
+@pytest.fixture(scope="module")
+def harness():
+    return build_harness("kernels_harness")
+
+
+def run(exe, path, mode="se", qualtype="sanger", q=20, l=20, x=False, n=False, singles=True, kernel="fused9", ctas=3, first=0, path2=None):
+    cmd = [exe, path, str(MODES[mode]), str(QT[qualtype]), str(q), str(l), str(int(x)), str(int(n)), str(int(singles)), kernel, str(ctas), str(first)]
+    if path2:
+        cmd.append(path2)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    return p.returncode, p.stdout.strip(), p.stderr
+
+
+def check(exe, path, tag, kernels=("fused5", "fused7", "fused9", "fused11", "general"), **kw):
+    """Every kernel path must agree with the oracle; a fused kernel may instead hand the batch over
+    (FASTFAIL), which is what capi.cu's rerun_if_needed then sends through the general path."""
+    seen = []
+    for k in kernels:
+        rc, out, err = run(exe, path, kernel=k, **kw)
+        assert rc == 0 and (out.startswith("OK") or (k != "general" and out.startswith("FASTFAIL"))), (tag, k, out, err[-500:])
+        seen.append(out.split()[0])
+    return seen
+
+
+def test_bench_workload_and_flag_combinations(harness, tmp_path):
+    from sickle_b200 import synth
+
+    se = str(tmp_path / "se.fq")
+    open(se, "wb").write(synth.fixed_length_records(3000, 150, "sanger", seed=5).tobytes())
+    f, r, inter = synth.paired_records(1200, 150, "sanger", seed=6)
+    pf, pr, il = (str(tmp_path / n) for n in ("f.fq", "r.fq", "il.fq"))
+    open(pf, "wb").write(f.tobytes()); open(pr, "wb").write(r.tobytes()); open(il, "wb").write(inter.tobytes())
+    for ctas in (1, 2, 5):
+        assert check(harness, se, ("se", ctas), ctas=ctas, first=ctas * 3) == ["OK"] * 5      # 150-base reads never leave the fused kernel
+    for q, l, x, n in ((30, 5, True, False), (10, 0, False, True), (25, 1, True, True), (0, 0, False, False), (41, 151, False, False)):
+        check(harness, se, ("se flags", q, l, x, n), q=q, l=l, x=x, n=n, first=7)
+    for singles in (True, False):
+        check(harness, il, ("pei", singles), mode="pei", singles=singles, first=11)
+    check(harness, il, "peM", mode="peM", singles=False)
+    check(harness, pf, "pe2", kernels=("general",), mode="pe2", path2=pr, first=4)
+    check(harness, pf, "pe2 no singles", kernels=("general",), mode="pe2", path2=pr, singles=False)
+
+
+def test_golden_inputs(harness, golden):
+    """The committed fixtures (reference-pinned through the oracle), all three encodings."""
+    done = 0
+    for case in golden["cases"]:
+        if case["threads"] > 1 or case["rc"] != 0 and "err_" not in case["id"]:
+            continue
+        fl = case["flags"]
+        if done % 5 and "err_" not in case["id"] and "ok_" not in case["id"]:
+            done += 1
+            continue
+        done += 1
+        kw = dict(qualtype=fl[fl.index("-t") + 1], q=int(fl[fl.index("-q") + 1]) if "-q" in fl else 20,
+                  l=int(fl[fl.index("-l") + 1]) if "-l" in fl else 20, x="-x" in fl, n="-n" in fl)
+        ins = case["inputs"]
+        if case["mode"] == "se":
+            check(harness, os.path.join(golden["dir"], ins["-f"]), case["id"], **kw)
+        elif "-c" in ins:
+            if "-M" in case["outputs"]:
+                continue
+            check(harness, os.path.join(golden["dir"], ins["-c"]), case["id"], mode="pei", singles="-s" in case["outputs"], **kw)
+        else:
+            check(harness, os.path.join(golden["dir"], ins["-f"]), case["id"], kernels=("general",), mode="pe2",
+                  path2=os.path.join(golden["dir"], ins["-r"]), singles="-s" in case["outputs"], **kw)
+    assert done > 100
+
+
+def test_read_lengths_from_1_to_12000(harness, tmp_path):
+    """Variable-length reads: short ones overflow the records-per-tile limit of the large tiles (FASTFAIL ->
+    smaller tile or general path), long ones exceed the halo (general path, whole warp per read)."""
+    from test_oracle_fuzz_vs_ref import _records
+
+    rng = np.random.default_rng(8)
+    for lmax, nrec in ((12, 4000), (40, 3000), (100, 2500), (250, 2000), (2000, 300), (12000, 60)):
+        for qualtype in ("sanger", "illumina", "solexa"):
+            p = str(tmp_path / ("l%d_%s.fq" % (lmax, qualtype)))
+            open(p, "wb").write(_records(rng, nrec, lmax, qualtype))
+            seen = check(harness, p, (lmax, qualtype), qualtype=qualtype, n=lmax == 100, x=lmax == 40, first=int(rng.integers(0, 16)))
+            if lmax == 250:
+                assert seen[0] == "OK"            # the smallest tile holds them; larger tiles may exceed 128 records
+            if lmax == 12000:
+                assert seen[:4] == ["FASTFAIL"] * 4
+
+
+def test_damaged_inputs(harness, tmp_path):
+    """Seeded random files, three quarters of them damaged (missing / blank / doubled line, flipped /
+    deleted / inserted byte, cut-off tail): same first data error (kind, record, position, byte) or same
+    bytes as the oracle, on the general path; the fused kernels either agree or hand the batch over."""
+    from test_oracle_fuzz_vs_ref import FLAGSETS, _damage, _records
+
+    rng = np.random.default_rng(2718)
+    n_err = n_ok = 0
+    p = str(tmp_path / "d.fq")
+    for case in range(160):
+        qualtype = ["sanger", "illumina", "solexa"][case % 3]
+        data = _records(rng, int(rng.integers(60, 300)), int(rng.choice([12, 40, 90, 160])), qualtype)
+        if case % 4:
+            data = _damage(rng, data)
+        if data and not data.endswith(b"\n"):
+            data = data[:-1] + b"\n"          # (the host patches an unterminated last line before the device sees it)
+        fl = FLAGSETS[case % len(FLAGSETS)]
+        open(p, "wb").write(data)
+        mode = "pei" if case % 5 == 0 else "se"
+        kw = dict(mode=mode, qualtype=qualtype, q=fl["q"], l=fl["l"], x=fl["x"], n=fl["n"], first=case % 16, ctas=1 + case % 4)
+        rc, out, err = run(harness, p, kernel="general", **kw)
+        assert rc == 0 and out.startswith("OK"), (case, out, err[-300:])
+        if out.startswith("OK error"):
+            n_err += 1
+        else:
+            n_ok += 1
+        for k in ("fused5", "fused9"):
+            rc, out2, err = run(harness, p, kernel=k, **kw)
+            assert rc == 0, (case, k, out2, err[-300:])
+            if out.startswith("OK error"):
+                assert out2.startswith("FASTFAIL"), (case, k, out2)       # data errors always go to the general path
+    assert n_err > 50 and n_ok > 40, (n_err, n_ok)
+
+
+def test_edge_inputs(harness, tmp_path):
+    rec = b"@r1\nACGTACGTACGTACGTACGTACGTA\n+\nIIIIIIIIIIIIIIIIIIIIIIIII\n"
+    cases = {"empty": b"", "one": rec, "newlines": b"\n\n\n\n", "tail": rec * 3 + b"@r2\nACGT\n+\n", "unterminated": rec * 2 + b"@r3\nAC",
+             "crlf": rec.replace(b"\n", b"\r\n") * 4, "plus_name": rec.replace(b"+\n", b"+r1 something\n") * 50,
+             "at_in_quals": b"".join(b"@r%d\nACGTACGTACGTACGTACGTACGT\n+\n@@@@@@@@@@@@++++++++++++\n" % i for i in range(300))}
+    for name, data in cases.items():
+        p = str(tmp_path / (name + ".fq"))
+        open(p, "wb").write(data)
+        for mode in ("se", "pei"):
+            check(harness, p, (name, mode), mode=mode, first=3)
+
+
+@pytest.mark.parametrize("defines", [("SK_LANE_SPLIT4",), ("SK_STAGE_LONG_FIRST",), ("SK_LANE_SPLIT4", "SK_STAGE_LONG_FIRST")])
+def test_experimental_variants(tmp_path, defines):
+    """The build variants kept for the next round's A/B runs (off in the shipped library) write the same bytes."""
+    from sickle_b200 import synth
+    from test_oracle_fuzz_vs_ref import _records
+
+    exe = build_harness("kernels_harness_" + "_".join(defines), defines)
+    rng = np.random.default_rng(99)
+    se, il, var = (str(tmp_path / n) for n in ("se.fq", "il.fq", "var.fq"))
+    open(se, "wb").write(synth.fixed_length_records(3000, 150, "sanger", seed=15).tobytes())
+    open(il, "wb").write(synth.paired_records(1200, 150, "sanger", seed=16)[2].tobytes())
+    open(var, "wb").write(_records(rng, 2500, 250, "illumina"))
+    assert check(exe, se, "se", first=5) == ["OK"] * 5
+    check(exe, se, "se -x -n", x=True, n=True, q=30, l=5)
+    check(exe, il, "pei", mode="pei", first=9)
+    check(exe, il, "peM", mode="peM", singles=False)
+    check(exe, var, "variable", qualtype="illumina", n=True)
