@@ -117,7 +117,8 @@ int main(int argc, char **argv) {
     static const int kQ[4][3] = {{0, 4, 60}, {33, 33, 126}, {64, 58, 112}, {64, 64, 110}};   // reference src/sickle.h:85-91
     P.qoff = kQ[qualtype][0]; P.qmin = kQ[qualtype][1]; P.qmax = kQ[qualtype][2];
     P.qthr = atoi(argv[4]); P.lthr = atoi(argv[5]); P.no_fiveprime = atoi(argv[6]); P.trunc_n = atoi(argv[7]);
-    P.mode = mode; P.emu_threads = 1; P.has_singles = atoi(argv[8]);
+    P.mode = mode; P.has_singles = atoi(argv[8]);
+    P.emu_threads = getenv("KH_THREADS") ? atoi(getenv("KH_THREADS")) : 1;   // reference -a N order inside the batch (general path only)
     const std::string path = argv[9];
     const unsigned ctas = (unsigned)atoi(argv[10]);
     const uint32_t first = (uint32_t)atoi(argv[11]);
@@ -183,7 +184,7 @@ int main(int argc, char **argv) {
     };
     const size_t c0 = cut(d0, u0 * ((mode == 2 || mode == 3) ? 8 : 4)), c1 = mode == 1 ? cut(d1, u0 * 4) : 0;
     int orc = 0;
-    if (u0) orc = so_run(mode, &sp, 1, (int64_t)1 << 60, P.has_singles, (const char *)d0.data(), c0, (const char *)d1.data(), c1, optr, ocap, olen, &ctr, &err);
+    if (u0) orc = so_run(mode, &sp, P.emu_threads, (int64_t)1 << 60, P.has_singles, (const char *)d0.data(), c0, (const char *)d1.data(), c1, optr, ocap, olen, &ctr, &err);
 
     std::string why;
     if (orc != 0 || res.err_kind != 0) {

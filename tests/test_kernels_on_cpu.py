@@ -43,11 +43,12 @@ def harness():
     return build_harness("kernels_harness")
 
 
-def run(exe, path, mode="se", qualtype="sanger", q=20, l=20, x=False, n=False, singles=True, kernel="fused9", ctas=3, first=0, path2=None):
+def run(exe, path, mode="se", qualtype="sanger", q=20, l=20, x=False, n=False, singles=True, kernel="fused9", ctas=3, first=0, path2=None,
+        threads=1):
     cmd = [exe, path, str(MODES[mode]), str(QT[qualtype]), str(q), str(l), str(int(x)), str(int(n)), str(int(singles)), kernel, str(ctas), str(first)]
     if path2:
         cmd.append(path2)
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, KH_THREADS=str(threads)))
     return p.returncode, p.stdout.strip(), p.stderr
 
 
@@ -79,6 +80,21 @@ def test_bench_workload_and_flag_combinations(harness, tmp_path):
     check(harness, il, "peM", mode="peM", singles=False)
     check(harness, pf, "pe2", kernels=("general",), mode="pe2", path2=pr, first=4)
     check(harness, pf, "pe2 no singles", kernels=("general",), mode="pe2", path2=pr, singles=False)
+
+
+def test_reference_thread_order(harness, tmp_path):
+    """-a N: the general path deals the records of a batch to N queues and emits queue after queue, as the
+    reference does (src/trim_single.cpp:263,273-274; src/trim_paired.cpp:349,388,403)."""
+    from sickle_b200 import synth
+
+    se, pf, pr, il = (str(tmp_path / n) for n in ("se.fq", "f.fq", "r.fq", "il.fq"))
+    open(se, "wb").write(synth.fixed_length_records(2500, 150, "sanger", seed=25).tobytes())
+    f, r, inter = synth.paired_records(1000, 150, "sanger", seed=26)
+    open(pf, "wb").write(f.tobytes()); open(pr, "wb").write(r.tobytes()); open(il, "wb").write(inter.tobytes())
+    for threads in (2, 3, 4, 8, 16):
+        check(harness, se, ("se", threads), kernels=("general",), threads=threads, first=threads)
+        check(harness, il, ("pei", threads), kernels=("general",), mode="pei", threads=threads)
+        check(harness, pf, ("pe2", threads), kernels=("general",), mode="pe2", path2=pr, threads=threads)
 
 
 def test_golden_inputs(harness, golden):
