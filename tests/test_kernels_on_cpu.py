@@ -82,6 +82,20 @@ def test_bench_workload_and_flag_combinations(harness, tmp_path):
     check(harness, pf, "pe2 no singles", kernels=("general",), mode="pe2", path2=pr, singles=False)
 
 
+def test_many_tiles_and_ctas(harness, tmp_path):
+    """Hundreds of tiles over 8 concurrent CTAs (tickets, both look-backs, deferred flush across many
+    predecessors): 60,000 fixed-length reads, 30,000 interleaved pairs of mixed lengths."""
+    from sickle_b200 import synth
+    from test_oracle_fuzz_vs_ref import _records
+
+    se, il = str(tmp_path / "se.fq"), str(tmp_path / "il.fq")
+    open(se, "wb").write(synth.fixed_length_records(60000, 150, "sanger", seed=35).tobytes())
+    rng = np.random.default_rng(36)
+    open(il, "wb").write(_records(rng, 60000, 220, "sanger"))
+    assert check(harness, se, "se 60k", kernels=("fused7", "fused9", "general"), ctas=8, first=13) == ["OK"] * 3
+    assert check(harness, il, "pei 60k", kernels=("fused5", "general"), mode="pei", ctas=8, first=2, n=True) == ["OK"] * 2
+
+
 def test_reference_thread_order(harness, tmp_path):
     """-a N: the general path deals the records of a batch to N queues and emits queue after queue, as the
     reference does (src/trim_single.cpp:263,273-274; src/trim_paired.cpp:349,388,403)."""
