@@ -95,6 +95,28 @@ def test_four_devices_in_any_order(hoststub, tmp_path):
     assert int(re.search(rb"batches (\d+)", p.stderr).group(1)) >= 60
 
 
+def test_gzip_in_and_out_over_several_contexts(hoststub, golden, tmp_path):
+    """Plain gzip and BGZF input, -g (BGZF) output, with the batches dealt to two contexts."""
+    import gzip
+
+    from sickle_b200 import synth
+
+    data = synth.fixed_length_records(20000, 150, "sanger", seed=51).tobytes()
+    want = orc.run(orc.MODE_SE, orc.make_params("sanger"), data)["out"][0]
+    plain, gz_in, bgzf_in = (str(tmp_path / n) for n in ("in.fq", "in.fq.gz", "in.bgzf.gz"))
+    open(plain, "wb").write(data)
+    with gzip.open(gz_in, "wb") as g:
+        g.write(data)
+    env = dict(os.environ, SICKLE_B200_DEVICES="0,0", SICKLE_B200_SLOT_KB="512")
+    o1 = str(tmp_path / "o1.fq.gz")
+    assert subprocess.run([hoststub, "se", "-f", plain, "-t", "sanger", "-o", bgzf_in, "-q", "0", "-l", "0", "-x", "-g"], env=env).returncode == 0
+    assert gzip.open(bgzf_in, "rb").read() == data            # -q 0 -l 0 -x keeps every base: a BGZF copy of the input
+    for src in (gz_in, bgzf_in):
+        p = subprocess.run([hoststub, "se", "-f", src, "-t", "sanger", "-o", o1, "-g", "-d"], env=env, capture_output=True)
+        assert p.returncode == 0 and b"(gzip)" in p.stderr, p.stderr
+        assert gzip.open(o1, "rb").read() == want, src
+
+
 def test_directory_driver_over_batch_workers(hoststub, golden, tmp_path):
     """trim_all.py (long-lived `sickle batch` workers whose context is reused from file to file) on CPU:
     single-end and paired directories, two workers per "GPU", outputs equal the reference's."""
