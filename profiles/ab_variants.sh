@@ -9,7 +9,7 @@ set -u
 ROUNDS=${1:-3}
 shift || true
 VARIANTS=("$@")
-[ ${#VARIANTS[@]} -eq 0 ] && VARIANTS=(SK_LANE_SPLIT4 SK_STAGE_LONG_FIRST "SK_LANE_SPLIT4 -DSK_STAGE_LONG_FIRST")
+[ ${#VARIANTS[@]} -eq 0 ] && VARIANTS=(SK_LANE_SPLIT4 SK_STAGE_LONG_FIRST SK_NL_BRANCHFREE "SK_LANE_SPLIT4 -DSK_STAGE_LONG_FIRST -DSK_NL_BRANCHFREE")
 BASE=sickle_b200/libsickle_b200.so
 one() {   # lib label
   SICKLE_B200_LIB=$PWD/$1 python bench.py --steps 30 --warmup 3 --kernel-only 2>&1 | tail -1 |

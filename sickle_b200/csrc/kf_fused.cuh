@@ -274,14 +274,28 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             // a 32-byte word of a FASTQ file holds 0, 1 or (around the '+' line) 2 newlines: two
             // predicated (branch-free) extractions keep the warp converged, a loop only for more
             uint32_t rank = wbase + incl - cnt;
+#ifdef SK_NL_BRANCHFREE
+            // Experimental (off by default; next round's A/B): the two common stores without branches -- a
+            // word without a (second) newline stores into a dump slot in the padding behind the region
+            // (bytes nobody interprets) instead of skipping the store.  ncu charged 5.5 % of all warp
+            // instructions to these two lines at 15 of 32 lanes active.
+            uint16_t *const dump = reinterpret_cast<uint16_t *>(s_in + Cfg::kRegion + 64);
+#endif
 #pragma unroll
             for (int k = 0; k < (CH + 1) / 2; ++k) {
                 const uint32_t m = mw[k];
                 const uint32_t m2 = m & (m - 1u);
+#ifdef SK_NL_BRANCHFREE
+                *(m ? s_nl + rank : dump) = (uint16_t)(b0 + 32u * k + (uint32_t)__ffs(m) - 1u);
+                rank += m ? 1u : 0u;
+                *(m2 ? s_nl + rank : dump) = (uint16_t)(b0 + 32u * k + (uint32_t)__ffs(m2) - 1u);
+                rank += m2 ? 1u : 0u;
+#else
                 if (m) s_nl[rank] = (uint16_t)(b0 + 32u * k + (uint32_t)__ffs(m) - 1u);
                 rank += m ? 1u : 0u;
                 if (m2) s_nl[rank] = (uint16_t)(b0 + 32u * k + (uint32_t)__ffs(m2) - 1u);
                 rank += m2 ? 1u : 0u;
+#endif
                 uint32_t m3 = m2 & (m2 - 1u);
                 while (m3) {
                     s_nl[rank++] = (uint16_t)(b0 + 32u * k + (uint32_t)__ffs(m3) - 1u);

@@ -200,7 +200,8 @@ def test_edge_inputs(harness, tmp_path):
             check(harness, p, (name, mode), mode=mode, first=3)
 
 
-@pytest.mark.parametrize("defines", [("SK_LANE_SPLIT4",), ("SK_STAGE_LONG_FIRST",), ("SK_LANE_SPLIT4", "SK_STAGE_LONG_FIRST")])
+@pytest.mark.parametrize("defines", [("SK_LANE_SPLIT4",), ("SK_STAGE_LONG_FIRST",), ("SK_NL_BRANCHFREE",),
+                                     ("SK_LANE_SPLIT4", "SK_STAGE_LONG_FIRST", "SK_NL_BRANCHFREE")])
 def test_experimental_variants(tmp_path, defines):
     """The build variants kept for the next round's A/B runs (off in the shipped library) write the same bytes."""
     from sickle_b200 import synth
