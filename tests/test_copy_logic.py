@@ -41,5 +41,5 @@ def test_harness_notices_a_wrong_copy(tmp_path, old, new):
     mutated = tmp_path / "mutated.cuh"
     mutated.write_text(src.replace(old, new))
     exe = build(str(mutated), str(tmp_path / "b"), str(tmp_path / "h"))
-    p = subprocess.run([exe, "1", "400000"], capture_output=True, text=True, timeout=600)
+    p = subprocess.run([exe, "1", "150000"], capture_output=True, text=True, timeout=600)
     assert p.returncode != 0 and "MISMATCH" in p.stderr
