@@ -185,8 +185,8 @@ __device__ __forceinline__ void group_sync(int id, int nthreads) {
 #if defined(__CUDACC__)
     if (id == 0) asm volatile("bar.sync 0, %0;" ::"r"(nthreads) : "memory");
     else asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
-#else
-    simt::bar_sync(id, nthreads);
+#else   // host build of the kernels: the test harness supplies the barrier (tests/host_stub/simt/simt_host.h)
+    SK_HOST_BAR_SYNC(id, nthreads);
 #endif
 }
 

@@ -160,6 +160,7 @@ inline void launch(dim3 grid, dim3 block, const std::function<void()> &body, siz
 #define gridDim (simt::cta->grid)
 #define blockDim (simt::cta->bdim)
 
+#define SK_HOST_BAR_SYNC(id, nthreads) simt::bar_sync((id), (nthreads))   // the kernels' named-barrier hook
 inline void __syncthreads() { simt::bar_sync(0, (int)simt::cta->bdim.x); }
 inline void __syncwarp(uint32_t = 0xffffffffu) {}
 inline void __nanosleep(unsigned) { simt::yield(); sched_yield(); }
