@@ -125,16 +125,18 @@ int main(int argc, char **argv) {
     std::vector<uint8_t> d1;
     if (mode == 1) { if (argc != 13) return 2; d1 = read_file(argv[12]); }
 
-    const uint32_t line_cap = (uint32_t)((std::max(d0.size(), d1.size()) + 64) / 2 + 64) & ~3u;
+    uint32_t line_cap = (uint32_t)((std::max(d0.size(), d1.size()) + 64) / 2 + 64) & ~3u;
+    if (getenv("KH_LINE_CAP")) line_cap = (uint32_t)atoi(getenv("KH_LINE_CAP")) & ~3u;        // capacity tests
     Input in0 = stage_input(d0, first, line_cap), in1 = stage_input(d1, mode == 1 ? (first * 7u) % 16u : 0u, line_cap);
     sk::DevInput di[2] = {in0.di, in1.di};
     if (mode != 1) { di[1].data = nullptr; di[1].first = 0; di[1].nbytes = 0; di[1].line_end = nullptr; di[1].line_cap = 0; }
     const size_t cap = d0.size() + d1.size() + 4096;
+    const size_t dev_cap = getenv("KH_OUT_CAP") ? (size_t)atoll(getenv("KH_OUT_CAP")) : cap;   // what the kernels are told
     sk::OutPtrs op;
     std::vector<uint8_t *> outs;
     for (int k = 0; k < 3; ++k) {
         op.p[k] = aligned_zero<uint8_t>(cap + 64) + ((k * 5 + first) % 16);   // output buffers at odd phases too
-        op.cap[k] = cap;
+        op.cap[k] = dev_cap;
     }
     if (mode == 0 || mode == 3) { op.cap[1] = op.cap[2] = 0; op.p[1] = op.p[2] = nullptr; }
     if (mode == 2) { op.cap[1] = 0; op.p[1] = nullptr; if (!P.has_singles) { op.cap[2] = 0; op.p[2] = nullptr; } }
@@ -157,6 +159,10 @@ int main(int argc, char **argv) {
         run_general(di, mode == 1 ? 2 : 1, P, ctl, op, ctas, &res);
     }
 
+    if (res.index_overflow & 3u) {   // capi.cu's check_capacity: SK_E_CAPACITY
+        printf("OVERFLOW line_index=%d output=%d\n", (int)(res.index_overflow & 1u), (int)((res.index_overflow >> 1) & 1u));
+        return 0;
+    }
     // ---- the oracle on the same bytes (one batch, input order)
     so_params sp = {qualtype, P.qthr, P.lthr, P.no_fiveprime, P.trunc_n};
     std::vector<char> ob[3];

@@ -44,11 +44,11 @@ def harness():
 
 
 def run(exe, path, mode="se", qualtype="sanger", q=20, l=20, x=False, n=False, singles=True, kernel="fused9", ctas=3, first=0, path2=None,
-        threads=1):
+        threads=1, env=None):
     cmd = [exe, path, str(MODES[mode]), str(QT[qualtype]), str(q), str(l), str(int(x)), str(int(n)), str(int(singles)), kernel, str(ctas), str(first)]
     if path2:
         cmd.append(path2)
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, KH_THREADS=str(threads)))
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, KH_THREADS=str(threads), **(env or {})))
     return p.returncode, p.stdout.strip(), p.stderr
 
 
@@ -198,6 +198,22 @@ def test_edge_inputs(harness, tmp_path):
         open(p, "wb").write(data)
         for mode in ("se", "pei"):
             check(harness, p, (name, mode), mode=mode, first=3)
+
+
+def test_capacity_overflows_are_flagged(harness, tmp_path):
+    """A line index or an output buffer that is too small is reported (capi.cu turns the flags into
+    SK_E_CAPACITY), never written past: the harness allocates the full size and tells the kernels less."""
+    from sickle_b200 import synth
+
+    se = str(tmp_path / "se.fq")
+    open(se, "wb").write(synth.fixed_length_records(2000, 150, "sanger", seed=45).tobytes())
+    rc, out, err = run(harness, se, kernel="general", env={"KH_LINE_CAP": "1000"})
+    assert rc == 0 and out == "OVERFLOW line_index=1 output=0", (out, err[-300:])
+    for k in ("general", "fused9", "fused5"):
+        rc, out, err = run(harness, se, kernel=k, env={"KH_OUT_CAP": "100000"})
+        assert rc == 0 and out == "OVERFLOW line_index=0 output=1", (k, out, err[-300:])
+        rc, out, err = run(harness, se, kernel=k, env={"KH_OUT_CAP": "560000"})      # 558 KB of output: just fits
+        assert rc == 0 and out.startswith("OK"), (k, out)
 
 
 @pytest.mark.parametrize("defines", [("SK_LANE_SPLIT4",), ("SK_STAGE_LONG_FIRST",), ("SK_NL_BRANCHFREE",),
