@@ -44,8 +44,8 @@ def case_args(case, gdir, tmp, tag=""):
     return args, outs
 
 
-def run_case(sickle, case, gdir, tmp, extra_env=None):
-    args, outs = case_args(case, gdir, tmp)
+def run_case(sickle, case, gdir, tmp, extra_env=None, tag=""):
+    args, outs = case_args(case, gdir, tmp, tag)
     cmd = [sickle] + args
     env = dict(os.environ, SICKLE_B200_SLOT_MB="1", SICKLE_B200_HEADROOM_MB="1")
     env.update(extra_env or {})
@@ -62,16 +62,16 @@ def counts(stdout):
 
 
 def test_golden_cases_through_cli(sickle, golden, tmp_path):
+    from concurrent.futures import ThreadPoolExecutor
+
+    # every seventh flag set plus all -a N and all edge/error cases keeps the run short; each case is a
+    # fresh process (~2 s of CUDA start-up), so four run side by side
+    picked = [(i, c) for i, c in enumerate(golden["cases"])
+              if i % 7 == 0 or c["threads"] > 1 or "err_" in c["id"] or "ok_" in c["id"]]
+    with ThreadPoolExecutor(max_workers=4) as pool:
+        results = list(pool.map(lambda ic: run_case(sickle, ic[1], golden["dir"], str(tmp_path), tag="%d" % ic[0]), picked))
     bad = []
-    n = 0
-    for i, case in enumerate(golden["cases"]):
-        # every seventh flag set plus all -a N and all edge/error cases keeps the run short
-        # (each case is a fresh process: ~2 s of CUDA start-up)
-        edge = "err_" in case["id"] or "ok_" in case["id"]
-        if not (i % 7 == 0 or case["threads"] > 1 or edge):
-            continue
-        n += 1
-        p, outs = run_case(sickle, case, golden["dir"], str(tmp_path))
+    for (i, case), (p, outs) in zip(picked, results):
         if p.returncode != case["rc"]:
             bad.append((case["id"], "rc", p.returncode, p.stderr[-300:]))
             continue
@@ -88,7 +88,7 @@ def test_golden_cases_through_cli(sickle, golden, tmp_path):
         elif p.stderr.decode("latin-1") != case["stderr"]:
             bad.append((case["id"], "stderr", p.stderr.decode("latin-1")[:400], case["stderr"][:400]))
     assert not bad, bad[:6]
-    assert n > 50
+    assert len(picked) > 50
 
 
 def test_gzip_input_and_output(sickle, golden, tmp_path):

@@ -72,6 +72,11 @@ def test_many_batches_over_several_contexts(hoststub, tmp_path):
     test_cli.test_several_devices_many_batches(hoststub, tmp_path)
 
 
+def test_golden_cases_side_by_side(hoststub, golden, tmp_path):
+    """The -m gpu test of the command line on golden cases (fresh processes, four at a time), against the stub."""
+    test_cli.test_golden_cases_through_cli(hoststub, golden, tmp_path)
+
+
 def test_golden_cases_in_one_batch_process(hoststub, golden, tmp_path):
     test_cli.test_several_devices_golden_cases(hoststub, golden, tmp_path)
 
