@@ -5,6 +5,8 @@
 # `make variant V=<macro>`, run the CUDA parity tests against it (SICKLE_B200_LIB), then alternate
 # kernel-only bench runs of the shipped library and the variant `rounds` times (default 3) and print
 # ms per 1M-read step and the roofline fraction of each run.  A variant that fails parity is not timed.
+# `profiles/ab_variants.sh 2 SK_KO_S6 SK_KO_S8A SK_KO_FLUSH SK_KO_LB1 SK_KO_LB2` times the knock-outs
+# (one phase removed each, output wrong by construction): what each phase costs in throughput.
 set -u
 ROUNDS=${1:-3}
 shift || true
@@ -21,9 +23,12 @@ for V in "${VARIANTS[@]}"; do
   echo "=== $V"
   /usr/local/cuda/bin/nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -lineinfo -Xcompiler -fPIC,-Wall,-Wno-unused-function \
       -D$V -shared sickle_b200/csrc/capi.cu -o $LIB 2> /dev/null || { echo "build failed"; continue; }
-  SICKLE_B200_LIB=$PWD/$LIB python -m pytest tests/test_cuda_parity.py -m gpu -x -q > /tmp/ab_parity.log 2>&1
-  RC=$?
-  tail -2 /tmp/ab_parity.log
-  [ $RC -ne 0 ] && { echo "PARITY FAILED: not timed"; continue; }
+  case "$V" in
+    SK_KO_*) echo "(timing-only knock-out: output is wrong by construction, no parity run)";;
+    *) SICKLE_B200_LIB=$PWD/$LIB python -m pytest tests/test_cuda_parity.py -m gpu -x -q > /tmp/ab_parity.log 2>&1
+       RC=$?
+       tail -2 /tmp/ab_parity.log
+       [ $RC -ne 0 ] && { echo "PARITY FAILED: not timed"; continue; };;
+  esac
   for r in $(seq 1 $ROUNDS); do one $BASE shipped; one $LIB "$NAME"; done
 done

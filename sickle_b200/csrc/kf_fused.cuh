@@ -58,6 +58,10 @@ __device__ unsigned long long g_phase_cycles[12];
 #define SK_TICK(k) do { } while (0)
 #endif
 
+// Timing-only knock-outs (-DSK_KO_S6 / SK_KO_S8A / SK_KO_FLUSH / SK_KO_LB1 / SK_KO_LB2, never in a shipped
+// build: the output is WRONG): each removes one phase so that `bench.py --kernel-only` shows what that
+// phase costs in throughput rather than in instruction share (profiles/ab_variants.sh).  SK_KO_LB1
+// assumes the bench's fixed 325-byte records.
 constexpr int kFThreads = 256;
 constexpr int kFTileThreads = 224;   // 7 warps own tile bytes, the 8th warp scans the halo
 constexpr int kFMaxNl = 1024;        // newline positions per region (2 KB; also holds 128 record descriptors)
@@ -89,7 +93,11 @@ __device__ __forceinline__ void flush_previous_tile(unsigned long long *const st
 #ifdef SK_PHASE_TIMING
     const long long t_in = clock64();
 #endif
+#ifdef SK_KO_LB2
+    ex[0] = (unsigned long long)p_tile * 30000ull; ex[1] = (unsigned long long)p_tile * 3000ull;   // no walk: made-up offsets
+#else
     block_walk(st_out, p_tile, agg, nstreams, epoch, gtid, s_lb, ex, gwarps, kFlushBarrier);
+#endif
 #ifdef SK_PHASE_TIMING
     if (gtid == 0) atomicAdd(&g_phase_cycles[5], (unsigned long long)(clock64() - t_in));   // look-back #2 (flush group)
 #endif
@@ -99,8 +107,10 @@ __device__ __forceinline__ void flush_previous_tile(unsigned long long *const st
         if (gtid == 0) ctl->index_overflow = 2u;
         return;
     }
+#ifndef SK_KO_FLUSH
     flush_realigned(outs.p[0] + ex[0], s_out, 0u, p_tot0, gtid, gwarps * 32);
     if (p_tot1) flush_realigned(outs.p[2] + ex[1], s_out, (p_tot0 + 15u) & ~15u, p_tot1, gtid, gwarps * 32);
+#endif
 #ifdef SK_PHASE_TIMING
     if (gtid == 0) atomicAdd(&g_phase_cycles[7], (unsigned long long)(clock64() - t_in));   // look-back #2 + flush (flush group)
 #endif
@@ -308,8 +318,14 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         {
             const unsigned long long agg[2] = {c_t, 0};
             unsigned long long ex[2];
+#ifdef SK_KO_LB1
+            (void)agg; (void)ex;
+            const uint32_t rem = t0 % 325u;   // newlines of a 325-byte record sit at offsets 20, 171, 173, 324
+            G = 4u * (t0 / 325u) + (rem > 20u) + (rem > 171u) + (rem > 173u) + (rem > 324u);
+#else
             block_walk(st_nl, tile, agg, 1, epoch, tid, s_lb, ex);
             G = (uint32_t)ex[0];
+#endif
         }
         __syncthreads();   // newline positions visible to every thread
         SK_TICK(3);   // S3 positions + S4 look-back #1
@@ -373,7 +389,11 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             // FQEntry::validate (src/FQEntry.cpp:53-97): any violation is a data error
             if (name_len <= 1u || s_in[start] != '@' || L < 1u || qlen < 1u || qlen != L) fail = true;
             else {
+#ifdef SK_KO_S6
+                cut.five = 0; cut.three = (int)L;   // nothing trimmed
+#else
                 cut = lane_sliding_window(s_in, e0 + 1u, L, e2 + 1u, P, rc, sub, nsub, lane);
+#endif
                 if (cut.error) fail = true;
             }
         }
@@ -496,8 +516,10 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 t = a_len; a_len = b_len; b_len = t;
             }
 #endif
+#ifndef SK_KO_S8A
             smem_copy(s_out, a_dst, s_in, a_src, a_len);
             if (__any_sync(0xffffffffu, b_len != 0)) smem_copy(s_out, b_dst, s_in, b_src, b_len);
+#endif
             if (nl_at >= 0) s_out[nl_at] = '\n';
             if (emit && nrec) {
                 if (sub == 0) { s_out[d + nlen + 1u] = 'N'; s_out[d + nlen + 2u] = '\n'; }
