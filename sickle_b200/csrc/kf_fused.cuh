@@ -73,12 +73,81 @@ struct FusedCfg {
     static constexpr int kRegion = kFThreads * kBytesPerThread;
     static constexpr int kTile = kFTileThreads * kBytesPerThread;
     static constexpr int kInBytes = kRegion + 96;        // the window loop reads up to ~50 bytes past a record
+#ifdef SK_DIRECT_EMIT
+    // Experimental (off by default; next round's A/B): no staging buffer.  The input tile is double-buffered
+    // and the flush group copies the previous tile's records straight from its input buffer to their
+    // final global addresses (the S8a copy with a global destination) while the record warps trim the
+    // next tile: S8a leaves the critical path and the flat flush disappears.  Descriptors get their own
+    // 2 KB (they must outlive the next tile's newline positions).
+    static constexpr int kOutBytes = 0;
+    static constexpr size_t kSmem = 2 * (size_t)kInBytes + kFMaxNl * 2 + 128 * 16;
+#else
     static constexpr int kOutBytes = kTile + 768 + 96;   // a tile of output + the last record's overhang + phase shifts
     // CH = 7: 56,768 B -> four CTAs per SM (4 x (56,768 + 248 static + 1,024 reserved) <= 232,448)
     static constexpr size_t kSmem = (size_t)kInBytes + kOutBytes + kFMaxNl * 2;
+#endif
     // CTAs per SM by shared memory (232,448 B per SM, 1,024 B reserved per CTA); also the register budget
     static constexpr int kCtasPerSm = (int)(232448 / (kSmem + 1024 + 256)) > 4 ? 4 : (int)(232448 / (kSmem + 1024 + 256));
 };
+
+#ifdef SK_DIRECT_EMIT
+// S8a's copy with global destinations, run by the flush group (gt = thread index in the group, gn = its size)
+// one tile late: two lanes per record, lane 0 takes [name '\n' seq), lane 1 takes ['\n' line3 '\n' qual '\n').
+// g0 / g1 = where the tile's bytes of the main / singles stream start in global memory.
+__device__ __forceinline__ void copy_records_direct(uint8_t *g0, uint8_t *g1, const uint8_t *__restrict__ src_in,
+                                                    const uint4 *__restrict__ desc, uint32_t nrec, int gt, int gn,
+                                                    const DevParams &P) {
+    // smem_copy wants a 16-byte aligned base: aligned-down pointer + phase
+    const uint32_t ph0 = (uint32_t)(reinterpret_cast<uintptr_t>(g0) & 15u), ph1 = (uint32_t)(reinterpret_cast<uintptr_t>(g1) & 15u);
+    uint8_t *const gal0 = g0 - ph0, *const gal1 = g1 - ph1;
+    const uint32_t sub = (uint32_t)gt & 1u;
+    for (uint32_t r0 = 0; r0 < nrec; r0 += (uint32_t)gn >> 1) {            // same trip count for every lane (votes inside)
+        const uint32_t r = r0 + ((uint32_t)gt >> 1);
+        uint4 dsc = make_uint4(0, 0, 0, 0);
+        if (r < nrec) dsc = desc[r];
+        uint32_t a_dst = 0, a_src = 0, a_len = 0, b_dst = 0, b_src = 0, b_len = 0;
+        int nl_at = -1;
+        const bool emit = (dsc.x & 0x20000000u) != 0;
+        const bool nrec_out = (dsc.x & 0x40000000u) != 0;
+        const bool singles = (dsc.x & 0x80000000u) != 0;
+        uint8_t *const ob = singles ? gal1 : gal0;
+        const uint32_t r_start = dsc.y & 0xffffu, r_e0 = dsc.y >> 16, r_e1 = dsc.z & 0xffffu, r_e2 = dsc.z >> 16;
+        const uint32_t five = dsc.w & 0xffffu, n = dsc.w >> 16;
+        const uint32_t nlen = r_e0 - r_start, plen = r_e2 - r_e1 - 1u;
+        const uint32_t d = (singles ? ph1 : ph0) + (dsc.x & 0xffffu);
+        if (emit) {
+            if (sub == 0) {
+                a_dst = d; a_src = r_start;
+                a_len = nlen + 1u + ((five == 0 && !nrec_out) ? n : 0u);
+                b_dst = d + nlen + 1u; b_src = r_e0 + 1u + five;
+                b_len = (five != 0 && !nrec_out) ? n : 0u;
+            } else if (!nrec_out) {
+                a_dst = d + nlen + 1u + n; a_src = r_e1;
+                a_len = plen + 2u + (five == 0 ? n : 0u);
+                b_dst = a_dst + plen + 2u; b_src = r_e2 + 1u + five;
+                b_len = five != 0 ? n : 0u;
+                nl_at = (int)(b_dst + n);
+            } else {
+                a_dst = d + nlen + 3u; a_src = r_e1 + 1u; a_len = plen + 1u;
+            }
+        }
+        const uint32_t n_dst = a_dst;                       // (the swap below must not move the N record's bytes)
+        if (b_len != 0) {                                   // the long piece first (see SK_STAGE_LONG_FIRST)
+            uint32_t t;
+            t = a_dst; a_dst = b_dst; b_dst = t;
+            t = a_src; a_src = b_src; b_src = t;
+            t = a_len; a_len = b_len; b_len = t;
+        }
+        smem_copy(ob, a_dst, src_in, a_src, a_len);
+        if (__any_sync(0xffffffffu, b_len != 0)) smem_copy(ob, b_dst, src_in, b_src, b_len);
+        if (nl_at >= 0) ob[nl_at] = '\n';
+        if (emit && nrec_out) {
+            if (sub == 0) { ob[d + nlen + 1u] = 'N'; ob[d + nlen + 2u] = '\n'; }
+            else { ob[n_dst + plen + 1u] = (uint8_t)P.qmin; ob[n_dst + plen + 2u] = '\n'; }
+        }
+    }
+}
+#endif
 
 // The deferred half of a tile (S7b + S8b), run by the "flush group" -- warps 4..7, which never own a
 // record -- while warps 0..3 validate and trim the next tile: look-back #2 over the output sizes,
@@ -87,7 +156,11 @@ constexpr int kFlushBarrier = 1;
 __device__ __forceinline__ void flush_previous_tile(unsigned long long *const st_out[2], uint32_t p_tile, uint32_t p_tot0,
                                                     uint32_t p_tot1, int nstreams, uint32_t epoch, int gtid, int gwarps,
                                                     unsigned long long (*s_lb)[2], Control *__restrict__ ctl,
-                                                    const OutPtrs &outs, const uint8_t *__restrict__ s_out, uint32_t num_tiles) {
+                                                    const OutPtrs &outs, const uint8_t *__restrict__ s_out, uint32_t num_tiles
+#ifdef SK_DIRECT_EMIT
+                                                    , const uint4 *__restrict__ p_desc, uint32_t p_nrec, const DevParams &P
+#endif
+                                                    ) {
     const unsigned long long agg[2] = {p_tot0, p_tot1};
     unsigned long long ex[2];
 #ifdef SK_PHASE_TIMING
@@ -107,7 +180,10 @@ __device__ __forceinline__ void flush_previous_tile(unsigned long long *const st
         if (gtid == 0) ctl->index_overflow = 2u;
         return;
     }
-#ifndef SK_KO_FLUSH
+#ifdef SK_DIRECT_EMIT
+    // s_out = the previous tile's INPUT buffer here
+    copy_records_direct(outs.p[0] + ex[0], p_tot1 ? outs.p[2] + ex[1] : outs.p[0], s_out, p_desc, p_nrec, gtid, gwarps * 32, P);
+#elif !defined(SK_KO_FLUSH)
     flush_realigned(outs.p[0] + ex[0], s_out, 0u, p_tot0, gtid, gwarps * 32);
     if (p_tot1) flush_realigned(outs.p[2] + ex[1], s_out, (p_tot0 + 15u) & ~15u, p_tot1, gtid, gwarps * 32);
 #endif
@@ -129,10 +205,18 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
          uint32_t status_stride, uint32_t num_tiles, uint32_t epoch) {
     using Cfg = FusedCfg<CH>;
     extern __shared__ __align__(16) uint8_t smem[];
+#ifdef SK_DIRECT_EMIT
+    uint8_t *s_in = smem;                                    // set per tile: the two input buffers alternate
+    uint8_t *s_out = smem + Cfg::kInBytes;                   // per tile: the OTHER input buffer (the previous tile's bytes)
+    uint16_t *s_nl = reinterpret_cast<uint16_t *>(smem + 2 * Cfg::kInBytes);
+    uint4 *s_desc = reinterpret_cast<uint4 *>(smem + 2 * Cfg::kInBytes + kFMaxNl * 2);
+    uint32_t parity = 0, p_nrec = 0;
+#else
     uint8_t *s_in = smem;
     uint8_t *s_out = smem + Cfg::kInBytes;
     uint16_t *s_nl = reinterpret_cast<uint16_t *>(smem + Cfg::kInBytes + Cfg::kOutBytes);
     uint4 *s_desc = reinterpret_cast<uint4 *>(s_nl);   // S7/S8a record descriptors alias the newline positions
+#endif
     __shared__ uint32_t s_tile;
     __shared__ uint32_t warp_tot[kFThreads / 32];
     __shared__ uint32_t warp_tot2[kFThreads / 32][2];
@@ -181,6 +265,11 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         __syncthreads();
         const uint32_t tile = s_tile;
         const bool done = tile >= num_tiles;
+#ifdef SK_DIRECT_EMIT
+        s_in = smem + (size_t)parity * Cfg::kInBytes;
+        s_out = smem + (size_t)(parity ^ 1u) * Cfg::kInBytes;
+        parity ^= 1u;
+#endif
         const uint32_t t0 = tile * (uint32_t)Cfg::kTile;
 
         uint32_t mw[(CH + 1) / 2];                               // newline bits, 32 bytes per word
@@ -276,7 +365,11 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         SK_TICK(2);   // (+ newline-count publish)
         if (done) {   // no tile left: only the last staged tile remains to be flushed
             if (have_prev && wid >= 4)
-                flush_previous_tile(st_out, p_tile, p_tot0, p_tot1, nstreams, epoch, tid - 128, 4, s_lb, ctl, outs, s_out, num_tiles);
+                flush_previous_tile(st_out, p_tile, p_tot0, p_tot1, nstreams, epoch, tid - 128, 4, s_lb, ctl, outs, s_out, num_tiles
+#ifdef SK_DIRECT_EMIT
+                                    , s_desc, p_nrec, P
+#endif
+                                    );
             break;
         }
 
@@ -352,7 +445,11 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         // was spent waiting there.)
         if (have_prev && wid >= flush_warp0)
             flush_previous_tile(st_out, p_tile, p_tot0, p_tot1, nstreams, epoch, tid - flush_warp0 * 32, kFThreads / 32 - flush_warp0,
-                                s_lb, ctl, outs, s_out, num_tiles);
+                                s_lb, ctl, outs, s_out, num_tiles
+#ifdef SK_DIRECT_EMIT
+                                , s_desc, p_nrec, P
+#endif
+                                );
         have_prev = false;
 
         // per-record state (nsub adjacent lanes = one record; mates of a pair are nsub lanes apart)
@@ -437,7 +534,11 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         }
         // the staging buffer holds a tile's worth of output; a tile whose (long, untrimmed) records
         // reach far into the halo can exceed it -> general path
+#ifdef SK_DIRECT_EMIT
+        const bool tile_fail = s_fail != 0 || tot0 >= 65536u || tot1 >= 65536u;   // (descriptor offsets are 16 bit)
+#else
         const bool tile_fail = s_fail != 0 || tot0 + tot1 + 64u > (uint32_t)Cfg::kOutBytes;
+#endif
         if (tile_fail) {   // bit 1: the tile simply holds too many records (the host then picks smaller tiles)
             tot0 = 0; tot1 = 0;
             if (tid == 0) atomicOr(&ctl->fast_fail, (nl_overflow || nrec_t > (uint32_t)kFThreads / 2u) ? 3u : 1u);
@@ -449,6 +550,9 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         if (tid == 0) held = atomicAdd(&ctl->tile_counter[3], 1u);   // looked at after S8a
         have_prev = true;
         p_tile = tile; p_tot0 = tot0; p_tot1 = tot1;
+#ifdef SK_DIRECT_EMIT
+        p_nrec = tile_fail ? 0u : nrec_t;
+#endif
         const uint32_t base1 = (tot0 + 15u) & ~15u;                    // singles staged after the main bytes
 
         // record descriptors for S8a (two lanes per record); they reuse the newline-position array,
@@ -469,6 +573,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
 
         // ---- S8a: two lanes per record copy it into the staging buffer (phase 0; the flush realigns):
         // lane 0 takes [name '\n' seq), lane 1 takes ['\n' line3 '\n' qual '\n')
+#ifndef SK_DIRECT_EMIT
         {
             const uint32_t r = (uint32_t)tid >> 1, sub = (uint32_t)tid & 1u;
             uint4 dsc = make_uint4(0, 0, 0, 0);
@@ -526,6 +631,9 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 else { s_out[a_dst + plen + 1u] = (uint8_t)P.qmin; s_out[a_dst + plen + 2u] = '\n'; }
             }
         }
+#else
+        (void)base1;
+#endif
         SK_TICK(6);   // S8a (thread 0's own copies)
 #ifdef SK_PHASE_TIMING
         __syncthreads();   // timing build only: how long the slowest warp takes beyond thread 0

@@ -216,8 +216,9 @@ def test_capacity_overflows_are_flagged(harness, tmp_path):
         assert rc == 0 and out.startswith("OK"), (k, out)
 
 
-@pytest.mark.parametrize("defines", [("SK_LANE_SPLIT4",), ("SK_STAGE_LONG_FIRST",), ("SK_NL_BRANCHFREE",),
-                                     ("SK_LANE_SPLIT4", "SK_STAGE_LONG_FIRST", "SK_NL_BRANCHFREE")])
+@pytest.mark.parametrize("defines", [("SK_LANE_SPLIT4",), ("SK_STAGE_LONG_FIRST",), ("SK_NL_BRANCHFREE",), ("SK_DIRECT_EMIT",),
+                                     ("SK_LANE_SPLIT4", "SK_STAGE_LONG_FIRST", "SK_NL_BRANCHFREE"),
+                                     ("SK_DIRECT_EMIT", "SK_LANE_SPLIT4", "SK_NL_BRANCHFREE")])
 def test_experimental_variants(tmp_path, defines):
     """The build variants kept for the next round's A/B runs (off in the shipped library) write the same bytes."""
     from sickle_b200 import synth
@@ -234,3 +235,6 @@ def test_experimental_variants(tmp_path, defines):
     check(exe, il, "pei", mode="pei", first=9)
     check(exe, il, "peM", mode="peM", singles=False)
     check(exe, var, "variable", qualtype="illumina", n=True)
+    big = str(tmp_path / "big.fq")
+    open(big, "wb").write(synth.fixed_length_records(30000, 150, "sanger", seed=17).tobytes())
+    assert check(exe, big, "se 30k, 8 CTAs", kernels=("fused7", "fused9"), ctas=8, first=3) == ["OK"] * 2
