@@ -11,7 +11,7 @@ set -u
 ROUNDS=${1:-3}
 shift || true
 VARIANTS=("$@")
-[ ${#VARIANTS[@]} -eq 0 ] && VARIANTS=(SK_LANE_SPLIT4 SK_STAGE_LONG_FIRST SK_NL_BRANCHFREE "SK_LANE_SPLIT4 -DSK_STAGE_LONG_FIRST -DSK_NL_BRANCHFREE" SK_DIRECT_EMIT)
+[ ${#VARIANTS[@]} -eq 0 ] && VARIANTS=(SK_LANE_SPLIT4 SK_STAGE_LONG_FIRST SK_NL_BRANCHFREE "SK_LANE_SPLIT4 -DSK_STAGE_LONG_FIRST -DSK_NL_BRANCHFREE" SK_DIRECT_EMIT "SK_DIRECT_EMIT -DSK_EARLY_LOAD")
 # (SK_DIRECT_EMIT doubles the input buffer: 2 CTAs per SM at the default 32 KB tile, 3 at 25 KB -- also run it as
 #  SICKLE_B200_FUSED_CH=7 profiles/ab_variants.sh 3 SK_DIRECT_EMIT, which pins both libraries to the 25 KB tile)
 BASE=sickle_b200/libsickle_b200.so

@@ -249,6 +249,29 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
 #endif
     __syncthreads();
 
+#ifdef SK_EARLY_LOAD
+#ifndef SK_DIRECT_EMIT
+#error "SK_EARLY_LOAD needs SK_DIRECT_EMIT (two input buffers)"
+#endif
+    // Experimental (off by default; next round's A/B): thread 0 starts the bulk copy of the next tile as
+    // soon as it holds the ticket, into the input buffer that has just become free.
+    bool early_issued = false;
+    auto issue_load = [&](uint8_t *buf, uint32_t tile_no) {
+        const uint32_t t0_ = tile_no * (uint32_t)Cfg::kTile;
+        const uint32_t have_ = nchunks - (t0_ >> 4);
+        const uint32_t n_ = (have_ < (uint32_t)(Cfg::kRegion / 16) ? have_ : (uint32_t)(Cfg::kRegion / 16)) * 16u;
+#if defined(__CUDACC__)
+        const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&s_mbar);
+        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(buf);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(n_) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                     ::"r"(dst), "l"(in.data + t0_), "r"(n_), "r"(mb) : "memory");
+#else
+        memcpy(buf, in.data + t0_, n_);
+#endif
+    };
+#endif
     // the tile whose output is staged in s_out and not flushed yet
     bool have_prev = false;
     uint32_t p_tile = 0, p_tot0 = 0, p_tot1 = 0;
@@ -281,7 +304,9 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             // mbarrier; the threads only zero what lies beyond the end of the batch (last tiles)
             const uint32_t have = nchunks - (t0 >> 4);                              // 16-byte chunks from t0 on (>= 1)
             const uint32_t cp_chunks = have < (uint32_t)(Cfg::kRegion / 16) ? have : (uint32_t)(Cfg::kRegion / 16);
-#if defined(__CUDACC__)
+#if defined(SK_EARLY_LOAD)
+            if (tid == 0 && !early_issued) issue_load(s_in, tile);
+#elif defined(__CUDACC__)
             if (tid == 0) {
                 const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&s_mbar);
                 const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_in);
@@ -548,6 +573,15 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             block_publish(st_out, tile, agg, nstreams, epoch, tid);
         }
         if (tid == 0) held = atomicAdd(&ctl->tile_counter[3], 1u);   // looked at after S8a
+#ifdef SK_EARLY_LOAD
+        // The buffer the next tile goes to held tile t-1, which the flush group finished before the barrier
+        // above: its load can start now and run under the descriptor writes, the bookkeeping and the
+        // barriers up to the next tile's S2.
+        if (tid == 0) {
+            early_issued = held < num_tiles;
+            if (early_issued) issue_load(smem + (size_t)parity * Cfg::kInBytes, held);
+        }
+#endif
         have_prev = true;
         p_tile = tile; p_tot0 = tot0; p_tot1 = tot1;
 #ifdef SK_DIRECT_EMIT

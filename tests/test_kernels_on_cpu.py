@@ -218,7 +218,7 @@ def test_capacity_overflows_are_flagged(harness, tmp_path):
 
 @pytest.mark.parametrize("defines", [("SK_LANE_SPLIT4",), ("SK_STAGE_LONG_FIRST",), ("SK_NL_BRANCHFREE",), ("SK_DIRECT_EMIT",),
                                      ("SK_LANE_SPLIT4", "SK_STAGE_LONG_FIRST", "SK_NL_BRANCHFREE"),
-                                     ("SK_DIRECT_EMIT", "SK_LANE_SPLIT4", "SK_NL_BRANCHFREE")])
+                                     ("SK_DIRECT_EMIT", "SK_EARLY_LOAD", "SK_LANE_SPLIT4", "SK_NL_BRANCHFREE")])
 def test_experimental_variants(tmp_path, defines):
     """The build variants kept for the next round's A/B runs (off in the shipped library) write the same bytes."""
     from sickle_b200 import synth
