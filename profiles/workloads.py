@@ -30,12 +30,12 @@ def device_bytes(mat, target_bytes, dev):
     return buf, t.numel() * rep, mat.shape[0] * rep
 
 
-def measure(name, mode, inputs, n_records, env=None, emulate_threads=1, steps=10):
+def measure(name, mode, inputs, n_records, env=None, emulate_threads=1, steps=10, qualtype="sanger", x=False, n=False):
     dev = torch.device("cuda:0")
     old = {k: os.environ.get(k) for k in (env or {})}
     os.environ.update(env or {})
     try:
-        p = capi.make_params("sanger", mode=mode, emulate_threads=emulate_threads, has_singles=True)
+        p = capi.make_params(qualtype, 20, 20, x, n, mode=mode, emulate_threads=emulate_threads, has_singles=True)
         slot = max(n for _, n in inputs) + 16
         ctx = capi.Context(p, slot, 0)
     finally:
@@ -102,6 +102,17 @@ def main():
     buf = torch.zeros(arr.size * rep + 64, dtype=torch.uint8, device=dev)
     buf[:arr.size * rep] = torch.from_numpy(arr.copy()).to(dev).repeat(rep)
     measure("se variable length 36-151", capi.MODE_SE, [(buf, arr.size * rep)], 150_000 * rep)
+    del buf
+    # BASELINE.json configs[3]: reads of 1-20 kb, -x -n, Illumina / Solexa encodings (general path: a warp per read)
+    for qualtype, seed in (("illumina", 70), ("solexa", 71)):
+        v = synth.variable_length_records(4000, 1000, 20000, qualtype, seed)
+        arr = np.frombuffer(v, dtype=np.uint8)
+        rep = max(1, target // arr.size)
+        buf = torch.zeros(arr.size * rep + 64, dtype=torch.uint8, device=dev)
+        buf[:arr.size * rep] = torch.from_numpy(arr.copy()).to(dev).repeat(rep)
+        measure("se long reads 1-20 kb, %s, -x -n (configs[3])" % qualtype, capi.MODE_SE, [(buf, arr.size * rep)], 4000 * rep,
+                qualtype=qualtype, x=True, n=True)
+        del buf
 
 
 if __name__ == "__main__":

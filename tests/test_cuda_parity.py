@@ -425,3 +425,20 @@ def test_sharded_plan_on_cuda_path(capi, world):
         kept += got["counters"]["kept"]
     assert b"".join(outs) == want["out"][0]
     assert kept == want["counters"]["kept"]
+
+
+@pytest.mark.parametrize("qualtype", ["illumina", "solexa"])
+def test_long_reads_config4(capi, qualtype):
+    """BASELINE.json configs[3]: variable-length reads of 1-20 kb (window = 0.1 x length) with -x and -n,
+    Illumina / Solexa encodings, every fifth record with '+name'.  Records of this size exceed the fused
+    kernel's halo, so every batch ends up on the general path (K2: a whole warp per read)."""
+    from sickle_b200 import synth
+
+    data = synth.variable_length_records(300, 1000, 20000, qualtype, 4)
+    for fl in (dict(q=20, l=20, x=True, n=True), dict(q=30, l=100, x=False, n=False)):
+        want = orc.run(orc.MODE_SE, orc.make_params(qualtype, fl["q"], fl["l"], fl["x"], fl["n"]), data)
+        assert want["rc"] == 0
+        got = _run_cuda(capi, capi.MODE_SE, dict(qualtype=qualtype, **fl), data, slot_bytes=1 << 20)
+        assert got["out"][0] == want["out"][0], (qualtype, fl)
+        assert (got["counters"]["kept"], got["counters"]["discard"]) == (want["counters"]["kept"], want["counters"]["discard"])
+        assert got["batches"] > 2 and got["fused_batches"] == 0

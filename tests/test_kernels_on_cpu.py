@@ -154,6 +154,17 @@ def test_read_lengths_from_1_to_12000(harness, tmp_path):
                 assert seen[:4] == ["FASTFAIL"] * 4
 
 
+def test_long_reads_config4(harness, tmp_path):
+    """BASELINE.json configs[3]: reads of 1-20 kb with -x and -n, Illumina / Solexa encodings, '+name' lines."""
+    from sickle_b200 import synth
+
+    for qualtype, seed in (("illumina", 4), ("solexa", 5)):
+        p = str(tmp_path / (qualtype + ".fq"))
+        open(p, "wb").write(synth.variable_length_records(50, 1000, 20000, qualtype, seed))
+        assert check(harness, p, qualtype, kernels=("fused9", "general"), qualtype=qualtype, x=True, n=True, ctas=4, first=3) == ["FASTFAIL", "OK"]
+        check(harness, p, (qualtype, "q30"), kernels=("general",), qualtype=qualtype, q=30, l=100, ctas=3)
+
+
 def test_damaged_inputs(harness, tmp_path):
     """Seeded random files, three quarters of them damaged (missing / blank / doubled line, flipped /
     deleted / inserted byte, cut-off tail): same first data error (kind, record, position, byte) or same
