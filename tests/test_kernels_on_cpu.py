@@ -160,7 +160,7 @@ def test_long_reads_config4(harness, tmp_path):
 
     for qualtype, seed in (("illumina", 4), ("solexa", 5)):
         p = str(tmp_path / (qualtype + ".fq"))
-        open(p, "wb").write(synth.variable_length_records(50, 1000, 20000, qualtype, seed))
+        open(p, "wb").write(synth.variable_length_records(16, 1000, 20000, qualtype, seed))
         assert check(harness, p, qualtype, kernels=("fused9", "general"), qualtype=qualtype, x=True, n=True, ctas=4, first=3) == ["FASTFAIL", "OK"]
         check(harness, p, (qualtype, "q30"), kernels=("general",), qualtype=qualtype, q=30, l=100, ctas=3)
 
