@@ -143,7 +143,7 @@ def test_read_lengths_from_1_to_12000(harness, tmp_path):
     from test_oracle_fuzz_vs_ref import _records
 
     rng = np.random.default_rng(8)
-    for lmax, nrec in ((12, 4000), (40, 3000), (100, 2500), (250, 2000), (2000, 300), (12000, 60)):
+    for lmax, nrec in ((12, 2000), (40, 1500), (100, 1200), (250, 1000), (2000, 150), (12000, 24)):
         for qualtype in ("sanger", "illumina", "solexa"):
             p = str(tmp_path / ("l%d_%s.fq" % (lmax, qualtype)))
             open(p, "wb").write(_records(rng, nrec, lmax, qualtype))
@@ -227,8 +227,7 @@ def test_capacity_overflows_are_flagged(harness, tmp_path):
         assert rc == 0 and out.startswith("OK"), (k, out)
 
 
-@pytest.mark.parametrize("defines", [("SK_LANE_SPLIT4",), ("SK_STAGE_LONG_FIRST",), ("SK_NL_BRANCHFREE",), ("SK_DIRECT_EMIT",),
-                                     ("SK_LANE_SPLIT4", "SK_STAGE_LONG_FIRST", "SK_NL_BRANCHFREE"),
+@pytest.mark.parametrize("defines", [("SK_LANE_SPLIT4", "SK_STAGE_LONG_FIRST", "SK_NL_BRANCHFREE"), ("SK_DIRECT_EMIT",),
                                      ("SK_DIRECT_EMIT", "SK_EARLY_LOAD", "SK_LANE_SPLIT4", "SK_NL_BRANCHFREE")])
 def test_experimental_variants(tmp_path, defines):
     """The build variants kept for the next round's A/B runs (off in the shipped library) write the same bytes."""
