@@ -26,11 +26,11 @@ QT = {"sanger": 1, "solexa": 2, "illumina": 3}
 MODES = {"se": 0, "pe2": 1, "pei": 2, "peM": 3}
 
 
-def build_harness(name, defines=()):
+def build_harness(name, defines=(), extra=()):
     os.makedirs(BUILD, exist_ok=True)
     out = os.path.join(BUILD, name)
     stub = os.path.join(ROOT, "tests", "host_stub")
-    subprocess.check_call(["g++", "-O1", "-std=c++17", "-w", "-fno-extern-tls-init"] + ["-D" + d for d in defines] +
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-w", "-fno-extern-tls-init"] + list(extra) + ["-D" + d for d in defines] +
                           ["-I" + os.path.join(stub, "simt"), "-I" + os.path.join(stub, "simt", "include"),
                            "-I" + os.path.join(ROOT, "sickle_b200", "csrc"), "-I" + os.path.join(ROOT, "oracle"),
                            "-x", "c++", os.path.join(stub, "kernels_harness.cpp"), "-x", "c", os.path.join(ROOT, "oracle", "sickle_oracle.c"),
@@ -209,6 +209,26 @@ def test_edge_inputs(harness, tmp_path):
         open(p, "wb").write(data)
         for mode in ("se", "pei"):
             check(harness, p, (name, mode), mode=mode, first=3)
+
+
+def test_no_out_of_bounds_access_under_asan(tmp_path):
+    """The kernels under AddressSanitizer with input and output buffers sized exactly as capi.cu sizes them
+    (64 bytes of padding, nothing more): no global read or write outside them, on either path."""
+    from sickle_b200 import synth
+    from test_oracle_fuzz_vs_ref import _records
+
+    exe = build_harness("kernels_harness_asan", extra=("-g", "-fsanitize=address"))
+    se, il, var = (str(tmp_path / n) for n in ("se.fq", "il.fq", "var.fq"))
+    open(se, "wb").write(synth.fixed_length_records(2000, 150, "sanger", seed=55).tobytes())
+    open(il, "wb").write(synth.paired_records(1000, 150, "sanger", seed=56)[2].tobytes())
+    open(var, "wb").write(_records(np.random.default_rng(57), 1500, 250, "sanger"))
+    env = {"KH_TIGHT": "1", "ASAN_OPTIONS": "detect_leaks=0"}
+    for path, kw in ((se, dict(kernel="fused9", first=0)), (se, dict(kernel="fused7", first=11, ctas=2)), (se, dict(kernel="general", first=7)),
+                     (il, dict(kernel="fused9", mode="pei", first=3)), (il, dict(kernel="fused5", mode="peM", singles=False)),
+                     (il, dict(kernel="general", mode="pei", first=9)), (var, dict(kernel="fused5", n=True, first=5)),
+                     (var, dict(kernel="general", x=True, n=True, ctas=4, first=2))):
+        rc, out, err = run(exe, path, env=env, **kw)
+        assert rc == 0 and out.startswith("OK") and "AddressSanitizer:" not in err, (kw, out, err[-1500:])
 
 
 def test_capacity_overflows_are_flagged(harness, tmp_path):
