@@ -64,7 +64,7 @@ Input stage_input(const std::vector<uint8_t> &data, uint32_t first, uint32_t lin
         in.buf = aligned_zero<uint8_t>(data.size() + first + 128);
     }
     memset(in.buf, 'x', first);                                     // bytes before the batch: ignored by the kernels
-    memcpy(in.buf + first, data.data(), data.size());
+    if (!data.empty()) memcpy(in.buf + first, data.data(), data.size());
     in.di.data = in.buf;
     in.di.first = first;
     in.di.nbytes = (uint32_t)(first + data.size());
