@@ -142,12 +142,26 @@ inline void launch(dim3 grid, dim3 block, const std::function<void()> &body, siz
                 f.ctx.uc_link = &c.sched;
                 makecontext(&f.ctx, (void (*)())fiber_entry, 0);
             }
-            while (c.alive > 0)
-                for (uint32_t t = 0; t < block.x; ++t) {
+            // SIMT_SHUFFLE=<seed>: run the fibers of every scheduling round in a random order instead of by
+            // thread index, so that code which only works because a lower-numbered thread ran first (a
+            // missing barrier, an unordered shared-memory hand-over) shows up as a mismatch.
+            const char *shuf = getenv("SIMT_SHUFFLE");
+            uint64_t rng = shuf ? (uint64_t)atoll(shuf) * 0x9E3779B97F4A7C15ULL + b * 0x632BE59BD9B4E019ULL + 1 : 0;
+            std::vector<uint32_t> order(block.x);
+            for (uint32_t t = 0; t < block.x; ++t) order[t] = t;
+            while (c.alive > 0) {
+                if (shuf)
+                    for (uint32_t i = block.x - 1; i > 0; --i) {
+                        rng = rng * 6364136223846793005ULL + 1442695040888963407ULL;
+                        std::swap(order[i], order[(uint32_t)((rng >> 33) % (i + 1))]);
+                    }
+                for (uint32_t k = 0; k < block.x; ++k) {
+                    const uint32_t t = order[k];
                     if (c.fibers[t].done) continue;
                     c.cur = (int)t;
                     swapcontext(&c.sched, &c.fibers[t].ctx);
                 }
+            }
             cta = nullptr;
         });
     for (auto &t : th) t.join();

@@ -211,6 +211,47 @@ def test_edge_inputs(harness, tmp_path):
             check(harness, p, (name, mode), mode=mode, first=3)
 
 
+def test_random_thread_order(harness, tmp_path):
+    """SIMT_SHUFFLE: the fibers of every scheduling round run in a random order instead of by thread index.
+    Code that only works because a lower-numbered thread happened to run first (a missing barrier, an
+    unordered hand-over through shared memory) then produces wrong bytes; the kernels do not care.  The
+    second half shows the check has teeth: with one __syncthreads removed the kernel no longer passes."""
+    import shutil
+
+    from sickle_b200 import synth
+    from test_oracle_fuzz_vs_ref import _records
+
+    se, il, var = (str(tmp_path / n) for n in ("se.fq", "il.fq", "var.fq"))
+    open(se, "wb").write(synth.fixed_length_records(2000, 150, "sanger", seed=65).tobytes())
+    open(il, "wb").write(synth.paired_records(1000, 150, "sanger", seed=66)[2].tobytes())
+    open(var, "wb").write(_records(np.random.default_rng(67), 1500, 250, "sanger"))
+    cases = ((se, dict(kernel="fused9", first=5)), (se, dict(kernel="general", first=5)), (il, dict(kernel="fused7", mode="pei", first=3)),
+             (il, dict(kernel="fused5", mode="peM", singles=False, ctas=2)), (var, dict(kernel="general", x=True, n=True, ctas=4, first=2)),
+             (var, dict(kernel="fused5", n=True, first=5)))
+    for seed in ("1", "2", "3"):
+        for path, kw in cases:
+            rc, out, err = run(harness, path, env={"SIMT_SHUFFLE": seed}, **kw)
+            assert rc == 0 and out.startswith("OK"), (seed, kw, out, err[-500:])
+    # mutation: drop the barrier that makes the newline positions visible before S5 reads them
+    mut = tmp_path / "csrc"
+    shutil.copytree(os.path.join(ROOT, "sickle_b200", "csrc"), mut)
+    src = (mut / "kf_fused.cuh").read_text()
+    barrier = "        __syncthreads();   // newline positions visible to every thread"
+    assert src.count(barrier) == 1
+    (mut / "kf_fused.cuh").write_text(src.replace(barrier, "        /* barrier removed */"))
+    stub = os.path.join(ROOT, "tests", "host_stub")
+    exe = str(tmp_path / "mutated_harness")
+    subprocess.check_call(["g++", "-O1", "-std=c++17", "-w", "-fno-extern-tls-init", "-I" + os.path.join(stub, "simt"),
+                           "-I" + os.path.join(stub, "simt", "include"), "-I" + str(mut), "-I" + os.path.join(ROOT, "oracle"),
+                           "-x", "c++", os.path.join(stub, "kernels_harness.cpp"), "-x", "c", os.path.join(ROOT, "oracle", "sickle_oracle.c"),
+                           "-o", exe, "-lpthread"])
+    verdicts = []
+    for seed in ("1", "2", "3"):
+        rc, out, err = run(exe, se, env={"SIMT_SHUFFLE": seed}, kernel="fused9", first=5)
+        verdicts.append(rc == 0 and out.startswith("OK"))
+    assert not any(verdicts), verdicts
+
+
 def test_no_out_of_bounds_access_under_asan(tmp_path):
     """The kernels under AddressSanitizer + UBSan with input and output buffers sized exactly as capi.cu sizes
     them (64 bytes of padding, nothing more): no global read or write outside them on either path, and no
