@@ -311,3 +311,4 @@ def test_experimental_variants(tmp_path, defines):
     big = str(tmp_path / "big.fq")
     open(big, "wb").write(synth.fixed_length_records(30000, 150, "sanger", seed=17).tobytes())
     assert check(exe, big, "se 30k, 8 CTAs", kernels=("fused7", "fused9"), ctas=8, first=3) == ["OK"] * 2
+    assert check(exe, il, "pei, random thread order", kernels=("fused5", "fused9"), mode="pei", first=1, env={"SIMT_SHUFFLE": "7"}) == ["OK"] * 2
