@@ -27,7 +27,7 @@ for V in "${VARIANTS[@]}"; do
       -D$V -shared sickle_b200/csrc/capi.cu -o $LIB 2> /dev/null || { echo "build failed"; continue; }
   case "$V" in
     SK_KO_*) echo "(timing-only knock-out: output is wrong by construction, no parity run)";;
-    *) SICKLE_B200_LIB=$PWD/$LIB python -m pytest tests/test_cuda_parity.py -m gpu -x -q > /tmp/ab_parity.log 2>&1
+    *) env -u SICKLE_B200_FUSED_CH SICKLE_B200_LIB=$PWD/$LIB python -m pytest tests/test_cuda_parity.py -m gpu -x -q > /tmp/ab_parity.log 2>&1   # (a pinned tile size is for the timing runs only)
        RC=$?
        tail -2 /tmp/ab_parity.log
        [ $RC -ne 0 ] && { echo "PARITY FAILED: not timed"; continue; };;
