@@ -6,7 +6,7 @@ sys.path.insert(0,'/root/repo/tests'); sys.path.insert(0,'/root/repo')
 import numpy as np
 from test_oracle_fuzz_vs_ref import _records, _damage, FLAGSETS
 import test_kernels_on_cpu as t
-exe = os.path.join(t.BUILD, "kernels_harness")
+exe = os.environ.get("KH_EXE") or os.path.join(t.BUILD, "kernels_harness")
 seed0 = int(sys.argv[1]); budget = float(sys.argv[2])
 rng = np.random.default_rng(seed0)
 t0 = time.time(); n = 0; bad = []; stats = {}
