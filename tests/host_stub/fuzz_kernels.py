@@ -13,10 +13,11 @@ t0 = time.time(); n = 0; bad = []; stats = {}
 p = '/tmp/fz_%d.fq' % seed0
 while time.time() - t0 < budget:
     qualtype = ["sanger", "illumina", "solexa"][n % 3]
-    lmax = int(rng.choice([8, 25, 60, 110, 151, 260, 700, 3000]))
+    clean = bool(os.environ.get("FZ_CLEAN"))        # undamaged reads of 70-260 bases: the fused kernels keep nearly all of them
+    lmax = int(rng.choice([90, 120, 151, 200, 260])) if clean else int(rng.choice([8, 25, 60, 110, 151, 260, 700, 3000]))
     nrec = int(rng.integers(2, 40)) if lmax > 700 else int(rng.integers(40, 1500))
     data = _records(rng, nrec, lmax, qualtype)
-    if rng.random() < 0.5:
+    if not clean and rng.random() < 0.5:
         data = _damage(rng, data)
     if data and not data.endswith(b"\n") and rng.random() < 0.7:
         data = data[:-1] + b"\n"
