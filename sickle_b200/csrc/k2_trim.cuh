@@ -214,7 +214,7 @@ __device__ __forceinline__ bool thread_trim_mate(const DevInput &in, uint32_t re
     m.cut = Cut{-1, -1};
     if (validate_record(in.data, r)) return false;
     if (r.len[1] > kThreadTrimMaxLen || (unsigned long long)r.start[3] + r.len[1] + 64ull > in.nbytes) return false;
-    const TrimOut t = lane_sliding_window(in.data, r.start[1], r.len[1], r.start[3], P, rc, 0u, 1u, lane);
+    const TrimOut t = lane_sliding_window(in.data, r.start[1], r.len[1], r.start[3], P, rc);
     if (t.error) return false;
     m.cut = Cut{t.five, t.three};
     return true;

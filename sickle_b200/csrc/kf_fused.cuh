@@ -73,81 +73,13 @@ struct FusedCfg {
     static constexpr int kRegion = kFThreads * kBytesPerThread;
     static constexpr int kTile = kFTileThreads * kBytesPerThread;
     static constexpr int kInBytes = kRegion + 96;        // the window loop reads up to ~50 bytes past a record
-#ifdef SK_DIRECT_EMIT
-    // Experimental (off by default; next round's A/B): no staging buffer.  The input tile is double-buffered
-    // and the flush group copies the previous tile's records straight from its input buffer to their
-    // final global addresses (the S8a copy with a global destination) while the record warps trim the
-    // next tile: S8a leaves the critical path and the flat flush disappears.  Descriptors get their own
-    // 2 KB (they must outlive the next tile's newline positions).
-    static constexpr int kOutBytes = 0;
-    static constexpr size_t kSmem = 2 * (size_t)kInBytes + kFMaxNl * 2 + 128 * 16;
-#else
     static constexpr int kOutBytes = kTile + 768 + 96;   // a tile of output + the last record's overhang + phase shifts
     // CH = 7: 56,768 B -> four CTAs per SM (4 x (56,768 + 248 static + 1,024 reserved) <= 232,448)
     static constexpr size_t kSmem = (size_t)kInBytes + kOutBytes + kFMaxNl * 2;
-#endif
     // CTAs per SM by shared memory (232,448 B per SM, 1,024 B reserved per CTA); also the register budget
     static constexpr int kCtasPerSm = (int)(232448 / (kSmem + 1024 + 256)) > 4 ? 4 : (int)(232448 / (kSmem + 1024 + 256));
 };
 
-#ifdef SK_DIRECT_EMIT
-// S8a's copy with global destinations, run by the flush group (gt = thread index in the group, gn = its size)
-// one tile late: two lanes per record, lane 0 takes [name '\n' seq), lane 1 takes ['\n' line3 '\n' qual '\n').
-// g0 / g1 = where the tile's bytes of the main / singles stream start in global memory.
-__device__ __forceinline__ void copy_records_direct(uint8_t *g0, uint8_t *g1, const uint8_t *__restrict__ src_in,
-                                                    const uint4 *__restrict__ desc, uint32_t nrec, int gt, int gn,
-                                                    const DevParams &P) {
-    // smem_copy wants a 16-byte aligned base: aligned-down pointer + phase
-    const uint32_t ph0 = (uint32_t)(reinterpret_cast<uintptr_t>(g0) & 15u), ph1 = (uint32_t)(reinterpret_cast<uintptr_t>(g1) & 15u);
-    uint8_t *const gal0 = g0 - ph0, *const gal1 = g1 - ph1;
-    const uint32_t sub = (uint32_t)gt & 1u;
-    for (uint32_t r0 = 0; r0 < nrec; r0 += (uint32_t)gn >> 1) {            // same trip count for every lane (votes inside)
-        const uint32_t r = r0 + ((uint32_t)gt >> 1);
-        uint4 dsc = make_uint4(0, 0, 0, 0);
-        if (r < nrec) dsc = desc[r];
-        uint32_t a_dst = 0, a_src = 0, a_len = 0, b_dst = 0, b_src = 0, b_len = 0;
-        int nl_at = -1;
-        const bool emit = (dsc.x & 0x20000000u) != 0;
-        const bool nrec_out = (dsc.x & 0x40000000u) != 0;
-        const bool singles = (dsc.x & 0x80000000u) != 0;
-        uint8_t *const ob = singles ? gal1 : gal0;
-        const uint32_t r_start = dsc.y & 0xffffu, r_e0 = dsc.y >> 16, r_e1 = dsc.z & 0xffffu, r_e2 = dsc.z >> 16;
-        const uint32_t five = dsc.w & 0xffffu, n = dsc.w >> 16;
-        const uint32_t nlen = r_e0 - r_start, plen = r_e2 - r_e1 - 1u;
-        const uint32_t d = (singles ? ph1 : ph0) + (dsc.x & 0xffffu);
-        if (emit) {
-            if (sub == 0) {
-                a_dst = d; a_src = r_start;
-                a_len = nlen + 1u + ((five == 0 && !nrec_out) ? n : 0u);
-                b_dst = d + nlen + 1u; b_src = r_e0 + 1u + five;
-                b_len = (five != 0 && !nrec_out) ? n : 0u;
-            } else if (!nrec_out) {
-                a_dst = d + nlen + 1u + n; a_src = r_e1;
-                a_len = plen + 2u + (five == 0 ? n : 0u);
-                b_dst = a_dst + plen + 2u; b_src = r_e2 + 1u + five;
-                b_len = five != 0 ? n : 0u;
-                nl_at = (int)(b_dst + n);
-            } else {
-                a_dst = d + nlen + 3u; a_src = r_e1 + 1u; a_len = plen + 1u;
-            }
-        }
-        const uint32_t n_dst = a_dst;                       // (the swap below must not move the N record's bytes)
-        if (b_len != 0) {                                   // the long piece first (see SK_STAGE_LONG_FIRST)
-            uint32_t t;
-            t = a_dst; a_dst = b_dst; b_dst = t;
-            t = a_src; a_src = b_src; b_src = t;
-            t = a_len; a_len = b_len; b_len = t;
-        }
-        smem_copy(ob, a_dst, src_in, a_src, a_len);
-        if (__any_sync(0xffffffffu, b_len != 0)) smem_copy(ob, b_dst, src_in, b_src, b_len);
-        if (nl_at >= 0) ob[nl_at] = '\n';
-        if (emit && nrec_out) {
-            if (sub == 0) { ob[d + nlen + 1u] = 'N'; ob[d + nlen + 2u] = '\n'; }
-            else { ob[n_dst + plen + 1u] = (uint8_t)P.qmin; ob[n_dst + plen + 2u] = '\n'; }
-        }
-    }
-}
-#endif
 
 // The deferred half of a tile (S7b + S8b), run by the "flush group" -- warps 4..7, which never own a
 // record -- while warps 0..3 validate and trim the next tile: look-back #2 over the output sizes,
@@ -157,9 +89,6 @@ __device__ __forceinline__ void flush_previous_tile(unsigned long long *const st
                                                     uint32_t p_tot1, int nstreams, uint32_t epoch, int gtid, int gwarps,
                                                     unsigned long long (*s_lb)[2], Control *__restrict__ ctl,
                                                     const OutPtrs &outs, const uint8_t *__restrict__ s_out, uint32_t num_tiles
-#ifdef SK_DIRECT_EMIT
-                                                    , const uint4 *__restrict__ p_desc, uint32_t p_nrec, const DevParams &P
-#endif
                                                     ) {
     const unsigned long long agg[2] = {p_tot0, p_tot1};
     unsigned long long ex[2];
@@ -180,10 +109,7 @@ __device__ __forceinline__ void flush_previous_tile(unsigned long long *const st
         if (gtid == 0) ctl->index_overflow = 2u;
         return;
     }
-#ifdef SK_DIRECT_EMIT
-    // s_out = the previous tile's INPUT buffer here
-    copy_records_direct(outs.p[0] + ex[0], p_tot1 ? outs.p[2] + ex[1] : outs.p[0], s_out, p_desc, p_nrec, gtid, gwarps * 32, P);
-#elif !defined(SK_KO_FLUSH)
+#if !defined(SK_KO_FLUSH)
     flush_realigned(outs.p[0] + ex[0], s_out, 0u, p_tot0, gtid, gwarps * 32);
     if (p_tot1) flush_realigned(outs.p[2] + ex[1], s_out, (p_tot0 + 15u) & ~15u, p_tot1, gtid, gwarps * 32);
 #endif
@@ -205,18 +131,10 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
          uint32_t status_stride, uint32_t num_tiles, uint32_t epoch) {
     using Cfg = FusedCfg<CH>;
     extern __shared__ __align__(16) uint8_t smem[];
-#ifdef SK_DIRECT_EMIT
-    uint8_t *s_in = smem;                                    // set per tile: the two input buffers alternate
-    uint8_t *s_out = smem + Cfg::kInBytes;                   // per tile: the OTHER input buffer (the previous tile's bytes)
-    uint16_t *s_nl = reinterpret_cast<uint16_t *>(smem + 2 * Cfg::kInBytes);
-    uint4 *s_desc = reinterpret_cast<uint4 *>(smem + 2 * Cfg::kInBytes + kFMaxNl * 2);
-    uint32_t parity = 0, p_nrec = 0;
-#else
     uint8_t *s_in = smem;
     uint8_t *s_out = smem + Cfg::kInBytes;
     uint16_t *s_nl = reinterpret_cast<uint16_t *>(smem + Cfg::kInBytes + Cfg::kOutBytes);
     uint4 *s_desc = reinterpret_cast<uint4 *>(s_nl);   // S7/S8a record descriptors alias the newline positions
-#endif
     __shared__ uint32_t s_tile;
     __shared__ uint32_t warp_tot[kFThreads / 32];
     __shared__ uint32_t warp_tot2[kFThreads / 32][2];
@@ -249,29 +167,6 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
 #endif
     __syncthreads();
 
-#ifdef SK_EARLY_LOAD
-#ifndef SK_DIRECT_EMIT
-#error "SK_EARLY_LOAD needs SK_DIRECT_EMIT (two input buffers)"
-#endif
-    // Experimental (off by default; next round's A/B): thread 0 starts the bulk copy of the next tile as
-    // soon as it holds the ticket, into the input buffer that has just become free.
-    bool early_issued = false;
-    auto issue_load = [&](uint8_t *buf, uint32_t tile_no) {
-        const uint32_t t0_ = tile_no * (uint32_t)Cfg::kTile;
-        const uint32_t have_ = nchunks - (t0_ >> 4);
-        const uint32_t n_ = (have_ < (uint32_t)(Cfg::kRegion / 16) ? have_ : (uint32_t)(Cfg::kRegion / 16)) * 16u;
-#if defined(__CUDACC__)
-        const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&s_mbar);
-        const uint32_t dst = (uint32_t)__cvta_generic_to_shared(buf);
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(n_) : "memory");
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                     ::"r"(dst), "l"(in.data + t0_), "r"(n_), "r"(mb) : "memory");
-#else
-        memcpy(buf, in.data + t0_, n_);
-#endif
-    };
-#endif
     // the tile whose output is staged in s_out and not flushed yet
     bool have_prev = false;
     uint32_t p_tile = 0, p_tot0 = 0, p_tot1 = 0;
@@ -288,11 +183,6 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         __syncthreads();
         const uint32_t tile = s_tile;
         const bool done = tile >= num_tiles;
-#ifdef SK_DIRECT_EMIT
-        s_in = smem + (size_t)parity * Cfg::kInBytes;
-        s_out = smem + (size_t)(parity ^ 1u) * Cfg::kInBytes;
-        parity ^= 1u;
-#endif
         const uint32_t t0 = tile * (uint32_t)Cfg::kTile;
 
         uint32_t mw[(CH + 1) / 2];                               // newline bits, 32 bytes per word
@@ -304,9 +194,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             // mbarrier; the threads only zero what lies beyond the end of the batch (last tiles)
             const uint32_t have = nchunks - (t0 >> 4);                              // 16-byte chunks from t0 on (>= 1)
             const uint32_t cp_chunks = have < (uint32_t)(Cfg::kRegion / 16) ? have : (uint32_t)(Cfg::kRegion / 16);
-#if defined(SK_EARLY_LOAD)
-            if (tid == 0 && !early_issued) issue_load(s_in, tile);
-#elif defined(__CUDACC__)
+#if defined(__CUDACC__)
             if (tid == 0) {
                 const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&s_mbar);
                 const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_in);
@@ -391,43 +279,20 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         if (done) {   // no tile left: only the last staged tile remains to be flushed
             if (have_prev && wid >= 4)
                 flush_previous_tile(st_out, p_tile, p_tot0, p_tot1, nstreams, epoch, tid - 128, 4, s_lb, ctl, outs, s_out, num_tiles
-#ifdef SK_DIRECT_EMIT
-                                    , s_desc, p_nrec, P
-#endif
                                     );
             break;
         }
 
         if (!nl_overflow) {
-            // a 32-byte word of a FASTQ file holds 0, 1 or (around the '+' line) 2 newlines: two
-            // predicated (branch-free) extractions keep the warp converged, a loop only for more
-            uint32_t rank = wbase + incl - cnt;
-#ifdef SK_NL_BRANCHFREE
-            // Experimental (off by default; next round's A/B): the two common stores without branches -- a
-            // word without a (second) newline stores into a dump slot in the padding behind the region
-            // (bytes nobody interprets) instead of skipping the store.  ncu charged 5.5 % of all warp
-            // instructions to these two lines at 15 of 32 lanes active.
-            uint16_t *const dump = reinterpret_cast<uint16_t *>(s_in + Cfg::kRegion + 64);
-#endif
+            // a thread's 16*CH bytes hold about two newlines: one short loop per 32-byte mask word (most
+            // words have none, and a warp leaves a word's loop as soon as none of its lanes has one left)
+            uint16_t *__restrict__ nl_out = s_nl + (wbase + incl - cnt);
 #pragma unroll
             for (int k = 0; k < (CH + 1) / 2; ++k) {
-                const uint32_t m = mw[k];
-                const uint32_t m2 = m & (m - 1u);
-#ifdef SK_NL_BRANCHFREE
-                *(m ? s_nl + rank : dump) = (uint16_t)(b0 + 32u * k + (uint32_t)__ffs(m) - 1u);
-                rank += m ? 1u : 0u;
-                *(m2 ? s_nl + rank : dump) = (uint16_t)(b0 + 32u * k + (uint32_t)__ffs(m2) - 1u);
-                rank += m2 ? 1u : 0u;
-#else
-                if (m) s_nl[rank] = (uint16_t)(b0 + 32u * k + (uint32_t)__ffs(m) - 1u);
-                rank += m ? 1u : 0u;
-                if (m2) s_nl[rank] = (uint16_t)(b0 + 32u * k + (uint32_t)__ffs(m2) - 1u);
-                rank += m2 ? 1u : 0u;
-#endif
-                uint32_t m3 = m2 & (m2 - 1u);
-                while (m3) {
-                    s_nl[rank++] = (uint16_t)(b0 + 32u * k + (uint32_t)__ffs(m3) - 1u);
-                    m3 &= m3 - 1;
+                uint32_t m = mw[k];
+                while (m) {
+                    *nl_out++ = (uint16_t)(b0 + 32u * k + (uint32_t)__ffs(m) - 1u);
+                    m &= m - 1u;
                 }
             }
         }
@@ -457,10 +322,8 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         const uint32_t rpu = paired ? 2u : 1u;
         const uint32_t nrec_t = n_units * rpu;
         bool fail = nl_overflow || nrec_t > (uint32_t)kFThreads / 2u;   // S8a gives every record two lanes
-        // Lanes per record in S6: two while the records then still leave three warps for the flush group
-        // (150-base reads: 77 records -> 154 lanes = warps 0..4), else one (warps 0..3, flush group 4..7).
-        const uint32_t nsub = nrec_t <= 80u ? 2u : 1u;
-        const int flush_warp0 = nsub == 2u ? 5 : 4;
+        // S6 gives every record one lane: records live in warps 0..3, warps 4..7 are the flush group
+        constexpr int flush_warp0 = 4;
 
         // ---- deferred S7b/S8b of the PREVIOUS tile, by the flush group, overlapped with S5-S7 of this
         // tile on the record warps: output offsets (look-back #2), then the flush.  s_desc (which aliases
@@ -471,16 +334,12 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         if (have_prev && wid >= flush_warp0)
             flush_previous_tile(st_out, p_tile, p_tot0, p_tot1, nstreams, epoch, tid - flush_warp0 * 32, kFThreads / 32 - flush_warp0,
                                 s_lb, ctl, outs, s_out, num_tiles
-#ifdef SK_DIRECT_EMIT
-                                , s_desc, p_nrec, P
-#endif
                                 );
         have_prev = false;
 
-        // per-record state (nsub adjacent lanes = one record; mates of a pair are nsub lanes apart)
-        const uint32_t rec = (uint32_t)tid / nsub, sub = (uint32_t)tid % nsub;
+        // per-record state (lane = record; the mates of a pair sit in adjacent lanes)
+        const uint32_t rec = (uint32_t)tid;
         const bool has_rec = !fail && rec < nrec_t;
-        const bool owner = sub == 0u;
         bool complete = false;
         uint32_t start = 0, e0 = 0, e1 = 0, e2 = 0, e3 = 0;
         if (has_rec) {
@@ -492,7 +351,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             }
         }
         if (paired) {   // a pair is complete only if both mates are (all lanes take part in the shuffle)
-            const int mate_complete = __shfl_xor_sync(0xffffffffu, (int)complete, (int)nsub);
+            const int mate_complete = __shfl_xor_sync(0xffffffffu, (int)complete, 1);
             complete = complete && mate_complete != 0;
         }
         // an incomplete unit is fine only as the unfinished tail of the batch
@@ -514,22 +373,22 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
 #ifdef SK_KO_S6
                 cut.five = 0; cut.three = (int)L;   // nothing trimmed
 #else
-                cut = lane_sliding_window(s_in, e0 + 1u, L, e2 + 1u, P, rc, sub, nsub, lane);
+                cut = lane_sliding_window(s_in, e0 + 1u, L, e2 + 1u, P, rc);
 #endif
                 if (cut.error) fail = true;
             }
         }
         if (fail) s_fail = 1u;
 
-        // ---- S7: routing + output sizes (the record's first lane speaks for it)
-        const bool live = has_rec && complete && owner;
+        // ---- S7: routing + output sizes
+        const bool live = has_rec && complete;
         const bool keep = live && cut.three >= 0;
         const uint32_t nkeep = keep ? (uint32_t)(cut.three - cut.five) : 0u;
         const uint32_t fixed = name_len + plus_len + 4u;
         uint32_t add0 = 0, add1 = 0;        // bytes for the main stream / the singles stream
         bool nrec_out = false;              // emit as an "N record" (-M)
         int stream = -1;
-        const bool other = paired && __shfl_xor_sync(0xffffffffu, (int)keep, (int)nsub) != 0;   // mate's keep flag
+        const bool other = paired && __shfl_xor_sync(0xffffffffu, (int)keep, 1) != 0;   // mate's keep flag
         if (live) {
             if (!paired) {
                 if (keep) { stream = 0; add0 = fixed + 2u * nkeep; }
@@ -559,11 +418,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         }
         // the staging buffer holds a tile's worth of output; a tile whose (long, untrimmed) records
         // reach far into the halo can exceed it -> general path
-#ifdef SK_DIRECT_EMIT
-        const bool tile_fail = s_fail != 0 || tot0 >= 65536u || tot1 >= 65536u;   // (descriptor offsets are 16 bit)
-#else
         const bool tile_fail = s_fail != 0 || tot0 + tot1 + 64u > (uint32_t)Cfg::kOutBytes;
-#endif
         if (tile_fail) {   // bit 1: the tile simply holds too many records (the host then picks smaller tiles)
             tot0 = 0; tot1 = 0;
             if (tid == 0) atomicOr(&ctl->fast_fail, (nl_overflow || nrec_t > (uint32_t)kFThreads / 2u) ? 3u : 1u);
@@ -573,25 +428,13 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             block_publish(st_out, tile, agg, nstreams, epoch, tid);
         }
         if (tid == 0) held = atomicAdd(&ctl->tile_counter[3], 1u);   // looked at after S8a
-#ifdef SK_EARLY_LOAD
-        // The buffer the next tile goes to held tile t-1, which the flush group finished before the barrier
-        // above: its load can start now and run under the descriptor writes, the bookkeeping and the
-        // barriers up to the next tile's S2.
-        if (tid == 0) {
-            early_issued = held < num_tiles;
-            if (early_issued) issue_load(smem + (size_t)parity * Cfg::kInBytes, held);
-        }
-#endif
         have_prev = true;
         p_tile = tile; p_tot0 = tot0; p_tot1 = tot1;
-#ifdef SK_DIRECT_EMIT
-        p_nrec = tile_fail ? 0u : nrec_t;
-#endif
         const uint32_t base1 = (tot0 + 15u) & ~15u;                    // singles staged after the main bytes
 
         // record descriptors for S8a (two lanes per record); they reuse the newline-position array,
         // which nobody reads after S5
-        if (has_rec && owner) {   // every slot S8a may look at is rewritten (x == 0: nothing to emit)
+        if (has_rec) {   // every slot S8a may look at is rewritten (x == 0: nothing to emit)
             uint4 dsc;
             dsc.x = (stream < 0 || tile_fail)
                         ? 0u
@@ -607,7 +450,6 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
 
         // ---- S8a: two lanes per record copy it into the staging buffer (phase 0; the flush realigns):
         // lane 0 takes [name '\n' seq), lane 1 takes ['\n' line3 '\n' qual '\n')
-#ifndef SK_DIRECT_EMIT
         {
             const uint32_t r = (uint32_t)tid >> 1, sub = (uint32_t)tid & 1u;
             uint4 dsc = make_uint4(0, 0, 0, 0);
@@ -643,7 +485,6 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                     a_dst = d + nlen + 3u; a_src = r_e1 + 1u; a_len = plen + 1u;
                 }
             }
-#ifdef SK_STAGE_LONG_FIRST
             // Experimental (off by default; next round's A/B): the two runs write disjoint bytes, so a lane
             // whose read is cut at the 5' end swaps them -- every lane then moves its LONG piece in the first
             // run and only the short one (name / line 3) in the second, instead of both runs being as long
@@ -654,7 +495,6 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 t = a_src; a_src = b_src; b_src = t;
                 t = a_len; a_len = b_len; b_len = t;
             }
-#endif
 #ifndef SK_KO_S8A
             smem_copy(s_out, a_dst, s_in, a_src, a_len);
             if (__any_sync(0xffffffffu, b_len != 0)) smem_copy(s_out, b_dst, s_in, b_src, b_len);
@@ -665,9 +505,6 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 else { s_out[a_dst + plen + 1u] = (uint8_t)P.qmin; s_out[a_dst + plen + 2u] = '\n'; }
             }
         }
-#else
-        (void)base1;
-#endif
         SK_TICK(6);   // S8a (thread 0's own copies)
 #ifdef SK_PHASE_TIMING
         __syncthreads();   // timing build only: how long the slowest warp takes beyond thread 0
@@ -685,8 +522,8 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             uint32_t m_other = 0;
             if (paired) {
                 // bit k = keep flag of lane k's mate
-                const uint32_t m1 = nsub == 2u ? 0x11111111u : 0x55555555u;   // owner lanes of first mates
-                m_other = ((m_keep & m1) << nsub) | ((m_keep & (m1 << nsub)) >> nsub);
+                const uint32_t m1 = 0x55555555u;   // lanes of first mates
+                m_other = ((m_keep & m1) << 1) | ((m_keep & (m1 << 1)) >> 1);
             }
             if (lane == 0 && m_live) {
                 atomicMax(&ctl->fast_consumed, end);
@@ -695,7 +532,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                     atomicAdd(&ctl->counters[0], (unsigned long long)__popc(m_keep));
                     atomicAdd(&ctl->counters[1], (unsigned long long)__popc(m_live & ~m_keep));
                 } else {
-                    const uint32_t even = (nsub == 2u ? 0x11111111u : 0x55555555u) & m_live;   // one bit per pair (mate 1's lane)
+                    const uint32_t even = 0x55555555u & m_live;   // one bit per pair (mate 1's lane)
                     const uint32_t k1 = m_keep & even, k2 = m_other & even;
                     atomicAdd(&ctl->counters[2], 2ull * __popc(k1 & k2));           // kept_p
                     atomicAdd(&ctl->counters[3], 2ull * __popc(even & ~k1 & ~k2));  // discard_p

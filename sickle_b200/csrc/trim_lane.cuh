@@ -45,6 +45,13 @@ struct RangeCheck {
         hi |= (x + add_hi) | x;      // bit 7: byte > qmax, or >= 0x80
         lo &= x + add_lo;            // bit 7 cleared: byte < qmin
     }
+    // Three-op form for words whose every byte is a quality byte: a word with a byte outside [qmin, qmax]
+    // leaves bit 7 of some byte of `acc` set.  No false negatives: for b < 0x80 neither sum carries, bit 7
+    // of (b + add_hi) says b > qmax and bit 7 of ~(b + add_lo) says b < qmin; a byte b >= 0x80 sets bit 7
+    // of (b + add_hi) unless that sum wraps (b >= 0x81 + qmax), and then (b + add_lo) wraps to less than
+    // 0x80 as well.  Only bytes >= 0x80 carry, so the lowest such byte of a word is always judged without
+    // a carry coming in; what a carry does to the bytes above it no longer matters.
+    __device__ __forceinline__ void screen3(uint32_t x, uint32_t &acc) const { acc |= (x + add_hi) | ~(x + add_lo); }
     __device__ __forceinline__ bool suspicious(uint32_t hi, uint32_t lo) const { return ((hi | ~lo) & 0x80808080u) != 0; }
     // 0x80 in every byte of x that is outside [qmin, qmax] (qmax <= 126)
     __device__ __forceinline__ uint32_t bad4(uint32_t x) const {
@@ -71,201 +78,163 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
 #endif
 }
 
-// Sliding window over shared memory by ONE or TWO lanes per read.  Same decisions as
-// warp_sliding_window.  Window i is "good" iff total(i) >= qthr*ws (trim.cpp:36,42,61).  Let i5 = first
-// good window, i3 = first bad window after it (or the first bad window at all with -x).  Quality bytes
-// are range-checked exactly where the reference's scalar loop touches them: the first window always,
-// and the byte entering window w+1 iff the loop gets past window w (w < i3 and w+1 < nwin).
+// Sliding window by ONE lane per read, coarse to fine.  Same decisions as warp_sliding_window.
+// Window i is "good" iff total(i) >= qthr*ws (trim.cpp:36,42,61); i5 = first good window, i3 = first
+// bad window after it (or the first bad window at all with -x).
 //
-// With nsub == 2 the windows are cut into two contiguous halves (whole 32-window steps); lane `sub`
-// scans its half without knowing what the other finds, and records what either outcome needs: its
-// first good window, its first bad window, its first bad window after its first good one, and the
-// first window whose entering byte is out of range.  The pair then exchanges these four numbers
-// (shuffles inside the pair only: both lanes of a read take the same branches up to there) and
-// both derive i5 / i3 / the error exactly as the sequential loop would have.  After that lane 0
-// looks for the 5' cut inside window i5 while lane 1 looks for the 3' cut inside window i3.
-struct HalfScan {
-    int g, b_any, b_after, o_first;
-};
+// Phase 1 walks the ALIGNED 4-byte words of the quality line once.  It (a) screens every quality byte
+// against [qmin, qmax] -- any byte outside it makes this function DECLINE (error = true): the callers
+// hand such a read to the exact warp-wide path, which knows which bytes the reference's scalar loop
+// really visits -- and (b) keeps a sliding sum R over k = (ws - 3) / 4 consecutive whole words.  Every
+// window contains k consecutive whole words whatever its phase, all other bytes of it are >= qmin, so
+//     total(i) >= R_A - 4k*qoff + (ws - 4k) * min(0, qmin - qoff)      for the windows i that cover words A..A+k-1
+// and these windows are i in [4(A+k) - ws - Q, 4A - Q] (Q = byte offset of the quality line): the ranges
+// of successive A overlap or abut and window 0 belongs to the first whole word.  So up to the first word
+// A_f whose bound falls below qthr*ws every window is known to be good without having been summed:
+// window 0 is the first good one and the exact scan may start at w_start = 4*A_f - Q - 3.
+// Cost: 2 dp4a + 1 funnel shift + 3 screen ops per 4 quality bytes, against (8 dp4a + 4 shifts + screen)
+// per 4 windows for the exact scan, which now only runs from w_start to the first bad window.
+//
+// Phase 2 is the exact scan: 32 windows per step, totals by dp4a straight from the packed quality
+// words (prefix sums of lead - trail inside a word), the sign of every total shifted into a bit mask.
 __device__ __forceinline__ TrimOut lane_sliding_window(const uint8_t *__restrict__ sm, uint32_t seq_off, uint32_t L,
-                                                       uint32_t qual_off, const DevParams &P, const RangeCheck &rc,
-                                                       uint32_t sub, uint32_t nsub, int lane) {
+                                                       uint32_t qual_off, const DevParams &P, const RangeCheck &rc) {
     TrimOut o;
     o.five = -1; o.three = -1; o.error = false;
-    if (L < (uint32_t)P.lthr) return o;                                  // trim.cpp:21-26 (same for both lanes)
+    if (L < (uint32_t)P.lthr) return o;                                  // trim.cpp:21-26 (nothing is looked at)
     uint32_t ws = L / 10u;                                               // trim.cpp:8
     if (ws == 0) ws = L;                                                 // trim.cpp:30
     const long long thr_ll = (long long)P.qthr * (long long)ws;
     // window totals of a record that fits a tile are < 2^23; clamp so that T - thr cannot overflow
     const int thr = thr_ll > 0x3fffffffLL ? 0x3fffffff : (int)thr_ll;
     const uint32_t nwin = L - ws + 1u;                                   // trim.cpp:34
-#ifdef SK_LANE_SPLIT4
-    // Experimental (off by default; next round's A/B): the two lanes get equal shares, cut at a multiple
-    // of 4 windows, and the last step of a share only runs the groups it needs -- instead of whole
-    // 32-window steps (136 windows = 96 + 40 becomes 68 + 68: 17 groups per lane instead of 24).
-    const uint32_t split = nsub == 2u ? min(nwin, (((nwin + 1u) >> 1) + 3u) & ~3u) : nwin;
-    const uint32_t w_lo = sub ? split : 0u;                              // first window of this lane
-    const uint32_t w_hi = sub ? nwin : split;                            // one past its last window
-#else
-    const uint32_t nseg = (nwin + 31u) >> 5;
-    const uint32_t half = nsub == 2u ? (nseg + 1u) >> 1 : nseg;
-    const uint32_t w_lo = sub ? half * 32u : 0u;                         // first window of this lane
-    const uint32_t w_hi = sub ? nwin : min(nwin, half * 32u);            // one past its last window
-#endif
     const bool x = P.no_fiveprime != 0;                                  // -x: as if the 5' end was already found
 
-    // ---- total of this lane's first window: dp4a sums, 4 bytes at a time.  Window 0 is also range
-    // checked here (trim.cpp:31-33); the bytes of lane 1's first window are entering bytes of lane 0's.
-    int T = 0;
-    uint32_t bad = 0;
-    if (w_lo < w_hi) {
-        Stream4 s;
-        s.init(sm, qual_off + w_lo);
-        uint32_t j = 0;
-        for (; j + 4 <= ws; j += 4) {
-            const uint32_t v = s.next();
-            bad |= rc.bad4(v);
-            T = (int)__dp4a(v, 0x01010101u, (uint32_t)T);
-        }
-        const uint8_t *__restrict__ q = sm + qual_off + w_lo;
-        for (; j < ws; ++j) {
-            const int b = q[j];
-            bad |= (uint32_t)((b < P.qmin) | (b > P.qmax));
-            T += b;
-        }
-        T -= (int)ws * P.qoff;
-    }
-    if (sub) bad = 0;
-    int Tm = T - thr;                          // sign bit set <=> window is bad
-    HalfScan me;
-    me.g = -1; me.b_any = -1; me.b_after = -1; me.o_first = 0x7fffffff;
-
-    Stream4 lead, trail;
-    lead.init(sm, qual_off + w_lo + ws);
-    trail.init(sm, qual_off + w_lo);
-    for (uint32_t base = w_lo; base < w_hi && bad == 0 && (x ? me.b_any : me.b_after) < 0; base += 32) {
-        // bit 31-k: window base+k is bad.  Each total's sign bit is shifted in from the right by one
-        // funnel shift, so the step's first window ends up in the top bit (first = __clz).
-        uint32_t negr = 0;
-        uint32_t r_hi = 0, r_lo = 0xffffffffu;   // range screen of the 32 entering bytes
-#ifdef SK_LANE_SPLIT4
-        const uint32_t span = min(32u, w_hi - base);                     // windows of this step (>= 1)
-        auto group = [&]() {
-            const uint32_t lw = lead.next(), tw = trail.next();
-            const int T1 = dp4a_us(lw, 0x00000001, dp4a_us(tw, 0x000000FF, Tm));
-            const int T2 = dp4a_us(lw, 0x00000101, dp4a_us(tw, 0x0000FFFF, Tm));
-            const int T3 = dp4a_us(lw, 0x00010101, dp4a_us(tw, 0x00FFFFFF, Tm));
-            const int T4 = dp4a_us(lw, 0x01010101, dp4a_us(tw, (int)0xFFFFFFFF, Tm));
-            negr = __funnelshift_l((uint32_t)Tm, negr, 1);
-            negr = __funnelshift_l((uint32_t)T1, negr, 1);
-            negr = __funnelshift_l((uint32_t)T2, negr, 1);
-            negr = __funnelshift_l((uint32_t)T3, negr, 1);
-            rc.screen(lw, r_hi, r_lo);
-            Tm = T4;
-        };
-        if (span == 32u) {
+    // ---- phase 1: screen + word-granular lower bounds
+    uint32_t w_start = 0;                     // every window before it is good
+    {
+        const uint32_t *__restrict__ W = reinterpret_cast<const uint32_t *>(sm);
+        const uint32_t Q = qual_off, E = qual_off + L;                   // quality bytes are [Q, E)
+        const uint32_t A0 = (Q + 3u) >> 2;                               // first whole word
+        const uint32_t A1 = E >> 2;                                      // one past the last whole word
+        uint32_t scr = 0;                                                // bit 7 of a byte set: a byte outside [qmin, qmax]
+        const uint32_t fill = rc.kmin;                                   // qmin in every byte: passes the screen
+        if (A0 > A1) {                                                   // no whole word: the line lies inside one word
+            const uint32_t m = (0xffffffffu << (8u * (Q & 3u))) & ~(0xffffffffu << (8u * (E & 3u)));
+            rc.screen3((W[Q >> 2] & m) | (fill & ~m), scr);
+        } else {
+            if (Q & 3u) {                                                // ragged head: bytes [Q, 4*A0)
+                const uint32_t m = 0xffffffffu << (8u * (Q & 3u));
+                rc.screen3((W[A0 - 1u] & m) | (fill & ~m), scr);
+            }
+            if (E & 3u) {                                                // ragged tail: bytes [4*A1, E)
+                const uint32_t m = ~(0xffffffffu << (8u * (E & 3u)));
+                rc.screen3((W[A1] & m) | (fill & ~m), scr);
+            }
+            const uint32_t nfull = A1 - A0;
+            const uint32_t k = ws >= 7u ? (ws - 3u) >> 2 : 0u;           // whole words inside every window
+            if (k == 0u || nfull < k) {                                  // short windows: screen only
+                for (uint32_t j = 0; j < nfull; ++j) rc.screen3(W[A0 + j], scr);
+            } else {
+                const int slack = P.qmin < P.qoff ? (int)(ws - 4u * k) * (P.qmin - P.qoff) : 0;
+                // R = (sum of the k words ending at the lead word) - bias; the word in front of the first
+                // whole word is added here and taken out again by the first trail subtraction
+                int R = (int)__dp4a(W[A0 - 1u], 0x01010101u, 0u) - (thr + (int)(4u * k) * P.qoff - slack);
+                for (uint32_t j = 0; j + 1u < k; ++j) {
+                    const uint32_t v = W[A0 + j];
+                    rc.screen3(v, scr);
+                    R = (int)__dp4a(v, 0x01010101u, (uint32_t)R);
+                }
+                const uint32_t *__restrict__ lead = W + A0 + (k - 1u);
+                const uint32_t *__restrict__ trail = W + A0 - 1u;
+                const uint32_t nstep = nfull - k + 1u;                   // bounds R_A for A = A0 .. A0 + nstep - 1
+                uint32_t jf = nstep;                                     // first A - A0 whose bound is below the threshold
+                uint32_t j = 0;
+                for (; j + 8u <= nstep; j += 8u) {
+                    uint32_t negr = 0;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) group();
-        } else {                                 // the share's last step: only the groups that hold its windows
-            const uint32_t ng = (span + 3u) >> 2;
-#pragma unroll 1
-            for (uint32_t g = 0; g < ng; ++g) group();
-            negr <<= 32u - 4u * ng;              // first window of the step back in the top bit
+                    for (int u = 0; u < 8; ++u) {
+                        const uint32_t lw = lead[j + u], tw = trail[j + u];
+                        rc.screen3(lw, scr);
+                        R = dp4a_us(lw, 0x01010101, dp4a_us(tw, (int)0xFFFFFFFF, R));
+                        negr = __funnelshift_l((uint32_t)R, negr, 1);
+                    }
+                    if (negr && jf == nstep) jf = j + (uint32_t)__clz(negr) - 24u;
+                }
+                for (; j < nstep; ++j) {
+                    const uint32_t lw = lead[j], tw = trail[j];
+                    rc.screen3(lw, scr);
+                    R = dp4a_us(lw, 0x01010101, dp4a_us(tw, (int)0xFFFFFFFF, R));
+                    if (R < 0 && jf == nstep) jf = j;
+                }
+                // windows up to 4*(A_f - 1) - Q are good; no failing word: every window is
+                const int ws_i = jf == nstep ? (int)nwin : 4 * (int)(A0 + jf) - (int)Q - 3;
+                w_start = ws_i < 0 ? 0u : min((uint32_t)ws_i, nwin);
+            }
         }
-        // ---- what the windows of this step contribute
-        const uint32_t left = nwin - base;                               // windows of the READ from base on (>= 1)
-        if ((left <= 32u || rc.suspicious(r_hi, r_lo)) && me.o_first == 0x7fffffff) {
-            // the read's last step (its words run past the quality line) or, rarely, a suspect byte:
-            // find the first window of this step whose entering byte is out of range, exactly
-            // (bit k of oorw: the byte entering window base+k+1)
-            Stream4 again;
-            again.init(sm, qual_off + base + ws);
-            uint32_t oorw = 0;
-#pragma unroll 1
-            for (int g = 0; g < 8; ++g) oorw += flags_to_nibble(rc.bad4(again.next())) << (4 * g);
-            // only this step's windows count, and the last window of the read has no entering byte
-            const uint32_t lim = min(span, left - 1u);
-            const uint32_t oo = oorw & (lim >= 32u ? 0xffffffffu : ((1u << lim) - 1u));
-            if (oo) me.o_first = (int)base + __ffs(oo) - 1;
+        if (scr & 0x80808080u) { o.error = true; return o; }
+    }
+
+    // ---- phase 2: exact scan from w_start.  w_start > 0 means window 0 is good (it is the first good one).
+    int g = w_start > 0 ? 0 : -1;              // first good window
+    int b_stop = -1;                           // the window the loop breaks at: first bad one after g (-x: first bad one)
+    if (w_start < nwin) {
+        int T = 0;
+        {
+            Stream4 s;
+            s.init(sm, qual_off + w_start);
+            uint32_t j = 0;
+            for (; j + 4 <= ws; j += 4) T = (int)__dp4a(s.next(), 0x01010101u, (uint32_t)T);
+            const uint8_t *__restrict__ q = sm + qual_off + w_start;
+            for (; j < ws; ++j) T += q[j];
+            T -= (int)ws * P.qoff;
         }
-        const uint32_t vmask = span >= 32u ? 0xffffffffu : ~(0xffffffffu >> span);   // top `span` bits
-#else
+        int Tm = T - thr;                      // sign bit set <=> window is bad
+        Stream4 lead, trail;
+        lead.init(sm, qual_off + w_start + ws);
+        trail.init(sm, qual_off + w_start);
+        for (uint32_t base = w_start; base < nwin && b_stop < 0; base += 32) {
+            // bit 31-k: window base+k is bad.  Each total's sign bit is shifted in from the right by one
+            // funnel shift, so the step's first window ends up in the top bit (first = __clz).
+            uint32_t negr = 0;
 #pragma unroll
-        for (int g = 0; g < 8; ++g) {
-            const uint32_t lw = lead.next(), tw = trail.next();
-            // totals of windows base+4g+1 .. +4: prefix sums of (lead - trail), independent of each other
-            const int T1 = dp4a_us(lw, 0x00000001, dp4a_us(tw, 0x000000FF, Tm));
-            const int T2 = dp4a_us(lw, 0x00000101, dp4a_us(tw, 0x0000FFFF, Tm));
-            const int T3 = dp4a_us(lw, 0x00010101, dp4a_us(tw, 0x00FFFFFF, Tm));
-            const int T4 = dp4a_us(lw, 0x01010101, dp4a_us(tw, (int)0xFFFFFFFF, Tm));
-            negr = __funnelshift_l((uint32_t)Tm, negr, 1);
-            negr = __funnelshift_l((uint32_t)T1, negr, 1);
-            negr = __funnelshift_l((uint32_t)T2, negr, 1);
-            negr = __funnelshift_l((uint32_t)T3, negr, 1);
-            rc.screen(lw, r_hi, r_lo);
-            Tm = T4;
+            for (int gq = 0; gq < 8; ++gq) {
+                const uint32_t lw = lead.next(), tw = trail.next();
+                // totals of windows base+4g+1 .. +4: prefix sums of (lead - trail), independent of each other
+                const int T1 = dp4a_us(lw, 0x00000001, dp4a_us(tw, 0x000000FF, Tm));
+                const int T2 = dp4a_us(lw, 0x00000101, dp4a_us(tw, 0x0000FFFF, Tm));
+                const int T3 = dp4a_us(lw, 0x00010101, dp4a_us(tw, 0x00FFFFFF, Tm));
+                const int T4 = dp4a_us(lw, 0x01010101, dp4a_us(tw, (int)0xFFFFFFFF, Tm));
+                negr = __funnelshift_l((uint32_t)Tm, negr, 1);
+                negr = __funnelshift_l((uint32_t)T1, negr, 1);
+                negr = __funnelshift_l((uint32_t)T2, negr, 1);
+                negr = __funnelshift_l((uint32_t)T3, negr, 1);
+                Tm = T4;
+            }
+            const uint32_t left = nwin - base;                               // windows from base on (>= 1)
+            const uint32_t vmask = left >= 32 ? 0xffffffffu : ~(0xffffffffu >> left);   // top `left` bits
+            const uint32_t goodw = ~negr & vmask, badw = negr & vmask;
+            uint32_t after = 0xffffffffu;
+            if (!x && g < 0) {                                               // first good window: trim.cpp:42
+                if (goodw) {
+                    const int kk = __clz(goodw);
+                    g = (int)base + kk;
+                    after = 0xffffffffu >> kk;
+                } else after = 0;
+            }
+            const uint32_t cand = badw & after;                              // first bad window after it: trim.cpp:61
+            if (cand) b_stop = (int)base + __clz(cand);
         }
-        // ---- what the 32 windows of this step contribute
-        const uint32_t left = nwin - base;                               // windows from base on (>= 1)
-        if ((left <= 32u || rc.suspicious(r_hi, r_lo)) && me.o_first == 0x7fffffff) {
-            // the read's last step (its words run past the quality line) or, rarely, a suspect byte:
-            // find the first window of this step whose entering byte is out of range, exactly
-            // (bit k of oorw: the byte entering window base+k+1)
-            Stream4 again;
-            again.init(sm, qual_off + base + ws);
-            uint32_t oorw = 0;
-#pragma unroll 1
-            for (int g = 0; g < 8; ++g) oorw += flags_to_nibble(rc.bad4(again.next())) << (4 * g);
-            // the last window of the read has no entering byte
-            const uint32_t oo = oorw & (left > 32 ? 0xffffffffu : ((1u << (left - 1u)) - 1u));
-            if (oo) me.o_first = (int)base + __ffs(oo) - 1;
-        }
-        const uint32_t vmask = left >= 32 ? 0xffffffffu : ~(0xffffffffu >> left);   // top `left` bits
-#endif
-        const uint32_t goodw = ~negr & vmask, badw = negr & vmask;
-        if (badw && me.b_any < 0) me.b_any = (int)base + __clz(badw);
-        uint32_t after = 0xffffffffu;
-        if (me.g < 0) {                                                  // first good window: trim.cpp:42
-            if (goodw) {
-                const int k = __clz(goodw);
-                me.g = (int)base + k;
-                after = 0xffffffffu >> k;
-            } else after = 0;
-        }
-        const uint32_t cand = badw & after;                              // first bad window after it: trim.cpp:61
-        if (cand && me.b_after < 0) me.b_after = (int)base + __clz(cand);
     }
+    const int i5 = x ? -1 : g;
+    const int i3 = b_stop;
 
-    // ---- the two halves in order (A = windows from 0, B = the rest)
-    HalfScan A = me, B;
-    B.g = -1; B.b_any = -1; B.b_after = -1; B.o_first = 0x7fffffff;
-    if (nsub == 2u) {
-        const uint32_t pm = 3u << (lane & 30);
-        HalfScan ot;
-        ot.g = __shfl_xor_sync(pm, me.g, 1);
-        ot.b_any = __shfl_xor_sync(pm, me.b_any, 1);
-        ot.b_after = __shfl_xor_sync(pm, me.b_after, 1);
-        ot.o_first = __shfl_xor_sync(pm, me.o_first, 1);
-        bad |= __shfl_xor_sync(pm, bad, 1);
-        if (sub) { A = ot; B = me; } else B = ot;
-    }
-    if (bad) { o.error = true; return o; }
-    int i5 = x ? -1 : A.g;
-    int i3 = x ? A.b_any : A.b_after;
-    if (i3 < 0) {                                   // the loop runs on into the second half
-        if (x || A.g >= 0) i3 = B.b_any;
-        else { i5 = B.g; i3 = B.b_after; }
-    }
-    // entering bytes are fetched for the windows before the break (or before the last window)
-    const int fetched = i3 >= 0 ? i3 : (int)nwin - 1;
-    if (min(A.o_first, B.o_first) < fetched) { o.error = true; return o; }
-
-    // The two in-window scans only touch bytes the loop above has range-checked (all < 128), so
+    // The two in-window scans only touch bytes phase 1 has range-checked (all < 128), so
     // "q - qoff >= qthr" is the SWAR test "(b | 0x80) - c has bit 7 set" with c = qthr + qoff.
     int five = 0, three = (int)L;
     const int cthr = P.qthr + P.qoff;
     const uint32_t c4 = (uint32_t)(cthr < 1 ? 0 : (cthr > 128 ? 128 : cthr)) * 0x01010101u;
-    if (i5 >= 0 && (nsub == 1u || sub == 0u)) {                          // trim.cpp:46-51
+    if (i5 >= 0) {                                                           // trim.cpp:46-51
         Stream4 s;
         s.init(sm, qual_off + (uint32_t)i5);
         for (uint32_t j = 0; j < ws; j += 4) {
@@ -275,7 +244,7 @@ __device__ __forceinline__ TrimOut lane_sliding_window(const uint8_t *__restrict
             if (nib) { five = i5 + (int)j + __ffs(nib) - 1; break; }
         }
     }
-    if (i3 >= 0 && (nsub == 1u || sub == 1u)) {                          // trim.cpp:65-70
+    if (i3 >= 0) {                                                           // trim.cpp:65-70
         Stream4 s;
         s.init(sm, qual_off + (uint32_t)i3);
         for (uint32_t j = 0; j < ws; j += 4) {
@@ -285,40 +254,22 @@ __device__ __forceinline__ TrimOut lane_sliding_window(const uint8_t *__restrict
             if (nib) { three = i3 + (int)j + __ffs(nib) - 1; break; }
         }
     }
-    int pn = -1;
-    uint32_t anyN = 0;
-    if (P.trunc_n) {                                                     // trim.cpp:86-98; each lane one half of the bases
-        const uint32_t mid = nsub == 2u ? ((L / 2u + 3u) & ~3u) : L;
-        const uint32_t j0 = sub ? mid : 0u, j1 = sub ? L : min(mid, L);
+    if (P.trunc_n) {                                                         // trim.cpp:86-98
+        int pn = -1;
+        uint32_t anyN = 0;
         Stream4 s;
-        s.init(sm, seq_off + j0);
-        for (uint32_t j = j0; j < j1; j += 4) {
+        s.init(sm, seq_off);
+        for (uint32_t j = 0; j < L; j += 4) {
             const uint32_t v = s.next();
             // exact zero-byte tests of v ^ 'n' and v ^ 'N' (same trick as newline_flags)
             const uint32_t tn = ((v ^ 0x6E6E6E6Eu) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
             const uint32_t tN = ((v ^ 0x4E4E4E4Eu) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
             uint32_t fn = flags_to_nibble(~(tn | v) & 0x80808080u);
             uint32_t fN = flags_to_nibble(~(tN | v) & 0x80808080u);
-            if (j1 - j < 4) { const uint32_t m = (1u << (j1 - j)) - 1u; fn &= m; fN &= m; }
-            if (fn) { pn = (int)j + __ffs(fn) - 1; break; }
+            if (L - j < 4) { const uint32_t m = (1u << (L - j)) - 1u; fn &= m; fN &= m; }
+            if (fn) { pn = (int)j + __ffs(fn) - 1; break; }                 // a lowercase n wins over any N (trim.cpp:88-93)
             anyN |= fN;
         }
-    }
-    if (nsub == 2u) {
-        const uint32_t pm = 3u << (lane & 30);
-        const int o_cut = __shfl_xor_sync(pm, sub ? three : five, 1);    // lane 0 sends five, lane 1 sends three
-        if (sub) five = o_cut; else three = o_cut;
-        if (P.trunc_n) {
-            const int o_pn = __shfl_xor_sync(pm, pn, 1);
-            const uint32_t o_any = __shfl_xor_sync(pm, anyN, 1);
-            // the scan stops at the first lowercase n: an uppercase N only counts if it comes before it
-            const int pn_a = sub ? o_pn : pn, pn_b = sub ? pn : o_pn;
-            const uint32_t any_a = sub ? o_any : anyN, any_b = sub ? anyN : o_any;
-            pn = pn_a >= 0 ? pn_a : pn_b;
-            anyN = any_a | (pn_a >= 0 ? 0u : any_b);
-        }
-    }
-    if (P.trunc_n) {
         if (pn >= 0) three = pn - 1;
         else if (anyN) three = -2;
     }

@@ -1,10 +1,9 @@
 // TEST INFRASTRUCTURE ONLY -- host stand-in for sickle_b200/csrc/sk_device.cuh.
 //
 // tests/test_lane_logic.py (and test_copy_logic.py, for sk_copy.cuh) copies sickle_b200/csrc/trim_lane.cuh (the device function that trims one
-// read with one or two lanes, shared by the fused kernel and K2) next to this file and k1_index.cuh,
+// read with one lane, shared by the fused kernel and K2) next to this file and k1_index.cuh,
 // and compiles it with g++: the CUDA qualifiers become empty macros, the integer intrinsics are
-// restated here, and the two lanes of a read are two host threads whose __shfl_xor_sync is a
-// rendezvous.  The integer logic that decides the cut points is then checked against the oracle on
+// restated here.  The integer logic that decides the cut points is then checked against the oracle on
 // CPU.  Nothing here is used by the product.
 #pragma once
 
@@ -58,36 +57,3 @@ inline uint32_t __dp4a(uint32_t a, uint32_t b, uint32_t c) {
     return c;
 }
 
-// ---- the pair of lanes that shares one read: two host threads, shuffles meet at a rendezvous
-struct LanePair {
-    std::atomic<int> arrived{0};
-    std::atomic<int> generation{0};
-    int slot[2] = {0, 0};
-    std::atomic<bool> broken{false};   // set by the harness when one lane returned early (a logic error)
-};
-extern thread_local LanePair *tl_pair;
-extern thread_local int tl_sub;
-
-inline void lane_rendezvous(LanePair *p) {
-    const int g = p->generation.load(std::memory_order_acquire);
-    if (p->arrived.fetch_add(1, std::memory_order_acq_rel) == 1) {
-        p->arrived.store(0, std::memory_order_relaxed);
-        p->generation.store(g + 1, std::memory_order_release);
-    } else {
-        long spins = 0;
-        while (p->generation.load(std::memory_order_acquire) == g) {
-            if (++spins > 2000000000L || p->broken.load(std::memory_order_relaxed)) { p->broken = true; return; }
-        }
-    }
-}
-template <class T>
-inline T __shfl_xor_sync(uint32_t, T v, int) {
-    static_assert(sizeof(T) == 4, "32-bit shuffles only");
-    LanePair *p = tl_pair;
-    memcpy(&p->slot[tl_sub], &v, 4);
-    lane_rendezvous(p);
-    T r;
-    memcpy(&r, &p->slot[tl_sub ^ 1], 4);
-    lane_rendezvous(p);
-    return r;
-}

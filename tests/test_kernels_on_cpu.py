@@ -288,27 +288,3 @@ def test_capacity_overflows_are_flagged(harness, tmp_path):
         assert rc == 0 and out == "OVERFLOW line_index=0 output=1", (k, out, err[-300:])
         rc, out, err = run(harness, se, kernel=k, env={"KH_OUT_CAP": "560000"})      # 558 KB of output: just fits
         assert rc == 0 and out.startswith("OK"), (k, out)
-
-
-@pytest.mark.parametrize("defines", [("SK_LANE_SPLIT4", "SK_STAGE_LONG_FIRST", "SK_NL_BRANCHFREE"), ("SK_DIRECT_EMIT",),
-                                     ("SK_DIRECT_EMIT", "SK_EARLY_LOAD", "SK_LANE_SPLIT4", "SK_NL_BRANCHFREE")])
-def test_experimental_variants(tmp_path, defines):
-    """The build variants kept for the next round's A/B runs (off in the shipped library) write the same bytes."""
-    from sickle_b200 import synth
-    from test_oracle_fuzz_vs_ref import _records
-
-    exe = build_harness("kernels_harness_" + "_".join(defines), defines)
-    rng = np.random.default_rng(99)
-    se, il, var = (str(tmp_path / n) for n in ("se.fq", "il.fq", "var.fq"))
-    open(se, "wb").write(synth.fixed_length_records(3000, 150, "sanger", seed=15).tobytes())
-    open(il, "wb").write(synth.paired_records(1200, 150, "sanger", seed=16)[2].tobytes())
-    open(var, "wb").write(_records(rng, 2500, 250, "illumina"))
-    assert check(exe, se, "se", first=5) == ["OK"] * 5
-    check(exe, se, "se -x -n", x=True, n=True, q=30, l=5)
-    check(exe, il, "pei", mode="pei", first=9)
-    check(exe, il, "peM", mode="peM", singles=False)
-    check(exe, var, "variable", qualtype="illumina", n=True)
-    big = str(tmp_path / "big.fq")
-    open(big, "wb").write(synth.fixed_length_records(30000, 150, "sanger", seed=17).tobytes())
-    assert check(exe, big, "se 30k, 8 CTAs", kernels=("fused7", "fused9"), ctas=8, first=3) == ["OK"] * 2
-    assert check(exe, il, "pei, random thread order", kernels=("fused5", "fused9"), mode="pei", first=1, env={"SIMT_SHUFFLE": "7"}) == ["OK"] * 2
