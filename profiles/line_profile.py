@@ -20,7 +20,7 @@ for ln in open(dis, errors="replace"):
     if m:
         cur = (m.group(1).split("/")[-1], int(m.group(2)), "inlined" in m.group(3))
         continue
-    if re.match(r"\s+/\*[0-9a-f]{4}\*/", ln):
+    if re.match(r"\s+/\*[0-9a-f]{4,6}\*/", ln):
         tags.append(cur)
 rows = list(csv.reader(open(src_csv)))
 H = rows[1]

@@ -11,12 +11,17 @@
 //
 // This is the general ("any read length") path.  A warp handles 32 consecutive units (reads, or
 // pairs) and lane k ends up holding unit k's result; routing, the 3-stream output-length scan (warp
-// scan + decoupled look-back) and the per-record descriptors are then lane-parallel.  Reads of up to
-// 600 bases are trimmed by their own lane (lane_sliding_window, shared with the single-pass kernel);
-// whatever that declines -- longer reads, malformed records, quality bytes out of range, the last
-// record before the end of the buffer -- is walked by the whole warp, 32 window positions per step,
-// window totals from a warp-shuffle prefix scan of q[i+ws]-q[i]; that path also finds the position
-// the reference reports for a bad quality byte.
+// scan + decoupled look-back) and the per-record descriptors are then lane-parallel.  Every read is
+// trimmed by its own lane (lane_sliding_window, shared with the single-pass kernel: a word-granular
+// pass over the quality line, then the exact scan only where a window can be bad -- about 2.5
+// instructions per base whatever the read length, 1 kb or 20 kb alike); whatever that declines --
+// malformed records, quality bytes out of range, the last record before the end of the buffer -- is
+// walked by the whole warp, 32 window positions per step, window totals from a warp-shuffle prefix
+// scan of q[i+ws]-q[i]; that path also finds the position the reference reports for a bad quality byte.
+//
+// Tile = 256 units (8 warps x 32) for short records.  When the batch averages 1.5 KB or more per
+// record a tile is 64 units (two warps trim, the others only take part in the scan): a 255 MB batch
+// of 1-20 kb reads is 20,000 units, i.e. 78 tiles of 256 -- fewer tiles than SMs -- but 313 of 64.
 #pragma once
 
 #include "sk_device.cuh"
@@ -25,7 +30,9 @@
 namespace sk {
 
 constexpr int kK2Threads = 256;
-constexpr int kK2UnitsPerTile = kK2Threads;  // 8 warps x 32 units
+constexpr int kK2UnitsPerTile = kK2Threads;  // 8 warps x 32 units (short records)
+constexpr uint32_t kK2LongUnitsPerTile = 64;  // 2 warps x 32 units (batches of long records)
+constexpr uint32_t kK2LongRecordBytes = 1500; // average record size from which a batch counts as "long"
 
 struct Cut {
     int five, three;  // three < 0 => discard (src/trim_single.cpp:368)
@@ -202,11 +209,12 @@ __device__ __forceinline__ MateInfo trim_mate(const DevInput &in, uint32_t rec, 
 
 // Short reads: one lane trims the record by itself, straight from global memory (the 32 lanes of a
 // warp work on 32 different records; each lane walks its own cache lines, which stay in L1/L2 for the
-// few hundred bytes of a read).  ~8x fewer warp instructions per read than the warp-wide scan above.
+// few hundred bytes of a read).  Far fewer warp instructions per read than the warp-wide scan above.
 // Returns false when the warp-wide path has to take the record: malformed (it reports the error),
-// a quality byte out of range (it finds the position), longer than kThreadTrimMaxLen, or so close to
-// the end of the buffer that the lane's word-wise look-ahead (< 64 bytes) could leave it.
-constexpr uint32_t kThreadTrimMaxLen = 600;
+// a quality byte out of range (it finds the position), longer than kThreadTrimMaxLen (window totals
+// must stay below 2^30), or so close to the end of the buffer that the lane's word-wise look-ahead
+// (< 64 bytes) could leave it.
+constexpr uint32_t kThreadTrimMaxLen = 1u << 22;
 __device__ __forceinline__ bool thread_trim_mate(const DevInput &in, uint32_t rec, const DevParams &P,
                                                  const RangeCheck &rc, int lane, MateInfo &m) {
     const RecLines r = record_lines(in, rec);
@@ -230,7 +238,13 @@ k2_trim_route(DevInput in0, DevInput in1, DevParams P, Control *__restrict__ ctl
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const Geometry g = batch_geometry(ctl, P);
-    const uint32_t num_tiles = (g.nunits + kK2UnitsPerTile - 1) / kK2UnitsPerTile;
+    // tile geometry (block-uniform, derived from what K1 counted)
+    const uint32_t nrec_all = g.nrec0 + g.nrec1;
+    const bool long_batch = nrec_all > 0 && (in0.nbytes + in1.nbytes) / nrec_all >= kK2LongRecordBytes &&
+                            (g.nunits + kK2LongUnitsPerTile - 1) / kK2LongUnitsPerTile < status_stride;
+    const uint32_t upt = long_batch ? kK2LongUnitsPerTile : (uint32_t)kK2UnitsPerTile;   // units per tile
+    const bool trim_warp = (uint32_t)wid * 32u < upt;                                     // this warp owns units
+    const uint32_t num_tiles = (g.nunits + upt - 1) / upt;
     const bool paired = P.mode != 0;
     const bool inter = P.mode >= 2;
     const bool mmode = P.mode == 3;
@@ -245,11 +259,11 @@ k2_trim_route(DevInput in0, DevInput in1, DevParams P, Control *__restrict__ ctl
 
         // ---- phase 1: lane k trims unit k by itself (short reads); whatever that path declines is
         // redone by the whole warp, one unit after the other ----
-        const uint32_t p0 = tile * kK2UnitsPerTile + wid * 32;
+        const uint32_t p0 = tile * upt + wid * 32;
         MateInfo mine0 = {{-1, -1}, 0}, mine1 = {{-1, -1}, 0};
         uint32_t my_unit = 0;
         bool redo = false;
-        if (p0 + lane < g.nunits) {
+        if (trim_warp && p0 + lane < g.nunits) {
             my_unit = position_to_unit(p0 + lane, g.nunits, P.emu_threads, paired);
             redo = !thread_trim_mate(in0, inter ? 2 * my_unit : my_unit, P, rc, lane, mine0);
             if (paired && !redo)
@@ -266,7 +280,7 @@ k2_trim_route(DevInput in0, DevInput in1, DevParams P, Control *__restrict__ ctl
         }
 
         // ---- phase 2: routing (lane = unit) ----
-        const bool active = p0 + lane < g.nunits;
+        const bool active = trim_warp && p0 + lane < g.nunits;
         const bool k1 = active && mine0.cut.three >= 0;
         const bool k2 = active && paired && mine1.cut.three >= 0;
         const uint32_t n1 = k1 ? (uint32_t)(mine0.cut.three - mine0.cut.five) : 0u;

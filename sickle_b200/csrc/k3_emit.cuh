@@ -103,16 +103,21 @@ k3_emit(DevInput in0, DevInput in1, DevParams P, const Control *__restrict__ ctl
     // instead of once per record); then the warp copies the records one after the other, the copy
     // parameters coming from the owning lane by shuffle.  Records cut at the 5' end and -M "N records"
     // (rare) take the four-piece path.
+    // Batches of long records (>= 1.5 KB on average, K2's rule) hand a warp 4 records at a time instead of
+    // 32: 20,000 reads of 1-20 kb would otherwise keep 625 of the grid's ~9,500 warps busy, each copying
+    // ~125 KB, while the others exit at once.
     const uint32_t nwarps = gridDim.x * (kK3Threads / 32);
-    const uint32_t chunks0 = (g.nrec0 + 31u) / 32u, chunks1 = (g.nrec1 + 31u) / 32u;
+    const uint32_t nrec_all = g.nrec0 + g.nrec1;
+    const uint32_t rpc = (nrec_all > 0 && (in0.nbytes + in1.nbytes) / nrec_all >= kK2LongRecordBytes) ? 4u : 32u;   // records per warp and round
+    const uint32_t chunks0 = (g.nrec0 + rpc - 1u) / rpc, chunks1 = (g.nrec1 + rpc - 1u) / rpc;
     for (uint32_t c = blockIdx.x * (kK3Threads / 32) + (threadIdx.x >> 5); c < chunks0 + chunks1; c += nwarps) {
         const bool second = c >= chunks0;
         const DevInput &in = second ? in1 : in0;
         const uint32_t nrec = second ? g.nrec1 : g.nrec0;
-        const uint32_t rec = (second ? c - chunks0 : c) * 32u + (uint32_t)lane;
+        const uint32_t rec = (second ? c - chunks0 : c) * rpc + (uint32_t)lane;
         RecDesc d;
         d.route = 0; d.dst_off = 0; d.five = 0; d.nkeep = 0;
-        if (rec < nrec) d = (second ? desc1 : desc0)[rec];
+        if ((uint32_t)lane < rpc && rec < nrec) d = (second ? desc1 : desc0)[rec];
         const bool emit = (d.route & kRouteEmit) != 0;
         const bool slow = emit && (d.route & kRouteNRec);              // -M "N records": four-piece path
         // Runs of a kept record, in output order: name '\n' | seq[five:three] | '\n' line3 '\n' | qual[five:three]
