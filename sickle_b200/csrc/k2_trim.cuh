@@ -20,8 +20,11 @@
 // scan of q[i+ws]-q[i]; that path also finds the position the reference reports for a bad quality byte.
 //
 // Tile = 256 units (8 warps x 32) for short records.  When the batch averages 1.5 KB or more per
-// record a tile is 64 units (two warps trim, the others only take part in the scan): a 255 MB batch
-// of 1-20 kb reads is 20,000 units, i.e. 78 tiles of 256 -- fewer tiles than SMs -- but 313 of 64.
+// record a tile is 64 units, 8 per warp (lanes 0..7): a 255 MB batch of 1-20 kb reads is 20,000 units,
+// i.e. 78 tiles of 256 -- fewer tiles than SMs, each warp walking up to 32 long reads one after the
+// other -- but 313 tiles of 64, 2,500 warps with at most 8 long reads each.  Reads above
+// kThreadTrimMaxLen bases go to the warp-wide path, whose coarse pass is warp-cooperative (a single
+// lane walking a 20 kb read alone is a 0.3 ms dependent chain).
 #pragma once
 
 #include "sk_device.cuh"
@@ -31,7 +34,8 @@ namespace sk {
 
 constexpr int kK2Threads = 256;
 constexpr int kK2UnitsPerTile = kK2Threads;  // 8 warps x 32 units (short records)
-constexpr uint32_t kK2LongUnitsPerTile = 64;  // 2 warps x 32 units (batches of long records)
+constexpr uint32_t kK2LongUnitsPerWarp = 8;   // batches of long records: 8 units per warp, 64 per tile
+constexpr uint32_t kK2LongUnitsPerTile = kK2LongUnitsPerWarp * (kK2Threads / 32);
 constexpr uint32_t kK2LongRecordBytes = 1500; // average record size from which a batch counts as "long"
 
 struct Cut {
@@ -91,30 +95,83 @@ __device__ __noinline__ Cut warp_sliding_window(const uint8_t *__restrict__ d, u
     uint32_t ws = L / 10u;                                       // trim.cpp:8
     if (ws == 0) ws = L;                                         // trim.cpp:30
     const long long thr_total = (long long)P.qthr * (long long)ws;
+    const uint32_t nwin = L - ws + 1u;                           // trim.cpp:34
 
-    int part = 0;                                                // trim.cpp:31-33
-    for (uint32_t j0 = 0; j0 < ws; j0 += 32) {
-        const uint32_t j = j0 + lane;
-        bool bad = false;
-        if (j < ws) {
-            const int b = q[j];
-            bad = (b < P.qmin) | (b > P.qmax);
-            part += b - P.qoff;
+    // ---- coarse pass for long reads (the warp-wide twin of phase 1 of lane_sliding_window, same bound):
+    // lane l takes word s0 + l of the quality line, 128 coalesced bytes per step; a warp scan of
+    // (lead word sum - trail word sum) gives the k-word sliding sums.  Up to the first word whose bound
+    // falls below the threshold every window is good, so the exact walk below starts at w_start instead of
+    // window 0.  A quality byte outside [qmin, qmax] anywhere in the words looked at (it may lie beyond
+    // what the reference visits) switches the shortcut off: the exact walk then runs from window 0 and
+    // reports the error exactly as before.
+    uint32_t w_start = 0;
+    if (L >= 256u && thr_total <= 0x3fffffffLL && (L >> 24) == 0u) {
+        RangeCheck rc;
+        rc.init(P);
+        const uint32_t *__restrict__ W = reinterpret_cast<const uint32_t *>(d);   // d is 16-byte aligned
+        const uint32_t Q = qual_off, E = qual_off + L;
+        const uint32_t A0 = (Q + 3u) >> 2, A1 = E >> 2;          // whole words [A0, A1)
+        const uint32_t k = (ws - 3u) >> 2;                       // ws >= 25 here: k >= 5, and A1 - A0 >= k
+        const uint32_t nfull = A1 - A0, nstep = nfull - k + 1u;
+        const int slack = P.qmin < P.qoff ? (int)(ws - 4u * k) * (P.qmin - P.qoff) : 0;
+        const int bias = (int)thr_total + (int)(4u * k) * P.qoff - slack;
+        uint32_t scr = 0;
+        if (lane == 0) {                                         // ragged head and tail of the line
+            if (Q & 3u) { const uint32_t m = 0xffffffffu << (8u * (Q & 3u)); rc.screen3((W[A0 - 1u] & m) | (rc.kmin & ~m), scr); }
+            if (E & 3u) { const uint32_t m = ~(0xffffffffu << (8u * (E & 3u))); rc.screen3((W[A1] & m) | (rc.kmin & ~m), scr); }
         }
-        const uint32_t bm = __ballot_sync(0xffffffffu, bad);
-        if (bm) { err_pos = (int)(j0 + __ffs(bm) - 1); return discard; }
+        int part = 0;
+        for (uint32_t j = (uint32_t)lane; j < k; j += 32) {
+            const uint32_t v = W[A0 + j];
+            rc.screen3(v, scr);
+            part = (int)__dp4a(v, 0x01010101u, (uint32_t)part);
+        }
+        int R = warp_sum_i(part) - bias;                         // bound of the first whole word (step 0)
+        uint32_t jf = nstep;                                     // first step whose bound is below the threshold
+        for (uint32_t s0 = 0; s0 < nstep; s0 += 32) {
+            const uint32_t s = s0 + (uint32_t)lane;
+            int D = 0;                                           // what step s+1 has over step s
+            if (s + 1u < nstep) {
+                const uint32_t lw = W[A0 + k + s], tw = W[A0 + s];
+                rc.screen3(lw, scr);
+                D = dp4a_us(lw, 0x01010101, dp4a_us(tw, (int)0xFFFFFFFF, 0));
+            }
+            const int incl = warp_incl_scan_i(D, lane);
+            const uint32_t bm = __ballot_sync(0xffffffffu, s < nstep && R + incl - D < 0);
+            if (bm) { jf = s0 + (uint32_t)__ffs(bm) - 1u; break; }
+            R += __shfl_sync(0xffffffffu, incl, 31);
+        }
+        if (!__any_sync(0xffffffffu, (scr & 0x80808080u) != 0)) {
+            const int ws_i = jf == nstep ? (int)nwin : 4 * (int)(A0 + jf) - (int)Q - 3;
+            w_start = ws_i < 0 ? 0u : min((uint32_t)ws_i, nwin);
+        }
+    }
+
+    int part = 0;                                                // trim.cpp:31-33 (total of window w_start)
+    if (w_start < nwin) {
+        for (uint32_t j0 = 0; j0 < ws; j0 += 32) {
+            const uint32_t j = j0 + lane;
+            bool bad = false;
+            if (j < ws) {
+                const int b = q[w_start + j];
+                bad = (b < P.qmin) | (b > P.qmax);
+                part += b - P.qoff;
+            }
+            const uint32_t bm = __ballot_sync(0xffffffffu, bad);
+            if (bm) { err_pos = (int)(w_start + j0 + __ffs(bm) - 1); return discard; }
+        }
     }
     int carry = warp_sum_i(part);
 
-    const uint32_t nwin = L - ws + 1u;                           // trim.cpp:34
-    bool found = false;
-    int i5 = -1, i3 = -1;
-    for (uint32_t c = 0; c < nwin; c += 32) {
+    // w_start > 0: windows 0 .. w_start-1 are good, so window 0 is the first good one
+    bool found = w_start > 0 && !P.no_fiveprime;
+    int i5 = found ? 0 : -1, i3 = -1;
+    for (uint32_t c = w_start; c < nwin; c += 32) {
         const uint32_t i = c + lane;
         const bool valid = i < nwin;
         int dlt = 0;
         bool bad = false;
-        if (valid && i > 0) {                                    // trim.cpp:76-79 for window i-1
+        if (valid && i > w_start) {                              // trim.cpp:76-79 for window i-1
             const int lead = q[i - 1 + ws], trail = q[i - 1];
             bad = (lead < P.qmin) | (lead > P.qmax);
             dlt = lead - trail;
@@ -211,10 +268,10 @@ __device__ __forceinline__ MateInfo trim_mate(const DevInput &in, uint32_t rec, 
 // warp work on 32 different records; each lane walks its own cache lines, which stay in L1/L2 for the
 // few hundred bytes of a read).  Far fewer warp instructions per read than the warp-wide scan above.
 // Returns false when the warp-wide path has to take the record: malformed (it reports the error),
-// a quality byte out of range (it finds the position), longer than kThreadTrimMaxLen (window totals
-// must stay below 2^30), or so close to the end of the buffer that the lane's word-wise look-ahead
-// (< 64 bytes) could leave it.
-constexpr uint32_t kThreadTrimMaxLen = 1u << 22;
+// a quality byte out of range (it finds the position), longer than kThreadTrimMaxLen (one lane walking
+// a long read alone is a long dependent chain; the warp-wide path spreads it over 32 lanes), or so close
+// to the end of the buffer that the lane's word-wise look-ahead (< 64 bytes) could leave it.
+constexpr uint32_t kThreadTrimMaxLen = 1024;
 __device__ __forceinline__ bool thread_trim_mate(const DevInput &in, uint32_t rec, const DevParams &P,
                                                  const RangeCheck &rc, int lane, MateInfo &m) {
     const RecLines r = record_lines(in, rec);
@@ -242,8 +299,9 @@ k2_trim_route(DevInput in0, DevInput in1, DevParams P, Control *__restrict__ ctl
     const uint32_t nrec_all = g.nrec0 + g.nrec1;
     const bool long_batch = nrec_all > 0 && (in0.nbytes + in1.nbytes) / nrec_all >= kK2LongRecordBytes &&
                             (g.nunits + kK2LongUnitsPerTile - 1) / kK2LongUnitsPerTile < status_stride;
-    const uint32_t upt = long_batch ? kK2LongUnitsPerTile : (uint32_t)kK2UnitsPerTile;   // units per tile
-    const bool trim_warp = (uint32_t)wid * 32u < upt;                                     // this warp owns units
+    const uint32_t upw = long_batch ? kK2LongUnitsPerWarp : 32u;                          // units per warp (lanes 0 .. upw-1)
+    const uint32_t upt = upw * (kK2Threads / 32);                                         // units per tile
+    const bool unit_lane = (uint32_t)lane < upw;
     const uint32_t num_tiles = (g.nunits + upt - 1) / upt;
     const bool paired = P.mode != 0;
     const bool inter = P.mode >= 2;
@@ -259,11 +317,11 @@ k2_trim_route(DevInput in0, DevInput in1, DevParams P, Control *__restrict__ ctl
 
         // ---- phase 1: lane k trims unit k by itself (short reads); whatever that path declines is
         // redone by the whole warp, one unit after the other ----
-        const uint32_t p0 = tile * upt + wid * 32;
+        const uint32_t p0 = tile * upt + wid * upw;
         MateInfo mine0 = {{-1, -1}, 0}, mine1 = {{-1, -1}, 0};
         uint32_t my_unit = 0;
         bool redo = false;
-        if (trim_warp && p0 + lane < g.nunits) {
+        if (unit_lane && p0 + lane < g.nunits) {
             my_unit = position_to_unit(p0 + lane, g.nunits, P.emu_threads, paired);
             redo = !thread_trim_mate(in0, inter ? 2 * my_unit : my_unit, P, rc, lane, mine0);
             if (paired && !redo)
@@ -280,7 +338,7 @@ k2_trim_route(DevInput in0, DevInput in1, DevParams P, Control *__restrict__ ctl
         }
 
         // ---- phase 2: routing (lane = unit) ----
-        const bool active = trim_warp && p0 + lane < g.nunits;
+        const bool active = unit_lane && p0 + lane < g.nunits;
         const bool k1 = active && mine0.cut.three >= 0;
         const bool k2 = active && paired && mine1.cut.three >= 0;
         const uint32_t n1 = k1 ? (uint32_t)(mine0.cut.three - mine0.cut.five) : 0u;

@@ -76,14 +76,7 @@ struct FusedCfg {
     static constexpr int kRegion = kFThreads * kBytesPerThread;
     static constexpr int kTile = kFTileThreads * kBytesPerThread;
     static constexpr int kInBytes = kRegion + 96;        // the window loop reads up to ~50 bytes past a record
-#ifdef SK_EMIT_NOW
-    // Experiment: no staging buffer.  Look-back #2 runs right after the sizes are published and the records
-    // are copied from the input tile straight to their global addresses; the shared memory this frees lets
-    // four CTAs share an SM at the 32 KB tile.
-    static constexpr int kOutBytes = 0;
-#else
     static constexpr int kOutBytes = kTile + 768 + 96;   // a tile of output + the last record's overhang + phase shifts
-#endif
     // CH = 7: 56,768 B -> four CTAs per SM (4 x (56,768 + 248 static + 1,024 reserved) <= 232,448)
     static constexpr size_t kSmem = (size_t)kInBytes + kOutBytes + kFMaxNl * 2;
     // CTAs per SM by shared memory (232,448 B per SM, 1,024 B reserved per CTA); also the register budget
@@ -428,11 +421,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         }
         // the staging buffer holds a tile's worth of output; a tile whose (long, untrimmed) records
         // reach far into the halo can exceed it -> general path
-#ifdef SK_EMIT_NOW
-        const bool tile_fail = s_fail != 0 || tot0 >= 65536u || tot1 >= 65536u;   // (descriptor offsets are 16 bit)
-#else
         const bool tile_fail = s_fail != 0 || tot0 + tot1 + 64u > (uint32_t)Cfg::kOutBytes;
-#endif
         if (tile_fail) {   // bit 1: the tile simply holds too many records (the host then picks smaller tiles)
             tot0 = 0; tot1 = 0;
             if (tid == 0) atomicOr(&ctl->fast_fail, (nl_overflow || nrec_t > (uint32_t)kFThreads / 2u) ? 3u : 1u);
@@ -442,9 +431,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             block_publish(st_out, tile, agg, nstreams, epoch, tid);
         }
         if (tid == 0) held = atomicAdd(&ctl->tile_counter[3], 1u);   // looked at after S8a
-#ifndef SK_EMIT_NOW
         have_prev = true;
-#endif
         p_tile = tile; p_tot0 = tot0; p_tot1 = tot1;
         const uint32_t base1 = (tot0 + 15u) & ~15u;                    // singles staged after the main bytes
 
@@ -463,36 +450,13 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         }
         __syncthreads();
         SK_TICK(8);   // S7b: totals, publish, descriptors, barrier
-#ifdef SK_EMIT_NOW
-        // look-back #2 at once (the CTA waits here for its predecessors' sizes; other CTAs of the SM run meanwhile)
-        uint8_t *gal0 = nullptr, *gal1 = nullptr;
-        uint32_t ph0 = 0, ph1 = 0;
-        bool emit_ok;
-        {
-            const unsigned long long agg2[2] = {tot0, tot1};
-            unsigned long long ex2[2];
-            block_walk(st_out, tile, agg2, nstreams, epoch, tid, s_lb, ex2);
-            if (tid == 0 && tile == num_tiles - 1) { ctl->out_bytes[0] = ex2[0] + tot0; ctl->out_bytes[2] = ex2[1] + tot1; }
-            emit_ok = ex2[0] + tot0 <= outs.cap[0] && (tot1 == 0 || (outs.p[2] && ex2[1] + tot1 <= outs.cap[2]));
-            if (!emit_ok && tid == 0) ctl->index_overflow = 2u;
-            uint8_t *g0 = outs.p[0] + ex2[0], *g1 = tot1 ? outs.p[2] + ex2[1] : outs.p[0];
-            ph0 = (uint32_t)(reinterpret_cast<uintptr_t>(g0) & 15u); ph1 = (uint32_t)(reinterpret_cast<uintptr_t>(g1) & 15u);
-            gal0 = g0 - ph0; gal1 = g1 - ph1;
-        }
-        SK_TICK(5);
-#endif
 
         // ---- S8a: two lanes per record copy it into the staging buffer (phase 0; the flush realigns):
         // lane 0 takes [name '\n' seq), lane 1 takes ['\n' line3 '\n' qual '\n')
         {
             const uint32_t r = (uint32_t)tid >> 1, sub = (uint32_t)tid & 1u;
             uint4 dsc = make_uint4(0, 0, 0, 0);
-#ifdef SK_EMIT_NOW
-            if (!tile_fail && emit_ok && r < nrec_t) dsc = s_desc[r];
-            uint8_t *const s_out = (dsc.x & 0x80000000u) ? gal1 : gal0;   // (global memory here)
-#else
             if (!tile_fail && r < nrec_t) dsc = s_desc[r];   // a failed tile wrote no descriptors
-#endif
             // Both lanes run the same copies with different arguments (lanes of one warp that took
             // different branches would serialise).  Run A, then -- only in warps where some read is cut
             // at its 5' end -- run B:
@@ -507,11 +471,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             const uint32_t r_start = dsc.y & 0xffffu, r_e0 = dsc.y >> 16, r_e1 = dsc.z & 0xffffu, r_e2 = dsc.z >> 16;
             const uint32_t five = dsc.w & 0xffffu, n = dsc.w >> 16;
             const uint32_t nlen = r_e0 - r_start, plen = r_e2 - r_e1 - 1u;
-#ifdef SK_EMIT_NOW
-            const uint32_t d = ((dsc.x & 0x80000000u) ? ph1 : ph0) + (dsc.x & 0xffffu);
-#else
             const uint32_t d = ((dsc.x & 0x80000000u) ? base1 : 0u) + (dsc.x & 0xffffu);
-#endif
             if (emit) {
                 if (sub == 0) {
                     a_dst = d; a_src = r_start;

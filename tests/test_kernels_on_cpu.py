@@ -165,6 +165,33 @@ def test_long_reads_config4(harness, tmp_path):
         check(harness, p, (qualtype, "q30"), kernels=("general",), qualtype=qualtype, q=30, l=100, ctas=3)
 
 
+def test_long_reads_with_out_of_range_quality_bytes(harness, tmp_path):
+    """Long reads take the warp-wide path, whose coarse pass screens more bytes than the reference's loop
+    visits: a quality byte outside the encoding's range -- at the front, in the middle, near the end, inside
+    or beyond the visited prefix -- must still give the reference's verdict (same error record / position /
+    byte, or no error at all when the loop never gets there)."""
+    from sickle_b200 import synth
+
+    rng = np.random.default_rng(77)
+    verdicts = set()
+    for case in range(24):
+        qualtype = ("sanger", "illumina", "solexa")[case % 3]
+        data = bytearray(synth.variable_length_records(6, 1100, 9000, qualtype, 300 + case, p_N=0.0, p_n=0.0))
+        lines = bytes(data).split(b"\n")
+        rec = int(rng.integers(0, 6))
+        qline_start = sum(len(x) + 1 for x in lines[:4 * rec + 3])
+        L = len(lines[4 * rec + 3])
+        where = (0, 1, L // 20, L // 3, L // 2, L - L // 12, L - 2, L - 1)[case % 8]
+        data[qline_start + where] = (0x1f, 0x7f, 0x80, 0xff, 0x20, 0x0b)[case % 6]
+        p = str(tmp_path / ("bad%d.fq" % case))
+        open(p, "wb").write(bytes(data))
+        for x in (False, True):
+            rc, out, err = run(harness, p, kernel="general", qualtype=qualtype, x=x, ctas=3, first=case % 16)
+            assert rc == 0 and out.startswith("OK"), (case, x, out, err[-400:])
+            verdicts.add("error" in out.lower())
+    assert verdicts == {True, False}      # some bytes are met by the loop, some lie beyond its break
+
+
 def test_damaged_inputs(harness, tmp_path):
     """Seeded random files, three quarters of them damaged (missing / blank / doubled line, flipped /
     deleted / inserted byte, cut-off tail): same first data error (kind, record, position, byte) or same
