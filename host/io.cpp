@@ -351,6 +351,12 @@ bool ByteSink::wait(unsigned long long ticket) {
     return !failed_;
 }
 
+void ByteSink::drain() {
+    if (fd_ < 0) return;
+    std::unique_lock<std::mutex> lk(mu_);
+    cv_done_.wait(lk, [&] { return completed_ >= submitted_; });
+}
+
 void ByteSink::run() {
     while (true) {
         Job j;

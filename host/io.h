@@ -65,6 +65,9 @@ public:
     // Block until every write up to `ticket` is on its way to the file; false if any write failed.
     bool wait(unsigned long long ticket);
     bool write(const char *src, unsigned long long n) { return wait(write_async(src, n)); }
+    // Block until every queued write has been carried out (or has failed): after this the writer thread
+    // holds no pointer into the caller's buffers.  Needed before those buffers are freed on an error path.
+    void drain();
     // Drain and close; false if any write failed.
     bool close();
     double busy_seconds() const { return busy_s_; }

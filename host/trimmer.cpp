@@ -96,9 +96,19 @@ struct CachedCtx {
     unsigned long long slot = 0;
 } g_cache;
 
+// The writer threads read straight out of a context's pinned result buffers (queue_outputs).  Whatever
+// path leaves run_device / run_devices -- a data error in batch k while batch k-1 is still being
+// written, a failed read, a CUDA error -- the queued writes must be over before those buffers are freed.
+void drain_sinks(ByteSink *const *sinks) {
+    if (!sinks) return;
+    for (int i = 0; i < 3; ++i)
+        if (sinks[i] && sinks[i]->is_open()) sinks[i]->drain();
+}
+
 struct Ctx {
     sk_ctx *c = nullptr;
     Totals *tot = nullptr;
+    ByteSink *const *sinks = nullptr;   // drained before the context (and its pinned buffers) goes away
     bool reusable = false;   // set once the run finished with every slot idle
     sk_params p{};
     int device = 0, nslots = 0;
@@ -118,6 +128,7 @@ struct Ctx {
     ~Ctx() {
         // SICKLE_B200_KEEP_CONTEXT=1: leave buffers and context to process exit (the CLI exits right after)
         static const bool keep = getenv("SICKLE_B200_KEEP_CONTEXT") && atoi(getenv("SICKLE_B200_KEEP_CONTEXT")) != 0;
+        drain_sinks(sinks);
         const double t0 = host::now_s();
         if (c && host::batch_mode && reusable) {
             g_cache.c = c; g_cache.p = p; g_cache.device = device; g_cache.nslots = nslots; g_cache.slot = slot;
@@ -211,7 +222,9 @@ public:
         sk_result res{};
     };
 
+    ByteSink *const *sinks = nullptr;   // drained before the contexts (and their pinned buffers) go away
     ~DeviceFarm() {
+        drain_sinks(sinks);
         for (auto &w : workers_) {
             { std::lock_guard<std::mutex> l(w->mu); w->stop = true; }
             w->cv.notify_all();
@@ -366,6 +379,7 @@ int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, Byt
         slot = std::min<unsigned long long>(slot, (1ull << 31) - 8192);
         Ctx ctx;
         ctx.tot = &tot;
+        ctx.sinks = outs;
         ctx.c = sk_create(device, slot, 1, &p);
         if (!ctx.c) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
         tot.t_init = host::now_s() - t_begin;
@@ -411,6 +425,7 @@ int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, Byt
     const int nslots = two ? 2 : 3;
     Ctx ctx;
     ctx.tot = &tot;
+    ctx.sinks = outs;
     if (!ctx.acquire(device, slot, nslots, p)) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
     tot.t_init = host::now_s() - t_begin;
     std::vector<Tickets> tickets((size_t)nslots);
@@ -502,6 +517,7 @@ int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, Byt
             if (r < 0) { fprintf(stderr, "****Error: read failed\n\n"); return EXIT_FAILURE; }
             bulk = (unsigned long long)r;
             if (bulk < bulk_cap) eof = true;
+            if (eof && bulk) patch_eof(h, H + bulk);   // before the bytes are handed to the copy engine
             if (bulk && sk_upload(ctx.c, cur, 0, H, bulk) != SK_OK) { fprintf(stderr, "****Error: %s\n\n", sk_last_error()); return EXIT_FAILURE; }
         }
         unsigned long long tail = 0;
@@ -574,6 +590,7 @@ int Abstract_Trimmer::run_devices(const std::vector<int> &devices, const sk_para
     }
     const int nslots = ref_order && slot > (256ull << 20) ? 1 : 2;
     DeviceFarm farm;
+    farm.sinks = outs;
     {
         std::string err;
         if (!farm.create(devices, slot, nslots, p, err)) { fprintf(stderr, "****Error: %s\n\n", err.c_str()); return EXIT_FAILURE; }

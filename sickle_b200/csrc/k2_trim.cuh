@@ -20,9 +20,10 @@
 // scan of q[i+ws]-q[i]; that path also finds the position the reference reports for a bad quality byte.
 //
 // Tile = 256 units (8 warps x 32) for short records.  When the batch averages 1.5 KB or more per
-// record a tile is 64 units, 8 per warp (lanes 0..7): a 255 MB batch of 1-20 kb reads is 20,000 units,
+// record a tile is 16 units, 2 per warp (lanes 0 and 1): a 255 MB batch of 1-20 kb reads is 20,000 units,
 // i.e. 78 tiles of 256 -- fewer tiles than SMs, each warp walking up to 32 long reads one after the
-// other -- but 313 tiles of 64, 2,500 warps with at most 8 long reads each.  Reads above
+// other, every step of the walk a trip to memory -- but 1,250 tiles of 16, 10,000 warps with at most two
+// long reads each.  Reads above
 // kThreadTrimMaxLen bases go to the warp-wide path, whose coarse pass is warp-cooperative (a single
 // lane walking a 20 kb read alone is a 0.3 ms dependent chain).
 #pragma once
@@ -34,7 +35,7 @@ namespace sk {
 
 constexpr int kK2Threads = 256;
 constexpr int kK2UnitsPerTile = kK2Threads;  // 8 warps x 32 units (short records)
-constexpr uint32_t kK2LongUnitsPerWarp = 8;   // batches of long records: 8 units per warp, 64 per tile
+constexpr uint32_t kK2LongUnitsPerWarp = 2;   // batches of long records: 2 units per warp, 16 per tile
 constexpr uint32_t kK2LongUnitsPerTile = kK2LongUnitsPerWarp * (kK2Threads / 32);
 constexpr uint32_t kK2LongRecordBytes = 1500; // average record size from which a batch counts as "long"
 
@@ -128,18 +129,28 @@ __device__ __noinline__ Cut warp_sliding_window(const uint8_t *__restrict__ d, u
         }
         int R = warp_sum_i(part) - bias;                         // bound of the first whole word (step 0)
         uint32_t jf = nstep;                                     // first step whose bound is below the threshold
-        for (uint32_t s0 = 0; s0 < nstep; s0 += 32) {
-            const uint32_t s = s0 + (uint32_t)lane;
-            int D = 0;                                           // what step s+1 has over step s
-            if (s + 1u < nstep) {
-                const uint32_t lw = W[A0 + k + s], tw = W[A0 + s];
-                rc.screen3(lw, scr);
-                D = dp4a_us(lw, 0x01010101, dp4a_us(tw, (int)0xFFFFFFFF, 0));
+        // 128 steps per round: the 8 loads of a lane (4 lead, 4 trail words, each warp-coalesced) are issued
+        // together, so that a round costs one trip to memory rather than four
+        for (uint32_t s0 = 0; s0 < nstep && jf == nstep; s0 += 128) {
+            uint32_t lw[4], tw[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t s = s0 + 32u * u + (uint32_t)lane;
+                const bool in = s + 1u < nstep;
+                lw[u] = in ? W[A0 + k + s] : rc.kmin;
+                tw[u] = in ? W[A0 + s] : rc.kmin;
             }
-            const int incl = warp_incl_scan_i(D, lane);
-            const uint32_t bm = __ballot_sync(0xffffffffu, s < nstep && R + incl - D < 0);
-            if (bm) { jf = s0 + (uint32_t)__ffs(bm) - 1u; break; }
-            R += __shfl_sync(0xffffffffu, incl, 31);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t s = s0 + 32u * u + (uint32_t)lane;
+                rc.screen3(lw[u], scr);
+                // what step s+1 has over step s (nothing past the last step: both words are the filler)
+                const int D = dp4a_us(lw[u], 0x01010101, dp4a_us(tw[u], (int)0xFFFFFFFF, 0));
+                const int incl = warp_incl_scan_i(D, lane);
+                const uint32_t bm = __ballot_sync(0xffffffffu, s < nstep && R + incl - D < 0);
+                if (bm) { jf = s0 + 32u * u + (uint32_t)__ffs(bm) - 1u; break; }
+                R += __shfl_sync(0xffffffffu, incl, 31);
+            }
         }
         if (!__any_sync(0xffffffffu, (scr & 0x80808080u) != 0)) {
             const int ws_i = jf == nstep ? (int)nwin : 4 * (int)(A0 + jf) - (int)Q - 3;

@@ -224,3 +224,37 @@ def test_product_binary_has_no_cpu_path():
     gdir = os.path.join(ROOT, "tests", "golden")
     p = subprocess.run([binary, "se", "-f", os.path.join(gdir, "se_r150.fastq"), "-t", "sanger", "-o", "/dev/null"], capture_output=True, timeout=120)
     assert p.returncode == 1 and b"no usable CUDA device" in p.stderr
+
+
+def test_error_return_waits_for_queued_writes_under_asan(tmp_path):
+    """A data error in a late batch while the previous batches' output is still queued on a slow sink
+    (-g deflates; a FIFO nobody drains quickly) must not free the pinned result buffers under the writer
+    thread: host code + stub built with AddressSanitizer, several paths (one context pipelined, two
+    files, -a N, several contexts, `sickle batch` which keeps serving files afterwards)."""
+    from sickle_b200 import synth
+
+    exe = os.path.join(ROOT, "tests", "_build", "sickle_hoststub_asan")
+    src = [os.path.join(ROOT, p) for p in ("host/sickle_main.cpp", "host/trimmer.cpp", "host/io.cpp",
+                                           "tests/host_stub/stub_abi.cpp", "oracle/sickle_oracle.c")]
+    subprocess.check_call(["g++", "-O1", "-g", "-fsanitize=address", "-fno-omit-frame-pointer", "-std=c++17",
+                           "-I" + os.path.join(ROOT, "include")] + src + ["-o", exe, "-lz", "-lpthread"])
+    n = 40000
+    lines = synth.fixed_length_records(n, 150, "sanger", seed=91).tobytes().split(b"\n")
+    rec = n - 300                                                   # the error sits in the last of many batches
+    lines[4 * rec + 3] = b"\x7f" + lines[4 * rec + 3][1:]
+    bad = str(tmp_path / "bad.fq")
+    open(bad, "wb").write(b"\n".join(lines))
+    good2 = str(tmp_path / "mate2.fq")
+    open(good2, "wb").write(synth.fixed_length_records(n, 150, "sanger", seed=92).tobytes())
+    out = [str(tmp_path / ("o%d.fq.gz" % k)) for k in range(3)]
+    base_env = dict(os.environ, ASAN_OPTIONS="detect_leaks=0:abort_on_error=0", SICKLE_B200_GZIP_LEVEL="9", SICKLE_B200_ZIP_THREADS="1")
+    cases = [
+        (["se", "-f", bad, "-t", "sanger", "-o", out[0], "-g"], {"SICKLE_B200_SLOT_MB": "1"}),
+        (["se", "-f", bad, "-t", "sanger", "-o", out[0], "-g", "-a", "3", "-b", "1"], {}),
+        (["pe", "-f", bad, "-r", good2, "-t", "sanger", "-o", out[0], "-p", out[1], "-s", out[2], "-g"], {"SICKLE_B200_SLOT_MB": "1"}),
+        (["se", "-f", bad, "-t", "sanger", "-o", out[0], "-g"], {"SICKLE_B200_DEVICES": "0,0,0", "SICKLE_B200_SLOT_KB": "256"}),
+    ]
+    for args, env in cases:
+        p = subprocess.run([exe] + args, capture_output=True, env=dict(base_env, **env), timeout=300)
+        assert p.returncode == 1, (args, p.returncode, p.stderr[-600:])
+        assert b"AddressSanitizer" not in p.stderr and b"Quality value (127)" in p.stderr, (args, p.stderr[-1500:])

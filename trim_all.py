@@ -119,27 +119,40 @@ def main(argv=None):
     def quote(arg):
         return '"%s"' % arg if (" " in arg or "\t" in arg) else arg
 
-    def worker(gpu):
-        proc = subprocess.Popen([sickle, "batch"], env=gpu_env(gpu), stdin=subprocess.PIPE, stdout=subprocess.PIPE,
+    def spawn(gpu):
+        return subprocess.Popen([sickle, "batch"], env=gpu_env(gpu), stdin=subprocess.PIPE, stdout=subprocess.PIPE,
                                 universal_newlines=True, bufsize=1)
+
+    def worker(gpu):
+        # A batch process that dies (crash, usage error) fails the file it was working on only: the worker
+        # starts another one and goes on with the queue, as the reference's driver does with one process per
+        # file (trim_all.py:62-108).  Three deaths in a row and the worker gives up -- what is then still
+        # queued is taken by the other workers or reported as failed below.
+        proc, deaths = spawn(gpu), 0
         try:
-            while True:
+            while deaths < 3:
                 try:
                     label, cmd = q.get_nowait()
                 except queue.Empty:
                     return
                 print("\t[gpu %d] > %s" % (gpu, " ".join(cmd)), flush=True)
-                proc.stdin.write(" ".join(quote(c) for c in cmd[1:]) + "\n")
-                proc.stdin.flush()
                 rc = None
-                for line in proc.stdout:
-                    if line.startswith("##rc "):
-                        rc = int(line.split()[1])
-                        break
-                    sys.stdout.write(line)
-                if rc is None:                      # the batch process died (usage error, crash)
+                try:
+                    proc.stdin.write(" ".join(quote(c) for c in cmd[1:]) + "\n")
+                    proc.stdin.flush()
+                    for line in proc.stdout:
+                        if line.startswith("##rc "):
+                            rc = int(line.split()[1])
+                            break
+                        sys.stdout.write(line)
+                except OSError:
+                    pass
+                if rc is None:                      # the batch process died
                     failed.append((label, proc.wait()))
-                    return
+                    deaths += 1
+                    proc = spawn(gpu)
+                    continue
+                deaths = 0
                 if rc != 0:
                     failed.append((label, rc))
         finally:
@@ -156,6 +169,12 @@ def main(argv=None):
         t.start()
     for t in threads:
         t.join()
+    while True:                                     # every worker gave up: nothing queued goes unreported
+        try:
+            label, _ = q.get_nowait()
+        except queue.Empty:
+            break
+        failed.append((label, -1))
     for label, rc in failed:
         print("FAILED (%d): %s" % (rc, label), file=sys.stderr)
     return 1 if failed else 0
