@@ -31,7 +31,7 @@ def one(tag, cmode, omode, data, data2=b"", qualtype="sanger", q=20, l=20, x=Fal
             assert err is None, (tag, err)
             for s in range(3):
                 assert got["out"][s] == want["out"][s], (tag, s)
-            print("%-44s ok   out %d+%d+%d bytes, fused batches %d/%d" % (tag, *[len(o) for o in got["out"]], got["fused_batches"], got["batches"]))
+            print("%-44s ok   out %d+%d+%d bytes, fused batches %d/%d" % (tag, *[len(o) for o in got["out"]], got.get("fused_batches", 0), got.get("batches", 0)))
         else:
             assert err is not None and err.kind == want["rc"] and err.record == want["err"]["record"], (tag, err, want)
             print("%-44s ok   data error kind %d at record %d" % (tag, err.kind, err.record))

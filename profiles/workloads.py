@@ -78,6 +78,16 @@ def main():
         buf, n, recs = device_bytes(m, target, dev)
         measure("se R150, general path (K1/K2/K3)", capi.MODE_SE, [(buf, n)], recs, env={"SICKLE_B200_PATH": "general"}, steps=3)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "--c4-only":        # short run for profiling the long-read kernels under ncu
+        v = synth.variable_length_records(4000, 1000, 20000, "illumina", 70)
+        arr = np.frombuffer(v, dtype=np.uint8)
+        rep = max(1, target // arr.size)
+        buf = torch.zeros(arr.size * rep + 64, dtype=torch.uint8, device=dev)
+        buf[:arr.size * rep] = torch.from_numpy(arr.copy()).to(dev).repeat(rep)
+        flags = dict(x="-x" in sys.argv, n="-n" in sys.argv)
+        measure("se long reads 1-20 kb, illumina, %s (configs[3])" % flags, capi.MODE_SE, [(buf, arr.size * rep)], 4000 * rep,
+                qualtype="illumina", steps=3, **flags)
+        return
     for L in (50, 75, 100, 150, 250):
         m = synth.fixed_length_records(200_000, L, "sanger", seed=40 + L)
         buf, n, recs = device_bytes(m, target, dev)

@@ -185,7 +185,11 @@ int alloc_slot(sk_ctx *c, Slot &s, bool host_buffers) {
     SK_CUDA(cudaEventCreateWithFlags(&s.ev_done, cudaEventDisableTiming));
     for (int i = 0; i < c->n_inputs; ++i) {
         if (host_buffers) {
-            SK_CUDA(cudaHostAlloc((void **)&s.h_in[i], sb + kPad, cudaHostAllocDefault));
+            // SICKLE_B200_WC_INPUT=1: write-combined pinned input slots (the host only ever writes them; the
+            // copy engine's reads then skip the CPU caches).  Off by default: the command line's carry of an
+            // unconsumed tail reads the slot back, which is slow on write-combined memory.
+            static const bool wc = getenv("SICKLE_B200_WC_INPUT") && atoi(getenv("SICKLE_B200_WC_INPUT")) != 0;
+            SK_CUDA(cudaHostAlloc((void **)&s.h_in[i], sb + kPad, wc ? cudaHostAllocWriteCombined : cudaHostAllocDefault));
             SK_CUDA(cudaMalloc((void **)&s.d_in[i], sb + kPad));
             SK_CUDA(cudaMemset(s.d_in[i], 0, sb + kPad));
         }
