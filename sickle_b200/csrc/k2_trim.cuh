@@ -230,15 +230,40 @@ __device__ __noinline__ Cut warp_sliding_window(const uint8_t *__restrict__ d, u
         }
     }
     if (P.trunc_n) {                                             // trim.cpp:86-98 (bug kept: 'N' only => -2)
-        const uint8_t *__restrict__ s = d + seq_off;
+        // first lowercase n (it wins), else any uppercase N.  Aligned words, four per lane and round (512
+        // coalesced bytes, the loads issued together): a byte-per-lane loop pays one trip to memory per 32 bases.
+        const uint32_t *__restrict__ W = reinterpret_cast<const uint32_t *>(d);
+        const uint32_t S0 = seq_off, SE = seq_off + L;
+        const uint32_t wa = S0 >> 2, nwords = ((SE + 3u) >> 2) - wa;
         int pn = -1;
         bool anyN = false;
-        for (uint32_t j0 = 0; j0 < L; j0 += 32) {
-            const uint32_t j = j0 + lane;
-            const int b = j < L ? s[j] : 0;
-            const uint32_t mn = __ballot_sync(0xffffffffu, b == 'n');
-            anyN |= __ballot_sync(0xffffffffu, b == 'N') != 0;
-            if (mn) { pn = (int)(j0 + __ffs(mn) - 1); break; }
+        for (uint32_t w0 = 0; w0 < nwords && pn < 0; w0 += 128) {
+            uint32_t v[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t idx = w0 + 32u * u + (uint32_t)lane;
+                v[u] = idx < nwords ? W[wa + idx] : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t idx = w0 + 32u * u + (uint32_t)lane;
+                const uint32_t base = 4u * (wa + idx);               // byte offset of this word
+                // bytes of the word that belong to the sequence line
+                const uint32_t lo = base < S0 ? S0 - base : 0u, hi = base + 4u > SE ? (SE > base ? SE - base : 0u) : 4u;
+                const uint32_t ok = idx < nwords ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+                const uint32_t tn = ((v[u] ^ 0x6E6E6E6Eu) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+                const uint32_t tN = ((v[u] ^ 0x4E4E4E4Eu) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
+                const uint32_t fn = flags_to_nibble(~(tn | v[u]) & 0x80808080u) & ok;
+                const uint32_t fN = flags_to_nibble(~(tN | v[u]) & 0x80808080u) & ok;
+                const uint32_t mn = __ballot_sync(0xffffffffu, fn != 0);
+                anyN |= __ballot_sync(0xffffffffu, fN != 0) != 0;
+                if (mn) {
+                    const int first = __ffs(mn) - 1;
+                    const uint32_t f1 = __shfl_sync(0xffffffffu, fn, first);
+                    pn = (int)(4u * (wa + w0 + 32u * u + (uint32_t)first) + (uint32_t)__ffs(f1) - 1u - S0);
+                    break;
+                }
+            }
         }
         if (pn >= 0) three = pn - 1;
         else if (anyN) three = -2;
