@@ -540,6 +540,13 @@ def run_cuda_arm(args):
     grp.barrier()
     pass_ms = grp.max_list([a.elapsed_time(b) for a, b in evs])          # per pass, max over ranks
     clk = clocks.stop() if rank == 0 else None
+    # per-kernel times of a step (library events), once more now that everything is warm
+    stage = [0.0] * 4
+    for b in range(nb):
+        step(b)
+        r = ctx.result_device(sp)
+        for k in range(4):
+            stage[k] += r.stage_ms[k] / nb
     ctx.close()
 
     ms = statistics.median(pass_ms)

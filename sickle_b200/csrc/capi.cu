@@ -126,6 +126,7 @@ struct sk_ctx {
     int fused_ok_streak = 0;
     int fused_grid_ch[4] = {0, 0, 0, 0};   // persistent grid per tile size, index (CH - 5) / 2
     int fused_backoff = 0;         // batches left on the general path after a fused failure
+    int fused_fail_streak = 0;     // fused failures without a fused success in between: each doubles the back-off
     uint64_t n_fused = 0, n_general = 0, n_rerun = 0;
 };
 
@@ -345,6 +346,7 @@ void adapt_fused(sk_ctx *c, const sk::DevResult &r, bool failed) {
         }
         return;
     }
+    c->fused_fail_streak = 0;
     if (++c->fused_ok_streak >= 64 && c->fused_ch_max < 9) { c->fused_ch_max += 2; c->fused_ok_streak = 0; }
     const uint64_t records = r.records[0] + r.records[1];
     if (records < 64) return;
@@ -386,8 +388,9 @@ int launch_fused(sk_ctx *c, Slot &s, const BatchArgs &a) {
 
 int launch_batch(sk_ctx *c, Slot &s, const BatchArgs &a) {
     s.last = a;
+    // (the back-off is counted down where results are read, rerun_if_needed: a caller that queues batches
+    //  without looking at their summaries never learns that a batch failed, so it must not drift back either)
     if (c->fused_eligible && c->fused_backoff == 0) return launch_fused(c, s, a);
-    if (c->fused_backoff > 0) c->fused_backoff--;
     return launch_general(c, s, a);
 }
 
@@ -395,10 +398,17 @@ int launch_batch(sk_ctx *c, Slot &s, const BatchArgs &a) {
 // the general path (same stream) and wait for its summary.
 int rerun_if_needed(sk_ctx *c, Slot &s) {
     if (!s.last_fused || !(s.h_res->index_overflow & 4u)) {
-        if (s.h_res->err_kind == 0 && !(s.h_res->index_overflow & 3u)) adapt_fused(c, *s.h_res, false);
+        if (!s.last_fused && c->fused_backoff > 0) c->fused_backoff--;
+        if (s.last_fused && s.h_res->err_kind == 0 && !(s.h_res->index_overflow & 3u)) adapt_fused(c, *s.h_res, false);
         return SK_OK;
     }
-    c->fused_backoff = 16;
+    // The single-pass kernel gave the batch up (a record longer than a tile's halo, a data error, ...): this batch
+    // runs again on the general path.  A first failure costs nothing more (one long read in a file of short ones
+    // must not push the following batches onto the slower path); a second one in a row sends the next 16 batches
+    // to the general path, then 32, 64, ... up to 4096 (a file of long reads pays one wasted -- and, since the
+    // kernel stops working once a tile has failed, short -- launch in thousands of batches, not one in 17).
+    c->fused_backoff = c->fused_fail_streak == 0 ? 0 : 16 << (c->fused_fail_streak < 9 ? c->fused_fail_streak - 1 : 8);
+    c->fused_fail_streak++;
     adapt_fused(c, *s.h_res, true);
     c->n_rerun++;
     if (int rc = launch_general(c, s, s.last)) return rc;

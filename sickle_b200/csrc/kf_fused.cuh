@@ -143,6 +143,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
     __shared__ uint32_t warp_tot2[kFThreads / 32][2];
     __shared__ unsigned long long s_lb[kFThreads / 32][2];   // look-back scratch
     __shared__ uint32_t s_fail;
+    __shared__ uint32_t s_abort;
     __shared__ __align__(8) unsigned long long s_mbar;   // completion of the S1 bulk copy
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -182,10 +183,26 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         // out without waiting for the atomic's round trip (-2 %).  Not earlier than that: a ticket held a
         // whole tile ahead was measured at 0.38 -> 0.56 ms, because a ticket in the hands of a CTA that
         // is still busy stalls every look-back behind it.
-        if (tid == 0) { s_tile = held; s_fail = 0; }
+        if (tid == 0) {
+            s_tile = held; s_fail = 0;
+            s_abort = held < num_tiles ? *reinterpret_cast<volatile uint32_t *>(&ctl->fast_fail) : 0u;
+        }
         __syncthreads();
         const uint32_t tile = s_tile;
         const bool done = tile >= num_tiles;
+        if (!done && s_abort) {
+            // Some tile has given the batch up (a record longer than the halo, a data error, ...): nothing this
+            // launch writes will be used, the host runs the batch again on the general path.  Do not spend
+            // 10,000 tiles' worth of work on it: mark this tile's look-back words "inclusive, 0" -- tiles
+            // already under way may be waiting for them -- drop the staged flush and draw the next ticket.
+            if (tid == 0) st_status(&status_nl[(size_t)tile * kWideStatusStride], pack_status(kFlagInclusive, epoch, 0));
+            if (tid == 1 || tid == 2)
+                st_status(&(status_out + (size_t)(tid - 1) * status_stride)[(size_t)tile * kWideStatusStride], pack_status(kFlagInclusive, epoch, 0));
+            if (tid == 0) held = atomicAdd(&ctl->tile_counter[3], 1u);
+            have_prev = false;
+            __syncthreads();   // s_tile / s_abort are rewritten at the top of the loop
+            continue;
+        }
         const uint32_t t0 = tile * (uint32_t)Cfg::kTile;
 
         uint32_t mw[(CH + 1) / 2];                               // newline bits, 32 bytes per word
