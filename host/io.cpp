@@ -322,14 +322,18 @@ bool ByteSink::open(const char *path, bool gzip) {
     if (fd_ < 0) return false;
     gzip_ = gzip;
     pos_ = 0;
-    // SICKLE_B200_MMAP_OUT=1: plain regular files are extended and filled through a shared mapping by
+    // SICKLE_B200_MMAP_OUT: plain regular files can be extended and filled through a shared mapping by
     // io_threads() threads (page-cache writes through write(2) serialise on the inode lock: 3.4 GB/s
-    // into tmpfs on the B200 host against 6.9 GB/s this way).  Opt-in: a full disk then surfaces as
-    // SIGBUS (reported and turned into exit 1 here) instead of a short write.
+    // into tmpfs on the B200 host against 6.9 GB/s this way).
+    //   1 = map after ftruncate: a full disk then surfaces as SIGBUS (reported and turned into exit 1 here);
+    //   2 = reserve the range with fallocate first: a full disk is an ordinary error before any byte is
+    //       copied, at the price of the kernel clearing the pages it hands out;
+    //   0 / unset = write(2).
     struct stat st;
     const char *e = getenv("SICKLE_B200_MMAP_OUT");
-    mmap_ = !gzip && e && atoi(e) != 0 && fstat(fd_, &st) == 0 && S_ISREG(st.st_mode) && (fcntl(fd_, F_GETFL) & O_ACCMODE) == O_RDWR;
-    if (mmap_) signal(SIGBUS, on_sigbus);
+    map_mode_ = e ? atoi(e) : 0;
+    mmap_ = !gzip && map_mode_ != 0 && fstat(fd_, &st) == 0 && S_ISREG(st.st_mode) && (fcntl(fd_, F_GETFL) & O_ACCMODE) == O_RDWR;
+    if (mmap_ && map_mode_ == 1) signal(SIGBUS, on_sigbus);
     stop_ = failed_ = false;
     submitted_ = completed_ = 0;
     bytes_in_ = 0;
@@ -382,7 +386,7 @@ void ByteSink::run() {
 bool ByteSink::put(const char *src, unsigned long long n) {
     bytes_in_ += n;
     if (!mmap_) return write_all(fd_, src, n);
-    if (n >= (8ull << 20) && ftruncate(fd_, (off_t)(pos_ + n)) == 0) {
+    if (n >= (8ull << 20) && (map_mode_ == 2 ? posix_fallocate(fd_, (off_t)pos_, (off_t)n) == 0 : ftruncate(fd_, (off_t)(pos_ + n)) == 0)) {
         const unsigned long long map_off = pos_ & ~4095ull, lead = pos_ - map_off;
         void *m = mmap(nullptr, (size_t)(lead + n), PROT_READ | PROT_WRITE, MAP_SHARED, fd_, (off_t)map_off);
         if (m != MAP_FAILED) {

@@ -79,6 +79,7 @@ private:
     bool put_gzip(const char *src, unsigned long long n);
     int fd_ = -1;
     bool gzip_ = false, mmap_ = false;
+    int map_mode_ = 0;
     unsigned long long bytes_in_ = 0, pos_ = 0;
     std::thread worker_;
     std::mutex mu_;

@@ -12,6 +12,7 @@
 // reads the next batch: src/trim_single.cpp:336-339, src/trim_paired.cpp:444-458).
 #include "../../include/sickle_b200.h"
 
+#include <chrono>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -488,7 +489,12 @@ sk_ctx *sk_create(int device, uint64_t slot_bytes, int n_slots, const sk_params 
         set_err("sk_create: CUDA device %d not available (%d devices) -- there is no CPU fallback", device, ndev);
         return nullptr;
     }
+    // SICKLE_B200_DEBUG_INIT=1: where the start-up time goes (CUDA context vs. pinned / device allocations)
+    const bool dbg_init = getenv("SICKLE_B200_DEBUG_INIT") != nullptr;
+    const auto t_init0 = std::chrono::steady_clock::now();
     if (cudaSetDevice(device) != cudaSuccess) { set_err("cudaSetDevice(%d) failed", device); return nullptr; }
+    if (dbg_init) cudaFree(nullptr);   // forces the context into existence here, so that the two figures separate
+    const auto t_init1 = std::chrono::steady_clock::now();
     sk_ctx *c = new (std::nothrow) sk_ctx();
     if (!c) { set_err("out of memory"); return nullptr; }
     c->device = device;
@@ -518,6 +524,12 @@ sk_ctx *sk_create(int device, uint64_t slot_bytes, int n_slots, const sk_params 
             delete c;
             return nullptr;
         }
+    }
+    if (dbg_init) {
+        const auto t_init2 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[sickle_b200] sk_create: CUDA context %.3f s, %d slot(s) of %llu bytes (pinned + device buffers, kernels' attributes) %.3f s\n",
+                std::chrono::duration<double>(t_init1 - t_init0).count(), ns, (unsigned long long)c->slot_bytes,
+                std::chrono::duration<double>(t_init2 - t_init1).count());
     }
     return c;
 }
