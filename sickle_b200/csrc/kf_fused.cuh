@@ -144,6 +144,11 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
     __shared__ unsigned long long s_lb[kFThreads / 32][2];   // look-back scratch
     __shared__ uint32_t s_fail;
     __shared__ uint32_t s_abort;
+    // Per-warp running totals of the batch summary (records, end of the last complete record, the reference's
+    // counters).  They go to the Control block once, when the CTA runs out of tiles: one atomic per counter and
+    // warp and TILE -- 10,000 tiles x 4 warps x up to 8 counters, all on one or two cache lines -- kept a single
+    // L2 slice busy for a good part of the launch (paired end: +37 % kernel time over single end).
+    __shared__ uint32_t s_acc[kFThreads / 32][8];
     __shared__ __align__(8) unsigned long long s_mbar;   // completion of the S1 bulk copy
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -163,6 +168,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
     uint32_t held = 0;   // thread 0: the next ticket (drawn while the previous tile is being staged)
     if (threadIdx.x == 0) held = atomicAdd(&ctl->tile_counter[3], 1u);
     uint32_t mbar_phase = 0;
+    if (threadIdx.x < (kFThreads / 32) * 8) (&s_acc[0][0])[threadIdx.x] = 0u;
 #if defined(__CUDACC__)
     if (threadIdx.x == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"((uint32_t)__cvta_generic_to_shared(&s_mbar)) : "memory");
@@ -545,26 +551,46 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 const uint32_t m1 = 0x55555555u;   // lanes of first mates
                 m_other = ((m_keep & m1) << 1) | ((m_keep & (m1 << 1)) >> 1);
             }
-            if (lane == 0 && m_live) {
-                atomicMax(&ctl->fast_consumed, end);
-                atomicAdd(&ctl->fast_records, (uint32_t)__popc(m_live));
+            if (lane == 0 && m_live) {   // (only this lane ever touches its warp's row)
+                uint32_t *__restrict__ acc = s_acc[wid];
+                acc[0] += (uint32_t)__popc(m_live);
+                acc[1] = max(acc[1], end);
                 if (!paired) {
-                    atomicAdd(&ctl->counters[0], (unsigned long long)__popc(m_keep));
-                    atomicAdd(&ctl->counters[1], (unsigned long long)__popc(m_live & ~m_keep));
+                    acc[2] += (uint32_t)__popc(m_keep);                 // kept
+                    acc[3] += (uint32_t)__popc(m_live & ~m_keep);       // discard
                 } else {
                     const uint32_t even = 0x55555555u & m_live;   // one bit per pair (mate 1's lane)
                     const uint32_t k1 = m_keep & even, k2 = m_other & even;
-                    atomicAdd(&ctl->counters[2], 2ull * __popc(k1 & k2));           // kept_p
-                    atomicAdd(&ctl->counters[3], 2ull * __popc(even & ~k1 & ~k2));  // discard_p
-                    atomicAdd(&ctl->counters[4], (unsigned long long)__popc(k1 & ~k2));   // kept_s1
-                    atomicAdd(&ctl->counters[7], (unsigned long long)__popc(k1 & ~k2));   // discard_s2
-                    atomicAdd(&ctl->counters[5], (unsigned long long)__popc(k2 & ~k1));   // kept_s2
-                    atomicAdd(&ctl->counters[6], (unsigned long long)__popc(k2 & ~k1));   // discard_s1
+                    acc[4] += (uint32_t)__popc(k1 & k2);                // pairs kept
+                    acc[5] += (uint32_t)__popc(even & ~k1 & ~k2);       // pairs discarded
+                    acc[6] += (uint32_t)__popc(k1 & ~k2);               // only mate 1 kept
+                    acc[7] += (uint32_t)__popc(k2 & ~k1);               // only mate 2 kept
                 }
             }
         }
         // the ticket barrier at the top of the loop orders S8a (reads s_in, writes s_out) before the
         // next tile's load (writes s_in) and flush (reads s_out)
+    }
+    // ---- the CTA's share of the batch summary
+    __syncthreads();
+    if (tid < 8) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int w = 0; w < kFThreads / 32; ++w) v = tid == 1 ? max(v, s_acc[w][tid]) : v + s_acc[w][tid];
+        if (v) {
+            switch (tid) {
+                case 0: atomicAdd(&ctl->fast_records, v); break;
+                case 1: atomicMax(&ctl->fast_consumed, v); break;
+                case 2: atomicAdd(&ctl->counters[0], (unsigned long long)v); break;          // kept
+                case 3: atomicAdd(&ctl->counters[1], (unsigned long long)v); break;          // discard
+                case 4: atomicAdd(&ctl->counters[2], 2ull * v); break;                       // kept_p
+                case 5: atomicAdd(&ctl->counters[3], 2ull * v); break;                       // discard_p
+                case 6: atomicAdd(&ctl->counters[4], (unsigned long long)v);                 // kept_s1
+                        atomicAdd(&ctl->counters[7], (unsigned long long)v); break;          // discard_s2
+                default: atomicAdd(&ctl->counters[5], (unsigned long long)v);                // kept_s2
+                         atomicAdd(&ctl->counters[6], (unsigned long long)v); break;         // discard_s1
+            }
+        }
     }
 }
 
