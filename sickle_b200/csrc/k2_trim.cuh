@@ -328,6 +328,7 @@ k2_trim_route(DevInput in0, DevInput in1, DevParams P, Control *__restrict__ ctl
     __shared__ uint32_t s_tile;
     __shared__ uint32_t warp_tot[kK2Threads / 32][kMaxStreams];
     __shared__ unsigned long long tile_prefix[kMaxStreams];
+    __shared__ uint32_t s_cnt[kK2Threads / 32][6];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const Geometry g = batch_geometry(ctl, P);
@@ -344,6 +345,7 @@ k2_trim_route(DevInput in0, DevInput in1, DevParams P, Control *__restrict__ ctl
     const bool mmode = P.mode == 3;
     RangeCheck rc;
     rc.init(P);
+    if (tid < (kK2Threads / 32) * 6) (&s_cnt[0][0])[tid] = 0u;
 
     while (true) {
         if (tid == 0) s_tile = atomicAdd(&ctl->tile_counter[2], 1u);
@@ -458,17 +460,30 @@ k2_trim_route(DevInput in0, DevInput in1, DevParams P, Control *__restrict__ ctl
         const uint32_t m_none = __ballot_sync(0xffffffffu, active && paired && !k1 && !k2);
         const uint32_t m_sekeep = __ballot_sync(0xffffffffu, active && !paired && k1);
         const uint32_t m_sedrop = __ballot_sync(0xffffffffu, active && !paired && !k1);
-        if (lane == 0) {
-            if (m_sekeep) atomicAdd(&ctl->counters[0], (unsigned long long)__popc(m_sekeep));
-            if (m_sedrop) atomicAdd(&ctl->counters[1], (unsigned long long)__popc(m_sedrop));
-            if (m_both) atomicAdd(&ctl->counters[2], 2ull * __popc(m_both));
-            if (m_none) atomicAdd(&ctl->counters[3], 2ull * __popc(m_none));
-            if (m_only1) { atomicAdd(&ctl->counters[4], (unsigned long long)__popc(m_only1));
-                           atomicAdd(&ctl->counters[7], (unsigned long long)__popc(m_only1)); }
-            if (m_only2) { atomicAdd(&ctl->counters[5], (unsigned long long)__popc(m_only2));
-                           atomicAdd(&ctl->counters[6], (unsigned long long)__popc(m_only2)); }
+        if (lane == 0) {   // per-warp running totals: they go to the Control block once, when the CTA runs out of tiles
+            uint32_t *__restrict__ acc = s_cnt[wid];
+            acc[0] += (uint32_t)__popc(m_sekeep); acc[1] += (uint32_t)__popc(m_sedrop);
+            acc[2] += (uint32_t)__popc(m_both);   acc[3] += (uint32_t)__popc(m_none);
+            acc[4] += (uint32_t)__popc(m_only1);  acc[5] += (uint32_t)__popc(m_only2);
         }
         __syncthreads();  // warp_tot / tile_prefix reused by the next tile
+    }
+    // counters: trim_single.cpp:391,397; trim_paired.cpp:551,557-562,566 -- one atomic per counter and CTA
+    // (one per warp and tile put thousands of atomics on one cache line of the Control block)
+    if (tid < 6) {
+        uint32_t v = 0;
+#pragma unroll
+        for (int w = 0; w < kK2Threads / 32; ++w) v += s_cnt[w][tid];
+        if (v) {
+            switch (tid) {
+                case 0: atomicAdd(&ctl->counters[0], (unsigned long long)v); break;
+                case 1: atomicAdd(&ctl->counters[1], (unsigned long long)v); break;
+                case 2: atomicAdd(&ctl->counters[2], 2ull * v); break;
+                case 3: atomicAdd(&ctl->counters[3], 2ull * v); break;
+                case 4: atomicAdd(&ctl->counters[4], (unsigned long long)v); atomicAdd(&ctl->counters[7], (unsigned long long)v); break;
+                default: atomicAdd(&ctl->counters[5], (unsigned long long)v); atomicAdd(&ctl->counters[6], (unsigned long long)v); break;
+            }
+        }
     }
 }
 

@@ -68,6 +68,7 @@ __device__ unsigned long long g_phase_cycles[12];
 constexpr int kFThreads = 256;
 constexpr int kFTileThreads = 224;   // 7 warps own tile bytes, the 8th warp scans the halo
 constexpr int kFMaxNl = 1024;        // newline positions per region (2 KB; also holds 128 record descriptors)
+constexpr uint32_t kTicketPoison = 0x40000000u;   // or-ed into the ticket counter by a tile that gives the batch up (tiles < 2^30)
 
 template <int CH>
 struct FusedCfg {
@@ -143,7 +144,6 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
     __shared__ uint32_t warp_tot2[kFThreads / 32][2];
     __shared__ unsigned long long s_lb[kFThreads / 32][2];   // look-back scratch
     __shared__ uint32_t s_fail;
-    __shared__ uint32_t s_abort;
     // Per-warp running totals of the batch summary (records, end of the last complete record, the reference's
     // counters).  They go to the Control block once, when the CTA runs out of tiles: one atomic per counter and
     // warp and TILE -- 10,000 tiles x 4 warps x up to 8 counters, all on one or two cache lines -- kept a single
@@ -189,26 +189,14 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         // out without waiting for the atomic's round trip (-2 %).  Not earlier than that: a ticket held a
         // whole tile ahead was measured at 0.38 -> 0.56 ms, because a ticket in the hands of a CTA that
         // is still busy stalls every look-back behind it.
-        if (tid == 0) {
-            s_tile = held; s_fail = 0;
-            s_abort = held < num_tiles ? *reinterpret_cast<volatile uint32_t *>(&ctl->fast_fail) : 0u;
-        }
+        if (tid == 0) { s_tile = held; s_fail = 0; }
         __syncthreads();
         const uint32_t tile = s_tile;
+        // (a tile that gives the batch up poisons the ticket counter -- see kTicketPoison -- so every ticket drawn
+        //  after that reads as "no tile left": the launch ends within one tile time instead of working through
+        //  10,000 tiles whose output nobody will use.  Tiles are drawn in order, so whatever a tile under way may
+        //  be waiting for in a look-back was drawn before the poison and is being finished normally.)
         const bool done = tile >= num_tiles;
-        if (!done && s_abort) {
-            // Some tile has given the batch up (a record longer than the halo, a data error, ...): nothing this
-            // launch writes will be used, the host runs the batch again on the general path.  Do not spend
-            // 10,000 tiles' worth of work on it: mark this tile's look-back words "inclusive, 0" -- tiles
-            // already under way may be waiting for them -- drop the staged flush and draw the next ticket.
-            if (tid == 0) st_status(&status_nl[(size_t)tile * kWideStatusStride], pack_status(kFlagInclusive, epoch, 0));
-            if (tid == 1 || tid == 2)
-                st_status(&(status_out + (size_t)(tid - 1) * status_stride)[(size_t)tile * kWideStatusStride], pack_status(kFlagInclusive, epoch, 0));
-            if (tid == 0) held = atomicAdd(&ctl->tile_counter[3], 1u);
-            have_prev = false;
-            __syncthreads();   // s_tile / s_abort are rewritten at the top of the loop
-            continue;
-        }
         const uint32_t t0 = tile * (uint32_t)Cfg::kTile;
 
         uint32_t mw[(CH + 1) / 2];                               // newline bits, 32 bytes per word
@@ -447,7 +435,10 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         const bool tile_fail = s_fail != 0 || tot0 + tot1 + 64u > (uint32_t)Cfg::kOutBytes;
         if (tile_fail) {   // bit 1: the tile simply holds too many records (the host then picks smaller tiles)
             tot0 = 0; tot1 = 0;
-            if (tid == 0) atomicOr(&ctl->fast_fail, (nl_overflow || nrec_t > (uint32_t)kFThreads / 2u) ? 3u : 1u);
+            if (tid == 0) {
+                atomicOr(&ctl->fast_fail, (nl_overflow || nrec_t > (uint32_t)kFThreads / 2u) ? 3u : 1u);
+                atomicOr(&ctl->tile_counter[3], kTicketPoison);
+            }
         }
         {   // the tile's output sizes go out now; its own offsets are asked for one tile later
             const unsigned long long agg[2] = {tot0, tot1};
