@@ -89,7 +89,8 @@ struct Slot {
     sk::RecDesc *d_desc[2] = {nullptr, nullptr};
     unsigned long long *d_status_k1[2] = {nullptr, nullptr};
     unsigned long long *d_status_k2 = nullptr;
-    unsigned long long *d_status_f = nullptr;   // fused: [3][fused_tiles_cap] (newlines, main, singles)
+    unsigned long long *d_status_f = nullptr;   // fused: [3][fused_tiles_cap] (newlines, main, singles); two files: [2 + 4]
+    unsigned long long *d_verdict[2] = {nullptr, nullptr};   // fused, two files: one 8-byte entry per record and file
     sk::Control *d_ctl = nullptr;
     sk::DevResult *d_res = nullptr;
     sk::DevResult *h_res = nullptr;
@@ -114,6 +115,7 @@ struct sk_ctx {
     uint32_t k1_tiles_cap = 0;
     uint32_t k2_tiles_cap = 0;
     uint32_t fused_tiles_cap = 0;
+    uint32_t verdict_cap = 0;    // two files: records per file the verdict tables hold
     int n_inputs = 1;
     sk_params params{};
     sk::DevParams dev{};
@@ -167,6 +169,7 @@ void free_slot(Slot &s) {
     }
     if (s.d_status_k2) cudaFree(s.d_status_k2);
     if (s.d_status_f) cudaFree(s.d_status_f);
+    for (auto &v : s.d_verdict) if (v) cudaFree(v);
     if (s.d_ctl) cudaFree(s.d_ctl);
     if (s.d_res) cudaFree(s.d_res);
     if (s.h_res) cudaFreeHost(s.h_res);
@@ -203,8 +206,11 @@ int alloc_slot(sk_ctx *c, Slot &s, bool host_buffers) {
     SK_CUDA(cudaMalloc((void **)&s.d_status_k2, (size_t)c->k2_tiles_cap * 8 * sk::kMaxStreams));
     SK_CUDA(cudaMemset(s.d_status_k2, 0, (size_t)c->k2_tiles_cap * 8 * sk::kMaxStreams));
     if (c->fused_eligible) {
-        SK_CUDA(cudaMalloc((void **)&s.d_status_f, (size_t)c->fused_tiles_cap * 8 * 3 * sk::kWideStatusStride));
-        SK_CUDA(cudaMemset(s.d_status_f, 0, (size_t)c->fused_tiles_cap * 8 * 3 * sk::kWideStatusStride));
+        const size_t chains = c->n_inputs == 2 ? 6 : 3;   // two files: a newline chain and two output chains per file
+        SK_CUDA(cudaMalloc((void **)&s.d_status_f, (size_t)c->fused_tiles_cap * 8 * chains * sk::kWideStatusStride));
+        SK_CUDA(cudaMemset(s.d_status_f, 0, (size_t)c->fused_tiles_cap * 8 * chains * sk::kWideStatusStride));
+        if (c->n_inputs == 2)
+            for (auto &v : s.d_verdict) SK_CUDA(cudaMalloc((void **)&v, (size_t)c->verdict_cap * 8));
     }
     if (host_buffers) {
         // stream capacities: an output stream never exceeds the bytes of the inputs feeding it
@@ -246,7 +252,7 @@ int next_epoch(sk_ctx *c, Slot &s, cudaStream_t st) {
     if ((s.epoch & (uint32_t)sk::kEpochMask) == 0) {  // epoch tag wrapped: clear the status words once
         for (int i = 0; i < c->n_inputs; ++i) SK_CUDA(cudaMemsetAsync(s.d_status_k1[i], 0, (size_t)c->k1_tiles_cap * 8 * sk::kWideStatusStride, st));
         SK_CUDA(cudaMemsetAsync(s.d_status_k2, 0, (size_t)c->k2_tiles_cap * 8 * sk::kMaxStreams, st));
-        if (s.d_status_f) SK_CUDA(cudaMemsetAsync(s.d_status_f, 0, (size_t)c->fused_tiles_cap * 8 * 3 * sk::kWideStatusStride, st));
+        if (s.d_status_f) SK_CUDA(cudaMemsetAsync(s.d_status_f, 0, (size_t)c->fused_tiles_cap * 8 * (c->n_inputs == 2 ? 6 : 3) * sk::kWideStatusStride, st));
         s.epoch += 1;
     }
     return SK_OK;
@@ -310,6 +316,30 @@ int launch_fused_ch(sk_ctx *c, Slot &s, const BatchArgs &a, const sk::DevInput &
     return SK_OK;
 }
 
+// Two files: both passes of kf_fused over the tiles of both inputs (see kf_fused.cuh), the small kernel between them.
+template <int CH>
+int launch_fused_two_ch(sk_ctx *c, Slot &s, const BatchArgs &a, const sk::DevInput di[2], const sk::OutPtrs &op) {
+    using Cfg = sk::FusedCfg<CH>;
+    cudaStream_t st = a.st;
+    const uint32_t tiles_a = (uint32_t)((a.n[0] + Cfg::kTile - 1) / Cfg::kTile), tiles_b = (uint32_t)((a.n[1] + Cfg::kTile - 1) / Cfg::kTile);
+    const uint32_t tiles = tiles_a + tiles_b;
+    const uint32_t stride = c->fused_tiles_cap * sk::kWideStatusStride;
+    if (tiles) {
+        const int full = c->fused_grid_ch[(CH - 5) / 2];
+        const int grid = tiles < (uint32_t)full ? (int)tiles : full;
+        sk::kf_fused<CH, 1><<<grid, sk::kFThreads, Cfg::kSmem, st>>>(di[0], c->dev, s.d_ctl, op, s.d_status_f, s.d_status_f + 2 * (size_t)stride,
+                                                                    stride, tiles, s.epoch, di[1], tiles_b, s.d_verdict[0], s.d_verdict[1], c->verdict_cap);
+        SK_DEBUG_SYNC(st, "kf_fused pass 1");
+        sk::kf2_between<<<1, 32, 0, st>>>(s.d_ctl);
+        if (int rc = next_epoch(c, s, st)) return rc;   // the newline chains are walked again
+        sk::kf_fused<CH, 2><<<grid, sk::kFThreads, Cfg::kSmemTwoFile, st>>>(di[0], c->dev, s.d_ctl, op, s.d_status_f, s.d_status_f + 2 * (size_t)stride,
+                                                                           stride, tiles, s.epoch, di[1], tiles_b, s.d_verdict[0], s.d_verdict[1], c->verdict_cap);
+        SK_DEBUG_SYNC(st, "kf_fused pass 2");
+        s.launches += 3;
+    }
+    return SK_OK;
+}
+
 template <int CH>
 int setup_fused_ch(sk_ctx *c) {
     using Cfg = sk::FusedCfg<CH>;
@@ -317,6 +347,14 @@ int setup_fused_ch(sk_ctx *c) {
     int per_sm = 0;
     SK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sk::kf_fused<CH>, sk::kFThreads, Cfg::kSmem));
     if (per_sm < 1) { set_err("fused kernel does not fit on this device"); return SK_E_CUDA; }
+    if constexpr (CH != 11) if (c->n_inputs == 2) {   // (two files: tiles of 18 / 25 / 32 KB)
+        SK_CUDA(cudaFuncSetAttribute(sk::kf_fused<CH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
+        SK_CUDA(cudaFuncSetAttribute(sk::kf_fused<CH, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemTwoFile));
+        int p2 = 0;
+        SK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p2, sk::kf_fused<CH, 2>, sk::kFThreads, Cfg::kSmemTwoFile));
+        if (p2 < 1) { set_err("fused kernel does not fit on this device"); return SK_E_CUDA; }
+        if (p2 < per_sm) per_sm = p2;   // one grid size for both passes
+    }
     c->fused_grid_ch[(CH - 5) / 2] = per_sm * c->sm_count;
     return SK_OK;
 }
@@ -368,17 +406,27 @@ int launch_fused(sk_ctx *c, Slot &s, const BatchArgs &a) {
     s.launches = 0;
     SK_CUDA(cudaEventRecord(s.ev_begin, st));
     int rc;
-    switch (c->fused_ch) {
-        case 5: rc = launch_fused_ch<5>(c, s, a, di[0], op); break;
-        case 9: rc = launch_fused_ch<9>(c, s, a, di[0], op); break;
-        case 11: rc = launch_fused_ch<11>(c, s, a, di[0], op); break;
-        default: rc = launch_fused_ch<7>(c, s, a, di[0], op); break;
+    const bool two = c->n_inputs == 2;
+    if (two) {
+        switch (c->fused_ch) {
+            case 5: rc = launch_fused_two_ch<5>(c, s, a, di, op); break;
+            case 9: case 11: rc = launch_fused_two_ch<9>(c, s, a, di, op); break;
+            default: rc = launch_fused_two_ch<7>(c, s, a, di, op); break;
+        }
+    } else {
+        switch (c->fused_ch) {
+            case 5: rc = launch_fused_ch<5>(c, s, a, di[0], op); break;
+            case 9: rc = launch_fused_ch<9>(c, s, a, di[0], op); break;
+            case 11: rc = launch_fused_ch<11>(c, s, a, di[0], op); break;
+            default: rc = launch_fused_ch<7>(c, s, a, di[0], op); break;
+        }
     }
     if (rc) return rc;
     SK_CUDA(cudaEventRecord(s.ev_stage[0], st));
     SK_CUDA(cudaEventRecord(s.ev_stage[1], st));
     SK_CUDA(cudaEventRecord(s.ev_stage[2], st));
-    sk::kf_finalize<<<1, 32, 0, st>>>(di[0], c->dev, s.d_ctl, s.d_res);
+    if (two) sk::kf2_finalize<<<1, 32, 0, st>>>(s.d_ctl, s.d_res);
+    else sk::kf_finalize<<<1, 32, 0, st>>>(di[0], c->dev, s.d_ctl, s.d_res);
     s.launches++;
     SK_CUDA(cudaEventRecord(s.ev_end, st));
     SK_CUDA(cudaGetLastError());
@@ -511,7 +559,8 @@ sk_ctx *sk_create(int device, uint64_t slot_bytes, int n_slots, const sk_params 
     c->k2_tiles_cap = (uint32_t)(((uint64_t)c->line_cap / 4 + sk::kK2UnitsPerTile - 1) / sk::kK2UnitsPerTile) + 2;
     c->fused_tiles_cap = (uint32_t)(c->slot_bytes / kFusedMinTile) + 2;
     // SICKLE_B200_PATH = auto (default) | general | fused ; SICKLE_B200_FUSED_CH = 5 | 7 | 9 | 11
-    c->fused_eligible = params->mode != SK_MODE_PE_2FILE && dp.emu_threads == 1;
+    c->fused_eligible = dp.emu_threads == 1;
+    c->verdict_cap = (uint32_t)(c->slot_bytes / 32 + 64);   // records of 32 bytes and more (shorter ones: general path)
     if (const char *e = getenv("SICKLE_B200_PATH")) { if (!strcmp(e, "general")) c->fused_eligible = false; }
     if (const char *e = getenv("SICKLE_B200_FUSED_CH")) { c->fused_ch = atoi(e); c->fused_ch_fixed = true; }
     if (c->fused_eligible && setup_fused(c) != SK_OK) { delete c; return nullptr; }

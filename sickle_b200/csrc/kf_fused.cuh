@@ -29,6 +29,21 @@
 //       record warps run S5-S7 of the next tile: look-back #2 -> byte offsets in the output streams,
 //       then the staged bytes go out with destination-aligned 16-byte stores (128-bit funnel shift
 //       for the destination's phase).
+// Two input files (SK_MODE_PE_2FILE: mate 1 in one file, mate 2 in the other, paired by record number,
+// reference src/trim_paired.cpp:328-338,483-567) run the same kernel twice, template parameter PASS:
+//   PASS 1  tiles of both files (tickets dealt in proportion to the files' sizes), S1-S6 only: every complete
+//           record's verdict {keep, five, kept bases, bytes of name + line 3} goes into an 8-byte entry of a
+//           per-file table indexed by record number; the files' record counts are summed up.
+//   (kf2_between: units = min of the two record counts; ticket counter back to zero)
+//   PASS 2  the same tiles again: S1-S5, then instead of trimming, a record looks up its own entry and its
+//           mate's, is routed (both kept -> its file's stream; one kept -> singles), and S7-S8 run as for
+//           interleaved pairs: stream 0 of a file-f tile is output stream f, flushed flat; the singles stream
+//           is laid out in pair order, so a tile also reserves room for the singles its mates' tiles write
+//           (sizes from the mates' entries) and copies its own singles out one by one.
+// The input is read twice (650 + 280 bytes per read instead of 325 + 280), which a kernel at 30 % of the
+// HBM roofline can afford; in exchange no tile ever waits for another tile's trimming.
+// PASS 0 is the single pass described above.
+//
 // CH (5, 7 or 9: 18 / 25 / 32 KB tiles) is chosen by the host per batch so that a tile holds at most
 // ~112 records.  Anything this kernel cannot handle exactly -- a record longer than the halo, more
 // than 128 records or 1024 newlines in a tile, or ANY data error -- sets Control::fast_fail; the host
@@ -80,6 +95,7 @@ struct FusedCfg {
     static constexpr int kOutBytes = kTile + 768 + 96;   // a tile of output + the last record's overhang + phase shifts
     // CH = 7: 56,768 B -> four CTAs per SM (4 x (56,768 + 248 static + 1,024 reserved) <= 232,448)
     static constexpr size_t kSmem = (size_t)kInBytes + kOutBytes + kFMaxNl * 2;
+    static constexpr size_t kSmemTwoFile = kSmem + 128 * 8;   // PASS 2: + one (offset, length) pair per record: its own singles
     // CTAs per SM by shared memory (232,448 B per SM, 1,024 B reserved per CTA); also the register budget
     static constexpr int kCtasPerSm = (int)(232448 / (kSmem + 1024 + 256)) > SK_MAX_CTAS ? SK_MAX_CTAS : (int)(232448 / (kSmem + 1024 + 256));
 };
@@ -89,11 +105,14 @@ struct FusedCfg {
 // record -- while warps 0..3 validate and trim the next tile: look-back #2 over the output sizes,
 // then the staged bytes go out.  gtid = thread index inside the group (0..127), named barrier 1.
 constexpr int kFlushBarrier = 1;
+// Two files (PASS 2): `main` = the output stream of the tile's file (0 or 1), `last` = the tile is its file's last
+// one, and the singles are not flushed flat -- the singles area has holes where the mates' tiles write -- but
+// copied record by record from the list (offset inside the tile's singles range, length; length 0 = not mine).
 __device__ __forceinline__ void flush_previous_tile(unsigned long long *const st_out[2], uint32_t p_tile, uint32_t p_tot0,
                                                     uint32_t p_tot1, int nstreams, uint32_t epoch, int gtid, int gwarps,
                                                     unsigned long long (*s_lb)[2], Control *__restrict__ ctl,
-                                                    const OutPtrs &outs, const uint8_t *__restrict__ s_out, uint32_t num_tiles
-                                                    ) {
+                                                    const OutPtrs &outs, const uint8_t *__restrict__ s_out, bool last,
+                                                    int main = 0, const uint2 *__restrict__ singles = nullptr, uint32_t nsingles = 0) {
     const unsigned long long agg[2] = {p_tot0, p_tot1};
     unsigned long long ex[2];
 #ifdef SK_PHASE_TIMING
@@ -107,15 +126,29 @@ __device__ __forceinline__ void flush_previous_tile(unsigned long long *const st
 #ifdef SK_PHASE_TIMING
     if (gtid == 0) atomicAdd(&g_phase_cycles[5], (unsigned long long)(clock64() - t_in));   // look-back #2 (flush group)
 #endif
-    if (gtid == 0 && p_tile == num_tiles - 1) { ctl->out_bytes[0] = ex[0] + agg[0]; ctl->out_bytes[2] = ex[1] + agg[1]; }
-    const bool cap_ok = ex[0] + p_tot0 <= outs.cap[0] && (p_tot1 == 0 || (outs.p[2] && ex[1] + p_tot1 <= outs.cap[2]));
+    if (gtid == 0 && last) {
+        ctl->out_bytes[main] = ex[0] + agg[0];
+        if (main == 0) ctl->out_bytes[2] = ex[1] + agg[1];   // (both files' singles chains end at the same total)
+    }
+    const bool cap_ok = ex[0] + p_tot0 <= outs.cap[main] && (p_tot1 == 0 || (outs.p[2] && ex[1] + p_tot1 <= outs.cap[2]));
     if (!cap_ok) {
         if (gtid == 0) ctl->index_overflow = 2u;
         return;
     }
 #if !defined(SK_KO_FLUSH)
-    flush_realigned(outs.p[0] + ex[0], s_out, 0u, p_tot0, gtid, gwarps * 32);
-    if (p_tot1) flush_realigned(outs.p[2] + ex[1], s_out, (p_tot0 + 15u) & ~15u, p_tot1, gtid, gwarps * 32);
+    flush_realigned(outs.p[main] + ex[0], s_out, 0u, p_tot0, gtid, gwarps * 32);
+    if (singles == nullptr) {
+        if (p_tot1) flush_realigned(outs.p[2] + ex[1], s_out, (p_tot0 + 15u) & ~15u, p_tot1, gtid, gwarps * 32);
+    } else if (p_tot1) {
+        // own singles, one thread per record (few per tile): staging -> global, both at arbitrary phases
+        uint8_t *const g = outs.p[2] + ex[1];
+        const uint32_t ph = (uint32_t)(reinterpret_cast<uintptr_t>(g) & 15u);
+        const uint32_t base1 = (p_tot0 + 15u) & ~15u;
+        for (uint32_t i = (uint32_t)gtid; i < nsingles; i += (uint32_t)gwarps * 32u) {
+            const uint2 e = singles[i];
+            if (e.y) smem_copy(g - ph, ph + e.x, s_out, base1 + e.x, e.y);
+        }
+    }
 #endif
 #ifdef SK_PHASE_TIMING
     if (gtid == 0) atomicAdd(&g_phase_cycles[7], (unsigned long long)(clock64() - t_in));   // look-back #2 + flush (flush group)
@@ -128,17 +161,28 @@ __device__ __forceinline__ void flush_previous_tile(unsigned long long *const st
 // long published its size, so the second look-back does not wait; with hundreds of heavy tiles in
 // flight an immediate look-back makes every tile wait for the slowest predecessor (measured: 22 % of
 // the tile time).
-template <int CH>
+// Entry of the two-file verdict table: [15:0] bytes of name + line 3 + 4 newlines, [31:16] kept bases,
+// [47:32] first kept base, [48] keep.
+__device__ __forceinline__ unsigned long long pack_verdict(bool keep, uint32_t five, uint32_t nkeep, uint32_t fixed) {
+    return (unsigned long long)(fixed & 0xffffu) | ((unsigned long long)(nkeep & 0xffffu) << 16) |
+           ((unsigned long long)(five & 0xffffu) << 32) | ((unsigned long long)(keep ? 1u : 0u) << 48);
+}
+
+template <int CH, int PASS = 0>
 __global__ void __launch_bounds__(kFThreads, FusedCfg<CH>::kCtasPerSm)
-kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
-         unsigned long long *__restrict__ status_nl, unsigned long long *__restrict__ status_out /* [2][stride] */,
-         uint32_t status_stride, uint32_t num_tiles, uint32_t epoch) {
+kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
+         unsigned long long *__restrict__ status_nl_all, unsigned long long *__restrict__ status_out_all /* [2][stride] per file */,
+         uint32_t status_stride, uint32_t num_tiles, uint32_t epoch,
+         // two files only (PASS 1, 2): the second input, its share of the tiles, the verdict tables
+         DevInput in_b = DevInput(), uint32_t tiles_b = 0, unsigned long long *__restrict__ tab_a = nullptr,
+         unsigned long long *__restrict__ tab_b = nullptr, uint32_t tab_cap = 0) {
     using Cfg = FusedCfg<CH>;
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *s_in = smem;
     uint8_t *s_out = smem + Cfg::kInBytes;
     uint16_t *s_nl = reinterpret_cast<uint16_t *>(smem + Cfg::kInBytes + Cfg::kOutBytes);
     uint4 *s_desc = reinterpret_cast<uint4 *>(s_nl);   // S7/S8a record descriptors alias the newline positions
+    uint2 *s_single = reinterpret_cast<uint2 *>(smem + Cfg::kSmem);   // PASS 2 only (Cfg::kSmemTwoFile)
     __shared__ uint32_t s_tile;
     __shared__ uint32_t warp_tot[kFThreads / 32];
     __shared__ uint32_t warp_tot2[kFThreads / 32][2];
@@ -152,14 +196,12 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
     __shared__ __align__(8) unsigned long long s_mbar;   // completion of the S1 bulk copy
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const uint4 *__restrict__ src = reinterpret_cast<const uint4 *>(in.data);
-    const uint32_t nchunks = (in.nbytes + 15u) >> 4;
-    const bool paired = P.mode != 0;
-    const bool mmode = P.mode == 3;
+    // PASS 1 / 2 treat every file as a stream of single records; the pairing happens through the verdict tables
+    const bool paired = PASS == 0 && P.mode != 0;
+    const bool mmode = PASS == 0 && P.mode == 3;
     const uint32_t lpu = paired ? 8u : 4u;   // lines per unit
-    const int nstreams = paired ? 2 : 1;
-    unsigned long long *const st_nl[2] = {status_nl, nullptr};
-    unsigned long long *const st_out[2] = {status_out, status_out + status_stride};
+    const int nstreams = (paired || PASS == 2) ? 2 : 1;
+    const uint32_t nunits2 = PASS == 2 ? ctl->fused_nunits : 0u;   // two files: pairs in this batch (kf2_between)
     RangeCheck rc;
     rc.init(P);
     SwarConsts swar;
@@ -178,8 +220,8 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
     __syncthreads();
 
     // the tile whose output is staged in s_out and not flushed yet
-    bool have_prev = false;
-    uint32_t p_tile = 0, p_tot0 = 0, p_tot1 = 0;
+    bool have_prev = false, p_last = false;
+    uint32_t p_tile = 0, p_tot0 = 0, p_tot1 = 0, p_fsel = 0, p_nrec = 0;
 
 #ifdef SK_PHASE_TIMING
     long long t_prev = clock64();
@@ -191,12 +233,29 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         // is still busy stalls every look-back behind it.
         if (tid == 0) { s_tile = held; s_fail = 0; }
         __syncthreads();
-        const uint32_t tile = s_tile;
+        const uint32_t ticket = s_tile;
         // (a tile that gives the batch up poisons the ticket counter -- see kTicketPoison -- so every ticket drawn
         //  after that reads as "no tile left": the launch ends within one tile time instead of working through
         //  10,000 tiles whose output nobody will use.  Tiles are drawn in order, so whatever a tile under way may
         //  be waiting for in a look-back was drawn before the poison and is being finished normally.)
-        const bool done = tile >= num_tiles;
+        const bool done = ticket >= num_tiles;
+        // two files: tickets are dealt to the files in proportion to their tile counts (ticket t belongs to file 1
+        // iff floor((t+1) * tiles_b / num_tiles) > floor(t * tiles_b / num_tiles)), so that both files are walked
+        // at the same relative pace; `tile` is the tile's number inside its file
+        uint32_t fsel = 0, tile = ticket;
+        if (PASS != 0 && !done) {
+            const uint32_t lo_ = (uint32_t)((unsigned long long)ticket * tiles_b / num_tiles);
+            const uint32_t hi_ = (uint32_t)(((unsigned long long)ticket + 1ull) * tiles_b / num_tiles);
+            fsel = hi_ > lo_ ? 1u : 0u;
+            tile = fsel ? lo_ : ticket - lo_;
+        }
+        const DevInput &in = (PASS != 0 && fsel) ? in_b : in_a;
+        const uint32_t file_tiles = PASS == 0 ? num_tiles : (fsel ? tiles_b : num_tiles - tiles_b);
+        unsigned long long *const status_nl = status_nl_all + (PASS != 0 ? (size_t)fsel * status_stride : 0);
+        unsigned long long *const status_out = status_out_all + (PASS != 0 ? (size_t)(2u * fsel) * status_stride : 0);
+        unsigned long long *const st_nl[2] = {status_nl, nullptr};
+        unsigned long long *const st_out[2] = {status_out, status_out + status_stride};
+        const uint32_t nchunks = (in.nbytes + 15u) >> 4;
         const uint32_t t0 = tile * (uint32_t)Cfg::kTile;
 
         uint32_t mw[(CH + 1) / 2];                               // newline bits, 32 bytes per word
@@ -224,7 +283,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 reinterpret_cast<uint4 *>(s_in)[c] = make_uint4(0, 0, 0, 0);
             {   // L2 prefetch, one 128-byte line per thread, of the tile one grid-width ahead: in steady
                 // state some CTA (this one, most likely) draws that ticket one tile time from now
-                const unsigned long long nb = ((unsigned long long)tile + gridDim.x) * Cfg::kTile + (unsigned long long)tid * 128u;
+                const unsigned long long nb = ((unsigned long long)tile + (PASS == 0 ? gridDim.x : gridDim.x / 2u)) * Cfg::kTile + (unsigned long long)tid * 128u;
 #if defined(__CUDACC__)
                 if (tid < Cfg::kTile / 128 && nb < in.nbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(in.data + nb));
 #else
@@ -291,9 +350,12 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
 
         SK_TICK(2);   // (+ newline-count publish)
         if (done) {   // no tile left: only the last staged tile remains to be flushed
-            if (have_prev && wid >= 4)
-                flush_previous_tile(st_out, p_tile, p_tot0, p_tot1, nstreams, epoch, tid - 128, 4, s_lb, ctl, outs, s_out, num_tiles
-                                    );
+            if (have_prev && wid >= 4) {
+                unsigned long long *const so = status_out_all + (PASS != 0 ? (size_t)(2u * p_fsel) * status_stride : 0);
+                unsigned long long *const st_prev[2] = {so, so + status_stride};
+                flush_previous_tile(st_prev, p_tile, p_tot0, p_tot1, nstreams, epoch, tid - 128, 4, s_lb, ctl, outs, s_out, p_last,
+                                    PASS == 2 ? (int)p_fsel : 0, PASS == 2 ? s_single : nullptr, p_nrec);
+            }
             break;
         }
 
@@ -345,10 +407,12 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         // again before the barrier in front of this tile's S8a.  (The flush group's warps never own a
         // record, so they have nothing else to do until that barrier: measured, 22 % of all warp time
         // was spent waiting there.)
-        if (have_prev && wid >= flush_warp0)
-            flush_previous_tile(st_out, p_tile, p_tot0, p_tot1, nstreams, epoch, tid - flush_warp0 * 32, kFThreads / 32 - flush_warp0,
-                                s_lb, ctl, outs, s_out, num_tiles
-                                );
+        if (have_prev && wid >= flush_warp0) {
+            unsigned long long *const so = status_out_all + (PASS != 0 ? (size_t)(2u * p_fsel) * status_stride : 0);
+            unsigned long long *const st_prev[2] = {so, so + status_stride};
+            flush_previous_tile(st_prev, p_tile, p_tot0, p_tot1, nstreams, epoch, tid - flush_warp0 * 32, kFThreads / 32 - flush_warp0,
+                                s_lb, ctl, outs, s_out, p_last, PASS == 2 ? (int)p_fsel : 0, PASS == 2 ? s_single : nullptr, p_nrec);
+        }
         have_prev = false;
 
         // per-record state (lane = record; the mates of a pair sit in adjacent lanes)
@@ -356,8 +420,10 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         const bool has_rec = !fail && rec < nrec_t;
         bool complete = false;
         uint32_t start = 0, e0 = 0, e1 = 0, e2 = 0, e3 = 0;
+        uint32_t recno = 0;                      // two files: the record's number in its file (= its pair's number)
         if (has_rec) {
             const int j = j_s + (int)(lpu * (rec / rpu)) + 4 * (int)(rec % rpu);
+            if (PASS != 0) recno = (uint32_t)((int)G + 1 + j) >> 2;
             if ((uint32_t)(j + 4) < n_all) {
                 complete = true;
                 start = j < 0 ? in.first : (uint32_t)s_nl[j] + 1u;
@@ -376,7 +442,19 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         TrimOut cut;
         cut.five = -1; cut.three = -1; cut.error = false;
         uint32_t name_len = 0, plus_len = 0, L = 0;
-        if (has_rec && complete) {
+        // PASS 2: a record beyond the shorter file's last one has no mate: it is not part of this batch
+        const bool in_batch = PASS != 2 || recno < nunits2;
+        unsigned long long mate_verdict = 0;
+        if (PASS == 2) {
+            if (has_rec && complete && in_batch) {
+                name_len = e0 - start;
+                L = e1 - e0 - 1u;
+                plus_len = e2 - e1 - 1u;
+                const unsigned long long v = (fsel ? tab_b : tab_a)[recno];   // PASS 1 validated and trimmed it
+                mate_verdict = (fsel ? tab_a : tab_b)[recno];
+                if ((v >> 48) & 1u) { cut.five = (int)((v >> 32) & 0xffffu); cut.three = cut.five + (int)((v >> 16) & 0xffffu); }
+            }
+        } else if (has_rec && complete) {
             name_len = e0 - start;
             L = e1 - e0 - 1u;
             plus_len = e2 - e1 - 1u;
@@ -392,19 +470,35 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 if (cut.error) fail = true;
             }
         }
+        if (PASS == 1 && has_rec && complete && !fail) {   // the verdict, for PASS 2
+            const uint32_t fixed1 = name_len + plus_len + 4u;
+            if (recno < tab_cap && fixed1 < 65536u)
+                (fsel ? tab_b : tab_a)[recno] = pack_verdict(cut.three >= 0, cut.three >= 0 ? (uint32_t)cut.five : 0u,
+                                                              cut.three >= 0 ? (uint32_t)(cut.three - cut.five) : 0u, fixed1);
+            else fail = true;
+        }
         if (fail) s_fail = 1u;
 
         // ---- S7: routing + output sizes
-        const bool live = has_rec && complete;
+        const bool live = has_rec && complete && in_batch;
         const bool keep = live && cut.three >= 0;
         const uint32_t nkeep = keep ? (uint32_t)(cut.three - cut.five) : 0u;
         const uint32_t fixed = name_len + plus_len + 4u;
         uint32_t add0 = 0, add1 = 0;        // bytes for the main stream / the singles stream
         bool nrec_out = false;              // emit as an "N record" (-M)
         int stream = -1;
-        const bool other = paired && __shfl_xor_sync(0xffffffffu, (int)keep, 1) != 0;   // mate's keep flag
-        if (live) {
-            if (!paired) {
+        // mate's keep flag: the neighbouring lane (interleaved pairs) or the mate's table entry (two files)
+        const bool other = PASS == 2 ? ((mate_verdict >> 48) & 1u) != 0
+                                     : (paired && __shfl_xor_sync(0xffffffffu, (int)keep, 1) != 0);
+        if (PASS == 1) {
+            // nothing is emitted in this pass
+        } else if (live) {
+            if (PASS == 2) {                                        // trim_paired.cpp:543-567, one mate per file
+                if (keep && other) { stream = 0; add0 = fixed + 2u * nkeep; }
+                else if (keep && P.has_singles) { stream = 1; add1 = fixed + 2u * nkeep; }
+                // the mate alone survives: its tile writes it, at this very place of the singles stream
+                else if (other && P.has_singles) add1 = (uint32_t)(mate_verdict & 0xffffu) + 2u * (uint32_t)((mate_verdict >> 16) & 0xffffu);
+            } else if (!paired) {
                 if (keep) { stream = 0; add0 = fixed + 2u * nkeep; }
             } else {
                 if (mmode) {                                        // README.md:116-120
@@ -416,7 +510,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             }
         }
         const uint32_t inc0 = warp_incl_scan(add0, lane);
-        const uint32_t inc1 = paired ? warp_incl_scan(add1, lane) : 0u;
+        const uint32_t inc1 = (paired || PASS == 2) ? warp_incl_scan(add1, lane) : 0u;
         if (lane == 31) { warp_tot2[wid][0] = inc0; warp_tot2[wid][1] = inc1; }
 #ifdef SK_PHASE_TIMING
         if (tid == 0) atomicAdd(&g_phase_cycles[0], (unsigned long long)(clock64() - t_prev));   // warp 0's own S5-S7 time
@@ -440,6 +534,13 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 atomicOr(&ctl->tile_counter[3], kTicketPoison);
             }
         }
+        if (PASS == 1) {   // verdicts are in the table: count the file's records, next tile
+            const uint32_t m_live1 = __ballot_sync(0xffffffffu, live);
+            if (!tile_fail && lane == 0 && m_live1) s_acc[wid][fsel ? 2 : 0] += (uint32_t)__popc(m_live1);
+            if (tid == 0) held = atomicAdd(&ctl->tile_counter[3], 1u);
+            __syncthreads();   // s_fail has been read by everybody before the top of the loop clears it
+            continue;
+        }
         {   // the tile's output sizes go out now; its own offsets are asked for one tile later
             const unsigned long long agg[2] = {tot0, tot1};
             block_publish(st_out, tile, agg, nstreams, epoch, tid);
@@ -447,6 +548,7 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         if (tid == 0) held = atomicAdd(&ctl->tile_counter[3], 1u);   // looked at after S8a
         have_prev = true;
         p_tile = tile; p_tot0 = tot0; p_tot1 = tot1;
+        p_fsel = fsel; p_last = tile == file_tiles - 1u; p_nrec = tile_fail ? 0u : nrec_t;
         const uint32_t base1 = (tot0 + 15u) & ~15u;                    // singles staged after the main bytes
 
         // record descriptors for S8a (two lanes per record); they reuse the newline-position array,
@@ -461,6 +563,8 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             dsc.z = e1 | (e2 << 16);
             dsc.w = (keep ? (uint32_t)cut.five : 0u) | (nkeep << 16);
             s_desc[rec] = dsc;
+            // two files: where this record's own single (if it is one) sits inside the tile's singles range
+            if (PASS == 2) s_single[rec] = make_uint2(wb1 + inc1 - add1, (stream == 1 && !tile_fail) ? add1 : 0u);
         }
         __syncthreads();
         SK_TICK(8);   // S7b: totals, publish, descriptors, barrier
@@ -542,7 +646,19 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 const uint32_t m1 = 0x55555555u;   // lanes of first mates
                 m_other = ((m_keep & m1) << 1) | ((m_keep & (m1 << 1)) >> 1);
             }
-            if (lane == 0 && m_live) {   // (only this lane ever touches its warp's row)
+            if (PASS == 2) m_other = __ballot_sync(0xffffffffu, live && other);
+            if (PASS == 2) {
+                if (lane == 0 && m_live) {
+                    uint32_t *__restrict__ acc = s_acc[wid];
+                    acc[fsel ? 3 : 1] = max(acc[fsel ? 3 : 1], end);    // end of the file's last record that is part of a pair
+                    if (fsel == 0) {                                        // a pair is counted where its first mate lives
+                        acc[4] += (uint32_t)__popc(m_keep & m_other);
+                        acc[5] += (uint32_t)__popc(m_live & ~m_keep & ~m_other);
+                        acc[6] += (uint32_t)__popc(m_keep & ~m_other);
+                        acc[7] += (uint32_t)__popc(m_other & ~m_keep);
+                    }
+                }
+            } else if (lane == 0 && m_live) {   // (only this lane ever touches its warp's row)
                 uint32_t *__restrict__ acc = s_acc[wid];
                 acc[0] += (uint32_t)__popc(m_live);
                 acc[1] = max(acc[1], end);
@@ -567,8 +683,15 @@ kf_fused(DevInput in, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
     if (tid < 8) {
         uint32_t v = 0;
 #pragma unroll
-        for (int w = 0; w < kFThreads / 32; ++w) v = tid == 1 ? max(v, s_acc[w][tid]) : v + s_acc[w][tid];
-        if (v) {
+        const bool is_max = tid == 1 || (PASS == 2 && tid == 3);
+        for (int w = 0; w < kFThreads / 32; ++w) v = is_max ? max(v, s_acc[w][tid]) : v + s_acc[w][tid];
+        if (v && PASS == 1) {            // records of file 0 (row entry 0) and of file 1 (entry 2)
+            if (tid == 0) atomicAdd(&ctl->fast_records2[0], v);
+            if (tid == 2) atomicAdd(&ctl->fast_records2[1], v);
+        } else if (v && PASS == 2 && tid < 4) {
+            if (tid == 1) atomicMax(&ctl->fast_consumed2[0], v);
+            if (tid == 3) atomicMax(&ctl->fast_consumed2[1], v);
+        } else if (v) {
             switch (tid) {
                 case 0: atomicAdd(&ctl->fast_records, v); break;
                 case 1: atomicMax(&ctl->fast_consumed, v); break;
@@ -593,6 +716,32 @@ __global__ void kf_finalize(DevInput in, DevParams P, Control *__restrict__ ctl,
     for (int s = 0; s < kMaxStreams; ++s) r.out_bytes[s] = ctl->out_bytes[s];
     r.records[0] = ctl->fast_records;
     r.consumed[0] = ctl->fast_consumed;
+    for (int k = 0; k < 8; ++k) r.counters[k] = (long long)ctl->counters[k];
+    r.index_overflow = (ctl->index_overflow & 2u) | (ctl->fast_fail ? 4u : 0u) | ((ctl->fast_fail & 2u) ? 8u : 0u);
+    *res = r;
+    Control z;
+    memset(&z, 0, sizeof z);
+    z.err_key = kNoError;
+    *ctl = z;
+}
+
+// Between the two passes of a two-file batch: pairs = the smaller of the two record counts; tickets start over
+// (a poisoned counter stays poisoned: PASS 2 of a batch PASS 1 gave up ends at once).
+__global__ void kf2_between(Control *__restrict__ ctl) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    ctl->fused_nunits = min(ctl->fast_records2[0], ctl->fast_records2[1]);
+    ctl->tile_counter[3] &= kTicketPoison;
+}
+
+// Batch summary of a two-file batch.
+__global__ void kf2_finalize(Control *__restrict__ ctl, DevResult *__restrict__ res) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    DevResult r;
+    memset(&r, 0, sizeof r);
+    for (int s = 0; s < kMaxStreams; ++s) r.out_bytes[s] = ctl->out_bytes[s];
+    r.records[0] = r.records[1] = ctl->fused_nunits;
+    r.consumed[0] = ctl->fast_consumed2[0];
+    r.consumed[1] = ctl->fast_consumed2[1];
     for (int k = 0; k < 8; ++k) r.counters[k] = (long long)ctl->counters[k];
     r.index_overflow = (ctl->index_overflow & 2u) | (ctl->fast_fail ? 4u : 0u) | ((ctl->fast_fail & 2u) ? 8u : 0u);
     *res = r;

@@ -56,6 +56,10 @@ struct Control {
     uint32_t fast_fail;           // fused path met something it does not handle (bit 0; bit 1: too many records in a tile): re-run on the general path
     uint32_t fast_consumed;       // fused path: end of the last complete unit (max over tiles)
     uint32_t fast_records;        // fused path: complete records
+    uint32_t fast_records2[2];    // fused path, two files: complete records per file (PASS 1)
+    uint32_t fast_consumed2[2];   // fused path, two files: end of the last paired record per file (PASS 2)
+    uint32_t fused_nunits;        // fused path, two files: pairs of the batch (kf2_between)
+    uint32_t pad_;
     unsigned long long err_key;   // min over offending (class, unit, mate, position); ~0 = none
     unsigned long long counters[8];  // kept, discard, kept_p, discard_p, kept_s1, kept_s2, discard_s1, discard_s2
     unsigned long long out_bytes[kMaxStreams];

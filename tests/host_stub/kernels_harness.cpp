@@ -90,6 +90,30 @@ void run_fused(const sk::DevInput &di, const sk::DevParams &P, sk::Control *ctl,
     free(st);
 }
 
+// two files: both passes of the single-pass kernel, as capi.cu's launch_fused_two_ch does
+template <int CH>
+void run_fused_two(const sk::DevInput di[2], const sk::DevParams &P, sk::Control *ctl, const sk::OutPtrs &op, unsigned ctas, sk::DevResult *res) {
+    using Cfg = sk::FusedCfg<CH>;
+    const uint32_t ta = (uint32_t)((di[0].nbytes + Cfg::kTile - 1) / Cfg::kTile), tb = (uint32_t)((di[1].nbytes + Cfg::kTile - 1) / Cfg::kTile);
+    const uint32_t tiles = ta + tb, cap = std::max(ta, tb) + 2;
+    const uint32_t stride = cap * sk::kWideStatusStride;
+    unsigned long long *st = aligned_zero<unsigned long long>((size_t)stride * 6);
+    const uint32_t tab_cap = (uint32_t)(std::max(di[0].nbytes, di[1].nbytes) / 32 + 64);
+    unsigned long long *tab[2] = {aligned_zero<unsigned long long>(tab_cap), aligned_zero<unsigned long long>(tab_cap)};
+    if (tiles) {
+        const unsigned grid = std::min<unsigned>(ctas, tiles);
+        simt::launch(dim3(grid), dim3(sk::kFThreads), [&] {
+            sk::kf_fused<CH, 1>(di[0], P, ctl, op, st, st + 2 * (size_t)stride, stride, tiles, 5u, di[1], tb, tab[0], tab[1], tab_cap);
+        });
+        simt::launch(dim3(1), dim3(32), [&] { sk::kf2_between(ctl); });
+        simt::launch(dim3(grid), dim3(sk::kFThreads), [&] {
+            sk::kf_fused<CH, 2>(di[0], P, ctl, op, st, st + 2 * (size_t)stride, stride, tiles, 6u, di[1], tb, tab[0], tab[1], tab_cap);
+        });
+    }
+    simt::launch(dim3(1), dim3(32), [&] { sk::kf2_finalize(ctl, res); });
+    free(st); free(tab[0]); free(tab[1]);
+}
+
 void run_general(const sk::DevInput di[2], int n_inputs, const sk::DevParams &P, sk::Control *ctl, const sk::OutPtrs &op, unsigned ctas,
                  sk::DevResult *res) {
     const uint32_t epoch = 9;
@@ -160,9 +184,13 @@ int main(int argc, char **argv) {
 
     bool fused = path.rfind("fused", 0) == 0;
     if (fused) {
-        if (mode == 1) { fprintf(stderr, "the fused kernel does not take two files\n"); return 2; }
         const int ch = atoi(path.c_str() + 5);
-        if (ch == 5) run_fused<5>(di[0], P, ctl, op, ctas, &res);
+        if (mode == 1) {
+            if (ch == 5) run_fused_two<5>(di, P, ctl, op, ctas, &res);
+            else if (ch == 7) run_fused_two<7>(di, P, ctl, op, ctas, &res);
+            else run_fused_two<9>(di, P, ctl, op, ctas, &res);
+        }
+        else if (ch == 5) run_fused<5>(di[0], P, ctl, op, ctas, &res);
         else if (ch == 7) run_fused<7>(di[0], P, ctl, op, ctas, &res);
         else if (ch == 9) run_fused<9>(di[0], P, ctl, op, ctas, &res);
         else run_fused<11>(di[0], P, ctl, op, ctas, &res);

@@ -78,8 +78,10 @@ def test_bench_workload_and_flag_combinations(harness, tmp_path):
     for singles in (True, False):
         check(harness, il, ("pei", singles), mode="pei", singles=singles, first=11)
     check(harness, il, "peM", mode="peM", singles=False)
-    check(harness, pf, "pe2", kernels=("general",), mode="pe2", path2=pr, first=4)
-    check(harness, pf, "pe2 no singles", kernels=("general",), mode="pe2", path2=pr, singles=False)
+    K2F = ("fused5", "fused7", "fused9", "general")     # two files: both passes of the single-pass kernel, and K1/K2/K3
+    assert check(harness, pf, "pe2", kernels=K2F, mode="pe2", path2=pr, first=4) == ["OK"] * 4
+    assert check(harness, pf, "pe2 no singles", kernels=K2F, mode="pe2", path2=pr, singles=False) == ["OK"] * 4
+    check(harness, pf, "pe2 -x -n", kernels=K2F, mode="pe2", path2=pr, q=30, l=5, x=True, n=True, first=9, ctas=5)
 
 
 def test_many_tiles_and_ctas(harness, tmp_path):
@@ -94,6 +96,48 @@ def test_many_tiles_and_ctas(harness, tmp_path):
     open(il, "wb").write(_records(rng, 60000, 220, "sanger"))
     assert check(harness, se, "se 60k", kernels=("fused7", "fused9", "general"), ctas=8, first=13) == ["OK"] * 3
     assert check(harness, il, "pei 60k", kernels=("fused5", "general"), mode="pei", ctas=8, first=2, n=True) == ["OK"] * 2
+
+
+def test_two_files_on_the_single_pass_kernel(harness, tmp_path):
+    """`pe -f -r` through both passes of kf_fused: mates whose records differ in size (the tickets are dealt in
+    proportion to the files' tile counts), files with unequal record counts or a cut-off tail (the extra records
+    are not part of the batch and stay unconsumed), many tiles over concurrent CTAs, random thread order, a
+    damaged record (the kernel hands the batch over), flags and encodings."""
+    from sickle_b200 import synth
+
+    K = ("fused5", "fused7", "fused9")
+
+    def files(a, b):
+        pa, pb = str(tmp_path / "a.fq"), str(tmp_path / "b.fq")
+        open(pa, "wb").write(a); open(pb, "wb").write(b)
+        return pa, pb
+
+    # mates of different, varying lengths: 9,000 pairs, file 2 about half as large as file 1
+    pa, pb = files(synth.variable_length_records(9000, 120, 320, "illumina", 81, log_uniform=False, plus_name_every=3),
+                   synth.variable_length_records(9000, 80, 170, "illumina", 82, log_uniform=False))
+    seen = check(harness, pa, "varlen", kernels=K + ("general",), mode="pe2", path2=pb, qualtype="illumina", ctas=6, first=5)
+    assert seen[-1] == "OK" and "OK" in seen[:3]
+    check(harness, pa, "varlen no singles -n", kernels=K, mode="pe2", path2=pb, qualtype="illumina", n=True, singles=False, ctas=3)
+    # unequal record counts / a file that ends inside a record
+    f, r, _ = synth.paired_records(2600, 150, "sanger", seed=78)
+    fb, rb = f.tobytes(), r.tobytes()
+    for a, b in ((fb, rb[:len(rb) * 3 // 4]), (fb[:len(fb) // 3 + 17], rb), (fb[:-60], rb), (fb, rb[:327 * 5]), (fb[:200], rb)):
+        pa, pb = files(a, b)
+        assert check(harness, pa, ("unequal", len(a), len(b)), kernels=K + ("general",), mode="pe2", path2=pb, ctas=4, first=11) == ["OK"] * 4
+    # many tiles, 8 CTAs, fibres in random order
+    f, r, _ = synth.paired_records(40000, 150, "sanger", seed=79)
+    pa, pb = files(f.tobytes(), r.tobytes())
+    assert check(harness, pa, "40k pairs", kernels=("fused7", "fused9"), mode="pe2", path2=pb, ctas=8, first=2) == ["OK"] * 2
+    for seed in (1, 2):
+        rc, out, err = run(harness, pa, mode="pe2", path2=pb, kernel="fused9", ctas=5, env={"SIMT_SHUFFLE": str(seed)})
+        assert rc == 0 and out.startswith("OK"), (seed, out, err[-300:])
+    # a damaged record in either file: the batch is handed to the general path (which reports the error)
+    lines = rb.split(b"\n")
+    lines[4 * 1700 + 3] = lines[4 * 1700 + 3][:90]
+    pa, pb = files(fb, b"\n".join(lines))
+    assert check(harness, pa, "damaged mate 2", kernels=K, mode="pe2", path2=pb) == ["FASTFAIL"] * 3
+    rc, out, err = run(harness, pa, mode="pe2", path2=pb, kernel="general")
+    assert rc == 0 and out.startswith("OK error kind=5 record=1700"), out
 
 
 def test_reference_thread_order(harness, tmp_path):
@@ -132,7 +176,7 @@ def test_golden_inputs(harness, golden):
                 continue
             check(harness, os.path.join(golden["dir"], ins["-c"]), case["id"], mode="pei", singles="-s" in case["outputs"], **kw)
         else:
-            check(harness, os.path.join(golden["dir"], ins["-f"]), case["id"], kernels=("general",), mode="pe2",
+            check(harness, os.path.join(golden["dir"], ins["-f"]), case["id"], kernels=("fused5", "fused9", "general"), mode="pe2",
                   path2=os.path.join(golden["dir"], ins["-r"]), singles="-s" in case["outputs"], **kw)
     assert done > 100
 
