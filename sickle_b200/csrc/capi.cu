@@ -128,6 +128,7 @@ struct sk_ctx {
     int fused_ch_max = 9;          // lowered after a failed fused batch, raised again after a streak of good ones
     int fused_ok_streak = 0;
     int fused_grid_ch[4] = {0, 0, 0, 0};   // persistent grid per tile size, index (CH - 5) / 2
+    int fused_grid_pass1[4] = {0, 0, 0, 0};   // two files, PASS 1 (no staging buffer: more CTAs per SM)
     int fused_backoff = 0;         // batches left on the general path after a fused failure
     int fused_fail_streak = 0;     // fused failures without a fused success in between: each doubles the back-off
     uint64_t n_fused = 0, n_general = 0, n_rerun = 0;
@@ -327,7 +328,8 @@ int launch_fused_two_ch(sk_ctx *c, Slot &s, const BatchArgs &a, const sk::DevInp
     if (tiles) {
         const int full = c->fused_grid_ch[(CH - 5) / 2];
         const int grid = tiles < (uint32_t)full ? (int)tiles : full;
-        sk::kf_fused<CH, 1><<<grid, sk::kFThreads, Cfg::kSmem, st>>>(di[0], c->dev, s.d_ctl, op, s.d_status_f, s.d_status_f + 2 * (size_t)stride,
+        const int grid1 = tiles < (uint32_t)c->fused_grid_pass1[(CH - 5) / 2] ? (int)tiles : c->fused_grid_pass1[(CH - 5) / 2];
+        sk::kf_fused<CH, 1><<<grid1, sk::kFThreads, Cfg::kSmemPass1, st>>>(di[0], c->dev, s.d_ctl, op, s.d_status_f, s.d_status_f + 2 * (size_t)stride,
                                                                     stride, tiles, s.epoch, di[1], tiles_b, s.d_verdict[0], s.d_verdict[1], c->verdict_cap);
         SK_DEBUG_SYNC(st, "kf_fused pass 1");
         sk::kf2_between<<<1, 32, 0, st>>>(s.d_ctl);
@@ -348,7 +350,11 @@ int setup_fused_ch(sk_ctx *c) {
     SK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, sk::kf_fused<CH>, sk::kFThreads, Cfg::kSmem));
     if (per_sm < 1) { set_err("fused kernel does not fit on this device"); return SK_E_CUDA; }
     if constexpr (CH != 11) if (c->n_inputs == 2) {   // (two files: tiles of 18 / 25 / 32 KB)
-        SK_CUDA(cudaFuncSetAttribute(sk::kf_fused<CH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmem));
+        SK_CUDA(cudaFuncSetAttribute(sk::kf_fused<CH, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemPass1));
+        int p1 = 0;
+        SK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p1, sk::kf_fused<CH, 1>, sk::kFThreads, Cfg::kSmemPass1));
+        if (p1 < 1) { set_err("fused kernel does not fit on this device"); return SK_E_CUDA; }
+        c->fused_grid_pass1[(CH - 5) / 2] = p1 * c->sm_count;
         SK_CUDA(cudaFuncSetAttribute(sk::kf_fused<CH, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemTwoFile));
         int p2 = 0;
         SK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p2, sk::kf_fused<CH, 2>, sk::kFThreads, Cfg::kSmemTwoFile));

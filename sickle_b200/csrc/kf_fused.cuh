@@ -96,6 +96,8 @@ struct FusedCfg {
     // CH = 7: 56,768 B -> four CTAs per SM (4 x (56,768 + 248 static + 1,024 reserved) <= 232,448)
     static constexpr size_t kSmem = (size_t)kInBytes + kOutBytes + kFMaxNl * 2;
     static constexpr size_t kSmemTwoFile = kSmem + 128 * 8;   // PASS 2: + one (offset, length) pair per record: its own singles
+    static constexpr size_t kSmemPass1 = (size_t)kInBytes + kFMaxNl * 2;   // PASS 1 stages nothing: four CTAs per SM
+    static constexpr int kCtasPerSmPass1 = (int)(232448 / (kSmemPass1 + 1024 + 256)) > SK_MAX_CTAS ? SK_MAX_CTAS : (int)(232448 / (kSmemPass1 + 1024 + 256));
     // CTAs per SM by shared memory (232,448 B per SM, 1,024 B reserved per CTA); also the register budget
     static constexpr int kCtasPerSm = (int)(232448 / (kSmem + 1024 + 256)) > SK_MAX_CTAS ? SK_MAX_CTAS : (int)(232448 / (kSmem + 1024 + 256));
 };
@@ -169,7 +171,7 @@ __device__ __forceinline__ unsigned long long pack_verdict(bool keep, uint32_t f
 }
 
 template <int CH, int PASS = 0>
-__global__ void __launch_bounds__(kFThreads, FusedCfg<CH>::kCtasPerSm)
+__global__ void __launch_bounds__(kFThreads, PASS == 1 ? FusedCfg<CH>::kCtasPerSmPass1 : FusedCfg<CH>::kCtasPerSm)
 kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
          unsigned long long *__restrict__ status_nl_all, unsigned long long *__restrict__ status_out_all /* [2][stride] per file */,
          uint32_t status_stride, uint32_t num_tiles, uint32_t epoch,
@@ -180,7 +182,7 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *s_in = smem;
     uint8_t *s_out = smem + Cfg::kInBytes;
-    uint16_t *s_nl = reinterpret_cast<uint16_t *>(smem + Cfg::kInBytes + Cfg::kOutBytes);
+    uint16_t *s_nl = reinterpret_cast<uint16_t *>(smem + Cfg::kInBytes + (PASS == 1 ? 0 : Cfg::kOutBytes));
     uint4 *s_desc = reinterpret_cast<uint4 *>(s_nl);   // S7/S8a record descriptors alias the newline positions
     uint2 *s_single = reinterpret_cast<uint2 *>(smem + Cfg::kSmem);   // PASS 2 only (Cfg::kSmemTwoFile)
     __shared__ uint32_t s_tile;
@@ -442,6 +444,13 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         TrimOut cut;
         cut.five = -1; cut.three = -1; cut.error = false;
         uint32_t name_len = 0, plus_len = 0, L = 0;
+        // reads of one length (the usual case) let every lane of a warp run the same specialised phase-1 loop
+        bool same_k = false;
+        if (PASS != 2) {
+            const uint32_t myk = (has_rec && complete) ? lane_window_words(e1 - e0 - 1u) : 0xffffffffu;
+            const uint32_t kmin = __reduce_min_sync(0xffffffffu, myk);
+            same_k = __all_sync(0xffffffffu, myk == kmin || myk == 0xffffffffu) != 0;
+        }
         // PASS 2: a record beyond the shorter file's last one has no mate: it is not part of this batch
         const bool in_batch = PASS != 2 || recno < nunits2;
         unsigned long long mate_verdict = 0;
@@ -465,7 +474,7 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
 #ifdef SK_KO_S6
                 cut.five = 0; cut.three = (int)L;   // nothing trimmed
 #else
-                cut = lane_sliding_window(s_in, e0 + 1u, L, e2 + 1u, P, rc);
+                cut = lane_sliding_window(s_in, e0 + 1u, L, e2 + 1u, P, rc, same_k);
 #endif
                 if (cut.error) fail = true;
             }

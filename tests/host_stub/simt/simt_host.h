@@ -213,6 +213,15 @@ inline uint32_t __ballot_sync(uint32_t mask, int pred) {
     return r;
 }
 inline int __any_sync(uint32_t mask, int pred) { return __ballot_sync(mask, pred) != 0; }
+inline uint32_t __reduce_min_sync(uint32_t mask, uint32_t v) {
+    uint64_t out[32];
+    simt::exchange(mask, v, out);
+    uint32_t r = 0xffffffffu;
+    for (int i = 0; i < 32; ++i)
+        if ((mask >> i) & 1u) r = std::min(r, (uint32_t)out[i]);
+    return r;
+}
+inline int __all_sync(uint32_t mask, int pred) { return __ballot_sync(mask, pred) == mask; }
 inline uint32_t __reduce_add_sync(uint32_t mask, uint32_t v) {
     uint64_t out[32];
     simt::exchange(mask, v, out);
