@@ -444,13 +444,6 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         TrimOut cut;
         cut.five = -1; cut.three = -1; cut.error = false;
         uint32_t name_len = 0, plus_len = 0, L = 0;
-        // reads of one length (the usual case) let every lane of a warp run the same specialised phase-1 loop
-        bool same_k = false;
-        if (PASS != 2) {
-            const uint32_t myk = (has_rec && complete) ? lane_window_words(e1 - e0 - 1u) : 0xffffffffu;
-            const uint32_t kmin = __reduce_min_sync(0xffffffffu, myk);
-            same_k = __all_sync(0xffffffffu, myk == kmin || myk == 0xffffffffu) != 0;
-        }
         // PASS 2: a record beyond the shorter file's last one has no mate: it is not part of this batch
         const bool in_batch = PASS != 2 || recno < nunits2;
         unsigned long long mate_verdict = 0;
@@ -474,7 +467,7 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
 #ifdef SK_KO_S6
                 cut.five = 0; cut.three = (int)L;   // nothing trimmed
 #else
-                cut = lane_sliding_window(s_in, e0 + 1u, L, e2 + 1u, P, rc, same_k);
+                cut = lane_sliding_window(s_in, e0 + 1u, L, e2 + 1u, P, rc);
 #endif
                 if (cut.error) fail = true;
             }

@@ -78,58 +78,6 @@ __device__ __forceinline__ int dp4a_us(uint32_t a, int b, int c) {
 #endif
 }
 
-// The steady part of phase 1 of lane_sliding_window (see there): `lead[j]` is the word entering the k-word sum
-// at step j, lead[j - k] the one leaving it; R = (k-word sum) - bias; jf = first step with R < 0 (nstep if none).
-// K = k for 1 <= k <= 8: the last 8 lead words stay in registers, so that the leaving word is not loaded again;
-// K = 0: any k (two loads per step).
-template <int K>
-__device__ __forceinline__ void phase1_steps(const uint32_t *__restrict__ lead, uint32_t nstep, int &R, uint32_t &scr, uint32_t &jf,
-                                             const RangeCheck &rc, uint32_t k_any = 0) {
-    const uint32_t k = K ? (uint32_t)K : k_any;
-    uint32_t j = 0;
-    if (K != 0) {
-        uint32_t hist[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) hist[i] = 0;
-#pragma unroll
-        for (int i = 0; i < K; ++i) hist[8 - K + i] = lead[i - K];
-        for (; j + 8u <= nstep; j += 8u) {
-            uint32_t lw[8];
-#pragma unroll
-            for (int u = 0; u < 8; ++u) lw[u] = lead[j + u];
-            uint32_t negr = 0;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint32_t tw = u < K ? hist[(8 - K + u) & 7] : lw[(u - K) & 7];
-                rc.screen3(lw[u], scr);
-                R = dp4a_us(lw[u], 0x01010101, dp4a_us(tw, (int)0xFFFFFFFF, R));
-                negr = __funnelshift_l((uint32_t)R, negr, 1);
-            }
-#pragma unroll
-            for (int u = 0; u < 8; ++u) hist[u] = lw[u];
-            if (negr && jf == nstep) jf = j + (uint32_t)__clz(negr) - 24u;
-        }
-    } else {
-        for (; j + 8u <= nstep; j += 8u) {
-            uint32_t negr = 0;
-#pragma unroll
-            for (int u = 0; u < 8; ++u) {
-                const uint32_t lw = lead[j + u], tw = lead[(int)(j + u) - (int)k];
-                rc.screen3(lw, scr);
-                R = dp4a_us(lw, 0x01010101, dp4a_us(tw, (int)0xFFFFFFFF, R));
-                negr = __funnelshift_l((uint32_t)R, negr, 1);
-            }
-            if (negr && jf == nstep) jf = j + (uint32_t)__clz(negr) - 24u;
-        }
-    }
-    for (; j < nstep; ++j) {
-        const uint32_t lw = lead[j], tw = lead[(int)j - (int)k];
-        rc.screen3(lw, scr);
-        R = dp4a_us(lw, 0x01010101, dp4a_us(tw, (int)0xFFFFFFFF, R));
-        if (R < 0 && jf == nstep) jf = j;
-    }
-}
-
 // Sliding window by ONE lane per read, coarse to fine.  Same decisions as warp_sliding_window.
 // Window i is "good" iff total(i) >= qthr*ws (trim.cpp:36,42,61); i5 = first good window, i3 = first
 // bad window after it (or the first bad window at all with -x).
@@ -149,18 +97,8 @@ __device__ __forceinline__ void phase1_steps(const uint32_t *__restrict__ lead, 
 //
 // Phase 2 is the exact scan: 32 windows per step, totals by dp4a straight from the packed quality
 // words (prefix sums of lead - trail inside a word), the sign of every total shifted into a bit mask.
-// whole words inside every window of a read of L bases (0: the windows are too short for phase 1's bound)
-__device__ __forceinline__ uint32_t lane_window_words(uint32_t L) {
-    uint32_t ws = L / 10u;
-    if (ws == 0) ws = L;
-    return ws >= 7u ? (ws - 3u) >> 2 : 0u;
-}
-
-// same_k: every lane of the warp that calls this has the same lane_window_words(L) (reads of one length, the
-// usual case): the specialised phase-1 loops may be used without the lanes of a warp running different ones in turn.
 __device__ __forceinline__ TrimOut lane_sliding_window(const uint8_t *__restrict__ sm, uint32_t seq_off, uint32_t L,
-                                                       uint32_t qual_off, const DevParams &P, const RangeCheck &rc,
-                                                       bool same_k = false) {
+                                                       uint32_t qual_off, const DevParams &P, const RangeCheck &rc) {
     TrimOut o;
     o.five = -1; o.three = -1; o.error = false;
     if (L < (uint32_t)P.lthr) return o;                                  // trim.cpp:21-26 (nothing is looked at)
@@ -208,20 +146,26 @@ __device__ __forceinline__ TrimOut lane_sliding_window(const uint8_t *__restrict
                     R = (int)__dp4a(v, 0x01010101u, (uint32_t)R);
                 }
                 const uint32_t *__restrict__ lead = W + A0 + (k - 1u);
+                const uint32_t *__restrict__ trail = W + A0 - 1u;
                 const uint32_t nstep = nfull - k + 1u;                   // bounds R_A for A = A0 .. A0 + nstep - 1
                 uint32_t jf = nstep;                                     // first A - A0 whose bound is below the threshold
-                // The word leaving the sum at step j entered it k steps earlier: for k <= 8 (reads of up to ~380
-                // bases) it is still in a register, and a step costs one shared-memory load instead of two.
-                switch (same_k ? k : 0u) {
-                    case 1: phase1_steps<1>(lead, nstep, R, scr, jf, rc); break;
-                    case 2: phase1_steps<2>(lead, nstep, R, scr, jf, rc); break;
-                    case 3: phase1_steps<3>(lead, nstep, R, scr, jf, rc); break;
-                    case 4: phase1_steps<4>(lead, nstep, R, scr, jf, rc); break;
-                    case 5: phase1_steps<5>(lead, nstep, R, scr, jf, rc); break;
-                    case 6: phase1_steps<6>(lead, nstep, R, scr, jf, rc); break;
-                    case 7: phase1_steps<7>(lead, nstep, R, scr, jf, rc); break;
-                    case 8: phase1_steps<8>(lead, nstep, R, scr, jf, rc); break;
-                    default: phase1_steps<0>(lead, nstep, R, scr, jf, rc, k); break;
+                uint32_t j = 0;
+                for (; j + 8u <= nstep; j += 8u) {
+                    uint32_t negr = 0;
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) {
+                        const uint32_t lw = lead[j + u], tw = trail[j + u];
+                        rc.screen3(lw, scr);
+                        R = dp4a_us(lw, 0x01010101, dp4a_us(tw, (int)0xFFFFFFFF, R));
+                        negr = __funnelshift_l((uint32_t)R, negr, 1);
+                    }
+                    if (negr && jf == nstep) jf = j + (uint32_t)__clz(negr) - 24u;
+                }
+                for (; j < nstep; ++j) {
+                    const uint32_t lw = lead[j], tw = trail[j];
+                    rc.screen3(lw, scr);
+                    R = dp4a_us(lw, 0x01010101, dp4a_us(tw, (int)0xFFFFFFFF, R));
+                    if (R < 0 && jf == nstep) jf = j;
                 }
                 // windows up to 4*(A_f - 1) - Q are good; no failing word: every window is
                 const int ws_i = jf == nstep ? (int)nwin : 4 * (int)(A0 + jf) - (int)Q - 3;

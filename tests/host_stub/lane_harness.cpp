@@ -84,11 +84,11 @@ Case make_case(Rng &r) {
     return c;
 }
 
-sk::TrimOut run_lane(const Case &c, bool same_k) {
+sk::TrimOut run_lane(const Case &c) {
     sk::RangeCheck rc;
     rc.init(c.P);
     // the buffer must be 4-byte aligned at offset 0 (the function reads aligned words)
-    return sk::lane_sliding_window(c.buf.data(), c.seq_off, c.L, c.qual_off, c.P, rc, same_k);
+    return sk::lane_sliding_window(c.buf.data(), c.seq_off, c.L, c.qual_off, c.P, rc);
 }
 }  // namespace
 
@@ -112,8 +112,7 @@ int main(int argc, char **argv) {
         bool any_oor = false;
         for (uint32_t j = 0; j < c.L; ++j) any_oor |= c.buf[c.qual_off + j] < c.P.qmin || c.buf[c.qual_off + j] > c.P.qmax;
         const bool may_decline = any_oor && c.L >= (uint32_t)c.P.lthr;
-        // (same_k: the phase-1 loops specialised by the number of whole words per window, and the general one)
-        const sk::TrimOut o = run_lane(c, (i & 1) != 0);
+        const sk::TrimOut o = run_lane(c);
         declined += o.error && !want_err;
         const bool keep = !o.error && o.three >= 0;
         const bool ok = o.error ? (want_err || may_decline)
