@@ -328,19 +328,31 @@ def plan_shard(torch, synth, sharding, grp, dev, rank, world, total_records, lin
     t0 = time.perf_counter()
     nbytes = total_records * RECORD_BYTES
     lo, hi = sharding.raw_range(nbytes, world, rank)
-    r0, r1 = lo // RECORD_BYTES, min(total_records, -(-hi // RECORD_BYTES) + 1)      # records overlapping the raw range (+1 for the snap)
-    buf = r150_range(torch, synth, dev, r0, r1 - r0)
-    off = r0 * RECORD_BYTES
-    mine = int((buf[lo - off:hi - off] == 10).sum().item())                        # newlines of the raw range
+    # newlines of the raw range, counted on the device piece by piece (a shard is tens of GB: no whole-range temporaries)
+    mine, window = 0, b""
+    r_first, r_end = lo // RECORD_BYTES, min(total_records, -(-hi // RECORD_BYTES))
+    r = r_first
+    while r < r_end:
+        n = min(PIECE - r % PIECE, r_end - r)
+        buf = r150_range(torch, synth, dev, r, n)
+        off = r * RECORD_BYTES
+        a, b = max(lo, off) - off, min(hi, off + n * RECORD_BYTES) - off
+        mine += int(torch.count_nonzero(buf[a:b] == 10).item())
+        if r == r_first and rank:
+            # the byte in front of the boundary and a few records after it are enough to move it to the next record start
+            window = bytes(buf[lo - off - 1:min(lo - off + 4096, buf.numel())].cpu().numpy().tobytes()) if lo > off else b""
+        del buf
+        r += n
+    if rank and not window:          # the raw boundary is the first byte of a piece: fetch the byte before it as well
+        buf = r150_range(torch, synth, dev, r_first - 1, 14)
+        window = bytes(buf[RECORD_BYTES - 1:RECORD_BYTES - 1 + 4097].cpu().numpy().tobytes())
+        del buf
     counts = grp.gather(mine)
     before = sum(counts[:rank])
-    # the byte in front of the boundary and a few records after it are enough to move it to the next record start
-    window = bytes(buf[lo - off - 1:min(lo - off + 4096, buf.numel())].cpu().numpy().tobytes()) if rank else b""
     start = lo - 1 + sharding.snap_forward(window, 1, before, lines_per_unit) if rank else 0
     starts = grp.gather(start) + [nbytes]
     b_lo, b_hi = starts[rank], starts[rank + 1]
     assert b_lo % RECORD_BYTES == 0 and b_hi % RECORD_BYTES == 0, (b_lo, b_hi)       # (fixed-size records: a check of the snap)
-    del buf
     return b_lo // RECORD_BYTES, (b_hi - b_lo) // RECORD_BYTES, {
         "raw_range": [lo, hi], "newlines_in_raw_range": mine, "lines_before": before, "snapped_range": [b_lo, b_hi],
         "plan_s": round(time.perf_counter() - t0, 3)}

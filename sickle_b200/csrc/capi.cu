@@ -64,7 +64,7 @@ void set_err(const char *fmt, ...) {
 
 constexpr uint64_t kPad = 64;           // readable padding after every device input buffer
 constexpr uint64_t kMaxSlotBytes = (1ull << 31) - 4096;
-constexpr int kFusedMinTile = sk::FusedCfg<5>::kTile;   // smallest tile of the instantiated configs
+constexpr int kFusedMinTile = sk::FusedCfg<3>::kTile;   // smallest tile of the instantiated configs
 
 // what a batch was launched with (kept so that a fused batch can be re-run on the general path)
 struct BatchArgs {
@@ -123,12 +123,12 @@ struct sk_ctx {
     bool host_buffers = false;
     // path selection
     bool fused_eligible = false;   // mode / order the fused kernel supports
-    int fused_ch = 7;              // 16-byte chunks per thread (5, 7, 9 or 11): the tile size in use
+    int fused_ch = 7;              // 16-byte chunks per thread (3, 5, 7, 9 or 11): the tile size in use
     bool fused_ch_fixed = false;   // SICKLE_B200_FUSED_CH given: no adaptation
     int fused_ch_max = 9;          // lowered after a failed fused batch, raised again after a streak of good ones
     int fused_ok_streak = 0;
-    int fused_grid_ch[4] = {0, 0, 0, 0};   // persistent grid per tile size, index (CH - 5) / 2
-    int fused_grid_pass1[4] = {0, 0, 0, 0};   // two files, PASS 1 (no staging buffer: more CTAs per SM)
+    int fused_grid_ch[5] = {0, 0, 0, 0, 0};   // persistent grid per tile size, index (CH - 3) / 2
+    int fused_grid_pass1[5] = {0, 0, 0, 0, 0};   // two files, PASS 1 (no staging buffer: more CTAs per SM)
     int fused_backoff = 0;         // batches left on the general path after a fused failure
     int fused_fail_streak = 0;     // fused failures without a fused success in between: each doubles the back-off
     uint64_t n_fused = 0, n_general = 0, n_rerun = 0;
@@ -305,7 +305,7 @@ int launch_fused_ch(sk_ctx *c, Slot &s, const BatchArgs &a, const sk::DevInput &
     cudaStream_t st = a.st;
     const uint32_t tiles = (uint32_t)((a.n[0] + Cfg::kTile - 1) / Cfg::kTile);
     if (tiles) {
-        const int full = c->fused_grid_ch[(CH - 5) / 2];
+        const int full = c->fused_grid_ch[(CH - 3) / 2];
         const int grid = tiles < (uint32_t)full ? (int)tiles : full;
         sk::kf_fused<CH><<<grid, sk::kFThreads, Cfg::kSmem, st>>>(di, c->dev, s.d_ctl, op, s.d_status_f,
                                                                  s.d_status_f + (size_t)c->fused_tiles_cap * sk::kWideStatusStride,
@@ -326,9 +326,9 @@ int launch_fused_two_ch(sk_ctx *c, Slot &s, const BatchArgs &a, const sk::DevInp
     const uint32_t tiles = tiles_a + tiles_b;
     const uint32_t stride = c->fused_tiles_cap * sk::kWideStatusStride;
     if (tiles) {
-        const int full = c->fused_grid_ch[(CH - 5) / 2];
+        const int full = c->fused_grid_ch[(CH - 3) / 2];
         const int grid = tiles < (uint32_t)full ? (int)tiles : full;
-        const int grid1 = tiles < (uint32_t)c->fused_grid_pass1[(CH - 5) / 2] ? (int)tiles : c->fused_grid_pass1[(CH - 5) / 2];
+        const int grid1 = tiles < (uint32_t)c->fused_grid_pass1[(CH - 3) / 2] ? (int)tiles : c->fused_grid_pass1[(CH - 3) / 2];
         sk::kf_fused<CH, 1><<<grid1, sk::kFThreads, Cfg::kSmemPass1, st>>>(di[0], c->dev, s.d_ctl, op, s.d_status_f, s.d_status_f + 2 * (size_t)stride,
                                                                     stride, tiles, s.epoch, di[1], tiles_b, s.d_verdict[0], s.d_verdict[1], c->verdict_cap);
         SK_DEBUG_SYNC(st, "kf_fused pass 1");
@@ -354,19 +354,20 @@ int setup_fused_ch(sk_ctx *c) {
         int p1 = 0;
         SK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p1, sk::kf_fused<CH, 1>, sk::kFThreads, Cfg::kSmemPass1));
         if (p1 < 1) { set_err("fused kernel does not fit on this device"); return SK_E_CUDA; }
-        c->fused_grid_pass1[(CH - 5) / 2] = p1 * c->sm_count;
+        c->fused_grid_pass1[(CH - 3) / 2] = p1 * c->sm_count;
         SK_CUDA(cudaFuncSetAttribute(sk::kf_fused<CH, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemTwoFile));
         int p2 = 0;
         SK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p2, sk::kf_fused<CH, 2>, sk::kFThreads, Cfg::kSmemTwoFile));
         if (p2 < 1) { set_err("fused kernel does not fit on this device"); return SK_E_CUDA; }
         if (p2 < per_sm) per_sm = p2;   // one grid size for both passes
     }
-    c->fused_grid_ch[(CH - 5) / 2] = per_sm * c->sm_count;
+    c->fused_grid_ch[(CH - 3) / 2] = per_sm * c->sm_count;
     return SK_OK;
 }
 
 int setup_fused(sk_ctx *c) {
-    if (c->fused_ch != 5 && c->fused_ch != 7 && c->fused_ch != 9 && c->fused_ch != 11) c->fused_ch = 7;
+    if (c->fused_ch != 3 && c->fused_ch != 5 && c->fused_ch != 7 && c->fused_ch != 9 && c->fused_ch != 11) c->fused_ch = 7;
+    if (int rc = setup_fused_ch<3>(c)) return rc;
     if (int rc = setup_fused_ch<5>(c)) return rc;
     if (int rc = setup_fused_ch<7>(c)) return rc;
     if (int rc = setup_fused_ch<9>(c)) return rc;
@@ -384,7 +385,7 @@ void adapt_fused(sk_ctx *c, const sk::DevResult &r, bool failed) {
     if (!c->fused_eligible || c->fused_ch_fixed) return;
     if (failed) {
         c->fused_ok_streak = 0;
-        if ((r.index_overflow & 8u) && c->fused_ch > 5) {   // too many records per tile: smaller tiles at once, no back-off
+        if ((r.index_overflow & 8u) && c->fused_ch > 3) {   // too many records per tile: smaller tiles at once, no back-off
             c->fused_ch_max = c->fused_ch - 2;
             c->fused_ch = c->fused_ch_max;
             c->fused_backoff = 0;
@@ -396,9 +397,9 @@ void adapt_fused(sk_ctx *c, const sk::DevResult &r, bool failed) {
     const uint64_t records = r.records[0] + r.records[1];
     if (records < 64) return;
     const uint64_t avg = (r.consumed[0] + r.consumed[1]) / records;
-    for (int ch = c->fused_ch_max; ch >= 5; ch -= 2)
+    for (int ch = c->fused_ch_max; ch >= 3; ch -= 2)
         if ((uint64_t)fused_tile_bytes(ch) <= avg * 112u) { c->fused_ch = ch; return; }
-    c->fused_ch = 5;
+    c->fused_ch = 3;
     if (c->fused_backoff < 4) c->fused_backoff = 4;   // short records: general path, looked at again after a few batches
 }
 
@@ -415,12 +416,14 @@ int launch_fused(sk_ctx *c, Slot &s, const BatchArgs &a) {
     const bool two = c->n_inputs == 2;
     if (two) {
         switch (c->fused_ch) {
+            case 3: rc = launch_fused_two_ch<3>(c, s, a, di, op); break;
             case 5: rc = launch_fused_two_ch<5>(c, s, a, di, op); break;
             case 9: case 11: rc = launch_fused_two_ch<9>(c, s, a, di, op); break;
             default: rc = launch_fused_two_ch<7>(c, s, a, di, op); break;
         }
     } else {
         switch (c->fused_ch) {
+            case 3: rc = launch_fused_ch<3>(c, s, a, di[0], op); break;
             case 5: rc = launch_fused_ch<5>(c, s, a, di[0], op); break;
             case 9: rc = launch_fused_ch<9>(c, s, a, di[0], op); break;
             case 11: rc = launch_fused_ch<11>(c, s, a, di[0], op); break;

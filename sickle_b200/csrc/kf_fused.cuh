@@ -44,7 +44,7 @@
 // HBM roofline can afford; in exchange no tile ever waits for another tile's trimming.
 // PASS 0 is the single pass described above.
 //
-// CH (5, 7 or 9: 18 / 25 / 32 KB tiles) is chosen by the host per batch so that a tile holds at most
+// CH (3, 5, 7 or 9: 11 / 18 / 25 / 32 KB tiles) is chosen by the host per batch so that a tile holds at most
 // ~112 records.  Anything this kernel cannot handle exactly -- a record longer than the halo, more
 // than 128 records or 1024 newlines in a tile, or ANY data error -- sets Control::fast_fail; the host
 // then re-runs the batch through the general path, which also produces the reference's error details.

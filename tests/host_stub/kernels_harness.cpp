@@ -186,10 +186,12 @@ int main(int argc, char **argv) {
     if (fused) {
         const int ch = atoi(path.c_str() + 5);
         if (mode == 1) {
-            if (ch == 5) run_fused_two<5>(di, P, ctl, op, ctas, &res);
+            if (ch == 3) run_fused_two<3>(di, P, ctl, op, ctas, &res);
+            else if (ch == 5) run_fused_two<5>(di, P, ctl, op, ctas, &res);
             else if (ch == 7) run_fused_two<7>(di, P, ctl, op, ctas, &res);
             else run_fused_two<9>(di, P, ctl, op, ctas, &res);
         }
+        else if (ch == 3) run_fused<3>(di[0], P, ctl, op, ctas, &res);
         else if (ch == 5) run_fused<5>(di[0], P, ctl, op, ctas, &res);
         else if (ch == 7) run_fused<7>(di[0], P, ctl, op, ctas, &res);
         else if (ch == 9) run_fused<9>(di[0], P, ctl, op, ctas, &res);
