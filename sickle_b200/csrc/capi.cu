@@ -131,6 +131,7 @@ struct sk_ctx {
     int fused_grid_pass1[5] = {0, 0, 0, 0, 0};   // two files, PASS 1 (no staging buffer: more CTAs per SM)
     int fused_backoff = 0;         // batches left on the general path after a fused failure
     int fused_fail_streak = 0;     // fused failures without a fused success in between: each doubles the back-off
+    bool long_records = false;     // the last general-path batch averaged 1.5 KB or more per record: K2 runs as two kernels
     uint64_t n_fused = 0, n_general = 0, n_rerun = 0;
 };
 
@@ -282,8 +283,16 @@ int launch_general(sk_ctx *c, Slot &s, const BatchArgs &a) {
     const uint64_t max_units = (a.n[0] + a.n[1]) / 4 + 1;
     const uint64_t tiles = (max_units + sk::kK2UnitsPerTile - 1) / sk::kK2UnitsPerTile;
     const int grid = tiles < (uint64_t)resident ? (int)tiles : resident;
-    sk::k2_trim_route<<<grid, sk::kK2Threads, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, s.d_desc[0], s.d_desc[1],
-                                                       s.d_status_k2, c->k2_tiles_cap, s.epoch);
+    if (c->long_records) {   // trimming on its own (no tile waits for another), then routing + scan from the verdicts
+        sk::k2_trim_only<<<resident, sk::kK2Threads, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, s.d_desc[0], s.d_desc[1]);
+        SK_DEBUG_SYNC(st, "k2_trim_only");
+        sk::k2_trim_route<true><<<grid, sk::kK2Threads, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, s.d_desc[0], s.d_desc[1],
+                                                                 s.d_status_k2, c->k2_tiles_cap, s.epoch);
+        s.launches++;
+    } else {
+        sk::k2_trim_route<false><<<grid, sk::kK2Threads, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, s.d_desc[0], s.d_desc[1],
+                                                                  s.d_status_k2, c->k2_tiles_cap, s.epoch);
+    }
     SK_DEBUG_SYNC(st, "k2_trim_route");
     SK_CUDA(cudaEventRecord(s.ev_stage[1], st));
     sk::k3_emit<<<resident, sk::kK3Threads, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, s.d_desc[0], s.d_desc[1], op);
@@ -457,6 +466,10 @@ int launch_batch(sk_ctx *c, Slot &s, const BatchArgs &a) {
 int rerun_if_needed(sk_ctx *c, Slot &s) {
     if (!s.last_fused || !(s.h_res->index_overflow & 4u)) {
         if (!s.last_fused && c->fused_backoff > 0) c->fused_backoff--;
+        if (!s.last_fused) {
+            const uint64_t nrec = s.h_res->records[0] + s.h_res->records[1];
+            if (nrec) c->long_records = (s.h_res->consumed[0] + s.h_res->consumed[1]) / nrec >= sk::kK2LongRecordBytes;
+        }
         if (s.last_fused && s.h_res->err_kind == 0 && !(s.h_res->index_overflow & 3u)) adapt_fused(c, *s.h_res, false);
         return SK_OK;
     }

@@ -321,7 +321,72 @@ __device__ __forceinline__ bool thread_trim_mate(const DevInput &in, uint32_t re
     return true;
 }
 
+// Phase 1 of K2 for the units a warp holds (lane k < upw holds unit `my_unit`; has = it holds one): lane k trims
+// unit k by itself (short reads); whatever that path declines is redone by the whole warp, one unit after
+// the other.
+__device__ __forceinline__ void trim_units(const DevInput &in0, const DevInput &in1, const DevParams &P, const RangeCheck &rc,
+                                           Control *ctl, bool has, uint32_t my_unit, int lane, MateInfo &mine0, MateInfo &mine1) {
+    const bool paired = P.mode != 0, inter = P.mode >= 2;
+    bool redo = false;
+    if (has) {
+        redo = !thread_trim_mate(in0, inter ? 2 * my_unit : my_unit, P, rc, lane, mine0);
+        if (paired && !redo)
+            redo = !(inter ? thread_trim_mate(in0, 2 * my_unit + 1, P, rc, lane, mine1)
+                           : thread_trim_mate(in1, my_unit, P, rc, lane, mine1));
+    }
+    for (uint32_t todo = __ballot_sync(0xffffffffu, redo); todo; todo &= todo - 1) {
+        const int k = __ffs(todo) - 1;
+        const uint32_t u = __shfl_sync(0xffffffffu, my_unit, k);
+        const MateInfo a = trim_mate(in0, inter ? 2 * u : u, u, 0, P, ctl, lane);
+        MateInfo b = {{-1, -1}, 0};
+        if (paired) b = inter ? trim_mate(in0, 2 * u + 1, u, 1, P, ctl, lane) : trim_mate(in1, u, u, 1, P, ctl, lane);
+        if (lane == k) { mine0 = a; mine1 = b; }
+    }
+}
+
+// K2a -- batches of long records: trimming only, every warp on its own.  A warp draws two units at a time and
+// leaves their verdicts {five, kept bases, keep} in the descriptor table; k2_trim_route<true> then does the routing
+// and the scan from those.  In one kernel a tile's look-back has to wait for every earlier tile, and with reads of
+// 1-20 kb the tiles' times differ by an order of magnitude: a quarter of K2's instructions were look-back polls and
+// its warps spent more time at the tile barriers than working (ncu, profiles/r2_final_long_*).
 __global__ void __launch_bounds__(kK2Threads)
+k2_trim_only(DevInput in0, DevInput in1, DevParams P, Control *__restrict__ ctl, RecDesc *__restrict__ desc0,
+             RecDesc *__restrict__ desc1) {
+    const int lane = threadIdx.x & 31;
+    const Geometry g = batch_geometry(ctl, P);
+    const bool paired = P.mode != 0, inter = P.mode >= 2;
+    RangeCheck rc;
+    rc.init(P);
+    while (true) {
+        uint32_t t = 0;
+        if (lane == 0) t = atomicAdd(&ctl->k2a_ticket, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        const uint32_t p0 = t * kK2LongUnitsPerWarp;
+        if (p0 >= g.nunits) break;
+        const bool has = (uint32_t)lane < kK2LongUnitsPerWarp && p0 + lane < g.nunits;
+        const uint32_t my_unit = p0 + (uint32_t)lane;
+        MateInfo mine0 = {{-1, -1}, 0}, mine1 = {{-1, -1}, 0};
+        trim_units(in0, in1, P, rc, ctl, has, my_unit, lane, mine0, mine1);
+        if (has) {
+            RecDesc d;
+            d.dst_off = 0;
+            d.route = mine0.cut.three >= 0 ? 1u : 0u;
+            d.five = d.route ? (uint32_t)mine0.cut.five : 0u;
+            d.nkeep = d.route ? (uint32_t)(mine0.cut.three - mine0.cut.five) : 0u;
+            desc0[inter ? 2 * my_unit : my_unit] = d;
+            if (paired) {
+                d.route = mine1.cut.three >= 0 ? 1u : 0u;
+                d.five = d.route ? (uint32_t)mine1.cut.five : 0u;
+                d.nkeep = d.route ? (uint32_t)(mine1.cut.three - mine1.cut.five) : 0u;
+                (inter ? desc0 : desc1)[inter ? 2 * my_unit + 1 : my_unit] = d;
+            }
+        }
+    }
+}
+
+// kPre: the verdicts are in the descriptor table already (k2_trim_only): routing, scan and descriptors only.
+template <bool kPre>
+__global__ void __launch_bounds__(kK2Threads, 4)
 k2_trim_route(DevInput in0, DevInput in1, DevParams P, Control *__restrict__ ctl, RecDesc *__restrict__ desc0,
               RecDesc *__restrict__ desc1, unsigned long long *__restrict__ status /* [3][max_tiles] */,
               uint32_t status_stride, uint32_t epoch) {
@@ -334,7 +399,7 @@ k2_trim_route(DevInput in0, DevInput in1, DevParams P, Control *__restrict__ ctl
     const Geometry g = batch_geometry(ctl, P);
     // tile geometry (block-uniform, derived from what K1 counted)
     const uint32_t nrec_all = g.nrec0 + g.nrec1;
-    const bool long_batch = nrec_all > 0 && (in0.nbytes + in1.nbytes) / nrec_all >= kK2LongRecordBytes &&
+    const bool long_batch = !kPre && nrec_all > 0 && (in0.nbytes + in1.nbytes) / nrec_all >= kK2LongRecordBytes &&
                             (g.nunits + kK2LongUnitsPerTile - 1) / kK2LongUnitsPerTile < status_stride;
     const uint32_t upw = long_batch ? kK2LongUnitsPerWarp : 32u;                          // units per warp (lanes 0 .. upw-1)
     const uint32_t upt = upw * (kK2Threads / 32);                                         // units per tile
@@ -358,21 +423,23 @@ k2_trim_route(DevInput in0, DevInput in1, DevParams P, Control *__restrict__ ctl
         const uint32_t p0 = tile * upt + wid * upw;
         MateInfo mine0 = {{-1, -1}, 0}, mine1 = {{-1, -1}, 0};
         uint32_t my_unit = 0;
-        bool redo = false;
-        if (unit_lane && p0 + lane < g.nunits) {
-            my_unit = position_to_unit(p0 + lane, g.nunits, P.emu_threads, paired);
-            redo = !thread_trim_mate(in0, inter ? 2 * my_unit : my_unit, P, rc, lane, mine0);
-            if (paired && !redo)
-                redo = !(inter ? thread_trim_mate(in0, 2 * my_unit + 1, P, rc, lane, mine1)
-                               : thread_trim_mate(in1, my_unit, P, rc, lane, mine1));
-        }
-        for (uint32_t todo = __ballot_sync(0xffffffffu, redo); todo; todo &= todo - 1) {
-            const int k = __ffs(todo) - 1;
-            const uint32_t u = __shfl_sync(0xffffffffu, my_unit, k);
-            const MateInfo a = trim_mate(in0, inter ? 2 * u : u, u, 0, P, ctl, lane);
-            MateInfo b = {{-1, -1}, 0};
-            if (paired) b = inter ? trim_mate(in0, 2 * u + 1, u, 1, P, ctl, lane) : trim_mate(in1, u, u, 1, P, ctl, lane);
-            if (lane == k) { mine0 = a; mine1 = b; }
+        const bool has_unit = unit_lane && p0 + lane < g.nunits;
+        if (has_unit) my_unit = position_to_unit(p0 + lane, g.nunits, P.emu_threads, paired);
+        if (!kPre) {
+            trim_units(in0, in1, P, rc, ctl, has_unit, my_unit, lane, mine0, mine1);
+        } else if (has_unit) {   // verdicts from k2_trim_only; the lines' lengths from the index
+            const uint32_t r0 = inter ? 2 * my_unit : my_unit;
+            const RecDesc v0 = desc0[r0];
+            const RecLines l0 = record_lines(in0, r0);
+            mine0.fixed_len = l0.len[0] + l0.len[2] + 4u;
+            if (v0.route) mine0.cut = Cut{(int)v0.five, (int)(v0.five + v0.nkeep)};
+            if (paired) {
+                const uint32_t r1 = inter ? 2 * my_unit + 1 : my_unit;
+                const RecDesc v1 = (inter ? desc0 : desc1)[r1];
+                const RecLines l1 = record_lines(inter ? in0 : in1, r1);
+                mine1.fixed_len = l1.len[0] + l1.len[2] + 4u;
+                if (v1.route) mine1.cut = Cut{(int)v1.five, (int)(v1.five + v1.nkeep)};
+            }
         }
 
         // ---- phase 2: routing (lane = unit) ----

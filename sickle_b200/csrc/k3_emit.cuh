@@ -36,6 +36,37 @@ __device__ __forceinline__ void warp_copy(uint8_t *__restrict__ dst, const uint8
     if ((uint32_t)lane < tail) dst[4 * nw + lane] = src[4 * nw + lane];
 }
 
+// Whole-warp copy for long runs, 16 bytes per lane and two chunks in flight per lane (1 KB per round): destination
+// chunks are written 16-byte aligned, source words fetched aligned and funnel-shifted.  May read up to 7 bytes past src+n.
+__device__ __forceinline__ void warp_copy16(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, uint32_t n, int lane) {
+    uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;
+    if (head > n) head = n;
+    if ((uint32_t)lane < head) dst[lane] = src[lane];
+    dst += head; src += head; n -= head;
+    const uint32_t nq = n >> 4;
+    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
+    const uint32_t *__restrict__ s32 = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
+    uint4 *__restrict__ d128 = reinterpret_cast<uint4 *>(dst);
+    for (uint32_t k0 = 0; k0 < nq; k0 += 64) {
+        uint32_t w[2][5];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const uint32_t k = k0 + 32u * u + (uint32_t)lane;
+#pragma unroll
+            for (int i = 0; i < 5; ++i) w[u][i] = (k < nq && (i < 4 || sh)) ? s32[4 * k + i] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+            const uint32_t k = k0 + 32u * u + (uint32_t)lane;
+            if (k < nq)
+                d128[k] = make_uint4(__funnelshift_r(w[u][0], w[u][1], sh), __funnelshift_r(w[u][1], w[u][2], sh),
+                                     __funnelshift_r(w[u][2], w[u][3], sh), __funnelshift_r(w[u][3], w[u][4], sh));
+        }
+    }
+    const uint32_t tail = n & 15u;
+    if ((uint32_t)lane < tail) dst[16 * nq + lane] = src[16 * nq + lane];
+}
+
 // Quarter-warp copy (8 lanes, `gl` = lane inside the group), 16 bytes per lane and step: destination
 // chunks are written 16-byte aligned, source words fetched aligned and funnel-shifted.  Four records
 // are copied side by side by the four quarters of a warp.  May read up to 7 bytes past src+n.
@@ -73,13 +104,13 @@ __device__ __forceinline__ void emit_record(const DevInput &in, uint32_t rec, co
         if (lane == 0) { dst[0] = (uint8_t)P.qmin; dst[1] = '\n'; }
         return;
     }
-    warp_copy(dst, src + r.start[1] + d.five, d.nkeep, lane);        // seq[five:three]
+    warp_copy16(dst, src + r.start[1] + d.five, d.nkeep, lane);      // seq[five:three]
     dst += d.nkeep;
     if (lane == 0) *dst = '\n';
     dst += 1;
     warp_copy(dst, src + r.start[2], r.len[2] + 1u, lane);           // line 3 verbatim incl. '\n'
     dst += r.len[2] + 1u;
-    warp_copy(dst, src + r.start[3] + d.five, d.nkeep, lane);        // qual[five:three]
+    warp_copy16(dst, src + r.start[3] + d.five, d.nkeep, lane);      // qual[five:three]
     dst += d.nkeep;
     if (lane == 0) *dst = '\n';
 }
@@ -103,12 +134,23 @@ k3_emit(DevInput in0, DevInput in1, DevParams P, const Control *__restrict__ ctl
     // instead of once per record); then the warp copies the records one after the other, the copy
     // parameters coming from the owning lane by shuffle.  Records cut at the 5' end and -M "N records"
     // (rare) take the four-piece path.
-    // Batches of long records (>= 1.5 KB on average, K2's rule) hand a warp 4 records at a time instead of
+    // Batches of long records (>= 1.5 KB on average, K2's rule) hand a warp one record at a time instead of
     // 32: 20,000 reads of 1-20 kb would otherwise keep 625 of the grid's ~9,500 warps busy, each copying
     // ~125 KB, while the others exit at once.
     const uint32_t nwarps = gridDim.x * (kK3Threads / 32);
     const uint32_t nrec_all = g.nrec0 + g.nrec1;
-    const uint32_t rpc = (nrec_all > 0 && (in0.nbytes + in1.nbytes) / nrec_all >= kK2LongRecordBytes) ? 4u : 32u;   // records per warp and round
+    const bool long_batch = nrec_all > 0 && (in0.nbytes + in1.nbytes) / nrec_all >= kK2LongRecordBytes;
+    if (long_batch) {   // one record per warp, the whole warp on each of its runs
+        const uint32_t nw = gridDim.x * (kK3Threads / 32);
+        for (uint32_t c = blockIdx.x * (kK3Threads / 32) + (threadIdx.x >> 5); c < g.nrec0 + g.nrec1; c += nw) {
+            const bool second = c >= g.nrec0;
+            const uint32_t rec = second ? c - g.nrec0 : c;
+            const RecDesc d = (second ? desc1 : desc0)[rec];
+            if (d.route & kRouteEmit) emit_record(second ? in1 : in0, rec, d, outs.p, P, lane);
+        }
+        return;
+    }
+    const uint32_t rpc = 32u;   // records per warp and round
     const uint32_t chunks0 = (g.nrec0 + rpc - 1u) / rpc, chunks1 = (g.nrec1 + rpc - 1u) / rpc;
     for (uint32_t c = blockIdx.x * (kK3Threads / 32) + (threadIdx.x >> 5); c < chunks0 + chunks1; c += nwarps) {
         const bool second = c >= chunks0;

@@ -59,7 +59,7 @@ struct Control {
     uint32_t fast_records2[2];    // fused path, two files: complete records per file (PASS 1)
     uint32_t fast_consumed2[2];   // fused path, two files: end of the last paired record per file (PASS 2)
     uint32_t fused_nunits;        // fused path, two files: pairs of the batch (kf2_between)
-    uint32_t pad_;
+    uint32_t k2a_ticket;          // k2_trim_only: next pair of units
     unsigned long long err_key;   // min over offending (class, unit, mate, position); ~0 = none
     unsigned long long counters[8];  // kept, discard, kept_p, discard_p, kept_s1, kept_s2, discard_s1, discard_s2
     unsigned long long out_bytes[kMaxStreams];

@@ -132,7 +132,15 @@ void run_general(const sk::DevInput di[2], int n_inputs, const sk::DevParams &P,
     const uint32_t k2_cap = (uint32_t)tiles + 2;
     unsigned long long *st2 = aligned_zero<unsigned long long>((size_t)k2_cap * sk::kMaxStreams);
     simt::launch(dim3((unsigned)std::min<uint64_t>(ctas, tiles)), dim3(sk::kK2Threads),
-                 [&] { sk::k2_trim_route(di[0], di[1], P, ctl, desc[0], desc[1], st2, k2_cap, epoch); });
+                 [&] {
+                     if (getenv("KH_K2_SPLIT")) return;
+                     sk::k2_trim_route<false>(di[0], di[1], P, ctl, desc[0], desc[1], st2, k2_cap, epoch);
+                 });
+    if (getenv("KH_K2_SPLIT")) {   // the two-kernel form capi.cu uses for batches of long records
+        simt::launch(dim3(ctas), dim3(sk::kK2Threads), [&] { sk::k2_trim_only(di[0], di[1], P, ctl, desc[0], desc[1]); });
+        simt::launch(dim3((unsigned)std::min<uint64_t>(ctas, tiles)), dim3(sk::kK2Threads),
+                     [&] { sk::k2_trim_route<true>(di[0], di[1], P, ctl, desc[0], desc[1], st2, k2_cap, epoch); });
+    }
     simt::launch(dim3(ctas), dim3(sk::kK3Threads), [&] { sk::k3_emit(di[0], di[1], P, ctl, desc[0], desc[1], op); });
     simt::launch(dim3(1), dim3(32), [&] { sk::k_finalize(di[0], di[1], P, ctl, op, res); });
     free(st2); free(desc[0]); free(desc[1]);

@@ -236,6 +236,41 @@ def test_long_reads_with_out_of_range_quality_bytes(harness, tmp_path):
     assert verdicts == {True, False}      # some bytes are met by the loop, some lie beyond its break
 
 
+def test_general_path_in_two_kernels(harness, tmp_path):
+    """Batches of long records run K2 as two kernels (k2_trim_only: trimming, every warp on its own; k2_trim_route<true>:
+    routing + scan from the stored verdicts) and K3 with one record per warp: long reads, and -- the form must be right
+    for any input -- short reads, -a N order, two files, interleaved pairs, -M, a data error."""
+    from sickle_b200 import synth
+
+    env = {"KH_K2_SPLIT": "1"}
+
+    def ok(path, **kw):
+        rc, out, err = run(harness, path, kernel="general", env=env, **kw)
+        assert rc == 0 and out.startswith("OK"), (path, kw, out, err[-300:])
+        return out
+
+    for qualtype, seed in (("illumina", 14), ("solexa", 15)):
+        p = str(tmp_path / (qualtype + ".fq"))
+        open(p, "wb").write(synth.variable_length_records(20, 1000, 20000, qualtype, seed))
+        ok(p, qualtype=qualtype, x=True, n=True, ctas=4, first=3)
+        ok(p, qualtype=qualtype, q=30, l=100, ctas=3)
+    se, pf, pr, il = (str(tmp_path / n) for n in ("se.fq", "f.fq", "r.fq", "il.fq"))
+    data = synth.fixed_length_records(3000, 150, "sanger", seed=5).tobytes()
+    open(se, "wb").write(data)
+    f, r, inter = synth.paired_records(1200, 150, "sanger", seed=6)
+    open(pf, "wb").write(f.tobytes()); open(pr, "wb").write(r.tobytes()); open(il, "wb").write(inter.tobytes())
+    ok(se, ctas=3)
+    ok(se, ctas=3, threads=4)
+    ok(pf, mode="pe2", path2=pr, ctas=3)
+    ok(il, mode="pei", ctas=3)
+    ok(il, mode="peM", singles=False, ctas=2)
+    lines = data.split(b"\n")
+    lines[4 * 2000 + 3] = b"\x7f" + lines[4 * 2000 + 3][1:]
+    bad = str(tmp_path / "bad.fq")
+    open(bad, "wb").write(b"\n".join(lines))
+    assert ok(bad, ctas=3).startswith("OK error kind=6 record=2000")
+
+
 def test_damaged_inputs(harness, tmp_path):
     """Seeded random files, three quarters of them damaged (missing / blank / doubled line, flipped /
     deleted / inserted byte, cut-off tail): same first data error (kind, record, position, byte) or same
