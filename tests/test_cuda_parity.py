@@ -223,9 +223,9 @@ def test_tile_size_follows_record_size(capi, L, min_fused_frac):
     bytes -- to the general path).  Same bytes either way."""
     from sickle_b200 import synth
 
-    data = synth.fixed_length_records(30000, L, "sanger", seed=31).tobytes()
-    flags = dict(qualtype="sanger", q=20, l=20, x=False, n=False)
-    want = orc.run(orc.MODE_SE, orc.make_params("sanger"), data)
+    data = synth.fixed_length_records(30000 if L > 12 else 80000, L, "sanger", seed=31).tobytes()
+    flags = dict(qualtype="sanger", q=20 if L > 12 else 2, l=20 if L > 12 else 5, x=False, n=False)
+    want = orc.run(orc.MODE_SE, orc.make_params("sanger", flags["q"], flags["l"]), data)
     got = _run_cuda(capi, capi.MODE_SE, flags, data, slot_bytes=1 << 18)
     assert got["out"][0] == want["out"][0]
     assert got["counters"]["kept"] == want["counters"]["kept"]
