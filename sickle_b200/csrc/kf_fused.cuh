@@ -190,7 +190,6 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
     __shared__ uint32_t warp_tot2[kFThreads / 32][2];
     __shared__ unsigned long long s_lb[kFThreads / 32][2];   // look-back scratch
     __shared__ uint32_t s_fail;
-    __shared__ uint32_t s_G;
     // Per-warp running totals of the batch summary (records, end of the last complete record, the reference's
     // counters).  They go to the Control block once, when the CTA runs out of tiles: one atomic per counter and
     // warp and TILE -- 10,000 tiles x 4 warps x up to 8 counters, all on one or two cache lines -- kept a single
@@ -362,13 +361,6 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             break;
         }
 
-        // S4 (look-back #1) is the last warp's job, and its first round trip to the predecessors' words runs under
-        // the position stores of S3: the loads go out here, the words are looked at after the stores.
-        constexpr int kWalkWarp = kFThreads / 32 - 1;
-        WalkWords ww;
-#ifndef SK_KO_LB1
-        if (wid == kWalkWarp) walk_issue(status_nl, tile, epoch, lane, ww);
-#endif
         if (!nl_overflow) {
             // a thread's 16*CH bytes hold about two newlines: one short loop per 32-byte mask word (most
             // words have none, and a warp leaves a word's loop as soon as none of its lanes has one left)
@@ -392,18 +384,11 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             const uint32_t rem = t0 % 325u;   // newlines of a 325-byte record sit at offsets 20, 171, 173, 324
             G = 4u * (t0 / 325u) + (rem > 20u) + (rem > 171u) + (rem > 173u) + (rem > 324u);
 #else
-            (void)agg; (void)ex;
-            if (wid == kWalkWarp) {
-                const uint32_t g_ = walk_finish(status_nl, tile, c_t, epoch, lane, ww);
-                if (lane == 0) s_G = g_;
-            }
-            __syncthreads();   // newline positions and the tile's line number visible to every thread
-            G = s_G;
+            block_walk(st_nl, tile, agg, 1, epoch, tid, s_lb, ex);
+            G = (uint32_t)ex[0];
 #endif
         }
-#ifdef SK_KO_LB1
         __syncthreads();   // newline positions visible to every thread
-#endif
         SK_TICK(3);   // S3 positions + S4 look-back #1
 
         // ---- S5: units owned by this tile.  Newline j (j < c_t) is global newline G+j; the line

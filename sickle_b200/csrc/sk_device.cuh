@@ -274,56 +274,6 @@ __device__ __forceinline__ void block_walk(unsigned long long *const status[2], 
                   pack_status(kFlagInclusive, epoch, (gtid ? ex1 : ex0) + aggregate[gtid]));
 }
 
-// Look-back of one stream by ONE warp, kWalkWords predecessors per lane (padded status words), in two halves so that
-// the caller can put independent work between them: walk_issue starts the loads of the nearest 32 * kWalkWords
-// predecessors' words, walk_finish consumes them (re-polling what was not ready, going further back if no inclusive
-// prefix was among them), publishes the tile's inclusive prefix and returns the exclusive one (same in all lanes).
-constexpr int kWalkWords = 4;
-struct WalkWords {
-    unsigned long long w[kWalkWords];
-};
-__device__ __forceinline__ void walk_issue(const unsigned long long *status, uint32_t tile, uint32_t epoch, int lane, WalkWords &ww) {
-#pragma unroll
-    for (int j = 0; j < kWalkWords; ++j) {
-        const int64_t my = (int64_t)tile - 1 - lane - 32 * j;
-        ww.w[j] = my >= 0 ? ld_status(&status[(size_t)my * kWideStatusStride]) : pack_status(kFlagInclusive, epoch, 0);
-    }
-}
-__device__ __forceinline__ uint32_t walk_finish(unsigned long long *status, uint32_t tile, uint32_t aggregate, uint32_t epoch,
-                                                int lane, WalkWords &ww) {
-    if (tile == 0) return 0u;                     // (published as inclusive by block_publish)
-    uint32_t ex = 0;
-    int64_t idx = (int64_t)tile - 1;
-    while (true) {
-        bool stop = false;
-#pragma unroll
-        for (int j = 0; j < kWalkWords; ++j) {
-            if (stop) continue;
-            const int64_t my = idx - lane - 32 * j;
-            uint32_t flag = status_flag(ww.w[j], epoch);
-            while (my >= 0 && flag == 0) {        // predecessor still on its way to the count
-                __nanosleep(40);
-                ww.w[j] = ld_status(&status[(size_t)my * kWideStatusStride]);
-                flag = status_flag(ww.w[j], epoch);
-            }
-            const uint32_t incl = __ballot_sync(0xffffffffu, flag == 2);
-            uint32_t v = (uint32_t)ww.w[j];
-            if (incl && lane > __ffs(incl) - 1) v = 0;    // nothing beyond the first inclusive prefix
-            ex += __reduce_add_sync(0xffffffffu, v);
-            if (incl) stop = true;
-        }
-        if (stop) break;
-        idx -= 32 * kWalkWords;
-#pragma unroll
-        for (int j = 0; j < kWalkWords; ++j) {
-            const int64_t my = idx - lane - 32 * j;
-            ww.w[j] = my >= 0 ? ld_status(&status[(size_t)my * kWideStatusStride]) : pack_status(kFlagInclusive, epoch, 0);
-        }
-    }
-    if (lane == 0) st_status(&status[(size_t)tile * kWideStatusStride], pack_status(kFlagInclusive, epoch, (unsigned long long)ex + aggregate));
-    return ex;
-}
-
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v, int lane) {
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {

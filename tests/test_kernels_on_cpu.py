@@ -342,7 +342,7 @@ def test_random_thread_order(harness, tmp_path):
     mut = tmp_path / "csrc"
     shutil.copytree(os.path.join(ROOT, "sickle_b200", "csrc"), mut)
     src = (mut / "kf_fused.cuh").read_text()
-    barrier = "            __syncthreads();   // newline positions and the tile's line number visible to every thread"
+    barrier = "        __syncthreads();   // newline positions visible to every thread"
     assert src.count(barrier) == 1
     (mut / "kf_fused.cuh").write_text(src.replace(barrier, "        /* barrier removed */"))
     stub = os.path.join(ROOT, "tests", "host_stub")
