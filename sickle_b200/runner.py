@@ -67,8 +67,8 @@ def trim_stream(ctx: capi.Context, in0: bytes, in1: bytes = b"", pipelined: bool
                 C.memmove(buf, chunk, len(chunk))
                 ends[i] = len(chunk)
                 _patch_eof(buf, ends[i], len(data[i]), pos[i] + len(chunk))
-            if not any(ends):
-                break
+            if not any(ends) or (n_in == 2 and not all(ends[:2])):
+                break         # (two files: no pair can be formed once either file is exhausted, as host/trimmer.cpp does)
             ctx.submit(0, 0, ends[0], 0, ends[1])
             res = ctx.wait(0)
             absorb(res, 0, list(records))
