@@ -375,7 +375,11 @@ int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, Byt
     // ---------------------------------------------------------------------------------------
     if (p.emulate_threads > 1) {
         const long long bl = host::recommended_batch_len(in0->file_size(), batch_mib, paired);
-        unsigned long long slot = (unsigned long long)bl + (unsigned long long)bl / 16 + (4ull << 20);
+        // A reference batch counts characters without their newlines (src/GZReader.cpp:68-75): its bytes are at most
+        // twice that (one-character lines), so 2 * batch_len always holds a batch of non-empty lines.  Up to 128 MiB
+        // that is what the slot gets; above it, the usual FASTQ ratio (records of 64 characters and more: 1/16 extra).
+        unsigned long long slot = (unsigned long long)bl <= (128ull << 20) ? 2ull * (unsigned long long)bl + (4ull << 20)
+                                                                         : (unsigned long long)bl + (unsigned long long)bl / 16 + (4ull << 20);
         slot = std::min<unsigned long long>(slot, (1ull << 31) - 8192);
         Ctx ctx;
         ctx.tot = &tot;
@@ -581,7 +585,8 @@ int Abstract_Trimmer::run_devices(const std::vector<int> &devices, const sk_para
     long long ref_batch_len = 0;
     if (ref_order) {
         ref_batch_len = host::recommended_batch_len(in0->file_size(), batch_mib, p.mode != SK_MODE_SE);
-        slot = (unsigned long long)ref_batch_len + (unsigned long long)ref_batch_len / 16 + (4ull << 20);
+        slot = (unsigned long long)ref_batch_len <= (128ull << 20) ? 2ull * (unsigned long long)ref_batch_len + (4ull << 20)
+                                                                   : (unsigned long long)ref_batch_len + (unsigned long long)ref_batch_len / 16 + (4ull << 20);
         slot = std::min<unsigned long long>(slot, (1ull << 31) - 8192);
     } else {
         slot = env_u64("SICKLE_B200_SLOT_KB", 0) << 10;   // (small slots: tests)
