@@ -29,11 +29,14 @@ for f in sorted(glob.glob('gpurun_out/r2_final_bench_*.json')):
           'e2e', e and round(e['value'] / 1e6, 1), e and round(e['frac_of_bound'], 3), 'cpu', (d.get('cpu_baseline') or {}).get('value'), 'clocks', d['clocks'])
 PY
 # ---- ncu: launch list of the bench command, then full sets
-ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/r2_final_launches.csv python bench.py --steps 2 --warmup 1 --kernel-only --min-timed-s 0.001 > gpurun_out/r2_final_ncu_launches.log 2>&1
+# (our kernels only: the synthetic input alone is thousands of torch launches)
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"kf_fused|kf_finalize|kf2_|k1_line_index|k2_trim|k3_emit|k_finalize" -c 400 --csv --log-file gpurun_out/r2_final_launches.csv python bench.py --steps 4 --warmup 3 --kernel-only --min-timed-s 0.001 > gpurun_out/r2_final_ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"kf_fused|kf_finalize|kf2_|k1_line_index|k2_trim|k3_emit|k_finalize" -c 400 --csv --log-file gpurun_out/r2_final_launches_c3.csv python bench.py --config c3 --steps 4 --warmup 3 --kernel-only --min-timed-s 0.001 >> gpurun_out/r2_final_ncu_launches.log 2>&1
+ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"kf_fused|kf_finalize|kf2_|k1_line_index|k2_trim|k3_emit|k_finalize" -c 400 --csv --log-file gpurun_out/r2_final_launches_c4.csv python bench.py --config c4 --steps 4 --warmup 3 --kernel-only --min-timed-s 0.001 >> gpurun_out/r2_final_ncu_launches.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:kf_fused -s 4 -c 1 -o gpurun_out/r2_final_fused -f python bench.py --steps 6 --warmup 3 --kernel-only --min-timed-s 0.001 > gpurun_out/r2_final_ncu1.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:kf_fused -s 8 -c 2 -o gpurun_out/r2_final_twofile -f python bench.py --config c3 --steps 6 --warmup 3 --kernel-only --min-timed-s 0.001 > gpurun_out/r2_final_ncu2.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:"k1_line_index|k2_trim_route|k3_emit" -s 6 -c 3 -o gpurun_out/r2_final_general -f python profiles/workloads.py --general-only > gpurun_out/r2_final_ncu3.log 2>&1
-ncu --set full --clock-control none --import-source on -k regex:"k1_line_index|k2_trim_route|k3_emit" -s 6 -c 3 -o gpurun_out/r2_final_long -f python profiles/workloads.py --c4-only -x -n > gpurun_out/r2_final_ncu4.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:"k1_line_index|k2_trim|k3_emit" -s 12 -c 4 -o gpurun_out/r2_final_long -f python profiles/workloads.py --c4-only -x -n > gpurun_out/r2_final_ncu4.log 2>&1
 for r in fused twofile general long; do
   ncu -i gpurun_out/r2_final_$r.ncu-rep --page raw --csv > gpurun_out/r2_final_${r}_raw.csv 2>/dev/null
 done
