@@ -342,6 +342,17 @@ private:
     std::vector<Done> done_;
 };
 
+// Does buf[0, n) hold four complete lines (one whole FASTQ record)?
+static bool holds_record(const char *buf, unsigned long long n) {
+    const char *p = buf, *end = buf + n;
+    for (int k = 0; k < 4; ++k) {
+        p = (const char *)memchr(p, '\n', (size_t)(end - p));
+        if (!p) return false;
+        ++p;
+    }
+    return true;
+}
+
 }  // namespace
 
 int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, ByteSink *outs[3], bool has_singles,
@@ -488,7 +499,10 @@ int Abstract_Trimmer::run_device(int mode, ByteSource *in0, ByteSource *in1, Byt
             prev = r;
             have_prev = true;
             if (r.consumed[0] == 0 && r.consumed[1] == 0) {
-                if (n[0] == slot || n[1] == slot) { fprintf(stderr, "****Error: a record does not fit in a %llu-byte slot (raise SICKLE_B200_SLOT_MB).\n\n", slot); return EXIT_FAILURE; }
+                // a full slot without one whole record is an error; a full slot of one file facing the other
+                // file's last, incomplete record is just the end of the pairs
+                const bool starved = (n[0] == slot && !holds_record(h[0], n[0])) || (n[1] == slot && !holds_record(h[1], n[1]));
+                if (starved) { fprintf(stderr, "****Error: a record does not fit in a %llu-byte slot (raise SICKLE_B200_SLOT_MB).\n\n", slot); return EXIT_FAILURE; }
                 break;   // only an incomplete pair is left: dropped, as the reference does at end of file
             }
             for (int i = 0; i < 2; ++i) { carry_ptr[i] = h[i] + r.consumed[i]; carry_len[i] = n[i] - r.consumed[i]; }

@@ -1,6 +1,6 @@
 """Same-GPU A/B of several builds of the library in ONE process (kernel path only, device-resident input).
 
-    python profiles/ab_multi.py [--rounds R] [--steps K] [--ch N] [--workload se|pe|pe2|a8] libA.so libB.so ...
+    python profiles/ab_multi.py [--rounds R] [--steps K] [--workload se|pe|pem|a8] libA.so libB.so[@ENV=VALUE,...] ...
 
 The synthetic batches (bench.py's configs[1] workload unless --workload says otherwise) are generated once;
 every library gets its own context (its own dlopen handle, so each build keeps its own kernels) and the
@@ -33,14 +33,26 @@ def peak():
 class Lib:
     """capi.Context against an explicit .so (capi.load() caches one library per process)."""
 
-    def __init__(self, path, params, slot_bytes):
-        self.path = path
+    def __init__(self, spec, params, slot_bytes):
+        # "lib.so@NAME=VALUE[,NAME=VALUE]": environment the library reads when the context is created
+        path, _, envs = spec.partition("@")
+        self.path = spec
         saved = capi._lib, capi.LIB_PATH
         capi._lib, capi.LIB_PATH = None, os.path.abspath(path)
+        old = {}
+        for kv in filter(None, envs.split(",")):
+            k, _, v = kv.partition("=")
+            old[k] = os.environ.get(k)
+            os.environ[k] = v
         try:
             self.ctx = capi.Context(params, slot_bytes, 0, device=0)
         finally:
             capi._lib, capi.LIB_PATH = saved
+            for k, v in old.items():
+                if v is None:
+                    os.environ.pop(k, None)
+                else:
+                    os.environ[k] = v
 
 
 def main():

@@ -73,7 +73,8 @@ def trim_stream(ctx: capi.Context, in0: bytes, in1: bytes = b"", pipelined: bool
             res = ctx.wait(0)
             absorb(res, 0, list(records))
             if not any(res.consumed[i] for i in range(n_in)):
-                if any(ends[i] == ctx.slot_bytes for i in range(n_in)):
+                # (a full slot of one file facing the other file's last, incomplete record is the end of the pairs)
+                if any(ends[i] == ctx.slot_bytes and bytes(ctx.in_buffer(0, i)[:ends[i]]).count(b"\n") < 4 for i in range(n_in)):
                     raise capi.SickleError("a record does not fit in a %d-byte slot" % ctx.slot_bytes)
                 break  # only an incomplete record (pair) is left: dropped, as the reference does at EOF
             for i in range(n_in):

@@ -299,6 +299,41 @@ def test_several_devices_many_batches(sickle, tmp_path):
         assert nb[0] >= len(se) // (int(slot_kb) << 10) and nb[1] == want_a3["counters"]["n_batches"], (devs, nb)
 
 
+def _nth_newline(data, n):
+    pos = -1
+    for _ in range(n):
+        pos = data.index(b"\n", pos + 1)
+    return pos
+
+
+def test_two_files_of_unequal_length(sickle, tmp_path):
+    """`pe -f -r` where one file holds fewer records than the other and ends inside a record: the pairs that exist
+    are trimmed, the rest is dropped (the reference refuses such input) -- in particular a full slot
+    of the longer file next to the other file's cut-off tail is not "a record that does not fit"."""
+    import oracle_py as orc
+    from sickle_b200 import synth
+
+    f, r, _ = synth.paired_records(20000, 150, "sanger", seed=33)
+    fb, rb = f.tobytes(), r.tobytes()
+    o = lambda name: str(tmp_path / name)
+    # (all three cuts fall inside a name or base line; one inside a quality line is a record with lines of
+    #  different lengths, an error here as in the reference)
+    for tag, a, b in (("b_short", fb, rb[:len(rb) * 2 // 3 + 11]), ("a_half", fb[:len(fb) // 2], rb), ("a_cut", fb[:_nth_newline(fb, 4 * 6001 + 1) + 60], rb)):
+        npairs = min(a.count(b"\n"), b.count(b"\n")) // 4
+        cut = lambda d: b"\n".join(d.split(b"\n")[:4 * npairs]) + b"\n"
+        want = orc.run(orc.MODE_PE_2FILE, orc.make_params("sanger"), cut(a), cut(b), batch_len=1 << 40)
+        assert want["rc"] == 0
+        open(o("a.fq"), "wb").write(a)
+        open(o("b.fq"), "wb").write(b)
+        for env in ({"SICKLE_B200_SLOT_MB": "1"}, {"SICKLE_B200_DEVICES": "0,0", "SICKLE_B200_SLOT_KB": "512"}):
+            p = subprocess.run([sickle, "pe", "-f", o("a.fq"), "-r", o("b.fq"), "-t", "sanger", "-o", o("p1"), "-p", o("p2"), "-s", o("ps")],
+                               capture_output=True, env=dict(os.environ, **env), timeout=120)
+            assert p.returncode == 0, (tag, env, p.stderr[-400:])
+            for name, k in (("p1", 0), ("p2", 1), ("ps", 2)):
+                assert open(o(name), "rb").read() == want["out"][k], (tag, env, name)
+            assert counts(p.stdout.decode())["kept_p"] == want["counters"]["kept_p"]
+
+
 def test_several_devices_errors(sickle, tmp_path):
     """A data error in a late batch: exit 1 with the reference's message and the record's true number
     (same text as with one context); a record that does not fit a slot; an unusable device number."""

@@ -87,6 +87,10 @@ def test_errors_over_several_contexts(hoststub, tmp_path):
     test_cli.test_several_devices_errors(hoststub, tmp_path)
 
 
+def test_two_files_of_unequal_length(hoststub, tmp_path):
+    test_cli.test_two_files_of_unequal_length(hoststub, tmp_path)
+
+
 def test_four_devices_in_any_order(hoststub, tmp_path):
     from sickle_b200 import synth
 
