@@ -140,12 +140,26 @@ __device__ __noinline__ Cut warp_sliding_window(const uint8_t *__restrict__ d, u
                 lw[u] = in ? W[A0 + k + s] : rc.kmin;
                 tw[u] = in ? W[A0 + s] : rc.kmin;
             }
+            // what step s+1 has over step s (nothing past the last step: both words are the filler)
+            int Dv[4], neg = 0, tot = 0;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                rc.screen3(lw[u], scr);
+                Dv[u] = dp4a_us(lw[u], 0x01010101, dp4a_us(tw[u], (int)0xFFFFFFFF, 0));
+                neg += min(Dv[u], 0);
+                tot += Dv[u];
+            }
+            // No prefix of the round's 128 differences is below the sum of the negative ones: while the bound stays
+            // that far above the threshold (all of a read's good stretch) a round is two warp reductions instead of
+            // four scans, four ballots and four broadcasts.
+            if (R + (int)__reduce_add_sync(0xffffffffu, (uint32_t)neg) >= 0) {
+                R += (int)__reduce_add_sync(0xffffffffu, (uint32_t)tot);
+                continue;
+            }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const uint32_t s = s0 + 32u * u + (uint32_t)lane;
-                rc.screen3(lw[u], scr);
-                // what step s+1 has over step s (nothing past the last step: both words are the filler)
-                const int D = dp4a_us(lw[u], 0x01010101, dp4a_us(tw[u], (int)0xFFFFFFFF, 0));
+                const int D = Dv[u];
                 const int incl = warp_incl_scan_i(D, lane);
                 const uint32_t bm = __ballot_sync(0xffffffffu, s < nstep && R + incl - D < 0);
                 if (bm) { jf = s0 + 32u * u + (uint32_t)__ffs(bm) - 1u; break; }
@@ -237,6 +251,9 @@ __device__ __noinline__ Cut warp_sliding_window(const uint8_t *__restrict__ d, u
         const uint32_t wa = S0 >> 2, nwords = ((SE + 3u) >> 2) - wa;
         int pn = -1;
         bool anyN = false;
+        // flag masks of the bytes that belong to the line, for its first and its last word
+        const uint32_t head_ok = 0x80808080u << (8u * (S0 & 3u));
+        const uint32_t tail_ok = (SE & 3u) ? 0x80808080u >> (8u * (4u - (SE & 3u))) : 0x80808080u;
         for (uint32_t w0 = 0; w0 < nwords && pn < 0; w0 += 128) {
             uint32_t v[4];
 #pragma unroll
@@ -244,17 +261,25 @@ __device__ __noinline__ Cut warp_sliding_window(const uint8_t *__restrict__ d, u
                 const uint32_t idx = w0 + 32u * u + (uint32_t)lane;
                 v[u] = idx < nwords ? W[wa + idx] : 0u;
             }
+            // a round without any n / N (nearly all of them) is one vote
+            uint32_t hn[4], hN[4], any = 0;
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const uint32_t idx = w0 + 32u * u + (uint32_t)lane;
-                const uint32_t base = 4u * (wa + idx);               // byte offset of this word
-                // bytes of the word that belong to the sequence line
-                const uint32_t lo = base < S0 ? S0 - base : 0u, hi = base + 4u > SE ? (SE > base ? SE - base : 0u) : 4u;
-                const uint32_t ok = idx < nwords ? (((1u << hi) - 1u) & ~((1u << lo) - 1u)) : 0u;
+                uint32_t okf = 0x80808080u;
+                okf = idx == 0u ? okf & head_ok : okf;
+                okf = idx + 1u == nwords ? okf & tail_ok : okf;
                 const uint32_t tn = ((v[u] ^ 0x6E6E6E6Eu) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
                 const uint32_t tN = ((v[u] ^ 0x4E4E4E4Eu) & 0x7F7F7F7Fu) + 0x7F7F7F7Fu;
-                const uint32_t fn = flags_to_nibble(~(tn | v[u]) & 0x80808080u) & ok;
-                const uint32_t fN = flags_to_nibble(~(tN | v[u]) & 0x80808080u) & ok;
+                hn[u] = ~(tn | v[u]) & okf;                          // (a word past the line was loaded as 0: no match)
+                hN[u] = ~(tN | v[u]) & okf;
+                any |= hn[u] | hN[u];
+            }
+            if (!__any_sync(0xffffffffu, any != 0)) continue;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const uint32_t fn = flags_to_nibble(hn[u]);
+                const uint32_t fN = flags_to_nibble(hN[u]);
                 const uint32_t mn = __ballot_sync(0xffffffffu, fn != 0);
                 anyN |= __ballot_sync(0xffffffffu, fN != 0) != 0;
                 if (mn) {
@@ -351,7 +376,7 @@ __device__ __forceinline__ void trim_units(const DevInput &in0, const DevInput &
 // its warps spent more time at the tile barriers than working (ncu, profiles/r2_final_long_*).
 __global__ void __launch_bounds__(kK2Threads)
 k2_trim_only(DevInput in0, DevInput in1, DevParams P, Control *__restrict__ ctl, RecDesc *__restrict__ desc0,
-             RecDesc *__restrict__ desc1) {
+             RecDesc *__restrict__ desc1, uint32_t upw /* units a warp draws at a time: 2 for long records, 32 otherwise */) {
     const int lane = threadIdx.x & 31;
     const Geometry g = batch_geometry(ctl, P);
     const bool paired = P.mode != 0, inter = P.mode >= 2;
@@ -361,9 +386,9 @@ k2_trim_only(DevInput in0, DevInput in1, DevParams P, Control *__restrict__ ctl,
         uint32_t t = 0;
         if (lane == 0) t = atomicAdd(&ctl->k2a_ticket, 1u);
         t = __shfl_sync(0xffffffffu, t, 0);
-        const uint32_t p0 = t * kK2LongUnitsPerWarp;
+        const uint32_t p0 = t * upw;
         if (p0 >= g.nunits) break;
-        const bool has = (uint32_t)lane < kK2LongUnitsPerWarp && p0 + lane < g.nunits;
+        const bool has = (uint32_t)lane < upw && p0 + lane < g.nunits;
         const uint32_t my_unit = p0 + (uint32_t)lane;
         MateInfo mine0 = {{-1, -1}, 0}, mine1 = {{-1, -1}, 0};
         trim_units(in0, in1, P, rc, ctl, has, my_unit, lane, mine0, mine1);

@@ -67,26 +67,98 @@ __device__ __forceinline__ void warp_copy16(uint8_t *__restrict__ dst, const uin
     if ((uint32_t)lane < tail) dst[16 * nq + lane] = src[16 * nq + lane];
 }
 
-// Quarter-warp copy (8 lanes, `gl` = lane inside the group), 16 bytes per lane and step: destination
-// chunks are written 16-byte aligned, source words fetched aligned and funnel-shifted.  Four records
-// are copied side by side by the four quarters of a warp.  May read up to 7 bytes past src+n.
-__device__ __forceinline__ void quarter_copy16(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, uint32_t n, int gl) {
-    uint32_t head = (16u - (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u)) & 15u;
-    if (head > n) head = n;
-    for (uint32_t j = gl; j < head; j += 8) dst[j] = src[j];
-    dst += head; src += head; n -= head;
-    const uint32_t nq = n >> 4;
-    const uint32_t sh = (uint32_t)(reinterpret_cast<uintptr_t>(src) & 3u) * 8u;
-    const uint32_t *__restrict__ s32 = reinterpret_cast<const uint32_t *>(reinterpret_cast<uintptr_t>(src) & ~(uintptr_t)3);
-    uint4 *__restrict__ d128 = reinterpret_cast<uint4 *>(dst);
-    for (uint32_t k = gl; k < nq; k += 8) {
-        const uint32_t a = s32[4 * k], b = s32[4 * k + 1], c = s32[4 * k + 2], e = s32[4 * k + 3];
-        const uint32_t f = sh ? s32[4 * k + 4] : 0u;
-        d128[k] = make_uint4(__funnelshift_r(a, b, sh), __funnelshift_r(b, c, sh), __funnelshift_r(c, e, sh),
-                             __funnelshift_r(e, f, sh));
+// One kept record by a quarter-warp (8 lanes, `gl` = lane inside the group); the four quarters of a warp emit four
+// records side by side.  The record is up to four source runs plus its final '\n' (run starts in output bytes: 0, b2,
+// b3, b4, b5).  The work is cut by 16-byte aligned DESTINATION chunks: a chunk that lies inside one run is five aligned
+// source words funnel-shifted into one 16-byte store; the chunks that hold a run boundary or one of the record's ragged
+// ends (at most five: lanes 0..4 take one each) are gathered byte by byte.  Nothing here depends on an earlier store, so
+// all the loads of a round (3 chunks per lane + the boundary chunk) are in flight together: the copy it replaces walked
+// head / body / tail of run after run, eight dependent DRAM round trips per record, and was bound by exactly that
+// (long-scoreboard stalls, 1.8 TB/s).  May read up to 3 bytes before and 7 bytes past a run (inside the buffer's padding).
+struct EmitRuns {
+    uint32_t d1, d2, d3, d4;   // source offset minus output offset, per run (d1 = source offset of run 1)
+    uint32_t b2, b3, b4, b5;   // output offsets at which runs 2, 3, 4 and the final newline start
+};
+
+// source offset of output byte o (selects, no branches: the arms are registers)
+__device__ __forceinline__ uint32_t emit_source(const EmitRuns &r, uint32_t o) {
+    uint32_t d = r.d1;
+    d = o >= r.b2 ? r.d2 : d;
+    d = o >= r.b3 ? r.d3 : d;
+    d = o >= r.b4 ? r.d4 : d;
+    return o + d;
+}
+
+__device__ __forceinline__ void quarter_emit(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, const EmitRuns r,
+                                             bool have, int gl) {
+    const uint32_t total = have ? r.b5 + 1u : 0u;
+    const uint32_t ph = (uint32_t)(reinterpret_cast<uintptr_t>(dst) & 15u);
+    uint8_t *__restrict__ gal = dst - ph;                     // 16-byte aligned
+    const uint32_t end = ph + total;                          // in bytes from gal
+    const uint32_t nch = (end + 15u) >> 4;
+    // ---- boundary chunk of this lane: loads
+    const uint32_t bnd = gl == 0 ? 0u : gl == 1 ? r.b2 : gl == 2 ? r.b3 : gl == 3 ? r.b4 : r.b5;
+    const bool special = have && gl < 5;
+    const uint32_t sc = (ph + bnd) >> 4;
+    uint32_t sb[4] = {0u, 0u, 0u, 0u};
+    uint32_t svalid = 0;
+    if (special) {
+        // sixteen unconditional byte loads (positions outside the record are clamped onto its last source byte), so that
+        // they are all in flight together: a load inside an `if` is followed by its use, and an in-order warp then
+        // pays one trip to memory per byte
+        uint32_t vb[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t o = 16u * sc + (uint32_t)i - ph;   // wraps below the record's first byte: clamped as well
+            vb[i] = (uint32_t)src[emit_source(r, min(o, r.b5 - 1u))];
+        }
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            const uint32_t pos = 16u * sc + (uint32_t)i;      // from gal
+            const uint32_t v = pos - ph == r.b5 ? (uint32_t)'\n' : vb[i];
+            sb[i >> 2] |= v << (8 * (i & 3));
+            svalid |= (pos >= ph && pos < end) ? 1u << i : 0u;
+        }
     }
-    const uint32_t tail = n & 15u;
-    for (uint32_t j = gl; j < tail; j += 8) dst[16 * nq + j] = src[16 * nq + j];
+    for (uint32_t c0 = 0; c0 < nch; c0 += 24u) {
+        // ---- chunks inside one run: loads of three chunks per lane, then their stores
+        uint32_t w[3][5];
+        uint32_t sh[3];
+        bool simple[3];
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const uint32_t c = c0 + 8u * (uint32_t)u + (uint32_t)gl;
+            const uint32_t o = 16u * c - ph;                  // meaningful when 16 c >= ph
+            uint32_t lim = r.b2;                              // end of the run that holds o
+            lim = o >= r.b2 ? r.b3 : lim;
+            lim = o >= r.b3 ? r.b4 : lim;
+            lim = o >= r.b4 ? r.b5 : lim;
+            simple[u] = c < nch && 16u * c >= ph && o + 16u <= lim;
+            const uint32_t a = emit_source(r, o);
+            sh[u] = (a & 3u) * 8u;
+            const uint32_t *__restrict__ s32 = reinterpret_cast<const uint32_t *>(src + (a & ~3u));
+#pragma unroll
+            for (int i = 0; i < 5; ++i) w[u][i] = (simple[u] && (i < 4 || sh[u])) ? s32[i] : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 3; ++u) {
+            const uint32_t c = c0 + 8u * (uint32_t)u + (uint32_t)gl;
+            if (simple[u])
+                *reinterpret_cast<uint4 *>(gal + 16u * c) =
+                    make_uint4(__funnelshift_r(w[u][0], w[u][1], sh[u]), __funnelshift_r(w[u][1], w[u][2], sh[u]),
+                               __funnelshift_r(w[u][2], w[u][3], sh[u]), __funnelshift_r(w[u][3], w[u][4], sh[u]));
+        }
+    }
+    // ---- boundary chunk: stores (a chunk shared with the neighbouring record is written byte by byte)
+    if (special) {
+        if (svalid == 0xffffu) {
+            *reinterpret_cast<uint4 *>(gal + 16u * sc) = make_uint4(sb[0], sb[1], sb[2], sb[3]);
+        } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i)
+                if (svalid & (1u << i)) gal[16u * sc + (uint32_t)i] = (uint8_t)(sb[i >> 2] >> (8 * (i & 3)));
+        }
+    }
 }
 
 __device__ __forceinline__ void emit_record(const DevInput &in, uint32_t rec, const RecDesc d, uint8_t *const *outs,
@@ -120,7 +192,10 @@ struct OutPtrs {
     unsigned long long cap[kMaxStreams];
 };
 
-__global__ void __launch_bounds__(kK3Threads)
+#ifndef SK_K3_MINCTAS
+#define SK_K3_MINCTAS 3
+#endif
+__global__ void __launch_bounds__(kK3Threads, SK_K3_MINCTAS)
 k3_emit(DevInput in0, DevInput in1, DevParams P, const Control *__restrict__ ctl, const RecDesc *__restrict__ desc0,
         const RecDesc *__restrict__ desc1, OutPtrs outs) {
     const int lane = threadIdx.x & 31;
@@ -195,15 +270,15 @@ k3_emit(DevInput in0, DevInput in1, DevParams P, const Control *__restrict__ ctl
             uint32_t n1 = __shfl_sync(0xffffffffu, l1, from), n3 = __shfl_sync(0xffffffffu, l3, from);
             uint32_t n2 = __shfl_sync(0xffffffffu, l2, from), n4 = __shfl_sync(0xffffffffu, l4, from);
             if (!have) { n1 = 0; n2 = 0; n3 = 0; n4 = 0; }
-            uint8_t *dst = outs.p[route & 3u] + off;
-            quarter_copy16(dst, in.data + a1, n1, gl);
+            uint32_t a2 = 0, a4 = 0;
             if (__any_sync(0xffffffffu, (n2 | n4) != 0)) {            // some read of the four is cut at its 5' end
-                const uint32_t a2 = __shfl_sync(0xffffffffu, s2, from), a4 = __shfl_sync(0xffffffffu, s4, from);
-                quarter_copy16(dst + n1, in.data + a2, n2, gl);
-                quarter_copy16(dst + n1 + n2 + n3, in.data + a4, n4, gl);
+                a2 = __shfl_sync(0xffffffffu, s2, from);
+                a4 = __shfl_sync(0xffffffffu, s4, from);
             }
-            quarter_copy16(dst + n1 + n2, in.data + a3, n3, gl);
-            if (have && gl == 0) dst[n1 + n2 + n3 + n4] = '\n';
+            EmitRuns er;
+            er.b2 = n1; er.b3 = n1 + n2; er.b4 = n1 + n2 + n3; er.b5 = n1 + n2 + n3 + n4;
+            er.d1 = a1; er.d2 = a2 - er.b2; er.d3 = a3 - er.b3; er.d4 = a4 - er.b4;
+            quarter_emit(outs.p[route & 3u] + off, in.data, er, have, gl);
         }
         for (uint32_t todo = __ballot_sync(0xffffffffu, slow); todo; todo &= todo - 1) {
             const int k = __ffs(todo) - 1;

@@ -242,10 +242,10 @@ def test_general_path_in_two_kernels(harness, tmp_path):
     for any input -- short reads, -a N order, two files, interleaved pairs, -M, a data error."""
     from sickle_b200 import synth
 
-    env = {"KH_K2_SPLIT": "1"}
+    env = {"KH_K2_SPLIT": "2"}   # units a warp of k2_trim_only draws at a time: 2 (long records) or 32
 
     def ok(path, **kw):
-        rc, out, err = run(harness, path, kernel="general", env=env, **kw)
+        rc, out, err = run(harness, path, kernel="general", env=kw.pop("env", env), **kw)
         assert rc == 0 and out.startswith("OK"), (path, kw, out, err[-300:])
         return out
 
@@ -259,11 +259,12 @@ def test_general_path_in_two_kernels(harness, tmp_path):
     open(se, "wb").write(data)
     f, r, inter = synth.paired_records(1200, 150, "sanger", seed=6)
     open(pf, "wb").write(f.tobytes()); open(pr, "wb").write(r.tobytes()); open(il, "wb").write(inter.tobytes())
-    ok(se, ctas=3)
-    ok(se, ctas=3, threads=4)
-    ok(pf, mode="pe2", path2=pr, ctas=3)
-    ok(il, mode="pei", ctas=3)
-    ok(il, mode="peM", singles=False, ctas=2)
+    for e in (env, {"KH_K2_SPLIT": "32"}):
+        ok(se, ctas=3, env=e)
+        ok(se, ctas=3, threads=4, env=e)
+        ok(pf, mode="pe2", path2=pr, ctas=3, env=e)
+        ok(il, mode="pei", ctas=3, env=e)
+        ok(il, mode="peM", singles=False, ctas=2, env=e)
     lines = data.split(b"\n")
     lines[4 * 2000 + 3] = b"\x7f" + lines[4 * 2000 + 3][1:]
     bad = str(tmp_path / "bad.fq")
