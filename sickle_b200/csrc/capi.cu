@@ -289,7 +289,7 @@ int launch_general(sk_ctx *c, Slot &s, const BatchArgs &a) {
     const bool split = c->k2_split < 0 ? (c->long_records || c->dev.emu_threads > 1) : c->k2_split != 0;
     if (split) {   // trimming on its own (no tile waits for another), then routing + scan from the verdicts
         sk::k2_trim_only<<<resident, sk::kK2Threads, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, s.d_desc[0], s.d_desc[1],
-                                                              c->long_records ? sk::kK2LongUnitsPerWarp : 32u);
+                                                              c->long_records ? sk::kK2aLongUnitsPerTicket : 32u);
         SK_DEBUG_SYNC(st, "k2_trim_only");
         sk::k2_trim_route<true><<<grid, sk::kK2Threads, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, s.d_desc[0], s.d_desc[1],
                                                                  s.d_status_k2, c->k2_tiles_cap, s.epoch);

@@ -36,6 +36,8 @@ namespace sk {
 constexpr int kK2Threads = 256;
 constexpr int kK2UnitsPerTile = kK2Threads;  // 8 warps x 32 units (short records)
 constexpr uint32_t kK2LongUnitsPerWarp = 2;   // batches of long records: 2 units per warp, 16 per tile
+constexpr uint32_t kK2aLongUnitsPerTicket = 2; // k2_trim_only, long records: units per ticket (1 and 256-step rounds: no change, profiles/r2_call21.log)
+constexpr int kCoarseU = 4, kNScanU = 4;       // warp_sliding_window: word loads per lane in flight per round (coarse pass: x2)
 constexpr uint32_t kK2LongUnitsPerTile = kK2LongUnitsPerWarp * (kK2Threads / 32);
 constexpr uint32_t kK2LongRecordBytes = 1500; // average record size from which a batch counts as "long"
 
@@ -129,35 +131,36 @@ __device__ __noinline__ Cut warp_sliding_window(const uint8_t *__restrict__ d, u
         }
         int R = warp_sum_i(part) - bias;                         // bound of the first whole word (step 0)
         uint32_t jf = nstep;                                     // first step whose bound is below the threshold
-        // 128 steps per round: the 8 loads of a lane (4 lead, 4 trail words, each warp-coalesced) are issued
-        // together, so that a round costs one trip to memory rather than four
-        for (uint32_t s0 = 0; s0 < nstep && jf == nstep; s0 += 128) {
-            uint32_t lw[4], tw[4];
+        // kCoarseU * 32 steps per round: the loads of a lane (kCoarseU lead and as many trail words, each
+        // warp-coalesced) are issued together, so that a round costs one trip to memory rather than kCoarseU.
+        // (256 steps per round and one read per ticket were measured against 128 and two: no change.)
+        for (uint32_t s0 = 0; s0 < nstep && jf == nstep; s0 += 32u * kCoarseU) {
+            uint32_t lw[kCoarseU], tw[kCoarseU];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kCoarseU; ++u) {
                 const uint32_t s = s0 + 32u * u + (uint32_t)lane;
                 const bool in = s + 1u < nstep;
                 lw[u] = in ? W[A0 + k + s] : rc.kmin;
                 tw[u] = in ? W[A0 + s] : rc.kmin;
             }
             // what step s+1 has over step s (nothing past the last step: both words are the filler)
-            int Dv[4], neg = 0, tot = 0;
+            int Dv[kCoarseU], neg = 0, tot = 0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kCoarseU; ++u) {
                 rc.screen3(lw[u], scr);
                 Dv[u] = dp4a_us(lw[u], 0x01010101, dp4a_us(tw[u], (int)0xFFFFFFFF, 0));
                 neg += min(Dv[u], 0);
                 tot += Dv[u];
             }
-            // No prefix of the round's 128 differences is below the sum of the negative ones: while the bound stays
+            // No prefix of the round's differences is below the sum of the negative ones: while the bound stays
             // that far above the threshold (all of a read's good stretch) a round is two warp reductions instead of
-            // four scans, four ballots and four broadcasts.
+            // a scan, a ballot and a broadcast per 32 steps.
             if (R + (int)__reduce_add_sync(0xffffffffu, (uint32_t)neg) >= 0) {
                 R += (int)__reduce_add_sync(0xffffffffu, (uint32_t)tot);
                 continue;
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kCoarseU; ++u) {
                 const uint32_t s = s0 + 32u * u + (uint32_t)lane;
                 const int D = Dv[u];
                 const int incl = warp_incl_scan_i(D, lane);
@@ -244,7 +247,7 @@ __device__ __noinline__ Cut warp_sliding_window(const uint8_t *__restrict__ d, u
         }
     }
     if (P.trunc_n) {                                             // trim.cpp:86-98 (bug kept: 'N' only => -2)
-        // first lowercase n (it wins), else any uppercase N.  Aligned words, four per lane and round (512
+        // first lowercase n (it wins), else any uppercase N.  Aligned words, kNScanU per lane and round (1 KB of
         // coalesced bytes, the loads issued together): a byte-per-lane loop pays one trip to memory per 32 bases.
         const uint32_t *__restrict__ W = reinterpret_cast<const uint32_t *>(d);
         const uint32_t S0 = seq_off, SE = seq_off + L;
@@ -254,17 +257,17 @@ __device__ __noinline__ Cut warp_sliding_window(const uint8_t *__restrict__ d, u
         // flag masks of the bytes that belong to the line, for its first and its last word
         const uint32_t head_ok = 0x80808080u << (8u * (S0 & 3u));
         const uint32_t tail_ok = (SE & 3u) ? 0x80808080u >> (8u * (4u - (SE & 3u))) : 0x80808080u;
-        for (uint32_t w0 = 0; w0 < nwords && pn < 0; w0 += 128) {
-            uint32_t v[4];
+        for (uint32_t w0 = 0; w0 < nwords && pn < 0; w0 += 32u * kNScanU) {
+            uint32_t v[kNScanU];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kNScanU; ++u) {
                 const uint32_t idx = w0 + 32u * u + (uint32_t)lane;
                 v[u] = idx < nwords ? W[wa + idx] : 0u;
             }
             // a round without any n / N (nearly all of them) is one vote
-            uint32_t hn[4], hN[4], any = 0;
+            uint32_t hn[kNScanU], hN[kNScanU], any = 0;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kNScanU; ++u) {
                 const uint32_t idx = w0 + 32u * u + (uint32_t)lane;
                 uint32_t okf = 0x80808080u;
                 okf = idx == 0u ? okf & head_ok : okf;
@@ -277,7 +280,7 @@ __device__ __noinline__ Cut warp_sliding_window(const uint8_t *__restrict__ d, u
             }
             if (!__any_sync(0xffffffffu, any != 0)) continue;
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < kNScanU; ++u) {
                 const uint32_t fn = flags_to_nibble(hn[u]);
                 const uint32_t fN = flags_to_nibble(hN[u]);
                 const uint32_t mn = __ballot_sync(0xffffffffu, fn != 0);

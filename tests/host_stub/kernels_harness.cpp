@@ -137,7 +137,7 @@ void run_general(const sk::DevInput di[2], int n_inputs, const sk::DevParams &P,
                      sk::k2_trim_route<false>(di[0], di[1], P, ctl, desc[0], desc[1], st2, k2_cap, epoch);
                  });
     if (getenv("KH_K2_SPLIT")) {   // the two-kernel form capi.cu uses for batches of long records
-        const uint32_t upw = atoi(getenv("KH_K2_SPLIT")) >= 32 ? 32u : sk::kK2LongUnitsPerWarp;   // as capi.cu: 2 for long records
+        const uint32_t upw = atoi(getenv("KH_K2_SPLIT")) >= 32 ? 32u : sk::kK2aLongUnitsPerTicket;   // as capi.cu: one for long records
         simt::launch(dim3(ctas), dim3(sk::kK2Threads), [&] { sk::k2_trim_only(di[0], di[1], P, ctl, desc[0], desc[1], upw); });
         simt::launch(dim3((unsigned)std::min<uint64_t>(ctas, tiles)), dim3(sk::kK2Threads),
                      [&] { sk::k2_trim_route<true>(di[0], di[1], P, ctl, desc[0], desc[1], st2, k2_cap, epoch); });

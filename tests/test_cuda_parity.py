@@ -6,6 +6,7 @@
 * batch-size invariance and the early-upload (pipelined) submit path.
 Bar: bit-exact (this path is byte/integer work).
 """
+import os
 import re
 
 import numpy as np
@@ -130,6 +131,9 @@ def _random_fastq(rng, n, lmax, qualtype, lower_n=True, plus_name=True):
     return out
 
 
+# SICKLE_B200_SOAK_SEED=<n>: the seeded random tests below draw other inputs (profiles/gpu_soak.sh loops over seeds)
+SOAK = [int(os.environ["SICKLE_B200_SOAK_SEED"])] if os.environ.get("SICKLE_B200_SOAK_SEED") else []
+
 FLAGSETS = [dict(q=20, l=20, x=False, n=False), dict(q=30, l=5, x=True, n=False), dict(q=10, l=0, x=False, n=True),
             dict(q=25, l=1, x=True, n=True), dict(q=0, l=0, x=False, n=False), dict(q=41, l=30, x=False, n=False)]
 
@@ -137,7 +141,7 @@ FLAGSETS = [dict(q=20, l=20, x=False, n=False), dict(q=30, l=5, x=True, n=False)
 @pytest.mark.parametrize("qualtype", ["sanger", "illumina", "solexa"])
 @pytest.mark.parametrize("lmax", [12, 70, 400, 3000])
 def test_random_se_vs_oracle(capi, qualtype, lmax, kernel_path):
-    rng = np.random.default_rng([1, lmax, len(qualtype)])
+    rng = np.random.default_rng([1, lmax, len(qualtype)] + SOAK)
     recs = _random_fastq(rng, 3000 if lmax <= 400 else 300, lmax, qualtype)
     data = b"".join(recs)
     for fl in FLAGSETS:
@@ -152,7 +156,7 @@ def test_random_se_vs_oracle(capi, qualtype, lmax, kernel_path):
 
 @pytest.mark.parametrize("mode_name", ["pe2", "pei", "pei_nosingles", "peiM"])
 def test_random_pe_vs_oracle(capi, mode_name, kernel_path):
-    rng = np.random.default_rng([2, len(mode_name)])
+    rng = np.random.default_rng([2, len(mode_name)] + SOAK)
     a = _random_fastq(rng, 2500, 200, "sanger")
     b = _random_fastq(rng, 2500, 120, "sanger")
     has_singles = mode_name != "pei_nosingles"
@@ -179,7 +183,7 @@ def test_random_pe_vs_oracle(capi, mode_name, kernel_path):
 @pytest.mark.parametrize("threads", [2, 3, 7])
 def test_emulated_thread_order_vs_oracle(capi, threads):
     """-a N output order (queue dealing inside reference batches), SE and PE."""
-    rng = np.random.default_rng([3, threads])
+    rng = np.random.default_rng([3, threads] + SOAK)
     data = b"".join(_random_fastq(rng, 4001, 90, "sanger"))
     from sickle_b200 import runner
 
@@ -335,7 +339,7 @@ def test_fuzzed_inputs_vs_oracle(capi, kernel_path):
     counters as the oracle, or the same first data error (kind, record, position, byte)."""
     from sickle_b200 import runner
 
-    rng = np.random.default_rng(20260101)
+    rng = np.random.default_rng([20260101] + SOAK)
     n_ok = n_err = 0
     for case in range(600):
         qualtype = ["sanger", "illumina", "solexa"][case % 3]
