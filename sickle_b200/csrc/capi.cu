@@ -91,6 +91,7 @@ struct Slot {
     unsigned long long *d_status_k2 = nullptr;
     unsigned long long *d_status_f = nullptr;   // fused: [3][fused_tiles_cap] (newlines, main, singles); two files: [2 + 4]
     unsigned long long *d_verdict[2] = {nullptr, nullptr};   // fused, two files: one 8-byte entry per record and file
+    uint8_t *d_nlsave[2] = {nullptr, nullptr};               // fused, two files: PASS 1's newline positions, kFNlSlot bytes per tile
     sk::Control *d_ctl = nullptr;
     sk::DevResult *d_res = nullptr;
     sk::DevResult *h_res = nullptr;
@@ -173,6 +174,7 @@ void free_slot(Slot &s) {
     if (s.d_status_k2) cudaFree(s.d_status_k2);
     if (s.d_status_f) cudaFree(s.d_status_f);
     for (auto &v : s.d_verdict) if (v) cudaFree(v);
+    for (auto &v : s.d_nlsave) if (v) cudaFree(v);
     if (s.d_ctl) cudaFree(s.d_ctl);
     if (s.d_res) cudaFree(s.d_res);
     if (s.h_res) cudaFreeHost(s.h_res);
@@ -214,6 +216,7 @@ int alloc_slot(sk_ctx *c, Slot &s, bool host_buffers) {
         SK_CUDA(cudaMemset(s.d_status_f, 0, (size_t)c->fused_tiles_cap * 8 * chains * sk::kWideStatusStride));
         if (c->n_inputs == 2)
             for (auto &v : s.d_verdict) SK_CUDA(cudaMalloc((void **)&v, (size_t)c->verdict_cap * 8));
+            for (auto &v : s.d_nlsave) SK_CUDA(cudaMalloc((void **)&v, (size_t)c->fused_tiles_cap * sk::kFNlSlot));
     }
     if (host_buffers) {
         // stream capacities: an output stream never exceeds the bytes of the inputs feeding it
@@ -344,12 +347,14 @@ int launch_fused_two_ch(sk_ctx *c, Slot &s, const BatchArgs &a, const sk::DevInp
         const int grid = tiles < (uint32_t)full ? (int)tiles : full;
         const int grid1 = tiles < (uint32_t)c->fused_grid_pass1[(CH - 3) / 2] ? (int)tiles : c->fused_grid_pass1[(CH - 3) / 2];
         sk::kf_fused<CH, 1><<<grid1, sk::kFThreads, Cfg::kSmemPass1, st>>>(di[0], c->dev, s.d_ctl, op, s.d_status_f, s.d_status_f + 2 * (size_t)stride,
-                                                                    stride, tiles, s.epoch, di[1], tiles_b, s.d_verdict[0], s.d_verdict[1], c->verdict_cap);
+                                                                    stride, tiles, s.epoch, di[1], tiles_b, s.d_verdict[0], s.d_verdict[1], c->verdict_cap,
+                                                                    s.d_nlsave[0], s.d_nlsave[1]);
         SK_DEBUG_SYNC(st, "kf_fused pass 1");
         sk::kf2_between<<<1, 32, 0, st>>>(s.d_ctl);
         if (int rc = next_epoch(c, s, st)) return rc;   // the newline chains are walked again
         sk::kf_fused<CH, 2><<<grid, sk::kFThreads, Cfg::kSmemTwoFile, st>>>(di[0], c->dev, s.d_ctl, op, s.d_status_f, s.d_status_f + 2 * (size_t)stride,
-                                                                           stride, tiles, s.epoch, di[1], tiles_b, s.d_verdict[0], s.d_verdict[1], c->verdict_cap);
+                                                                           stride, tiles, s.epoch, di[1], tiles_b, s.d_verdict[0], s.d_verdict[1], c->verdict_cap,
+                                                                    s.d_nlsave[0], s.d_nlsave[1]);
         SK_DEBUG_SYNC(st, "kf_fused pass 2");
         s.launches += 3;
     }

@@ -83,6 +83,10 @@ __device__ unsigned long long g_phase_cycles[12];
 constexpr int kFThreads = 256;
 constexpr int kFTileThreads = 224;   // 7 warps own tile bytes, the 8th warp scans the halo
 constexpr int kFMaxNl = 1024;        // newline positions per region (2 KB; also holds 128 record descriptors)
+// Two files: PASS 1 leaves every tile's newline positions and {global line number, newlines in the tile, newlines
+// in the region} in global memory, kFNlSlot bytes per tile, and PASS 2 fetches them with the tile's bytes instead of
+// finding the newlines again (no masks, no scan, no position stores, no look-back #1).
+constexpr int kFNlSlot = kFMaxNl * 2 + 16;
 constexpr uint32_t kTicketPoison = 0x40000000u;   // or-ed into the ticket counter by a tile that gives the batch up (tiles < 2^30)
 
 template <int CH>
@@ -95,7 +99,7 @@ struct FusedCfg {
     static constexpr int kOutBytes = kTile + 768 + 96;   // a tile of output + the last record's overhang + phase shifts
     // CH = 7: 56,768 B -> four CTAs per SM (4 x (56,768 + 248 static + 1,024 reserved) <= 232,448)
     static constexpr size_t kSmem = (size_t)kInBytes + kOutBytes + kFMaxNl * 2;
-    static constexpr size_t kSmemTwoFile = kSmem + 128 * 8;   // PASS 2: + one (offset, length) pair per record: its own singles
+    static constexpr size_t kSmemTwoFile = kSmem + 16 + 128 * 8;   // PASS 2: + the tile's saved line numbers, + one (offset, length) pair per record: its own singles
     static constexpr size_t kSmemPass1 = (size_t)kInBytes + kFMaxNl * 2;   // PASS 1 stages nothing: four CTAs per SM
     static constexpr int kCtasPerSmPass1 = (int)(232448 / (kSmemPass1 + 1024 + 256)) > SK_MAX_CTAS ? SK_MAX_CTAS : (int)(232448 / (kSmemPass1 + 1024 + 256));
     // CTAs per SM by shared memory (232,448 B per SM, 1,024 B reserved per CTA); also the register budget
@@ -177,14 +181,16 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
          uint32_t status_stride, uint32_t num_tiles, uint32_t epoch,
          // two files only (PASS 1, 2): the second input, its share of the tiles, the verdict tables
          DevInput in_b = DevInput(), uint32_t tiles_b = 0, unsigned long long *__restrict__ tab_a = nullptr,
-         unsigned long long *__restrict__ tab_b = nullptr, uint32_t tab_cap = 0) {
+         unsigned long long *__restrict__ tab_b = nullptr, uint32_t tab_cap = 0,
+         uint8_t *__restrict__ nlsave_a = nullptr, uint8_t *__restrict__ nlsave_b = nullptr /* kFNlSlot bytes per tile */) {
     using Cfg = FusedCfg<CH>;
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *s_in = smem;
     uint8_t *s_out = smem + Cfg::kInBytes;
     uint16_t *s_nl = reinterpret_cast<uint16_t *>(smem + Cfg::kInBytes + (PASS == 1 ? 0 : Cfg::kOutBytes));
     uint4 *s_desc = reinterpret_cast<uint4 *>(s_nl);   // S7/S8a record descriptors alias the newline positions
-    uint2 *s_single = reinterpret_cast<uint2 *>(smem + Cfg::kSmem);   // PASS 2 only (Cfg::kSmemTwoFile)
+    const uint4 *s_meta = reinterpret_cast<const uint4 *>(smem + Cfg::kSmem);   // PASS 2 only: lands right behind s_nl
+    uint2 *s_single = reinterpret_cast<uint2 *>(smem + Cfg::kSmem + 16);   // PASS 2 only (Cfg::kSmemTwoFile)
     __shared__ uint32_t s_tile;
     __shared__ uint32_t warp_tot[kFThreads / 32];
     __shared__ uint32_t warp_tot2[kFThreads / 32][2];
@@ -274,12 +280,19 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&s_mbar);
                 const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_in);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // S8a's reads of s_in come first
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(cp_chunks * 16u) : "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(cp_chunks * 16u + (PASS == 2 ? (uint32_t)kFNlSlot : 0u)) : "memory");
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"(dst), "l"(in.data + t0), "r"(cp_chunks * 16u), "r"(mb) : "memory");
+                if (PASS == 2)   // the tile's newline positions and line numbers, as PASS 1 left them
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"((uint32_t)__cvta_generic_to_shared(s_nl)), "l"((fsel ? nlsave_b : nlsave_a) + (size_t)tile * kFNlSlot),
+                                   "r"((uint32_t)kFNlSlot), "r"(mb) : "memory");
             }
 #else   // host build of the kernels (tests/host_stub/simt): the bulk copy is a memcpy by thread 0
-            if (tid == 0) memcpy(s_in, in.data + t0, (size_t)cp_chunks * 16u);
+            if (tid == 0) {
+                memcpy(s_in, in.data + t0, (size_t)cp_chunks * 16u);
+                if (PASS == 2) memcpy(s_nl, (fsel ? nlsave_b : nlsave_a) + (size_t)tile * kFNlSlot, (size_t)kFNlSlot);
+            }
 #endif
             for (uint32_t c = cp_chunks + tid; c < (uint32_t)(Cfg::kRegion / 16); c += kFThreads)
                 reinterpret_cast<uint4 *>(s_in)[c] = make_uint4(0, 0, 0, 0);
@@ -307,10 +320,14 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             __syncthreads();
             SK_TICK(1);   // S1 load
 
+            if (PASS == 2) {   // found, counted and numbered by PASS 1
+                const uint4 m = *s_meta;
+                c_t = m.y; n_all = m.z;
+            }
             // ---- S2: newline masks of this thread's CH*16 contiguous bytes
 #pragma unroll
             for (int k = 0; k < (CH + 1) / 2; ++k) mw[k] = 0;
-            {
+            if (PASS != 2) {
                 // only the first tile (bytes before the batch start) and the tiles touching the end of
                 // the batch have bytes to mask off
                 const bool edge = tile == 0 || (unsigned long long)t0 + Cfg::kRegion > in.nbytes;
@@ -328,23 +345,23 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                     mw[k >> 1] |= mk << (16 * (k & 1));
                 }
             }
+            if (PASS != 2) {
 #pragma unroll
-            for (int k = 0; k < (CH + 1) / 2; ++k) cnt += __popc(mw[k]);
-            // ---- S3: ranks
-            incl = warp_incl_scan(cnt, lane);
-            if (lane == 31) warp_tot[wid] = incl;
-            __syncthreads();
-            SK_TICK(2);   // S2 masks + warp scan
+                for (int k = 0; k < (CH + 1) / 2; ++k) cnt += __popc(mw[k]);
+                // ---- S3: ranks
+                incl = warp_incl_scan(cnt, lane);
+                if (lane == 31) warp_tot[wid] = incl;
+                __syncthreads();
+                SK_TICK(2);   // S2 masks + warp scan
 #pragma unroll
-            for (int w = 0; w < kFThreads / 32; ++w) {
-                const uint32_t t = warp_tot[w];
-                if (w < wid) wbase += t;
-                if (w < kFTileThreads / 32) c_t += t;
-                n_all += t;
-            }
-            nl_overflow = n_all > (uint32_t)kFMaxNl;
-            // the tile's newline count goes out before anything else is done with the tile
-            {
+                for (int w = 0; w < kFThreads / 32; ++w) {
+                    const uint32_t t = warp_tot[w];
+                    if (w < wid) wbase += t;
+                    if (w < kFTileThreads / 32) c_t += t;
+                    n_all += t;
+                }
+                nl_overflow = n_all > (uint32_t)kFMaxNl;
+                // the tile's newline count goes out before anything else is done with the tile
                 const unsigned long long agg[2] = {c_t, 0};
                 block_publish(st_nl, tile, agg, 1, epoch, tid);
             }
@@ -361,7 +378,7 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             break;
         }
 
-        if (!nl_overflow) {
+        if (PASS != 2 && !nl_overflow) {
             // a thread's 16*CH bytes hold about two newlines: one short loop per 32-byte mask word (most
             // words have none, and a warp leaves a word's loop as soon as none of its lanes has one left)
             uint16_t *__restrict__ nl_out = s_nl + (wbase + incl - cnt);
@@ -376,7 +393,9 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         }
         // ---- S4: global line number of the tile
         uint32_t G;
-        {
+        if (PASS == 2) {
+            G = s_meta->x;
+        } else {
             const unsigned long long agg[2] = {c_t, 0};
             unsigned long long ex[2];
 #ifdef SK_KO_LB1
@@ -388,8 +407,14 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             G = (uint32_t)ex[0];
 #endif
         }
-        __syncthreads();   // newline positions visible to every thread
+        if (PASS != 2) __syncthreads();   // newline positions visible to every thread (PASS 2: they came with the tile)
         SK_TICK(3);   // S3 positions + S4 look-back #1
+        if (PASS == 1 && !nl_overflow) {   // for PASS 2: positions (whole 16-byte chunks) and the three numbers
+            uint4 *__restrict__ slot = reinterpret_cast<uint4 *>((fsel ? nlsave_b : nlsave_a) + (size_t)tile * kFNlSlot);
+            const uint32_t nq = (2u * n_all + 15u) >> 4;
+            for (uint32_t c = (uint32_t)tid; c < nq; c += kFThreads) slot[c] = reinterpret_cast<const uint4 *>(s_nl)[c];
+            if (tid == 0) slot[kFMaxNl * 2 / 16] = make_uint4(G, c_t, n_all, 0u);
+        }
 
         // ---- S5: units owned by this tile.  Newline j (j < c_t) is global newline G+j; the line
         // after it is line G+j+1; a unit starts at every line that is a multiple of lpu.  Tile 0

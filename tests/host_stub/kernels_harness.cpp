@@ -100,18 +100,19 @@ void run_fused_two(const sk::DevInput di[2], const sk::DevParams &P, sk::Control
     unsigned long long *st = aligned_zero<unsigned long long>((size_t)stride * 6);
     const uint32_t tab_cap = (uint32_t)(std::max(di[0].nbytes, di[1].nbytes) / 32 + 64);
     unsigned long long *tab[2] = {aligned_zero<unsigned long long>(tab_cap), aligned_zero<unsigned long long>(tab_cap)};
+    uint8_t *nls[2] = {aligned_zero<uint8_t>((size_t)cap * sk::kFNlSlot), aligned_zero<uint8_t>((size_t)cap * sk::kFNlSlot)};   // sized as capi.cu sizes them
     if (tiles) {
         const unsigned grid = std::min<unsigned>(ctas, tiles);
         simt::launch(dim3(grid), dim3(sk::kFThreads), [&] {
-            sk::kf_fused<CH, 1>(di[0], P, ctl, op, st, st + 2 * (size_t)stride, stride, tiles, 5u, di[1], tb, tab[0], tab[1], tab_cap);
+            sk::kf_fused<CH, 1>(di[0], P, ctl, op, st, st + 2 * (size_t)stride, stride, tiles, 5u, di[1], tb, tab[0], tab[1], tab_cap, nls[0], nls[1]);
         });
         simt::launch(dim3(1), dim3(32), [&] { sk::kf2_between(ctl); });
         simt::launch(dim3(grid), dim3(sk::kFThreads), [&] {
-            sk::kf_fused<CH, 2>(di[0], P, ctl, op, st, st + 2 * (size_t)stride, stride, tiles, 6u, di[1], tb, tab[0], tab[1], tab_cap);
+            sk::kf_fused<CH, 2>(di[0], P, ctl, op, st, st + 2 * (size_t)stride, stride, tiles, 6u, di[1], tb, tab[0], tab[1], tab_cap, nls[0], nls[1]);
         });
     }
     simt::launch(dim3(1), dim3(32), [&] { sk::kf2_finalize(ctl, res); });
-    free(st); free(tab[0]); free(tab[1]);
+    free(st); free(tab[0]); free(tab[1]); free(nls[0]); free(nls[1]);
 }
 
 void run_general(const sk::DevInput di[2], int n_inputs, const sk::DevParams &P, sk::Control *ctl, const sk::OutPtrs &op, unsigned ctas,

@@ -314,7 +314,7 @@ def _mutate(rng, data):
     if kind == 2:
         k = int(rng.integers(0, len(lines)))
         return b"\n".join(lines[:k] + [b""] + lines[k:])       # a blank line
-    if kind == 3:
+    if kind == 3 and len(lines) > 1:
         k = int(rng.integers(0, len(lines) - 1))
         return b"\n".join(lines[:k] + [lines[k]] + lines[k:])  # a doubled line
     if kind == 4:
