@@ -124,6 +124,7 @@ struct sk_ctx {
     bool host_buffers = false;
     // path selection
     bool fused_eligible = false;   // mode / order the fused kernel supports
+    bool hybrid_eligible = false;  // -a N on one input: the fused kernel's index + verdict pass, then k2_trim_route<true> and K3
     int fused_ch = 7;              // 16-byte chunks per thread (3, 5, 7, 9 or 11): the tile size in use
     bool fused_ch_fixed = false;   // SICKLE_B200_FUSED_CH given: no adaptation
     int fused_ch_max = 9;          // lowered after a failed fused batch, raised again after a streak of good ones
@@ -210,13 +211,14 @@ int alloc_slot(sk_ctx *c, Slot &s, bool host_buffers) {
     }
     SK_CUDA(cudaMalloc((void **)&s.d_status_k2, (size_t)c->k2_tiles_cap * 8 * sk::kMaxStreams));
     SK_CUDA(cudaMemset(s.d_status_k2, 0, (size_t)c->k2_tiles_cap * 8 * sk::kMaxStreams));
-    if (c->fused_eligible) {
+    if (c->fused_eligible || c->hybrid_eligible) {
         const size_t chains = c->n_inputs == 2 ? 6 : 3;   // two files: a newline chain and two output chains per file
         SK_CUDA(cudaMalloc((void **)&s.d_status_f, (size_t)c->fused_tiles_cap * 8 * chains * sk::kWideStatusStride));
         SK_CUDA(cudaMemset(s.d_status_f, 0, (size_t)c->fused_tiles_cap * 8 * chains * sk::kWideStatusStride));
-        if (c->n_inputs == 2)
+        if (c->n_inputs == 2) {
             for (auto &v : s.d_verdict) SK_CUDA(cudaMalloc((void **)&v, (size_t)c->verdict_cap * 8));
             for (auto &v : s.d_nlsave) SK_CUDA(cudaMalloc((void **)&v, (size_t)c->fused_tiles_cap * sk::kFNlSlot));
+        }
     }
     if (host_buffers) {
         // stream capacities: an output stream never exceeds the bytes of the inputs feeding it
@@ -380,6 +382,13 @@ int setup_fused_ch(sk_ctx *c) {
         if (p2 < 1) { set_err("fused kernel does not fit on this device"); return SK_E_CUDA; }
         if (p2 < per_sm) per_sm = p2;   // one grid size for both passes
     }
+    if constexpr (CH != 11) if (c->hybrid_eligible) {   // the index + verdict pass stages nothing, like PASS 1
+        SK_CUDA(cudaFuncSetAttribute(sk::kf_fused<CH, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemPass1));
+        int p3 = 0;
+        SK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p3, sk::kf_fused<CH, 3>, sk::kFThreads, Cfg::kSmemPass1));
+        if (p3 < 1) { set_err("fused kernel does not fit on this device"); return SK_E_CUDA; }
+        c->fused_grid_pass1[(CH - 3) / 2] = p3 * c->sm_count;
+    }
     c->fused_grid_ch[(CH - 3) / 2] = per_sm * c->sm_count;
     return SK_OK;
 }
@@ -401,7 +410,7 @@ int setup_fused(sk_ctx *c) {
 uint32_t fused_tile_bytes(int ch) { return (uint32_t)sk::kFTileThreads * 16u * (uint32_t)ch; }
 
 void adapt_fused(sk_ctx *c, const sk::DevResult &r, bool failed) {
-    if (!c->fused_eligible || c->fused_ch_fixed) return;
+    if (!(c->fused_eligible || c->hybrid_eligible) || c->fused_ch_fixed) return;
     if (failed) {
         c->fused_ok_streak = 0;
         if ((r.index_overflow & 8u) && c->fused_ch > 3) {   // too many records per tile: smaller tiles at once, no back-off
@@ -463,11 +472,69 @@ int launch_fused(sk_ctx *c, Slot &s, const BatchArgs &a) {
     return SK_OK;
 }
 
+// -a N on one input: the single-pass kernel's S1-S6 as an index + verdict pass (kf_fused<CH, 3>: line index and
+// {keep, five, kept bases} per record, what K1 and k2_trim_only leave behind, out of one read of the input), then the
+// general path's k2_trim_route<true> (reference order, scan), K3 and summary.  The pass gives a batch up exactly
+// where the single-pass kernel does; the batch then runs again on K1/K2/K3.
+template <int CH>
+int launch_index_pass_ch(sk_ctx *c, Slot &s, const BatchArgs &a, const sk::DevInput di[2], const sk::OutPtrs &op) {
+    using Cfg = sk::FusedCfg<CH>;
+    const uint32_t tiles = (uint32_t)((a.n[0] + Cfg::kTile - 1) / Cfg::kTile);
+    const uint32_t stride = c->fused_tiles_cap * sk::kWideStatusStride;
+    if (tiles) {
+        const int full = c->fused_grid_pass1[(CH - 3) / 2];
+        const int grid = tiles < (uint32_t)full ? (int)tiles : full;
+        sk::kf_fused<CH, 3><<<grid, sk::kFThreads, Cfg::kSmemPass1, a.st>>>(di[0], c->dev, s.d_ctl, op, s.d_status_f, s.d_status_f + (size_t)stride, stride,
+                                                                         tiles, s.epoch, sk::DevInput(), 0u, nullptr, nullptr,
+                                                                         (uint32_t)(c->line_cap / 4 + 1), nullptr, nullptr, s.d_desc[0]);
+        s.launches++;
+        SK_DEBUG_SYNC(a.st, "kf_fused index pass");
+    }
+    return SK_OK;
+}
+
+int launch_hybrid(sk_ctx *c, Slot &s, const BatchArgs &a) {
+    cudaStream_t st = a.st;
+    if (int rc = next_epoch(c, s, st)) return rc;
+    sk::DevInput di[2];
+    sk::OutPtrs op;
+    make_inputs(c, s, a, di, op);
+    s.launches = 0;
+    SK_CUDA(cudaEventRecord(s.ev_begin, st));
+    int rc;
+    switch (c->fused_ch) {
+        case 3: rc = launch_index_pass_ch<3>(c, s, a, di, op); break;
+        case 5: rc = launch_index_pass_ch<5>(c, s, a, di, op); break;
+        case 9: case 11: rc = launch_index_pass_ch<9>(c, s, a, di, op); break;
+        default: rc = launch_index_pass_ch<7>(c, s, a, di, op); break;
+    }
+    if (rc) return rc;
+    SK_CUDA(cudaEventRecord(s.ev_stage[0], st));
+    const int resident = c->sm_count * 8;
+    const uint64_t max_units = a.n[0] / 4 + 1;
+    const uint64_t tiles = (max_units + sk::kK2UnitsPerTile - 1) / sk::kK2UnitsPerTile;
+    const int grid = tiles < (uint64_t)resident ? (int)tiles : resident;
+    sk::k2_trim_route<true><<<grid, sk::kK2Threads, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, s.d_desc[0], s.d_desc[1], s.d_status_k2, c->k2_tiles_cap, s.epoch);
+    SK_DEBUG_SYNC(st, "k2_trim_route");
+    SK_CUDA(cudaEventRecord(s.ev_stage[1], st));
+    sk::k3_emit<<<resident, sk::kK3Threads, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, s.d_desc[0], s.d_desc[1], op);
+    SK_DEBUG_SYNC(st, "k3_emit");
+    SK_CUDA(cudaEventRecord(s.ev_stage[2], st));
+    sk::k_finalize<<<1, 32, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, op, s.d_res);
+    s.launches += 3;
+    SK_CUDA(cudaEventRecord(s.ev_end, st));
+    SK_CUDA(cudaGetLastError());
+    s.last_fused = true;
+    c->n_fused++;
+    return SK_OK;
+}
+
 int launch_batch(sk_ctx *c, Slot &s, const BatchArgs &a) {
     s.last = a;
     // (the back-off is counted down where results are read, rerun_if_needed: a caller that queues batches
     //  without looking at their summaries never learns that a batch failed, so it must not drift back either)
     if (c->fused_eligible && c->fused_backoff == 0) return launch_fused(c, s, a);
+    if (c->hybrid_eligible && c->fused_backoff == 0) return launch_hybrid(c, s, a);
     return launch_general(c, s, a);
 }
 
@@ -592,11 +659,12 @@ sk_ctx *sk_create(int device, uint64_t slot_bytes, int n_slots, const sk_params 
     c->fused_tiles_cap = (uint32_t)(c->slot_bytes / kFusedMinTile) + 2;
     // SICKLE_B200_PATH = auto (default) | general | fused ; SICKLE_B200_FUSED_CH = 5 | 7 | 9 | 11
     c->fused_eligible = dp.emu_threads == 1;
+    c->hybrid_eligible = dp.emu_threads > 1 && c->n_inputs == 1;
     c->verdict_cap = (uint32_t)(c->slot_bytes / 32 + 64);   // records of 32 bytes and more (shorter ones: general path)
     if (const char *e = getenv("SICKLE_B200_K2_SPLIT")) c->k2_split = atoi(e) != 0;
-    if (const char *e = getenv("SICKLE_B200_PATH")) { if (!strcmp(e, "general")) c->fused_eligible = false; }
+    if (const char *e = getenv("SICKLE_B200_PATH")) { if (!strcmp(e, "general")) c->fused_eligible = c->hybrid_eligible = false; }
     if (const char *e = getenv("SICKLE_B200_FUSED_CH")) { c->fused_ch = atoi(e); c->fused_ch_fixed = true; }
-    if (c->fused_eligible && setup_fused(c) != SK_OK) { delete c; return nullptr; }
+    if ((c->fused_eligible || c->hybrid_eligible) && setup_fused(c) != SK_OK) { delete c; return nullptr; }
     c->host_buffers = n_slots > 0;
     const int ns = n_slots > 0 ? n_slots : 1;
     c->slots.resize(ns);

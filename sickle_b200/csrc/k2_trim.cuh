@@ -424,6 +424,7 @@ k2_trim_route(DevInput in0, DevInput in1, DevParams P, Control *__restrict__ ctl
     __shared__ uint32_t s_cnt[kK2Threads / 32][6];
 
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (kPre && ctl->fast_fail) return;   // the index + verdict pass (kf_fused<CH, 3>) gave the batch up: nothing here is valid
     const Geometry g = batch_geometry(ctl, P);
     // tile geometry (block-uniform, derived from what K1 counted)
     const uint32_t nrec_all = g.nrec0 + g.nrec1;

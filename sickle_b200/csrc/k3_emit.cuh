@@ -200,7 +200,7 @@ k3_emit(DevInput in0, DevInput in1, DevParams P, const Control *__restrict__ ctl
         const RecDesc *__restrict__ desc1, OutPtrs outs) {
     const int lane = threadIdx.x & 31;
     const Geometry g = batch_geometry(ctl, P);
-    if (ctl->err_key != kNoError) return;  // outputs of a failing batch are never used
+    if (ctl->err_key != kNoError || ctl->fast_fail) return;  // outputs of a failing batch are never used (fast_fail: the index pass gave up)
 #pragma unroll
     for (int s = 0; s < kMaxStreams; ++s)
         if (ctl->out_bytes[s] > outs.cap[s]) return;  // reported by finalize as a capacity error
@@ -304,7 +304,8 @@ __global__ void k_finalize(DevInput in0, DevInput in1, DevParams P, Control *__r
     r.consumed[0] = g.nrec0 ? (unsigned long long)in0.line_end[4ull * g.nrec0 - 1] + 1ull : 0ull;
     r.consumed[1] = g.nrec1 ? (unsigned long long)in1.line_end[4ull * g.nrec1 - 1] + 1ull : 0ull;
     for (int k = 0; k < 8; ++k) r.counters[k] = (long long)ctl->counters[k];
-    r.index_overflow = ctl->index_overflow;
+    // (fast_fail: the single-pass kernel's index + verdict pass in front of K2/K3 gave the batch up -- bits 2, 3 as in kf_finalize)
+    r.index_overflow = ctl->index_overflow | (ctl->fast_fail ? 4u : 0u) | ((ctl->fast_fail & 2u) ? 8u : 0u);
     for (int s = 0; s < kMaxStreams; ++s)
         if (ctl->out_bytes[s] > outs.cap[s]) r.index_overflow |= 2u;
     r.pad = 0;

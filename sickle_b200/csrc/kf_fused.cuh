@@ -175,19 +175,22 @@ __device__ __forceinline__ unsigned long long pack_verdict(bool keep, uint32_t f
 }
 
 template <int CH, int PASS = 0>
-__global__ void __launch_bounds__(kFThreads, PASS == 1 ? FusedCfg<CH>::kCtasPerSmPass1 : FusedCfg<CH>::kCtasPerSm)
+__global__ void __launch_bounds__(kFThreads, (PASS == 1 || PASS == 3) ? FusedCfg<CH>::kCtasPerSmPass1 : FusedCfg<CH>::kCtasPerSm)
 kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
          unsigned long long *__restrict__ status_nl_all, unsigned long long *__restrict__ status_out_all /* [2][stride] per file */,
          uint32_t status_stride, uint32_t num_tiles, uint32_t epoch,
          // two files only (PASS 1, 2): the second input, its share of the tiles, the verdict tables
          DevInput in_b = DevInput(), uint32_t tiles_b = 0, unsigned long long *__restrict__ tab_a = nullptr,
          unsigned long long *__restrict__ tab_b = nullptr, uint32_t tab_cap = 0,
-         uint8_t *__restrict__ nlsave_a = nullptr, uint8_t *__restrict__ nlsave_b = nullptr /* kFNlSlot bytes per tile */) {
+         uint8_t *__restrict__ nlsave_a = nullptr, uint8_t *__restrict__ nlsave_b = nullptr /* kFNlSlot bytes per tile */,
+         // PASS 3 only: the general path's descriptor table (tab_cap entries); the line index goes to in_a.line_end
+         RecDesc *__restrict__ desc_out = nullptr) {
     using Cfg = FusedCfg<CH>;
+    constexpr bool kNoEmit = PASS == 1 || PASS == 3;   // these passes stage and write no records
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *s_in = smem;
     uint8_t *s_out = smem + Cfg::kInBytes;
-    uint16_t *s_nl = reinterpret_cast<uint16_t *>(smem + Cfg::kInBytes + (PASS == 1 ? 0 : Cfg::kOutBytes));
+    uint16_t *s_nl = reinterpret_cast<uint16_t *>(smem + Cfg::kInBytes + (kNoEmit ? 0 : Cfg::kOutBytes));
     uint4 *s_desc = reinterpret_cast<uint4 *>(s_nl);   // S7/S8a record descriptors alias the newline positions
     const uint4 *s_meta = reinterpret_cast<const uint4 *>(smem + Cfg::kSmem);   // PASS 2 only: lands right behind s_nl
     uint2 *s_single = reinterpret_cast<uint2 *>(smem + Cfg::kSmem + 16);   // PASS 2 only (Cfg::kSmemTwoFile)
@@ -298,7 +301,7 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 reinterpret_cast<uint4 *>(s_in)[c] = make_uint4(0, 0, 0, 0);
             {   // L2 prefetch, one 128-byte line per thread, of the tile one grid-width ahead: in steady
                 // state some CTA (this one, most likely) draws that ticket one tile time from now
-                const unsigned long long nb = ((unsigned long long)tile + (PASS == 0 ? gridDim.x : gridDim.x / 2u)) * Cfg::kTile + (unsigned long long)tid * 128u;
+                const unsigned long long nb = ((unsigned long long)tile + ((PASS == 0 || PASS == 3) ? gridDim.x : gridDim.x / 2u)) * Cfg::kTile + (unsigned long long)tid * 128u;
 #if defined(__CUDACC__)
                 if (tid < Cfg::kTile / 128 && nb < in.nbytes) asm volatile("prefetch.global.L2 [%0];" ::"l"(in.data + nb));
 #else
@@ -409,6 +412,13 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         }
         if (PASS != 2) __syncthreads();   // newline positions visible to every thread (PASS 2: they came with the tile)
         SK_TICK(3);   // S3 positions + S4 look-back #1
+        if (PASS == 3 && !nl_overflow) {   // the general path's line index (K1's output), and the line count with the last tile
+            for (uint32_t j = (uint32_t)tid; j < c_t; j += kFThreads) {
+                if (G + j < in.line_cap) in.line_end[G + j] = t0 + (uint32_t)s_nl[j];
+                else ctl->index_overflow = 1u;
+            }
+            if (tid == 0 && tile == file_tiles - 1u) ctl->nlines[0] = G + c_t;
+        }
         if (PASS == 1 && !nl_overflow) {   // for PASS 2: positions (whole 16-byte chunks) and the three numbers
             uint4 *__restrict__ slot = reinterpret_cast<uint4 *>((fsel ? nlsave_b : nlsave_a) + (size_t)tile * kFNlSlot);
             const uint32_t nq = (2u * n_all + 15u) >> 4;
@@ -504,6 +514,16 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                                                               cut.three >= 0 ? (uint32_t)(cut.three - cut.five) : 0u, fixed1);
             else fail = true;
         }
+        if (PASS == 3 && has_rec && complete && !fail) {   // the verdict, as k2_trim_only leaves it for k2_trim_route<true>
+            if (recno < tab_cap) {
+                RecDesc d;
+                d.dst_off = 0;
+                d.route = cut.three >= 0 ? 1u : 0u;
+                d.five = d.route ? (uint32_t)cut.five : 0u;
+                d.nkeep = d.route ? (uint32_t)(cut.three - cut.five) : 0u;
+                desc_out[recno] = d;
+            } else fail = true;
+        }
         if (fail) s_fail = 1u;
 
         // ---- S7: routing + output sizes
@@ -517,7 +537,7 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         // mate's keep flag: the neighbouring lane (interleaved pairs) or the mate's table entry (two files)
         const bool other = PASS == 2 ? ((mate_verdict >> 48) & 1u) != 0
                                      : (paired && __shfl_xor_sync(0xffffffffu, (int)keep, 1) != 0);
-        if (PASS == 1) {
+        if (kNoEmit) {
             // nothing is emitted in this pass
         } else if (live) {
             if (PASS == 2) {                                        // trim_paired.cpp:543-567, one mate per file
@@ -561,7 +581,7 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 atomicOr(&ctl->tile_counter[3], kTicketPoison);
             }
         }
-        if (PASS == 1) {   // verdicts are in the table: count the file's records, next tile
+        if (kNoEmit) {   // verdicts are in the table: count the file's records, next tile
             const uint32_t m_live1 = __ballot_sync(0xffffffffu, live);
             if (!tile_fail && lane == 0 && m_live1) s_acc[wid][fsel ? 2 : 0] += (uint32_t)__popc(m_live1);
             if (tid == 0) held = atomicAdd(&ctl->tile_counter[3], 1u);
@@ -712,7 +732,7 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
 #pragma unroll
         const bool is_max = tid == 1 || (PASS == 2 && tid == 3);
         for (int w = 0; w < kFThreads / 32; ++w) v = is_max ? max(v, s_acc[w][tid]) : v + s_acc[w][tid];
-        if (v && PASS == 1) {            // records of file 0 (row entry 0) and of file 1 (entry 2)
+        if (v && kNoEmit) {            // records of file 0 (row entry 0) and of file 1 (entry 2)
             if (tid == 0) atomicAdd(&ctl->fast_records2[0], v);
             if (tid == 2) atomicAdd(&ctl->fast_records2[1], v);
         } else if (v && PASS == 2 && tid < 4) {

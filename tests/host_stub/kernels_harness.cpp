@@ -5,7 +5,7 @@
 // consumed bytes and the first data error with the CPU oracle's so_run on the same bytes.
 //
 //   kernels_harness <fastq> <mode 0|2|3 (se, interleaved, -M) or 1 with <fastq2>> <qualtype 1..3> <q> <l> <x> <n>
-//                   <has_singles> <path: fused5|fused7|fused9|fused11|general> <ctas> <first 0..15> [<fastq2>]
+//                   <has_singles> <path: fused3..fused11|index3..index9|general> <ctas> <first 0..15> [<fastq2>]
 // prints one line: "OK ..." / "FASTFAIL ..." (the fused kernel handed the batch to the general path) /
 // "MISMATCH ...", exit 0 / 0 / 1.
 #include <cstdio>
@@ -115,6 +115,34 @@ void run_fused_two(const sk::DevInput di[2], const sk::DevParams &P, sk::Control
     free(st); free(tab[0]); free(tab[1]); free(nls[0]); free(nls[1]);
 }
 
+// -a N on one input, as capi.cu's launch_hybrid does: the single-pass kernel's index + verdict pass, then the general
+// path's routing, K3 and summary
+template <int CH>
+void run_hybrid(const sk::DevInput di[2], const sk::DevParams &P, sk::Control *ctl, const sk::OutPtrs &op, unsigned ctas, sk::DevResult *res) {
+    using Cfg = sk::FusedCfg<CH>;
+    const uint32_t tiles = (uint32_t)((di[0].nbytes + Cfg::kTile - 1) / Cfg::kTile);
+    const uint32_t cap = tiles + 2, stride = cap * sk::kWideStatusStride;
+    unsigned long long *st = aligned_zero<unsigned long long>((size_t)stride * 3);
+    const uint32_t desc_cap = di[0].line_cap / 4 + 1;
+    sk::RecDesc *desc[2] = {aligned_zero<sk::RecDesc>(desc_cap + 1), nullptr};
+    if (tiles) {
+        const unsigned grid = std::min<unsigned>(ctas, tiles);
+        simt::launch(dim3(grid), dim3(sk::kFThreads), [&] {
+            sk::kf_fused<CH, 3>(di[0], P, ctl, op, st, st + (size_t)stride, stride, tiles, 5u, sk::DevInput(), 0u, nullptr, nullptr, desc_cap,
+                                nullptr, nullptr, desc[0]);
+        });
+    }
+    const uint64_t max_units = (uint64_t)di[0].nbytes / 4 + 1;
+    const uint64_t t2 = (max_units + sk::kK2UnitsPerTile - 1) / sk::kK2UnitsPerTile;
+    const uint32_t k2_cap = (uint32_t)t2 + 2;
+    unsigned long long *st2 = aligned_zero<unsigned long long>((size_t)k2_cap * sk::kMaxStreams);
+    simt::launch(dim3((unsigned)std::min<uint64_t>(ctas, t2)), dim3(sk::kK2Threads),
+                 [&] { sk::k2_trim_route<true>(di[0], di[1], P, ctl, desc[0], desc[1], st2, k2_cap, 5u); });
+    simt::launch(dim3(ctas), dim3(sk::kK3Threads), [&] { sk::k3_emit(di[0], di[1], P, ctl, desc[0], desc[1], op); });
+    simt::launch(dim3(1), dim3(32), [&] { sk::k_finalize(di[0], di[1], P, ctl, op, res); });
+    free(st); free(st2); free(desc[0]);
+}
+
 void run_general(const sk::DevInput di[2], int n_inputs, const sk::DevParams &P, sk::Control *ctl, const sk::OutPtrs &op, unsigned ctas,
                  sk::DevResult *res) {
     const uint32_t epoch = 9;
@@ -206,6 +234,14 @@ int main(int argc, char **argv) {
         else if (ch == 7) run_fused<7>(di[0], P, ctl, op, ctas, &res);
         else if (ch == 9) run_fused<9>(di[0], P, ctl, op, ctas, &res);
         else run_fused<11>(di[0], P, ctl, op, ctas, &res);
+        if (res.index_overflow & 4u) { printf("FASTFAIL too_many_records=%d\n", (res.index_overflow & 8u) ? 1 : 0); return 0; }
+    } else if (path.rfind("index", 0) == 0) {
+        const int ch = atoi(path.c_str() + 5);
+        if (mode == 1) return 2;
+        if (ch == 3) run_hybrid<3>(di, P, ctl, op, ctas, &res);
+        else if (ch == 5) run_hybrid<5>(di, P, ctl, op, ctas, &res);
+        else if (ch == 7) run_hybrid<7>(di, P, ctl, op, ctas, &res);
+        else run_hybrid<9>(di, P, ctl, op, ctas, &res);
         if (res.index_overflow & 4u) { printf("FASTFAIL too_many_records=%d\n", (res.index_overflow & 8u) ? 1 : 0); return 0; }
     } else {
         run_general(di, mode == 1 ? 2 : 1, P, ctl, op, ctas, &res);

@@ -272,6 +272,37 @@ def test_general_path_in_two_kernels(harness, tmp_path):
     assert ok(bad, ctas=3).startswith("OK error kind=6 record=2000")
 
 
+def test_reference_order_on_the_index_pass(harness, tmp_path):
+    """-a N on one input (capi.cu's launch_hybrid): the single-pass kernel's S1-S6 as an index + verdict pass
+    (kf_fused<CH, 3>: the line index K1 writes and the verdicts k2_trim_only writes, from one read of the input), then
+    k2_trim_route<true>, K3 and the summary.  Same bytes as the oracle in the reference's -a N order, single end and
+    interleaved pairs (+ -M), every tile size; a data error or a record longer than the halo hands the batch over."""
+    from sickle_b200 import synth
+    from test_oracle_fuzz_vs_ref import _records
+
+    se, il, var, lng, bad = (str(tmp_path / n) for n in ("se.fq", "il.fq", "var.fq", "long.fq", "bad.fq"))
+    data = synth.fixed_length_records(3000, 150, "sanger", seed=5).tobytes()
+    open(se, "wb").write(data)
+    open(il, "wb").write(synth.paired_records(1200, 150, "sanger", seed=6)[2].tobytes())
+    open(var, "wb").write(_records(np.random.default_rng(91), 1500, 250, "sanger"))
+    open(lng, "wb").write(synth.variable_length_records(12, 6000, 9000, "illumina", 3))
+    for k in ("index3", "index5", "index7", "index9"):
+        for threads in (1, 2, 3, 8, 32):
+            for path, kw in ((se, dict(first=5)), (se, dict(x=True, n=True, q=30, l=5, ctas=2)), (il, dict(mode="pei", first=3)),
+                             (il, dict(mode="pei", singles=False)), (il, dict(mode="peM", singles=False, ctas=2)), (var, dict(n=True, first=9))):
+                rc, out, err = run(harness, path, kernel=k, threads=threads, **kw)
+                assert rc == 0 and (out.startswith("OK") or out.startswith("FASTFAIL")), (k, threads, kw, out, err[-400:])
+                if k == "index9" and path != var:
+                    assert out.startswith("OK"), (k, threads, kw, out)
+    rc, out, err = run(harness, lng, kernel="index9", qualtype="illumina", threads=4)
+    assert rc == 0 and out.startswith("FASTFAIL"), out              # records longer than the halo
+    lines = data.split(b"\n")
+    lines[4 * 2000 + 3] = b"\x7f" + lines[4 * 2000 + 3][1:]
+    open(bad, "wb").write(b"\n".join(lines))
+    rc, out, err = run(harness, bad, kernel="index9", threads=4)
+    assert rc == 0 and out.startswith("FASTFAIL"), out              # a data error: the general path reports it
+
+
 def test_damaged_inputs(harness, tmp_path):
     """Seeded random files, three quarters of them damaged (missing / blank / doubled line, flipped /
     deleted / inserted byte, cut-off tail): same first data error (kind, record, position, byte) or same
