@@ -94,7 +94,7 @@ def main():
         measure("se R%d" % L, capi.MODE_SE, [(buf, n)], recs)
         if L == 150:
             measure("se R150, general path (K1/K2/K3)", capi.MODE_SE, [(buf, n)], recs, env={"SICKLE_B200_PATH": "general"})
-            measure("se R150, -a 8 order emulation (general path)", capi.MODE_SE, [(buf, n)], recs, emulate_threads=8)
+            measure("se R150, -a 8 reference order (index pass + routing + K3)", capi.MODE_SE, [(buf, n)], recs, emulate_threads=8)
         del buf
     f, r, inter = synth.paired_records(100_000, 150, "sanger", seed=50)
     buf, n, recs = device_bytes(inter, target, dev)
@@ -103,7 +103,7 @@ def main():
     del buf
     b0, n0, r0 = device_bytes(f, target // 2, dev)
     b1, n1, r1 = device_bytes(r, target // 2, dev)
-    measure("pe two files R150 (-f -r, -o -p -s; general path)", capi.MODE_PE_2FILE, [(b0, n0), (b1, n1)], r0 + r1)
+    measure("pe two files R150 (-f -r, -o -p -s; two passes of the single-pass kernel)", capi.MODE_PE_2FILE, [(b0, n0), (b1, n1)], r0 + r1)
     # variable-length reads (adapter-trimmed input), 36..151 bases
     v = synth.variable_length_records(150_000, 36, 151, "sanger", 60)
     vb = v if isinstance(v, (bytes, bytearray)) else v.tobytes()

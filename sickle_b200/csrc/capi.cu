@@ -91,7 +91,8 @@ struct Slot {
     unsigned long long *d_status_k2 = nullptr;
     unsigned long long *d_status_f = nullptr;   // fused: [3][fused_tiles_cap] (newlines, main, singles); two files: [2 + 4]
     unsigned long long *d_verdict[2] = {nullptr, nullptr};   // fused, two files: one 8-byte entry per record and file
-    uint8_t *d_nlsave[2] = {nullptr, nullptr};               // fused, two files: PASS 1's newline positions, kFNlSlot bytes per tile
+    uint8_t *d_nlsave[2] = {nullptr, nullptr};               // fused, two files / -a N: the first pass's newline positions, kFNlSlot bytes per tile
+    uint32_t *d_tq = nullptr;                                // -a N: kept bytes per tile and queue, [tiles + 1][32]
     sk::Control *d_ctl = nullptr;
     sk::DevResult *d_res = nullptr;
     sk::DevResult *h_res = nullptr;
@@ -125,6 +126,8 @@ struct sk_ctx {
     // path selection
     bool fused_eligible = false;   // mode / order the fused kernel supports
     bool hybrid_eligible = false;  // -a N on one input: the fused kernel's index + verdict pass, then k2_trim_route<true> and K3
+    bool ordered_eligible = false; // -a N, N <= 32, single end: index + verdict pass, then the fused kernel's ordered emit (no K3)
+    int fused_grid_ordered[5] = {0, 0, 0, 0, 0};
     int fused_ch = 7;              // 16-byte chunks per thread (3, 5, 7, 9 or 11): the tile size in use
     bool fused_ch_fixed = false;   // SICKLE_B200_FUSED_CH given: no adaptation
     int fused_ch_max = 9;          // lowered after a failed fused batch, raised again after a streak of good ones
@@ -176,6 +179,7 @@ void free_slot(Slot &s) {
     if (s.d_status_f) cudaFree(s.d_status_f);
     for (auto &v : s.d_verdict) if (v) cudaFree(v);
     for (auto &v : s.d_nlsave) if (v) cudaFree(v);
+    if (s.d_tq) cudaFree(s.d_tq);
     if (s.d_ctl) cudaFree(s.d_ctl);
     if (s.d_res) cudaFree(s.d_res);
     if (s.h_res) cudaFreeHost(s.h_res);
@@ -218,6 +222,10 @@ int alloc_slot(sk_ctx *c, Slot &s, bool host_buffers) {
         if (c->n_inputs == 2) {
             for (auto &v : s.d_verdict) SK_CUDA(cudaMalloc((void **)&v, (size_t)c->verdict_cap * 8));
             for (auto &v : s.d_nlsave) SK_CUDA(cudaMalloc((void **)&v, (size_t)c->fused_tiles_cap * sk::kFNlSlot));
+        }
+        if (c->ordered_eligible) {
+            SK_CUDA(cudaMalloc((void **)&s.d_nlsave[0], (size_t)c->fused_tiles_cap * sk::kFNlSlot));
+            SK_CUDA(cudaMalloc((void **)&s.d_tq, ((size_t)c->fused_tiles_cap + 1) * 32 * sizeof(uint32_t)));
         }
     }
     if (host_buffers) {
@@ -388,6 +396,13 @@ int setup_fused_ch(sk_ctx *c) {
         SK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p3, sk::kf_fused<CH, 3>, sk::kFThreads, Cfg::kSmemPass1));
         if (p3 < 1) { set_err("fused kernel does not fit on this device"); return SK_E_CUDA; }
         c->fused_grid_pass1[(CH - 3) / 2] = p3 * c->sm_count;
+        if (c->ordered_eligible) {
+            SK_CUDA(cudaFuncSetAttribute(sk::kf_fused<CH, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::kSmemOrdered));
+            int p4 = 0;
+            SK_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&p4, sk::kf_fused<CH, 4>, sk::kFThreads, Cfg::kSmemOrdered));
+            if (p4 < 1) { set_err("fused kernel does not fit on this device"); return SK_E_CUDA; }
+            c->fused_grid_ordered[(CH - 3) / 2] = p4 * c->sm_count;
+        }
     }
     c->fused_grid_ch[(CH - 3) / 2] = per_sm * c->sm_count;
     return SK_OK;
@@ -493,6 +508,66 @@ int launch_index_pass_ch(sk_ctx *c, Slot &s, const BatchArgs &a, const sk::DevIn
     return SK_OK;
 }
 
+// -a N (N <= 32), single end, all on the single-pass kernel: the index + verdict pass also leaves every tile's newline
+// positions and its kept bytes per queue; two small kernels turn those into every (tile, queue) segment's place in the
+// output; the ordered emit pass (kf_fused<CH, 4>) stages a tile queue by queue and flushes up to N segments -- no look-back,
+// no K2, no K3.
+template <int CH>
+int launch_ordered_ch(sk_ctx *c, Slot &s, const BatchArgs &a, const sk::DevInput di[2], const sk::OutPtrs &op) {
+    using Cfg = sk::FusedCfg<CH>;
+    cudaStream_t st = a.st;
+    const uint32_t tiles = (uint32_t)((a.n[0] + Cfg::kTile - 1) / Cfg::kTile);
+    const uint32_t stride = c->fused_tiles_cap * sk::kWideStatusStride;
+    const uint32_t desc_cap = (uint32_t)(c->line_cap / 4 + 1);
+    if (tiles) {
+        const int full1 = c->fused_grid_pass1[(CH - 3) / 2], full4 = c->fused_grid_ordered[(CH - 3) / 2];
+        sk::kf_fused<CH, 3><<<tiles < (uint32_t)full1 ? (int)tiles : full1, sk::kFThreads, Cfg::kSmemPass1, st>>>(
+            di[0], c->dev, s.d_ctl, op, s.d_status_f, s.d_status_f + (size_t)stride, stride, tiles, s.epoch, sk::DevInput(), 0u, nullptr, nullptr,
+            desc_cap, s.d_nlsave[0], nullptr, s.d_desc[0], s.d_tq);
+        SK_DEBUG_SYNC(st, "kf_fused index pass");
+        SK_CUDA(cudaEventRecord(s.ev_stage[0], st));
+        sk::kfo_scan<<<c->dev.emu_threads, 256, 0, st>>>(s.d_tq, tiles);
+        sk::kfo_bases<<<1, 32, 0, st>>>(s.d_ctl, s.d_tq, tiles, c->dev.emu_threads, op.cap[0]);
+        SK_DEBUG_SYNC(st, "kfo_scan / kfo_bases");
+        SK_CUDA(cudaEventRecord(s.ev_stage[1], st));
+        sk::kf_fused<CH, 4><<<tiles < (uint32_t)full4 ? (int)tiles : full4, sk::kFThreads, Cfg::kSmemOrdered, st>>>(
+            di[0], c->dev, s.d_ctl, op, s.d_status_f, s.d_status_f + (size_t)stride, stride, tiles, s.epoch, sk::DevInput(), 0u, nullptr, nullptr,
+            desc_cap, s.d_nlsave[0], nullptr, s.d_desc[0], s.d_tq);
+        SK_DEBUG_SYNC(st, "kf_fused ordered emit");
+        s.launches += 4;
+    } else {
+        SK_CUDA(cudaEventRecord(s.ev_stage[0], st));
+        SK_CUDA(cudaEventRecord(s.ev_stage[1], st));
+    }
+    return SK_OK;
+}
+
+int launch_ordered(sk_ctx *c, Slot &s, const BatchArgs &a) {
+    cudaStream_t st = a.st;
+    if (int rc = next_epoch(c, s, st)) return rc;
+    sk::DevInput di[2];
+    sk::OutPtrs op;
+    make_inputs(c, s, a, di, op);
+    s.launches = 0;
+    SK_CUDA(cudaEventRecord(s.ev_begin, st));
+    int rc;
+    switch (c->fused_ch) {
+        case 3: rc = launch_ordered_ch<3>(c, s, a, di, op); break;
+        case 5: rc = launch_ordered_ch<5>(c, s, a, di, op); break;
+        case 9: case 11: rc = launch_ordered_ch<9>(c, s, a, di, op); break;
+        default: rc = launch_ordered_ch<7>(c, s, a, di, op); break;
+    }
+    if (rc) return rc;
+    SK_CUDA(cudaEventRecord(s.ev_stage[2], st));
+    sk::kf_finalize<<<1, 32, 0, st>>>(di[0], c->dev, s.d_ctl, s.d_res);
+    s.launches++;
+    SK_CUDA(cudaEventRecord(s.ev_end, st));
+    SK_CUDA(cudaGetLastError());
+    s.last_fused = true;
+    c->n_fused++;
+    return SK_OK;
+}
+
 int launch_hybrid(sk_ctx *c, Slot &s, const BatchArgs &a) {
     cudaStream_t st = a.st;
     if (int rc = next_epoch(c, s, st)) return rc;
@@ -534,6 +609,7 @@ int launch_batch(sk_ctx *c, Slot &s, const BatchArgs &a) {
     // (the back-off is counted down where results are read, rerun_if_needed: a caller that queues batches
     //  without looking at their summaries never learns that a batch failed, so it must not drift back either)
     if (c->fused_eligible && c->fused_backoff == 0) return launch_fused(c, s, a);
+    if (c->ordered_eligible && c->fused_backoff == 0) return launch_ordered(c, s, a);
     if (c->hybrid_eligible && c->fused_backoff == 0) return launch_hybrid(c, s, a);
     return launch_general(c, s, a);
 }
@@ -660,9 +736,11 @@ sk_ctx *sk_create(int device, uint64_t slot_bytes, int n_slots, const sk_params 
     // SICKLE_B200_PATH = auto (default) | general | fused ; SICKLE_B200_FUSED_CH = 5 | 7 | 9 | 11
     c->fused_eligible = dp.emu_threads == 1;
     c->hybrid_eligible = dp.emu_threads > 1 && c->n_inputs == 1;
+    c->ordered_eligible = c->hybrid_eligible && dp.emu_threads <= 32 && params->mode == SK_MODE_SE;
+    if (const char *e = getenv("SICKLE_B200_ORDERED")) { if (atoi(e) == 0) c->ordered_eligible = false; }
     c->verdict_cap = (uint32_t)(c->slot_bytes / 32 + 64);   // records of 32 bytes and more (shorter ones: general path)
     if (const char *e = getenv("SICKLE_B200_K2_SPLIT")) c->k2_split = atoi(e) != 0;
-    if (const char *e = getenv("SICKLE_B200_PATH")) { if (!strcmp(e, "general")) c->fused_eligible = c->hybrid_eligible = false; }
+    if (const char *e = getenv("SICKLE_B200_PATH")) { if (!strcmp(e, "general")) c->fused_eligible = c->hybrid_eligible = c->ordered_eligible = false; }
     if (const char *e = getenv("SICKLE_B200_FUSED_CH")) { c->fused_ch = atoi(e); c->fused_ch_fixed = true; }
     if ((c->fused_eligible || c->hybrid_eligible) && setup_fused(c) != SK_OK) { delete c; return nullptr; }
     c->host_buffers = n_slots > 0;

@@ -100,6 +100,9 @@ struct FusedCfg {
     // CH = 7: 56,768 B -> four CTAs per SM (4 x (56,768 + 248 static + 1,024 reserved) <= 232,448)
     static constexpr size_t kSmem = (size_t)kInBytes + kOutBytes + kFMaxNl * 2;
     static constexpr size_t kSmemTwoFile = kSmem + 16 + 128 * 8;   // PASS 2: + the tile's saved line numbers, + one (offset, length) pair per record: its own singles
+    // PASS 4: + the tile's saved line numbers, + bytes per record (128 x 4), queue totals (32 x 4), and the staged
+    // tile's segments for the deferred flush: start, length (32 x 4 each), destination (32 x 8)
+    static constexpr size_t kSmemOrdered = kSmem + 16 + 512 + 128 + 128 + 128 + 256;
     static constexpr size_t kSmemPass1 = (size_t)kInBytes + kFMaxNl * 2;   // PASS 1 stages nothing: four CTAs per SM
     static constexpr int kCtasPerSmPass1 = (int)(232448 / (kSmemPass1 + 1024 + 256)) > SK_MAX_CTAS ? SK_MAX_CTAS : (int)(232448 / (kSmemPass1 + 1024 + 256));
     // CTAs per SM by shared memory (232,448 B per SM, 1,024 B reserved per CTA); also the register budget
@@ -161,6 +164,18 @@ __device__ __forceinline__ void flush_previous_tile(unsigned long long *const st
 #endif
 }
 
+// PASS 4 (-a N order): the staged tile is up to 32 segments, one per queue of the reference's round-robin dealing,
+// each with its own place in the output (known before the pass starts: no look-back).  Warp gw of the flush group
+// takes the queues gw, gw + 4, ...
+__device__ __forceinline__ void flush_ordered_tile(const OutPtrs &outs, const uint8_t *__restrict__ s_out, const uint32_t *__restrict__ seg,
+                                                   const uint32_t *__restrict__ len, const unsigned long long *__restrict__ dst, int nq, int gtid) {
+    const int gw = gtid >> 5, gl = gtid & 31;
+    for (int q = gw; q < nq; q += 4) {
+        const uint32_t n = len[q];
+        if (n) flush_realigned(outs.p[0] + dst[q], s_out, seg[q], n, gl, 32);
+    }
+}
+
 // Software-pipelined over tiles: the output of tile t is staged in shared memory right after it is
 // trimmed, its size is published, and only one tile later -- after the next tile has been loaded and
 // scanned -- does the CTA ask for tile t's output offset and flush.  By then every predecessor has
@@ -184,16 +199,24 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
          unsigned long long *__restrict__ tab_b = nullptr, uint32_t tab_cap = 0,
          uint8_t *__restrict__ nlsave_a = nullptr, uint8_t *__restrict__ nlsave_b = nullptr /* kFNlSlot bytes per tile */,
          // PASS 3 only: the general path's descriptor table (tab_cap entries); the line index goes to in_a.line_end
-         RecDesc *__restrict__ desc_out = nullptr) {
+         RecDesc *__restrict__ desc_out = nullptr,
+         // PASS 3 (optional) / PASS 4: [num_tiles + 1][32] kept bytes per tile and queue (record k of the batch is dealt to
+         // queue (k+1) % N, src/trim_single.cpp:263,273-274); kfo_scan / kfo_bases turn the columns into output offsets
+         uint32_t *__restrict__ tq = nullptr) {
     using Cfg = FusedCfg<CH>;
     constexpr bool kNoEmit = PASS == 1 || PASS == 3;   // these passes stage and write no records
+    constexpr bool kSaved = PASS == 2 || PASS == 4;    // newline positions and line numbers come from the pass before
     extern __shared__ __align__(16) uint8_t smem[];
     uint8_t *s_in = smem;
     uint8_t *s_out = smem + Cfg::kInBytes;
     uint16_t *s_nl = reinterpret_cast<uint16_t *>(smem + Cfg::kInBytes + (kNoEmit ? 0 : Cfg::kOutBytes));
     uint4 *s_desc = reinterpret_cast<uint4 *>(s_nl);   // S7/S8a record descriptors alias the newline positions
-    const uint4 *s_meta = reinterpret_cast<const uint4 *>(smem + Cfg::kSmem);   // PASS 2 only: lands right behind s_nl
+    const uint4 *s_meta = reinterpret_cast<const uint4 *>(smem + Cfg::kSmem);   // PASS 2, 4: lands right behind s_nl
     uint2 *s_single = reinterpret_cast<uint2 *>(smem + Cfg::kSmem + 16);   // PASS 2 only (Cfg::kSmemTwoFile)
+    uint32_t *s_rbytes = reinterpret_cast<uint32_t *>(smem + Cfg::kSmem + 16);            // PASS 4 only (Cfg::kSmemOrdered)
+    uint32_t *s_qacc = s_rbytes + 128, *s_fseg = s_qacc + 32, *s_flen = s_fseg + 32;
+    unsigned long long *s_fdst = reinterpret_cast<unsigned long long *>(s_flen + 32);
+    __shared__ uint32_t s_q[32];   // PASS 3: kept bytes of the tile per queue
     __shared__ uint32_t s_tile;
     __shared__ uint32_t warp_tot[kFThreads / 32];
     __shared__ uint32_t warp_tot2[kFThreads / 32][2];
@@ -243,6 +266,8 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         // whole tile ahead was measured at 0.38 -> 0.56 ms, because a ticket in the hands of a CTA that
         // is still busy stalls every look-back behind it.
         if (tid == 0) { s_tile = held; s_fail = 0; }
+        if (PASS == 3 && tid < 32) s_q[tid] = 0u;
+        if (PASS == 4 && tid < 32) s_qacc[tid] = 0u;
         __syncthreads();
         const uint32_t ticket = s_tile;
         // (a tile that gives the batch up poisons the ticket counter -- see kTicketPoison -- so every ticket drawn
@@ -283,10 +308,10 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 const uint32_t mb = (uint32_t)__cvta_generic_to_shared(&s_mbar);
                 const uint32_t dst = (uint32_t)__cvta_generic_to_shared(s_in);
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // S8a's reads of s_in come first
-                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(cp_chunks * 16u + (PASS == 2 ? (uint32_t)kFNlSlot : 0u)) : "memory");
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(mb), "r"(cp_chunks * 16u + (kSaved ? (uint32_t)kFNlSlot : 0u)) : "memory");
                 asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                              ::"r"(dst), "l"(in.data + t0), "r"(cp_chunks * 16u), "r"(mb) : "memory");
-                if (PASS == 2)   // the tile's newline positions and line numbers, as PASS 1 left them
+                if (kSaved)   // the tile's newline positions and line numbers, as the pass before left them
                     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
                                  ::"r"((uint32_t)__cvta_generic_to_shared(s_nl)), "l"((fsel ? nlsave_b : nlsave_a) + (size_t)tile * kFNlSlot),
                                    "r"((uint32_t)kFNlSlot), "r"(mb) : "memory");
@@ -294,7 +319,7 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
 #else   // host build of the kernels (tests/host_stub/simt): the bulk copy is a memcpy by thread 0
             if (tid == 0) {
                 memcpy(s_in, in.data + t0, (size_t)cp_chunks * 16u);
-                if (PASS == 2) memcpy(s_nl, (fsel ? nlsave_b : nlsave_a) + (size_t)tile * kFNlSlot, (size_t)kFNlSlot);
+                if (kSaved) memcpy(s_nl, (fsel ? nlsave_b : nlsave_a) + (size_t)tile * kFNlSlot, (size_t)kFNlSlot);
             }
 #endif
             for (uint32_t c = cp_chunks + tid; c < (uint32_t)(Cfg::kRegion / 16); c += kFThreads)
@@ -323,14 +348,14 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             __syncthreads();
             SK_TICK(1);   // S1 load
 
-            if (PASS == 2) {   // found, counted and numbered by PASS 1
+            if (kSaved) {   // found, counted and numbered by the pass before
                 const uint4 m = *s_meta;
                 c_t = m.y; n_all = m.z;
             }
             // ---- S2: newline masks of this thread's CH*16 contiguous bytes
 #pragma unroll
             for (int k = 0; k < (CH + 1) / 2; ++k) mw[k] = 0;
-            if (PASS != 2) {
+            if (!kSaved) {
                 // only the first tile (bytes before the batch start) and the tiles touching the end of
                 // the batch have bytes to mask off
                 const bool edge = tile == 0 || (unsigned long long)t0 + Cfg::kRegion > in.nbytes;
@@ -348,7 +373,7 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                     mw[k >> 1] |= mk << (16 * (k & 1));
                 }
             }
-            if (PASS != 2) {
+            if (!kSaved) {
 #pragma unroll
                 for (int k = 0; k < (CH + 1) / 2; ++k) cnt += __popc(mw[k]);
                 // ---- S3: ranks
@@ -372,7 +397,9 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
 
         SK_TICK(2);   // (+ newline-count publish)
         if (done) {   // no tile left: only the last staged tile remains to be flushed
-            if (have_prev && wid >= 4) {
+            if (PASS == 4) {
+                if (have_prev && wid >= 4) flush_ordered_tile(outs, s_out, s_fseg, s_flen, s_fdst, P.emu_threads, tid - 128);
+            } else if (have_prev && wid >= 4) {
                 unsigned long long *const so = status_out_all + (PASS != 0 ? (size_t)(2u * p_fsel) * status_stride : 0);
                 unsigned long long *const st_prev[2] = {so, so + status_stride};
                 flush_previous_tile(st_prev, p_tile, p_tot0, p_tot1, nstreams, epoch, tid - 128, 4, s_lb, ctl, outs, s_out, p_last,
@@ -381,7 +408,7 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             break;
         }
 
-        if (PASS != 2 && !nl_overflow) {
+        if (!kSaved && !nl_overflow) {
             // a thread's 16*CH bytes hold about two newlines: one short loop per 32-byte mask word (most
             // words have none, and a warp leaves a word's loop as soon as none of its lanes has one left)
             uint16_t *__restrict__ nl_out = s_nl + (wbase + incl - cnt);
@@ -396,7 +423,7 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         }
         // ---- S4: global line number of the tile
         uint32_t G;
-        if (PASS == 2) {
+        if (kSaved) {
             G = s_meta->x;
         } else {
             const unsigned long long agg[2] = {c_t, 0};
@@ -410,7 +437,7 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             G = (uint32_t)ex[0];
 #endif
         }
-        if (PASS != 2) __syncthreads();   // newline positions visible to every thread (PASS 2: they came with the tile)
+        if (!kSaved) __syncthreads();   // newline positions visible to every thread (PASS 2, 4: they came with the tile)
         SK_TICK(3);   // S3 positions + S4 look-back #1
         if (PASS == 3 && !nl_overflow) {   // the general path's line index (K1's output), and the line count with the last tile
             for (uint32_t j = (uint32_t)tid; j < c_t; j += kFThreads) {
@@ -419,7 +446,7 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
             }
             if (tid == 0 && tile == file_tiles - 1u) ctl->nlines[0] = G + c_t;
         }
-        if (PASS == 1 && !nl_overflow) {   // for PASS 2: positions (whole 16-byte chunks) and the three numbers
+        if ((PASS == 1 || (PASS == 3 && nlsave_a != nullptr)) && !nl_overflow) {   // for PASS 2 / 4: positions (whole 16-byte chunks) and the three numbers
             uint4 *__restrict__ slot = reinterpret_cast<uint4 *>((fsel ? nlsave_b : nlsave_a) + (size_t)tile * kFNlSlot);
             const uint32_t nq = (2u * n_all + 15u) >> 4;
             for (uint32_t c = (uint32_t)tid; c < nq; c += kFThreads) slot[c] = reinterpret_cast<const uint4 *>(s_nl)[c];
@@ -444,7 +471,9 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         // again before the barrier in front of this tile's S8a.  (The flush group's warps never own a
         // record, so they have nothing else to do until that barrier: measured, 22 % of all warp time
         // was spent waiting there.)
-        if (have_prev && wid >= flush_warp0) {
+        if (PASS == 4) {
+            if (have_prev && wid >= flush_warp0) flush_ordered_tile(outs, s_out, s_fseg, s_flen, s_fdst, P.emu_threads, tid - flush_warp0 * 32);
+        } else if (have_prev && wid >= flush_warp0) {
             unsigned long long *const so = status_out_all + (PASS != 0 ? (size_t)(2u * p_fsel) * status_stride : 0);
             unsigned long long *const st_prev[2] = {so, so + status_stride};
             flush_previous_tile(st_prev, p_tile, p_tot0, p_tot1, nstreams, epoch, tid - flush_warp0 * 32, kFThreads / 32 - flush_warp0,
@@ -491,6 +520,16 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 mate_verdict = (fsel ? tab_a : tab_b)[recno];
                 if ((v >> 48) & 1u) { cut.five = (int)((v >> 32) & 0xffffu); cut.three = cut.five + (int)((v >> 16) & 0xffffu); }
             }
+        } else if (PASS == 4) {
+            if (has_rec && complete) {   // validated and trimmed by the index pass
+                name_len = e0 - start;
+                L = e1 - e0 - 1u;
+                plus_len = e2 - e1 - 1u;
+                if (recno < tab_cap) {
+                    const RecDesc v = desc_out[recno];
+                    if (v.route) { cut.five = (int)v.five; cut.three = (int)(v.five + v.nkeep); }
+                } else fail = true;
+            }
         } else if (has_rec && complete) {
             name_len = e0 - start;
             L = e1 - e0 - 1u;
@@ -522,6 +561,8 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 d.five = d.route ? (uint32_t)cut.five : 0u;
                 d.nkeep = d.route ? (uint32_t)(cut.three - cut.five) : 0u;
                 desc_out[recno] = d;
+                if (tq != nullptr && d.route)
+                    atomicAdd(&s_q[(recno + 1u) % (uint32_t)P.emu_threads], name_len + plus_len + 4u + 2u * d.nkeep);
             } else fail = true;
         }
         if (fail) s_fail = 1u;
@@ -556,6 +597,13 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 else if (keep && P.has_singles) { stream = 1; add1 = fixed + 2u * nkeep; } // trim_paired.cpp:552-563
             }
         }
+        // PASS 4: the records of a tile are staged queue by queue (the reference's dealing: record k of the batch goes to
+        // queue (k+1) % N and the queues are written one after the other, src/trim_single.cpp:263,273-274,374-428)
+        const uint32_t myq = PASS == 4 ? (recno + 1u) % (uint32_t)P.emu_threads : 0u;
+        if (PASS == 4 && rec < 128u) {
+            s_rbytes[rec] = add0;
+            if (add0) atomicAdd(&s_qacc[myq], add0);
+        }
         const uint32_t inc0 = warp_incl_scan(add0, lane);
         const uint32_t inc1 = (paired || PASS == 2) ? warp_incl_scan(add1, lane) : 0u;
         if (lane == 31) { warp_tot2[wid][0] = inc0; warp_tot2[wid][1] = inc1; }
@@ -573,7 +621,8 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         }
         // the staging buffer holds a tile's worth of output; a tile whose (long, untrimmed) records
         // reach far into the halo can exceed it -> general path
-        const bool tile_fail = s_fail != 0 || tot0 + tot1 + 64u > (uint32_t)Cfg::kOutBytes;
+        // (PASS 4: every queue's segment starts on a 16-byte boundary of the staging buffer)
+        const bool tile_fail = s_fail != 0 || tot0 + tot1 + 64u + (PASS == 4 ? 16u * 32u : 0u) > (uint32_t)Cfg::kOutBytes;
         if (tile_fail) {   // bit 1: the tile simply holds too many records (the host then picks smaller tiles)
             tot0 = 0; tot1 = 0;
             if (tid == 0) {
@@ -584,13 +633,25 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         if (kNoEmit) {   // verdicts are in the table: count the file's records, next tile
             const uint32_t m_live1 = __ballot_sync(0xffffffffu, live);
             if (!tile_fail && lane == 0 && m_live1) s_acc[wid][fsel ? 2 : 0] += (uint32_t)__popc(m_live1);
+            if (PASS == 3 && tq != nullptr && !tile_fail && tid < 32) tq[(size_t)tile * 32u + (uint32_t)tid] = s_q[tid];
             if (tid == 0) held = atomicAdd(&ctl->tile_counter[3], 1u);
             __syncthreads();   // s_fail has been read by everybody before the top of the loop clears it
             continue;
         }
-        {   // the tile's output sizes go out now; its own offsets are asked for one tile later
+        if (PASS != 4) {   // the tile's output sizes go out now; its own offsets are asked for one tile later
             const unsigned long long agg[2] = {tot0, tot1};
             block_publish(st_out, tile, agg, nstreams, epoch, tid);
+        } else {
+            // segments of this tile: start in the staging buffer, length, place in the output (the flush group has
+            // finished the previous tile: it passed the barrier above)
+            if (wid == 0) {
+                const uint32_t n = tile_fail ? 0u : s_qacc[lane];
+                const uint32_t al = (n + 15u) & ~15u;
+                s_fseg[lane] = warp_incl_scan(al, lane) - al;
+                s_flen[lane] = n;
+                if (lane < P.emu_threads) s_fdst[lane] = (unsigned long long)tq[(size_t)num_tiles * 32u + (uint32_t)lane] + tq[(size_t)tile * 32u + (uint32_t)lane];
+            }
+            __syncthreads();
         }
         if (tid == 0) held = atomicAdd(&ctl->tile_counter[3], 1u);   // looked at after S8a
         have_prev = true;
@@ -602,9 +663,14 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         // which nobody reads after S5
         if (has_rec) {   // every slot S8a may look at is rewritten (x == 0: nothing to emit)
             uint4 dsc;
+            uint32_t stage_off = stream == 1 ? wb1 + inc1 - add1 : wb0 + inc0 - add0;
+            if (PASS == 4 && stream == 0 && !tile_fail) {   // behind the tile's earlier records of the same queue
+                stage_off = s_fseg[myq];
+                for (int r2 = (int)rec - P.emu_threads; r2 >= 0; r2 -= P.emu_threads) stage_off += s_rbytes[r2];
+            }
             dsc.x = (stream < 0 || tile_fail)
                         ? 0u
-                        : ((stream == 1 ? wb1 + inc1 - add1 : wb0 + inc0 - add0) | (stream == 1 ? 0x80000000u : 0u) |
+                        : (stage_off | (stream == 1 ? 0x80000000u : 0u) |
                            (nrec_out ? 0x40000000u : 0u) | 0x20000000u);
             dsc.y = start | (e0 << 16);
             dsc.z = e1 | (e2 << 16);
@@ -778,6 +844,55 @@ __global__ void kf2_between(Control *__restrict__ ctl) {
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     ctl->fused_nunits = min(ctl->fast_records2[0], ctl->fast_records2[1]);
     ctl->tile_counter[3] &= kTicketPoison;
+}
+
+// -a N order, between the index pass (kf_fused<CH, 3>) and the ordered emit (kf_fused<CH, 4>).  tq[t][q] = kept bytes of
+// tile t that go to queue q.  kfo_scan (one CTA per queue) turns every column into its exclusive prefix over the tiles and
+// leaves the queue's total in row `tiles`; kfo_bases (one warp) turns that row into the queues' places in the output
+// (the reference writes queue 0, then queue 1, ...: src/trim_single.cpp:374-428), sets the size of the output and hands
+// the tickets out again (a poisoned counter stays poisoned).
+__global__ void __launch_bounds__(256) kfo_scan(uint32_t *__restrict__ tq, uint32_t tiles) {
+    __shared__ uint32_t part[256];
+    const uint32_t q = blockIdx.x, tid = threadIdx.x;
+    const uint32_t chunk = (tiles + 255u) / 256u;
+    const uint32_t lo = min(tiles, tid * chunk), hi = min(tiles, lo + chunk);
+    uint32_t sum = 0;
+    for (uint32_t t = lo; t < hi; ++t) sum += tq[(size_t)t * 32u + q];
+    part[tid] = sum;
+    __syncthreads();
+    uint32_t run = 0, total = 0;
+    for (uint32_t k = 0; k < 256u; ++k) {
+        const uint32_t v = part[k];
+        if (k < tid) run += v;
+        total += v;
+    }
+    for (uint32_t t = lo; t < hi; ++t) {
+        const uint32_t v = tq[(size_t)t * 32u + q];
+        tq[(size_t)t * 32u + q] = run;
+        run += v;
+    }
+    if (tid == 0) tq[(size_t)tiles * 32u + q] = total;
+}
+
+__global__ void kfo_bases(Control *__restrict__ ctl, uint32_t *__restrict__ tq, uint32_t tiles, int nq, unsigned long long cap) {
+    const int lane = threadIdx.x;
+    if (blockIdx.x != 0 || lane >= 32) return;
+    const uint32_t tot = lane < nq ? tq[(size_t)tiles * 32u + (uint32_t)lane] : 0u;
+    unsigned long long incl = tot;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane < nq) tq[(size_t)tiles * 32u + (uint32_t)lane] = (uint32_t)(incl - tot);
+    if (lane == 31) {
+        ctl->out_bytes[0] = incl;
+        if (incl > cap) {   // reported by the summary as a capacity error; nothing is written
+            ctl->index_overflow |= 2u;
+            ctl->tile_counter[3] |= kTicketPoison;
+        }
+        ctl->tile_counter[3] &= kTicketPoison;
+    }
 }
 
 // Batch summary of a two-file batch.

@@ -113,8 +113,9 @@ __device__ __noinline__ void flush_realigned(uint8_t *__restrict__ gdst, const u
         const uint32_t b = (uint32_t)tid;
         if (b >= ph && b < end) gal[b] = s_out[sb + b - ph];
     }
-    if ((end & 15u) && c_hi >= c_lo && tid >= 32 && tid < 48) {
-        const uint32_t b = 16u * c_hi + (uint32_t)(tid - 32);
+    const int tail0 = nthreads >= 48 ? 32 : 16;               // (a single warp flushing: lanes 16..31)
+    if ((end & 15u) && c_hi >= c_lo && tid >= tail0 && tid < tail0 + 16) {
+        const uint32_t b = 16u * c_hi + (uint32_t)(tid - tail0);
         if (b < end && (c_hi > 0 || ph == 0)) gal[b] = s_out[sb + b - ph];
     }
 }

@@ -193,6 +193,7 @@ def trim_stream_reference_order(ctx: capi.Context, in0: bytes, in1: bytes = b"",
     r1 = reference_batches(in1, bl, 4) if mode == capi.MODE_PE_2FILE else [(0, 0)] * len(r0)
     outs = [[], [], []]
     totals = dict.fromkeys(capi.Result.COUNTERS, 0)
+    stats = dict(batches=0, fused_batches=0)
     for (a0, e0), (a1, e1) in zip(r0, r1):
         for i, (a, e, d) in enumerate(((a0, e0, in0), (a1, e1, in1))):
             if e > a:
@@ -210,4 +211,6 @@ def trim_stream_reference_order(ctx: capi.Context, in0: bytes, in1: bytes = b"",
                 outs[s].append(ctx.out_bytes(res, s))
         for k in totals:
             totals[k] += getattr(res, k)
-    return dict(out=[b"".join(o) for o in outs], counters=totals)
+        stats["batches"] += 1
+        stats["fused_batches"] += res.fused
+    return dict(out=[b"".join(o) for o in outs], counters=totals, **stats)

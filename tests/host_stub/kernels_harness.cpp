@@ -5,7 +5,7 @@
 // consumed bytes and the first data error with the CPU oracle's so_run on the same bytes.
 //
 //   kernels_harness <fastq> <mode 0|2|3 (se, interleaved, -M) or 1 with <fastq2>> <qualtype 1..3> <q> <l> <x> <n>
-//                   <has_singles> <path: fused3..fused11|index3..index9|general> <ctas> <first 0..15> [<fastq2>]
+//                   <has_singles> <path: fused3..fused11|index3..index9|order3..order9|general> <ctas> <first 0..15> [<fastq2>]
 // prints one line: "OK ..." / "FASTFAIL ..." (the fused kernel handed the batch to the general path) /
 // "MISMATCH ...", exit 0 / 0 / 1.
 #include <cstdio>
@@ -113,6 +113,35 @@ void run_fused_two(const sk::DevInput di[2], const sk::DevParams &P, sk::Control
     }
     simt::launch(dim3(1), dim3(32), [&] { sk::kf2_finalize(ctl, res); });
     free(st); free(tab[0]); free(tab[1]); free(nls[0]); free(nls[1]);
+}
+
+// -a N (N <= 32), single end, as capi.cu's launch_ordered does: index + verdict pass (+ newline positions, bytes per tile
+// and queue), kfo_scan / kfo_bases, ordered emit pass, summary
+template <int CH>
+void run_ordered(const sk::DevInput di[2], const sk::DevParams &P, sk::Control *ctl, const sk::OutPtrs &op, unsigned ctas, sk::DevResult *res) {
+    using Cfg = sk::FusedCfg<CH>;
+    const uint32_t tiles = (uint32_t)((di[0].nbytes + Cfg::kTile - 1) / Cfg::kTile);
+    const uint32_t cap = tiles + 2, stride = cap * sk::kWideStatusStride;
+    unsigned long long *st = aligned_zero<unsigned long long>((size_t)stride * 3);
+    const uint32_t desc_cap = di[0].line_cap / 4 + 1;
+    sk::RecDesc *desc = aligned_zero<sk::RecDesc>(desc_cap + 1);
+    uint8_t *nls = aligned_zero<uint8_t>((size_t)cap * sk::kFNlSlot);
+    uint32_t *tq = aligned_zero<uint32_t>(((size_t)cap + 1) * 32);
+    if (tiles) {
+        const unsigned grid = std::min<unsigned>(ctas, tiles);
+        simt::launch(dim3(grid), dim3(sk::kFThreads), [&] {
+            sk::kf_fused<CH, 3>(di[0], P, ctl, op, st, st + (size_t)stride, stride, tiles, 5u, sk::DevInput(), 0u, nullptr, nullptr, desc_cap,
+                                nls, nullptr, desc, tq);
+        });
+        simt::launch(dim3((unsigned)P.emu_threads), dim3(256), [&] { sk::kfo_scan(tq, tiles); });
+        simt::launch(dim3(1), dim3(32), [&] { sk::kfo_bases(ctl, tq, tiles, P.emu_threads, op.cap[0]); });
+        simt::launch(dim3(grid), dim3(sk::kFThreads), [&] {
+            sk::kf_fused<CH, 4>(di[0], P, ctl, op, st, st + (size_t)stride, stride, tiles, 5u, sk::DevInput(), 0u, nullptr, nullptr, desc_cap,
+                                nls, nullptr, desc, tq);
+        });
+    }
+    simt::launch(dim3(1), dim3(32), [&] { sk::kf_finalize(di[0], P, ctl, res); });
+    free(st); free(desc); free(nls); free(tq);
 }
 
 // -a N on one input, as capi.cu's launch_hybrid does: the single-pass kernel's index + verdict pass, then the general
@@ -234,6 +263,14 @@ int main(int argc, char **argv) {
         else if (ch == 7) run_fused<7>(di[0], P, ctl, op, ctas, &res);
         else if (ch == 9) run_fused<9>(di[0], P, ctl, op, ctas, &res);
         else run_fused<11>(di[0], P, ctl, op, ctas, &res);
+        if (res.index_overflow & 4u) { printf("FASTFAIL too_many_records=%d\n", (res.index_overflow & 8u) ? 1 : 0); return 0; }
+    } else if (path.rfind("order", 0) == 0) {
+        const int ch = atoi(path.c_str() + 5);
+        if (mode != 0 || P.emu_threads < 2 || P.emu_threads > 32) return 2;
+        if (ch == 3) run_ordered<3>(di, P, ctl, op, ctas, &res);
+        else if (ch == 5) run_ordered<5>(di, P, ctl, op, ctas, &res);
+        else if (ch == 7) run_ordered<7>(di, P, ctl, op, ctas, &res);
+        else run_ordered<9>(di, P, ctl, op, ctas, &res);
         if (res.index_overflow & 4u) { printf("FASTFAIL too_many_records=%d\n", (res.index_overflow & 8u) ? 1 : 0); return 0; }
     } else if (path.rfind("index", 0) == 0) {
         const int ch = atoi(path.c_str() + 5);

@@ -192,6 +192,8 @@ def test_emulated_thread_order_vs_oracle(capi, threads):
     got = _run_cuda(capi, capi.MODE_SE, dict(qualtype="sanger", q=20, l=20, x=False, n=False), data,
                     slot_bytes=1 << 20, threads=threads)
     assert got["out"][0] == want["out"][0]
+    # single end, N <= 32: every batch stays on the single-pass kernel (index pass + ordered emit), no K1/K2/K3
+    assert got["batches"] >= 1 and got["fused_batches"] == got["batches"], (got["fused_batches"], got["batches"])
     a = _random_fastq(rng, 1500, 100, "sanger")
     b = _random_fastq(rng, 1500, 100, "sanger")
     inter = b"".join(x + y for x, y in zip(a, b))
@@ -200,6 +202,7 @@ def test_emulated_thread_order_vs_oracle(capi, threads):
     got = _run_cuda(capi, capi.MODE_PE_INTER, dict(qualtype="sanger", q=20, l=20, x=False, n=False), inter,
                     slot_bytes=1 << 20, threads=threads)
     assert got["out"][0] == want["out"][0] and got["out"][2] == want["out"][2]
+    assert got["fused_batches"] == got["batches"]   # (pairs: index pass + k2_trim_route<true> + K3)
 
 
 def test_batch_size_invariance_and_pipelined_upload(capi):

@@ -303,6 +303,40 @@ def test_reference_order_on_the_index_pass(harness, tmp_path):
     assert rc == 0 and out.startswith("FASTFAIL"), out              # a data error: the general path reports it
 
 
+def test_reference_order_on_the_single_pass_kernel(harness, tmp_path):
+    """-a N (N <= 32), single end (capi.cu's launch_ordered): index + verdict pass, kfo_scan / kfo_bases, then the ordered
+    emit pass -- a tile staged queue by queue and flushed as up to N segments, every segment's place in the output known
+    beforehand.  The oracle's bytes in the reference's -a N order, for every tile size, N from 2 to 32, several CTA
+    counts and input phases; hand-over on a data error and on records longer than the halo."""
+    from sickle_b200 import synth
+    from test_oracle_fuzz_vs_ref import _records
+
+    se, var, lng, bad, big = (str(tmp_path / n) for n in ("se.fq", "var.fq", "long.fq", "bad.fq", "big.fq"))
+    data = synth.fixed_length_records(3000, 150, "sanger", seed=5).tobytes()
+    open(se, "wb").write(data)
+    open(var, "wb").write(_records(np.random.default_rng(92), 1500, 250, "sanger"))
+    open(lng, "wb").write(synth.variable_length_records(12, 6000, 9000, "illumina", 3))
+    open(big, "wb").write(synth.fixed_length_records(40000, 150, "sanger", seed=37).tobytes())
+    for k in ("order3", "order5", "order7", "order9"):
+        for threads in (2, 3, 5, 8, 16, 31, 32):
+            for path, kw in ((se, dict(first=5)), (se, dict(x=True, n=True, q=30, l=5, ctas=2)), (se, dict(q=41, l=30, ctas=1, first=15)),
+                             (var, dict(n=True, first=9, ctas=4))):
+                rc, out, err = run(harness, path, kernel=k, threads=threads, **kw)
+                assert rc == 0 and (out.startswith("OK") or out.startswith("FASTFAIL")), (k, threads, kw, out, err[-400:])
+                if k == "order9" and path != var:
+                    assert out.startswith("OK"), (k, threads, kw, out)
+    for threads in (2, 8, 32):   # hundreds of tiles over 8 concurrent CTAs
+        rc, out, err = run(harness, big, kernel="order9", threads=threads, ctas=8, first=13)
+        assert rc == 0 and out.startswith("OK"), (threads, out, err[-400:])
+    rc, out, err = run(harness, lng, kernel="order9", qualtype="illumina", threads=4)
+    assert rc == 0 and out.startswith("FASTFAIL"), out
+    lines = data.split(b"\n")
+    lines[4 * 2000 + 3] = b"\x7f" + lines[4 * 2000 + 3][1:]
+    open(bad, "wb").write(b"\n".join(lines))
+    rc, out, err = run(harness, bad, kernel="order9", threads=4)
+    assert rc == 0 and out.startswith("FASTFAIL"), out
+
+
 def test_damaged_inputs(harness, tmp_path):
     """Seeded random files, three quarters of them damaged (missing / blank / doubled line, flipped /
     deleted / inserted byte, cut-off tail): same first data error (kind, record, position, byte) or same
@@ -365,7 +399,8 @@ def test_random_thread_order(harness, tmp_path):
     open(var, "wb").write(_records(np.random.default_rng(67), 1500, 250, "sanger"))
     cases = ((se, dict(kernel="fused9", first=5)), (se, dict(kernel="general", first=5)), (il, dict(kernel="fused7", mode="pei", first=3)),
              (il, dict(kernel="fused5", mode="peM", singles=False, ctas=2)), (var, dict(kernel="general", x=True, n=True, ctas=4, first=2)),
-             (var, dict(kernel="fused5", n=True, first=5)))
+             (var, dict(kernel="fused5", n=True, first=5)), (se, dict(kernel="order9", threads=8, first=4)),
+             (se, dict(kernel="index7", threads=3, first=2)))
     for seed in ("1", "2", "3"):
         for path, kw in cases:
             rc, out, err = run(harness, path, env={"SIMT_SHUFFLE": seed}, **kw)
@@ -374,7 +409,7 @@ def test_random_thread_order(harness, tmp_path):
     mut = tmp_path / "csrc"
     shutil.copytree(os.path.join(ROOT, "sickle_b200", "csrc"), mut)
     src = (mut / "kf_fused.cuh").read_text()
-    barrier = "        if (PASS != 2) __syncthreads();   // newline positions visible to every thread"
+    barrier = "        if (!kSaved) __syncthreads();   // newline positions visible to every thread"
     assert src.count(barrier) == 1
     (mut / "kf_fused.cuh").write_text(src.replace(barrier, "        // barrier removed:"))
     stub = os.path.join(ROOT, "tests", "host_stub")
@@ -407,7 +442,9 @@ def test_no_out_of_bounds_access_under_asan(tmp_path):
     for path, kw in ((se, dict(kernel="fused9", first=0)), (se, dict(kernel="fused7", first=11, ctas=2)), (se, dict(kernel="general", first=7)),
                      (il, dict(kernel="fused9", mode="pei", first=3)), (il, dict(kernel="fused5", mode="peM", singles=False)),
                      (il, dict(kernel="general", mode="pei", first=9)), (var, dict(kernel="fused5", n=True, first=5)),
-                     (var, dict(kernel="general", x=True, n=True, ctas=4, first=2))):
+                     (var, dict(kernel="general", x=True, n=True, ctas=4, first=2)),
+                     (se, dict(kernel="order9", threads=8, first=3)), (se, dict(kernel="order5", threads=32, first=14, ctas=2)),
+                     (se, dict(kernel="index9", threads=3, first=6)), (il, dict(kernel="index7", mode="pei", threads=5, first=1))):
         rc, out, err = run(exe, path, env=env, **kw)
         assert rc == 0 and out.startswith("OK") and "AddressSanitizer:" not in err and "runtime error" not in err, (kw, out, err[-1500:])
 
@@ -421,8 +458,8 @@ def test_capacity_overflows_are_flagged(harness, tmp_path):
     open(se, "wb").write(synth.fixed_length_records(2000, 150, "sanger", seed=45).tobytes())
     rc, out, err = run(harness, se, kernel="general", env={"KH_LINE_CAP": "1000"})
     assert rc == 0 and out == "OVERFLOW line_index=1 output=0", (out, err[-300:])
-    for k in ("general", "fused9", "fused5"):
-        rc, out, err = run(harness, se, kernel=k, env={"KH_OUT_CAP": "100000"})
+    for k, threads in (("general", 1), ("fused9", 1), ("fused5", 1), ("order9", 4), ("index9", 4)):
+        rc, out, err = run(harness, se, kernel=k, threads=threads, env={"KH_OUT_CAP": "100000"})
         assert rc == 0 and out == "OVERFLOW line_index=0 output=1", (k, out, err[-300:])
-        rc, out, err = run(harness, se, kernel=k, env={"KH_OUT_CAP": "560000"})      # 558 KB of output: just fits
+        rc, out, err = run(harness, se, kernel=k, threads=threads, env={"KH_OUT_CAP": "560000"})      # 558 KB of output: just fits
         assert rc == 0 and out.startswith("OK"), (k, out)
