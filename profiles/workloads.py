@@ -78,6 +78,12 @@ def main():
         buf, n, recs = device_bytes(m, target, dev)
         measure("se R150, general path (K1/K2/K3)", capi.MODE_SE, [(buf, n)], recs, env={"SICKLE_B200_PATH": "general"}, steps=3)
         return
+    if len(sys.argv) > 1 and sys.argv[1] == "--a8-only":        # short run for profiling the -a N passes under ncu
+        m = synth.fixed_length_records(200_000, 150, "sanger", seed=190)
+        buf, n, recs = device_bytes(m, target, dev)
+        measure("se R150, -a 8 reference order (index pass + ordered emit)", capi.MODE_SE, [(buf, n)], recs, emulate_threads=8, steps=3)
+        measure("pe interleaved R150, -a 8 (index pass + routing + K3)", capi.MODE_PE_INTER, [(buf, n)], recs, emulate_threads=8, steps=3)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "--c4-only":        # short run for profiling the long-read kernels under ncu
         v = synth.variable_length_records(4000, 1000, 20000, "illumina", 70)
         arr = np.frombuffer(v, dtype=np.uint8)
@@ -94,7 +100,9 @@ def main():
         measure("se R%d" % L, capi.MODE_SE, [(buf, n)], recs)
         if L == 150:
             measure("se R150, general path (K1/K2/K3)", capi.MODE_SE, [(buf, n)], recs, env={"SICKLE_B200_PATH": "general"})
-            measure("se R150, -a 8 reference order (index pass + routing + K3)", capi.MODE_SE, [(buf, n)], recs, emulate_threads=8)
+            measure("se R150, -a 8 reference order (index pass + ordered emit)", capi.MODE_SE, [(buf, n)], recs, emulate_threads=8)
+            measure("se R150, -a 64 reference order (index pass + routing + K3)", capi.MODE_SE, [(buf, n)], recs, emulate_threads=64)
+            measure("se R150, -a 8, K1/K2/K3 only", capi.MODE_SE, [(buf, n)], recs, emulate_threads=8, env={"SICKLE_B200_PATH": "general"})
         del buf
     f, r, inter = synth.paired_records(100_000, 150, "sanger", seed=50)
     buf, n, recs = device_bytes(inter, target, dev)

@@ -203,6 +203,16 @@ def test_emulated_thread_order_vs_oracle(capi, threads):
                     slot_bytes=1 << 20, threads=threads)
     assert got["out"][0] == want["out"][0] and got["out"][2] == want["out"][2]
     assert got["fused_batches"] == got["batches"]   # (pairs: index pass + k2_trim_route<true> + K3)
+    # a data error under -a N: the index pass hands the batch to K1/K2/K3, which report it as the oracle does
+    lines = data.split(b"\n")
+    k = next(k for k in range(2345, 4000) if len(lines[4 * k + 3]) >= 30)   # (reads shorter than -l are not looked at)
+    lines[4 * k + 3] = b"\x7f" + lines[4 * k + 3][1:]
+    bad = b"\n".join(lines)
+    want = orc.run(orc.MODE_SE, orc.make_params("sanger"), bad, threads=threads, batch_len=runner.recommended_batch_len(len(bad), 512, False))
+    assert want["rc"] == 6
+    with pytest.raises(runner.DataError) as ei:
+        _run_cuda(capi, capi.MODE_SE, dict(qualtype="sanger", q=20, l=20, x=False, n=False), bad, slot_bytes=1 << 20, threads=threads)
+    assert ei.value.kind == 6 and (ei.value.position, ei.value.byte) == (want["err"]["position"], want["err"]["byte"])
 
 
 def test_batch_size_invariance_and_pipelined_upload(capi):
