@@ -225,7 +225,7 @@ int alloc_slot(sk_ctx *c, Slot &s, bool host_buffers) {
         }
         if (c->ordered_eligible) {
             SK_CUDA(cudaMalloc((void **)&s.d_nlsave[0], (size_t)c->fused_tiles_cap * sk::kFNlSlot));
-            SK_CUDA(cudaMalloc((void **)&s.d_tq, ((size_t)c->fused_tiles_cap + 1) * 32 * sizeof(uint32_t)));
+            SK_CUDA(cudaMalloc((void **)&s.d_tq, ((size_t)c->fused_tiles_cap + 1 + c->fused_tiles_cap / sk::kFTqGroup + 2) * 32 * sizeof(uint32_t)));
         }
     }
     if (host_buffers) {
@@ -509,7 +509,7 @@ int launch_index_pass_ch(sk_ctx *c, Slot &s, const BatchArgs &a, const sk::DevIn
 }
 
 // -a N (N <= 32), single end, all on the single-pass kernel: the index + verdict pass also leaves every tile's newline
-// positions and its kept bytes per queue; two small kernels turn those into every (tile, queue) segment's place in the
+// positions and its kept bytes per queue; one small kernel turns those into every (tile, queue) segment's place in the
 // output; the ordered emit pass (kf_fused<CH, 4>) stages a tile queue by queue and flushes up to N segments -- no look-back,
 // no K2, no K3.
 template <int CH>
@@ -521,20 +521,20 @@ int launch_ordered_ch(sk_ctx *c, Slot &s, const BatchArgs &a, const sk::DevInput
     const uint32_t desc_cap = (uint32_t)(c->line_cap / 4 + 1);
     if (tiles) {
         const int full1 = c->fused_grid_pass1[(CH - 3) / 2], full4 = c->fused_grid_ordered[(CH - 3) / 2];
+        SK_CUDA(cudaMemsetAsync(s.d_tq + ((size_t)tiles + 1) * 32, 0, ((size_t)tiles / sk::kFTqGroup + 1) * 32 * sizeof(uint32_t), st));   // the group rows
         sk::kf_fused<CH, 3><<<tiles < (uint32_t)full1 ? (int)tiles : full1, sk::kFThreads, Cfg::kSmemPass1, st>>>(
             di[0], c->dev, s.d_ctl, op, s.d_status_f, s.d_status_f + (size_t)stride, stride, tiles, s.epoch, sk::DevInput(), 0u, nullptr, nullptr,
             desc_cap, s.d_nlsave[0], nullptr, s.d_desc[0], s.d_tq);
         SK_DEBUG_SYNC(st, "kf_fused index pass");
         SK_CUDA(cudaEventRecord(s.ev_stage[0], st));
-        sk::kfo_scan<<<c->dev.emu_threads, 256, 0, st>>>(s.d_tq, tiles);
-        sk::kfo_bases<<<1, 32, 0, st>>>(s.d_ctl, s.d_tq, tiles, c->dev.emu_threads, op.cap[0]);
-        SK_DEBUG_SYNC(st, "kfo_scan / kfo_bases");
+        sk::kfo_offsets<<<1, 1024, 0, st>>>(s.d_ctl, s.d_tq, tiles, c->dev.emu_threads, op.cap[0]);
+        SK_DEBUG_SYNC(st, "kfo_offsets");
         SK_CUDA(cudaEventRecord(s.ev_stage[1], st));
         sk::kf_fused<CH, 4><<<tiles < (uint32_t)full4 ? (int)tiles : full4, sk::kFThreads, Cfg::kSmemOrdered, st>>>(
             di[0], c->dev, s.d_ctl, op, s.d_status_f, s.d_status_f + (size_t)stride, stride, tiles, s.epoch, sk::DevInput(), 0u, nullptr, nullptr,
             desc_cap, s.d_nlsave[0], nullptr, s.d_desc[0], s.d_tq);
         SK_DEBUG_SYNC(st, "kf_fused ordered emit");
-        s.launches += 4;
+        s.launches += 3;
     } else {
         SK_CUDA(cudaEventRecord(s.ev_stage[0], st));
         SK_CUDA(cudaEventRecord(s.ev_stage[1], st));

@@ -87,6 +87,8 @@ constexpr int kFMaxNl = 1024;        // newline positions per region (2 KB; also
 // in the region} in global memory, kFNlSlot bytes per tile, and PASS 2 fetches them with the tile's bytes instead of
 // finding the newlines again (no masks, no scan, no position stores, no look-back #1).
 constexpr int kFNlSlot = kFMaxNl * 2 + 16;
+// -a N: d_tq holds one row of 32 counters per tile, one row of queue bases, and one row per group of kFTqGroup tiles
+constexpr uint32_t kFTqGroup = 16;
 constexpr uint32_t kTicketPoison = 0x40000000u;   // or-ed into the ticket counter by a tile that gives the batch up (tiles < 2^30)
 
 template <int CH>
@@ -103,8 +105,13 @@ struct FusedCfg {
     // PASS 4: + the tile's saved line numbers, + bytes per record (128 x 4), queue totals (32 x 4), and the staged
     // tile's segments for the deferred flush: start, length (32 x 4 each), destination (32 x 8)
     static constexpr size_t kSmemOrdered = kSmem + 16 + 512 + 128 + 128 + 128 + 256;
-    static constexpr size_t kSmemPass1 = (size_t)kInBytes + kFMaxNl * 2;   // PASS 1 stages nothing: four CTAs per SM
-    static constexpr int kCtasPerSmPass1 = (int)(232448 / (kSmemPass1 + 1024 + 256)) > SK_MAX_CTAS ? SK_MAX_CTAS : (int)(232448 / (kSmemPass1 + 1024 + 256));
+    static constexpr size_t kSmemPass1 = (size_t)kInBytes + kFMaxNl * 2;   // PASS 1 stages nothing: five CTAs per SM
+    // (the passes that stage nothing compile to 48 registers without a spill: five CTAs per SM instead of four,
+    //  -3 % on two files and on -a 8, profiles/r2_call25.log)
+#ifndef SK_MAX_CTAS_PASS1
+#define SK_MAX_CTAS_PASS1 5
+#endif
+    static constexpr int kCtasPerSmPass1 = (int)(232448 / (kSmemPass1 + 1024 + 256)) > SK_MAX_CTAS_PASS1 ? SK_MAX_CTAS_PASS1 : (int)(232448 / (kSmemPass1 + 1024 + 256));
     // CTAs per SM by shared memory (232,448 B per SM, 1,024 B reserved per CTA); also the register budget
     static constexpr int kCtasPerSm = (int)(232448 / (kSmem + 1024 + 256)) > SK_MAX_CTAS ? SK_MAX_CTAS : (int)(232448 / (kSmem + 1024 + 256));
 };
@@ -201,7 +208,7 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
          // PASS 3 only: the general path's descriptor table (tab_cap entries); the line index goes to in_a.line_end
          RecDesc *__restrict__ desc_out = nullptr,
          // PASS 3 (optional) / PASS 4: [num_tiles + 1][32] kept bytes per tile and queue (record k of the batch is dealt to
-         // queue (k+1) % N, src/trim_single.cpp:263,273-274); kfo_scan / kfo_bases turn the columns into output offsets
+         // queue (k+1) % N, src/trim_single.cpp:263,273-274); kfo_offsets turns the counters into output offsets
          uint32_t *__restrict__ tq = nullptr) {
     using Cfg = FusedCfg<CH>;
     constexpr bool kNoEmit = PASS == 1 || PASS == 3;   // these passes stage and write no records
@@ -439,7 +446,7 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         }
         if (!kSaved) __syncthreads();   // newline positions visible to every thread (PASS 2, 4: they came with the tile)
         SK_TICK(3);   // S3 positions + S4 look-back #1
-        if (PASS == 3 && !nl_overflow) {   // the general path's line index (K1's output), and the line count with the last tile
+        if (PASS == 3 && tq == nullptr && !nl_overflow) {   // (not for the ordered emit) the general path's line index (K1's output), and the line count with the last tile
             for (uint32_t j = (uint32_t)tid; j < c_t; j += kFThreads) {
                 if (G + j < in.line_cap) in.line_end[G + j] = t0 + (uint32_t)s_nl[j];
                 else ctl->index_overflow = 1u;
@@ -633,7 +640,11 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
         if (kNoEmit) {   // verdicts are in the table: count the file's records, next tile
             const uint32_t m_live1 = __ballot_sync(0xffffffffu, live);
             if (!tile_fail && lane == 0 && m_live1) s_acc[wid][fsel ? 2 : 0] += (uint32_t)__popc(m_live1);
-            if (PASS == 3 && tq != nullptr && !tile_fail && tid < 32) tq[(size_t)tile * 32u + (uint32_t)tid] = s_q[tid];
+            if (PASS == 3 && tq != nullptr && !tile_fail && tid < 32) {   // the tile's row, and its share of its group's row
+                const uint32_t v = s_q[tid];
+                tq[(size_t)tile * 32u + (uint32_t)tid] = v;
+                if (v) atomicAdd(&tq[((size_t)num_tiles + 1u + tile / kFTqGroup) * 32u + (uint32_t)tid], v);
+            }
             if (tid == 0) held = atomicAdd(&ctl->tile_counter[3], 1u);
             __syncthreads();   // s_fail has been read by everybody before the top of the loop clears it
             continue;
@@ -649,7 +660,12 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 const uint32_t al = (n + 15u) & ~15u;
                 s_fseg[lane] = warp_incl_scan(al, lane) - al;
                 s_flen[lane] = n;
-                if (lane < P.emu_threads) s_fdst[lane] = (unsigned long long)tq[(size_t)num_tiles * 32u + (uint32_t)lane] + tq[(size_t)tile * 32u + (uint32_t)lane];
+                if (lane < P.emu_threads) {   // queue's place + the groups before this tile's + the group's earlier tiles
+                    unsigned long long d = (unsigned long long)tq[(size_t)num_tiles * 32u + (uint32_t)lane] +
+                                           tq[((size_t)num_tiles + 1u + tile / kFTqGroup) * 32u + (uint32_t)lane];
+                    for (uint32_t t2 = tile - tile % kFTqGroup; t2 < tile; ++t2) d += tq[(size_t)t2 * 32u + (uint32_t)lane];
+                    s_fdst[lane] = d;
+                }
             }
             __syncthreads();
         }
@@ -846,52 +862,54 @@ __global__ void kf2_between(Control *__restrict__ ctl) {
     ctl->tile_counter[3] &= kTicketPoison;
 }
 
-// -a N order, between the index pass (kf_fused<CH, 3>) and the ordered emit (kf_fused<CH, 4>).  tq[t][q] = kept bytes of
-// tile t that go to queue q.  kfo_scan (one CTA per queue) turns every column into its exclusive prefix over the tiles and
-// leaves the queue's total in row `tiles`; kfo_bases (one warp) turns that row into the queues' places in the output
-// (the reference writes queue 0, then queue 1, ...: src/trim_single.cpp:374-428), sets the size of the output and hands
-// the tickets out again (a poisoned counter stays poisoned).
-__global__ void __launch_bounds__(256) kfo_scan(uint32_t *__restrict__ tq, uint32_t tiles) {
-    __shared__ uint32_t part[256];
-    const uint32_t q = blockIdx.x, tid = threadIdx.x;
-    const uint32_t chunk = (tiles + 255u) / 256u;
-    const uint32_t lo = min(tiles, tid * chunk), hi = min(tiles, lo + chunk);
+// -a N order, between the index pass (kf_fused<CH, 3>) and the ordered emit (kf_fused<CH, 4>).  The index pass left
+// tq[t][q] = kept bytes of tile t that go to queue q, and, in the rows behind row `tiles`, the same summed over groups of
+// kFTqGroup tiles (atomics; the host zeroes those rows per batch).  One CTA: warp w takes a contiguous run of group rows
+// (lane = queue, so a row is one coalesced load), sums it, the warps' sums are scanned through shared memory, and the
+// second sweep turns every group row into the exclusive prefix over the groups.  Row `tiles` gets the queues' places in
+// the output (the reference writes queue 0, then queue 1, ...: src/trim_single.cpp:374-428); the output size is set and
+// the tickets are handed out again (a poisoned counter stays poisoned).  A tile's segment for queue q then starts at
+// base[q] + group prefix + the rows of the group's earlier tiles (at most kFTqGroup - 1 loads, in kf_fused<CH, 4>).
+__global__ void __launch_bounds__(1024) kfo_offsets(Control *__restrict__ ctl, uint32_t *__restrict__ tq, uint32_t tiles, int nq,
+                                                    unsigned long long cap) {
+    __shared__ uint32_t part[32][33];
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const uint32_t ngroups = (tiles + kFTqGroup - 1u) / kFTqGroup;
+    uint32_t *__restrict__ grp = tq + ((size_t)tiles + 1u) * 32u;
+    const uint32_t chunk = (ngroups + 31u) / 32u;
+    const uint32_t lo = min(ngroups, (uint32_t)w * chunk), hi = min(ngroups, lo + chunk);
     uint32_t sum = 0;
-    for (uint32_t t = lo; t < hi; ++t) sum += tq[(size_t)t * 32u + q];
-    part[tid] = sum;
+    for (uint32_t g = lo; g < hi; ++g) sum += grp[(size_t)g * 32u + (uint32_t)lane];
+    part[w][lane] = sum;
     __syncthreads();
     uint32_t run = 0, total = 0;
-    for (uint32_t k = 0; k < 256u; ++k) {
-        const uint32_t v = part[k];
-        if (k < tid) run += v;
+    for (int k = 0; k < 32; ++k) {
+        const uint32_t v = part[k][lane];
+        if (k < w) run += v;
         total += v;
     }
-    for (uint32_t t = lo; t < hi; ++t) {
-        const uint32_t v = tq[(size_t)t * 32u + q];
-        tq[(size_t)t * 32u + q] = run;
+    for (uint32_t g = lo; g < hi; ++g) {
+        const uint32_t v = grp[(size_t)g * 32u + (uint32_t)lane];
+        grp[(size_t)g * 32u + (uint32_t)lane] = run;
         run += v;
     }
-    if (tid == 0) tq[(size_t)tiles * 32u + q] = total;
-}
-
-__global__ void kfo_bases(Control *__restrict__ ctl, uint32_t *__restrict__ tq, uint32_t tiles, int nq, unsigned long long cap) {
-    const int lane = threadIdx.x;
-    if (blockIdx.x != 0 || lane >= 32) return;
-    const uint32_t tot = lane < nq ? tq[(size_t)tiles * 32u + (uint32_t)lane] : 0u;
-    unsigned long long incl = tot;
+    if (w == 0) {   // the queues' places: exclusive prefix of their totals
+        const uint32_t tot = lane < nq ? total : 0u;
+        unsigned long long incl = tot;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= o) incl += t;
-    }
-    if (lane < nq) tq[(size_t)tiles * 32u + (uint32_t)lane] = (uint32_t)(incl - tot);
-    if (lane == 31) {
-        ctl->out_bytes[0] = incl;
-        if (incl > cap) {   // reported by the summary as a capacity error; nothing is written
-            ctl->index_overflow |= 2u;
-            ctl->tile_counter[3] |= kTicketPoison;
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
         }
-        ctl->tile_counter[3] &= kTicketPoison;
+        tq[(size_t)tiles * 32u + (uint32_t)lane] = (uint32_t)(incl - tot);
+        if (lane == 31) {
+            ctl->out_bytes[0] = incl;
+            if (incl > cap) {   // reported by the summary as a capacity error; nothing is written
+                ctl->index_overflow |= 2u;
+                ctl->tile_counter[3] |= kTicketPoison;
+            }
+            ctl->tile_counter[3] &= kTicketPoison;
+        }
     }
 }
 

@@ -116,7 +116,7 @@ void run_fused_two(const sk::DevInput di[2], const sk::DevParams &P, sk::Control
 }
 
 // -a N (N <= 32), single end, as capi.cu's launch_ordered does: index + verdict pass (+ newline positions, bytes per tile
-// and queue), kfo_scan / kfo_bases, ordered emit pass, summary
+// and queue), kfo_offsets, ordered emit pass, summary
 template <int CH>
 void run_ordered(const sk::DevInput di[2], const sk::DevParams &P, sk::Control *ctl, const sk::OutPtrs &op, unsigned ctas, sk::DevResult *res) {
     using Cfg = sk::FusedCfg<CH>;
@@ -126,15 +126,14 @@ void run_ordered(const sk::DevInput di[2], const sk::DevParams &P, sk::Control *
     const uint32_t desc_cap = di[0].line_cap / 4 + 1;
     sk::RecDesc *desc = aligned_zero<sk::RecDesc>(desc_cap + 1);
     uint8_t *nls = aligned_zero<uint8_t>((size_t)cap * sk::kFNlSlot);
-    uint32_t *tq = aligned_zero<uint32_t>(((size_t)cap + 1) * 32);
+    uint32_t *tq = aligned_zero<uint32_t>(((size_t)cap + 1 + cap / sk::kFTqGroup + 2) * 32);   // (zeroed: capi.cu memsets the group rows)
     if (tiles) {
         const unsigned grid = std::min<unsigned>(ctas, tiles);
         simt::launch(dim3(grid), dim3(sk::kFThreads), [&] {
             sk::kf_fused<CH, 3>(di[0], P, ctl, op, st, st + (size_t)stride, stride, tiles, 5u, sk::DevInput(), 0u, nullptr, nullptr, desc_cap,
                                 nls, nullptr, desc, tq);
         });
-        simt::launch(dim3((unsigned)P.emu_threads), dim3(256), [&] { sk::kfo_scan(tq, tiles); });
-        simt::launch(dim3(1), dim3(32), [&] { sk::kfo_bases(ctl, tq, tiles, P.emu_threads, op.cap[0]); });
+        simt::launch(dim3(1), dim3(1024), [&] { sk::kfo_offsets(ctl, tq, tiles, P.emu_threads, op.cap[0]); });
         simt::launch(dim3(grid), dim3(sk::kFThreads), [&] {
             sk::kf_fused<CH, 4>(di[0], P, ctl, op, st, st + (size_t)stride, stride, tiles, 5u, sk::DevInput(), 0u, nullptr, nullptr, desc_cap,
                                 nls, nullptr, desc, tq);

@@ -304,7 +304,7 @@ def test_reference_order_on_the_index_pass(harness, tmp_path):
 
 
 def test_reference_order_on_the_single_pass_kernel(harness, tmp_path):
-    """-a N (N <= 32), single end (capi.cu's launch_ordered): index + verdict pass, kfo_scan / kfo_bases, then the ordered
+    """-a N (N <= 32), single end (capi.cu's launch_ordered): index + verdict pass, kfo_offsets, then the ordered
     emit pass -- a tile staged queue by queue and flushed as up to N segments, every segment's place in the output known
     beforehand.  The oracle's bytes in the reference's -a N order, for every tile size, N from 2 to 32, several CTA
     counts and input phases; hand-over on a data error and on records longer than the halo."""
