@@ -52,5 +52,7 @@ PY
   echo "== command line, 24 M reads"
   python profiles/cli_bench.py --reads 24000000 --skip-ref --repeat 2
   python profiles/cli_bench.py --reads 8000000 --repeat 1
+  echo "== tile sizes, single end (same process)"
+  python profiles/ab_multi.py --workload se --rounds 3 --steps 24 sickle_b200/libsickle_b200.so@SICKLE_B200_FUSED_CH=7 sickle_b200/libsickle_b200.so@SICKLE_B200_FUSED_CH=9 sickle_b200/libsickle_b200.so@SICKLE_B200_FUSED_CH=11
 } >> $L 2>&1
 tail -60 $L | cut -c1-420
