@@ -313,7 +313,8 @@ int launch_general(sk_ctx *c, Slot &s, const BatchArgs &a) {
     }
     SK_DEBUG_SYNC(st, "k2_trim_route");
     SK_CUDA(cudaEventRecord(s.ev_stage[1], st));
-    sk::k3_emit<<<resident, sk::kK3Threads, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, s.d_desc[0], s.d_desc[1], op);
+    if (c->long_records) sk::k3_emit_long<<<resident, 256, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, s.d_desc[0], s.d_desc[1], op);
+    else sk::k3_emit<<<resident, sk::kK3Threads, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, s.d_desc[0], s.d_desc[1], op);
     SK_DEBUG_SYNC(st, "k3_emit");
     SK_CUDA(cudaEventRecord(s.ev_stage[2], st));
     sk::k_finalize<<<1, 32, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, op, s.d_res);

@@ -192,6 +192,28 @@ struct OutPtrs {
     unsigned long long cap[kMaxStreams];
 };
 
+// K3 for batches of long records (what capi.cu launches while the previous general-path batch averaged 1.5 KB or more per
+// record): one record per warp, the whole warp on each of its runs.  The same loop is the `long_batch` branch of
+// k3_emit; as a kernel of its own it keeps the registers (and CTAs per SM) it had before k3_emit's quarter-warp path
+// grew (same-GPU: 0.074 -> 0.06x ms per 255 MB of 1-20 kb reads).  Correct for any batch, merely slow on short records.
+__global__ void __launch_bounds__(256, 4)
+k3_emit_long(DevInput in0, DevInput in1, DevParams P, const Control *__restrict__ ctl, const RecDesc *__restrict__ desc0,
+             const RecDesc *__restrict__ desc1, OutPtrs outs) {
+    const int lane = threadIdx.x & 31;
+    const Geometry g = batch_geometry(ctl, P);
+    if (ctl->err_key != kNoError || ctl->fast_fail) return;
+#pragma unroll
+    for (int s = 0; s < kMaxStreams; ++s)
+        if (ctl->out_bytes[s] > outs.cap[s]) return;
+    const uint32_t nw = gridDim.x * (256 / 32);
+    for (uint32_t c = blockIdx.x * (256 / 32) + (threadIdx.x >> 5); c < g.nrec0 + g.nrec1; c += nw) {
+        const bool second = c >= g.nrec0;
+        const uint32_t rec = second ? c - g.nrec0 : c;
+        const RecDesc d = (second ? desc1 : desc0)[rec];
+        if (d.route & kRouteEmit) emit_record(second ? in1 : in0, rec, d, outs.p, P, lane);
+    }
+}
+
 #ifndef SK_K3_MINCTAS
 #define SK_K3_MINCTAS 3
 #endif

@@ -199,7 +199,10 @@ void run_general(const sk::DevInput di[2], int n_inputs, const sk::DevParams &P,
         simt::launch(dim3((unsigned)std::min<uint64_t>(ctas, tiles)), dim3(sk::kK2Threads),
                      [&] { sk::k2_trim_route<true>(di[0], di[1], P, ctl, desc[0], desc[1], st2, k2_cap, epoch); });
     }
-    simt::launch(dim3(ctas), dim3(sk::kK3Threads), [&] { sk::k3_emit(di[0], di[1], P, ctl, desc[0], desc[1], op); });
+    if (getenv("KH_K2_SPLIT") && atoi(getenv("KH_K2_SPLIT")) < 32)   // long records, as capi.cu: K3 with one record per warp
+        simt::launch(dim3(ctas), dim3(256), [&] { sk::k3_emit_long(di[0], di[1], P, ctl, desc[0], desc[1], op); });
+    else
+        simt::launch(dim3(ctas), dim3(sk::kK3Threads), [&] { sk::k3_emit(di[0], di[1], P, ctl, desc[0], desc[1], op); });
     simt::launch(dim3(1), dim3(32), [&] { sk::k_finalize(di[0], di[1], P, ctl, op, res); });
     free(st2); free(desc[0]); free(desc[1]);
 }

@@ -180,7 +180,7 @@ def test_random_pe_vs_oracle(capi, mode_name, kernel_path):
             assert got["counters"][k] == want["counters"][k], (mode_name, fl, k)
 
 
-@pytest.mark.parametrize("threads", [2, 3, 7])
+@pytest.mark.parametrize("threads", [2, 3, 7, 32, 33])
 def test_emulated_thread_order_vs_oracle(capi, threads):
     """-a N output order (queue dealing inside reference batches), SE and PE."""
     rng = np.random.default_rng([3, threads] + SOAK)
