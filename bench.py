@@ -79,14 +79,43 @@ def lib_sha256():
     return h.hexdigest()
 
 
+def src_sha256():
+    """sha256 over the kernel sources (path + bytes, sorted): nvcc's output is not byte-reproducible, so a library
+    rebuilt from the very sources of the capture has another lib_sha256."""
+    import glob
+
+    h = hashlib.sha256()
+    files = sorted(glob.glob(os.path.join(ROOT, "sickle_b200", "csrc", "*.cu")) + glob.glob(os.path.join(ROOT, "sickle_b200", "csrc", "*.cuh")) +
+                   [os.path.join(ROOT, "include", "sickle_b200.h"), os.path.join(ROOT, "Makefile")])
+    for f in files:
+        h.update(os.path.relpath(f, ROOT).encode() + b"\0")
+        h.update(open(f, "rb").read())
+    return h.hexdigest()
+
+
+def lib_is_built_from_tree():
+    """The loaded library is the in-tree one and not older than any kernel source."""
+    import glob
+
+    from sickle_b200 import capi
+
+    default = os.path.join(ROOT, "sickle_b200", "libsickle_b200.so")
+    if os.path.abspath(capi.LIB_PATH) != default:
+        return False
+    srcs = glob.glob(os.path.join(ROOT, "sickle_b200", "csrc", "*.cu*")) + [os.path.join(ROOT, "include", "sickle_b200.h")]
+    return os.path.getmtime(default) >= max(os.path.getmtime(f) for f in srcs)
+
+
 def ncu_traffic(config):
     """DRAM bytes (read + write) of the dominant kernel's launch over one batch of this workload, from the
     committed `ncu --set full` capture -- only if that capture was taken from the very library that is
-    loaded now (profiles/ncu_traffic.json records the sha256 of the .so next to the numbers); else None."""
+    loaded now (profiles/ncu_traffic.json records the sha256 of the .so next to the numbers), or from a build of the
+    very kernel sources the loaded in-tree library was built from (src_sha256); else None."""
     try:
         d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
         e = d.get(config)
-        if e and e.get("lib_sha256") == lib_sha256():
+        if e and (e.get("lib_sha256") == lib_sha256() or
+                  (e.get("src_sha256") and e.get("src_sha256") == src_sha256() and lib_is_built_from_tree())):
             return float(e["dram_bytes_per_launch"])
     except Exception:  # noqa: BLE001
         pass

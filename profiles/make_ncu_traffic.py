@@ -37,7 +37,7 @@ def main():
                 i = h.index(k)
                 tot += float(r[i]) * UNIT[units[i]]
             kernels.append(r[h.index("Kernel Name")] if "Kernel Name" in h else "?")
-        out[cfg] = {"lib_sha256": sha, "dram_bytes_per_launch": tot, "launches_summed": len(kernels), "kernels": kernels, "source": os.path.basename(path)}
+        out[cfg] = {"lib_sha256": sha, "src_sha256": bench.src_sha256(), "dram_bytes_per_launch": tot, "launches_summed": len(kernels), "kernels": kernels, "source": os.path.basename(path)}
     json.dump(out, open(out_path, "w"), indent=1)
     print(json.dumps(out, indent=1))
 

@@ -377,10 +377,9 @@ __device__ __forceinline__ void trim_units(const DevInput &in0, const DevInput &
 // and the scan from those.  In one kernel a tile's look-back has to wait for every earlier tile, and with reads of
 // 1-20 kb the tiles' times differ by an order of magnitude: a quarter of K2's instructions were look-back polls and
 // its warps spent more time at the tile barriers than working (ncu, profiles/r2_final_long_*).
-#ifndef SK_K2A_MINCTAS
-#define SK_K2A_MINCTAS 1
-#endif
-__global__ void __launch_bounds__(kK2Threads, SK_K2A_MINCTAS)
+// (five and six CTAs per SM -- 48 / 40 registers -- were measured against the four this compiles to: no change,
+//  profiles/r2_call29.log; the kernel ends with its slowest warp, a 20 kb read walked by one warp)
+__global__ void __launch_bounds__(kK2Threads)
 k2_trim_only(DevInput in0, DevInput in1, DevParams P, Control *__restrict__ ctl, RecDesc *__restrict__ desc0,
              RecDesc *__restrict__ desc1, uint32_t upw /* units a warp draws at a time: 2 for long records, 32 otherwise */) {
     const int lane = threadIdx.x & 31;
