@@ -27,8 +27,14 @@ while time.time() - t0 < budget:
     kw = dict(mode=mode, qualtype=qualtype, q=fl["q"], l=fl["l"], x=fl["x"], n=fl["n"], singles=bool(rng.integers(0, 2)) if mode == "pei" else (mode != "peM"),
               first=int(rng.integers(0, 16)), ctas=int(rng.integers(1, 7)))
     env = {"SIMT_SHUFFLE": str(int(rng.integers(1, 1000)))} if rng.random() < 0.3 else None
-    for k in ("general", ["fused5", "fused7", "fused9", "fused11"][int(rng.integers(0, 4))]):
-        rc, out, err = t.run(exe, p, kernel=k, env=env, **kw)
+    # FZ_ORDER=1: the -a N paths instead -- index pass + routing + K3 (any mode), index pass + ordered emit (single end, N <= 32)
+    threads = int(rng.choice([2, 3, 4, 7, 8, 16, 31, 32])) if os.environ.get("FZ_ORDER") else 1
+    if threads > 1:
+        kernels = ["general", "index%d" % int(rng.choice([3, 5, 7, 9]))] + (["order%d" % int(rng.choice([3, 5, 7, 9]))] if mode == "se" else [])
+    else:
+        kernels = ("general", ["fused5", "fused7", "fused9", "fused11"][int(rng.integers(0, 4))])
+    for k in kernels:
+        rc, out, err = t.run(exe, p, kernel=k, env=env, threads=threads, **kw)
         key = (k[:5], out.split()[0] if out else "rc%d" % rc)
         stats[key] = stats.get(key, 0) + 1
         ok = rc == 0 and (out.startswith("OK") or (k != "general" and out.startswith("FASTFAIL")))
