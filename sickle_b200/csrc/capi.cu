@@ -215,11 +215,11 @@ int alloc_slot(sk_ctx *c, Slot &s, bool host_buffers) {
     }
     SK_CUDA(cudaMalloc((void **)&s.d_status_k2, (size_t)c->k2_tiles_cap * 8 * sk::kMaxStreams));
     SK_CUDA(cudaMemset(s.d_status_k2, 0, (size_t)c->k2_tiles_cap * 8 * sk::kMaxStreams));
-    if (c->fused_eligible || c->hybrid_eligible) {
+    if (c->fused_eligible || c->hybrid_eligible) {   // (-a N on two files: the index pass walks a newline chain per file)
         const size_t chains = c->n_inputs == 2 ? 6 : 3;   // two files: a newline chain and two output chains per file
         SK_CUDA(cudaMalloc((void **)&s.d_status_f, (size_t)c->fused_tiles_cap * 8 * chains * sk::kWideStatusStride));
         SK_CUDA(cudaMemset(s.d_status_f, 0, (size_t)c->fused_tiles_cap * 8 * chains * sk::kWideStatusStride));
-        if (c->n_inputs == 2) {
+        if (c->n_inputs == 2 && c->fused_eligible) {
             for (auto &v : s.d_verdict) SK_CUDA(cudaMalloc((void **)&v, (size_t)c->verdict_cap * 8));
             for (auto &v : s.d_nlsave) SK_CUDA(cudaMalloc((void **)&v, (size_t)c->fused_tiles_cap * sk::kFNlSlot));
         }
@@ -495,14 +495,17 @@ int launch_fused(sk_ctx *c, Slot &s, const BatchArgs &a) {
 template <int CH>
 int launch_index_pass_ch(sk_ctx *c, Slot &s, const BatchArgs &a, const sk::DevInput di[2], const sk::OutPtrs &op) {
     using Cfg = sk::FusedCfg<CH>;
-    const uint32_t tiles = (uint32_t)((a.n[0] + Cfg::kTile - 1) / Cfg::kTile);
+    // two input files: one launch over the tiles of both (tickets dealt in proportion, as in the two-file passes)
+    const uint32_t tiles_a = (uint32_t)((a.n[0] + Cfg::kTile - 1) / Cfg::kTile);
+    const uint32_t tiles_b = c->n_inputs == 2 ? (uint32_t)((a.n[1] + Cfg::kTile - 1) / Cfg::kTile) : 0u;
+    const uint32_t tiles = tiles_a + tiles_b;
     const uint32_t stride = c->fused_tiles_cap * sk::kWideStatusStride;
     if (tiles) {
         const int full = c->fused_grid_pass1[(CH - 3) / 2];
         const int grid = tiles < (uint32_t)full ? (int)tiles : full;
-        sk::kf_fused<CH, 3><<<grid, sk::kFThreads, Cfg::kSmemPass1, a.st>>>(di[0], c->dev, s.d_ctl, op, s.d_status_f, s.d_status_f + (size_t)stride, stride,
-                                                                         tiles, s.epoch, sk::DevInput(), 0u, nullptr, nullptr,
-                                                                         (uint32_t)(c->line_cap / 4 + 1), nullptr, nullptr, s.d_desc[0]);
+        sk::kf_fused<CH, 3><<<grid, sk::kFThreads, Cfg::kSmemPass1, a.st>>>(di[0], c->dev, s.d_ctl, op, s.d_status_f, s.d_status_f + 2 * (size_t)stride, stride,
+                                                                         tiles, s.epoch, di[1], tiles_b, nullptr, nullptr,
+                                                                         (uint32_t)(c->line_cap / 4 + 1), nullptr, nullptr, s.d_desc[0], nullptr, s.d_desc[1]);
         s.launches++;
         SK_DEBUG_SYNC(a.st, "kf_fused index pass");
     }
@@ -587,7 +590,7 @@ int launch_hybrid(sk_ctx *c, Slot &s, const BatchArgs &a) {
     if (rc) return rc;
     SK_CUDA(cudaEventRecord(s.ev_stage[0], st));
     const int resident = c->sm_count * 8;
-    const uint64_t max_units = a.n[0] / 4 + 1;
+    const uint64_t max_units = (a.n[0] + a.n[1]) / 4 + 1;
     const uint64_t tiles = (max_units + sk::kK2UnitsPerTile - 1) / sk::kK2UnitsPerTile;
     const int grid = tiles < (uint64_t)resident ? (int)tiles : resident;
     sk::k2_trim_route<true><<<grid, sk::kK2Threads, 0, st>>>(di[0], di[1], c->dev, s.d_ctl, s.d_desc[0], s.d_desc[1], s.d_status_k2, c->k2_tiles_cap, s.epoch);
@@ -736,7 +739,7 @@ sk_ctx *sk_create(int device, uint64_t slot_bytes, int n_slots, const sk_params 
     c->fused_tiles_cap = (uint32_t)(c->slot_bytes / kFusedMinTile) + 2;
     // SICKLE_B200_PATH = auto (default) | general | fused ; SICKLE_B200_FUSED_CH = 5 | 7 | 9 | 11
     c->fused_eligible = dp.emu_threads == 1;
-    c->hybrid_eligible = dp.emu_threads > 1 && c->n_inputs == 1;
+    c->hybrid_eligible = dp.emu_threads > 1;
     c->ordered_eligible = c->hybrid_eligible && dp.emu_threads <= 32 && params->mode == SK_MODE_SE;
     if (const char *e = getenv("SICKLE_B200_ORDERED")) { if (atoi(e) == 0) c->ordered_eligible = false; }
     c->verdict_cap = (uint32_t)(c->slot_bytes / 32 + 64);   // records of 32 bytes and more (shorter ones: general path)

@@ -209,7 +209,9 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
          RecDesc *__restrict__ desc_out = nullptr,
          // PASS 3 (optional) / PASS 4: [num_tiles + 1][32] kept bytes per tile and queue (record k of the batch is dealt to
          // queue (k+1) % N, src/trim_single.cpp:263,273-274); kfo_offsets turns the counters into output offsets
-         uint32_t *__restrict__ tq = nullptr) {
+         uint32_t *__restrict__ tq = nullptr,
+         // PASS 3 on two input files (tiles_b > 0): the second file's descriptor table; its line index goes to in_b.line_end
+         RecDesc *__restrict__ desc_out_b = nullptr) {
     using Cfg = FusedCfg<CH>;
     constexpr bool kNoEmit = PASS == 1 || PASS == 3;   // these passes stage and write no records
     constexpr bool kSaved = PASS == 2 || PASS == 4;    // newline positions and line numbers come from the pass before
@@ -451,7 +453,7 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 if (G + j < in.line_cap) in.line_end[G + j] = t0 + (uint32_t)s_nl[j];
                 else ctl->index_overflow = 1u;
             }
-            if (tid == 0 && tile == file_tiles - 1u) ctl->nlines[0] = G + c_t;
+            if (tid == 0 && tile == file_tiles - 1u) ctl->nlines[fsel] = G + c_t;
         }
         if ((PASS == 1 || (PASS == 3 && nlsave_a != nullptr)) && !nl_overflow) {   // for PASS 2 / 4: positions (whole 16-byte chunks) and the three numbers
             uint4 *__restrict__ slot = reinterpret_cast<uint4 *>((fsel ? nlsave_b : nlsave_a) + (size_t)tile * kFNlSlot);
@@ -567,7 +569,7 @@ kf_fused(DevInput in_a, DevParams P, Control *__restrict__ ctl, OutPtrs outs,
                 d.route = cut.three >= 0 ? 1u : 0u;
                 d.five = d.route ? (uint32_t)cut.five : 0u;
                 d.nkeep = d.route ? (uint32_t)(cut.three - cut.five) : 0u;
-                desc_out[recno] = d;
+                (fsel ? desc_out_b : desc_out)[recno] = d;
                 if (tq != nullptr && d.route)
                     atomicAdd(&s_q[(recno + 1u) % (uint32_t)P.emu_threads], name_len + plus_len + 4u + 2u * d.nkeep);
             } else fail = true;

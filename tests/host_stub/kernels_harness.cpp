@@ -146,21 +146,23 @@ void run_ordered(const sk::DevInput di[2], const sk::DevParams &P, sk::Control *
 // -a N on one input, as capi.cu's launch_hybrid does: the single-pass kernel's index + verdict pass, then the general
 // path's routing, K3 and summary
 template <int CH>
-void run_hybrid(const sk::DevInput di[2], const sk::DevParams &P, sk::Control *ctl, const sk::OutPtrs &op, unsigned ctas, sk::DevResult *res) {
+void run_hybrid(const sk::DevInput di[2], int n_inputs, const sk::DevParams &P, sk::Control *ctl, const sk::OutPtrs &op, unsigned ctas, sk::DevResult *res) {
     using Cfg = sk::FusedCfg<CH>;
-    const uint32_t tiles = (uint32_t)((di[0].nbytes + Cfg::kTile - 1) / Cfg::kTile);
-    const uint32_t cap = tiles + 2, stride = cap * sk::kWideStatusStride;
-    unsigned long long *st = aligned_zero<unsigned long long>((size_t)stride * 3);
+    const uint32_t ta = (uint32_t)((di[0].nbytes + Cfg::kTile - 1) / Cfg::kTile);
+    const uint32_t tb = n_inputs == 2 ? (uint32_t)((di[1].nbytes + Cfg::kTile - 1) / Cfg::kTile) : 0u;
+    const uint32_t tiles = ta + tb;
+    const uint32_t cap = std::max(ta, tb) + 2, stride = cap * sk::kWideStatusStride;
+    unsigned long long *st = aligned_zero<unsigned long long>((size_t)stride * 6);
     const uint32_t desc_cap = di[0].line_cap / 4 + 1;
-    sk::RecDesc *desc[2] = {aligned_zero<sk::RecDesc>(desc_cap + 1), nullptr};
+    sk::RecDesc *desc[2] = {aligned_zero<sk::RecDesc>(desc_cap + 1), aligned_zero<sk::RecDesc>(desc_cap + 1)};
     if (tiles) {
         const unsigned grid = std::min<unsigned>(ctas, tiles);
         simt::launch(dim3(grid), dim3(sk::kFThreads), [&] {
-            sk::kf_fused<CH, 3>(di[0], P, ctl, op, st, st + (size_t)stride, stride, tiles, 5u, sk::DevInput(), 0u, nullptr, nullptr, desc_cap,
-                                nullptr, nullptr, desc[0]);
+            sk::kf_fused<CH, 3>(di[0], P, ctl, op, st, st + 2 * (size_t)stride, stride, tiles, 5u, di[1], tb, nullptr, nullptr, desc_cap,
+                                nullptr, nullptr, desc[0], nullptr, desc[1]);
         });
     }
-    const uint64_t max_units = (uint64_t)di[0].nbytes / 4 + 1;
+    const uint64_t max_units = ((uint64_t)di[0].nbytes + di[1].nbytes) / 4 + 1;
     const uint64_t t2 = (max_units + sk::kK2UnitsPerTile - 1) / sk::kK2UnitsPerTile;
     const uint32_t k2_cap = (uint32_t)t2 + 2;
     unsigned long long *st2 = aligned_zero<unsigned long long>((size_t)k2_cap * sk::kMaxStreams);
@@ -168,7 +170,7 @@ void run_hybrid(const sk::DevInput di[2], const sk::DevParams &P, sk::Control *c
                  [&] { sk::k2_trim_route<true>(di[0], di[1], P, ctl, desc[0], desc[1], st2, k2_cap, 5u); });
     simt::launch(dim3(ctas), dim3(sk::kK3Threads), [&] { sk::k3_emit(di[0], di[1], P, ctl, desc[0], desc[1], op); });
     simt::launch(dim3(1), dim3(32), [&] { sk::k_finalize(di[0], di[1], P, ctl, op, res); });
-    free(st); free(st2); free(desc[0]);
+    free(st); free(st2); free(desc[0]); free(desc[1]);
 }
 
 void run_general(const sk::DevInput di[2], int n_inputs, const sk::DevParams &P, sk::Control *ctl, const sk::OutPtrs &op, unsigned ctas,
@@ -276,11 +278,11 @@ int main(int argc, char **argv) {
         if (res.index_overflow & 4u) { printf("FASTFAIL too_many_records=%d\n", (res.index_overflow & 8u) ? 1 : 0); return 0; }
     } else if (path.rfind("index", 0) == 0) {
         const int ch = atoi(path.c_str() + 5);
-        if (mode == 1) return 2;
-        if (ch == 3) run_hybrid<3>(di, P, ctl, op, ctas, &res);
-        else if (ch == 5) run_hybrid<5>(di, P, ctl, op, ctas, &res);
-        else if (ch == 7) run_hybrid<7>(di, P, ctl, op, ctas, &res);
-        else run_hybrid<9>(di, P, ctl, op, ctas, &res);
+        const int ni = mode == 1 ? 2 : 1;
+        if (ch == 3) run_hybrid<3>(di, ni, P, ctl, op, ctas, &res);
+        else if (ch == 5) run_hybrid<5>(di, ni, P, ctl, op, ctas, &res);
+        else if (ch == 7) run_hybrid<7>(di, ni, P, ctl, op, ctas, &res);
+        else run_hybrid<9>(di, ni, P, ctl, op, ctas, &res);
         if (res.index_overflow & 4u) { printf("FASTFAIL too_many_records=%d\n", (res.index_overflow & 8u) ? 1 : 0); return 0; }
     } else {
         run_general(di, mode == 1 ? 2 : 1, P, ctl, op, ctas, &res);

@@ -209,6 +209,17 @@ def test_emulated_thread_order_vs_oracle(capi, threads):
     got = _run_cuda(capi, capi.MODE_PE_INTER, dict(qualtype="sanger", q=20, l=20, x=False, n=False), inter,
                     slot_bytes=1 << 20, threads=threads)
     assert got["out"][0] == want["out"][0] and got["out"][2] == want["out"][2]
+    # two files under -a N (mates of equal length, so that the reference's batches of the two files hold the same records):
+    # the index pass runs over the tiles of both files, then K2 routing + K3
+    f2, r2, _ = synth.paired_records(9000, 150, "sanger", seed=40 + threads)
+    f2, r2 = f2.tobytes(), r2.tobytes()
+    bl = runner.recommended_batch_len(len(f2), 512, True)
+    want2 = orc.run(orc.MODE_PE_2FILE, orc.make_params("sanger"), f2, r2, threads=threads, batch_len=bl)
+    assert want2["rc"] == 0
+    got2 = _run_cuda(capi, capi.MODE_PE_2FILE, dict(qualtype="sanger", q=20, l=20, x=False, n=False), f2, r2, slot_bytes=1 << 20, threads=threads)
+    for s_ in range(3):
+        assert got2["out"][s_] == want2["out"][s_], (threads, s_)
+    assert got2["batches"] >= 4 and got2["fused_batches"] == got2["batches"], (got2["fused_batches"], got2["batches"])
     # a data error under -a N: the index pass hands the batch to K1/K2/K3, which report it as the oracle does
     lines = data.split(b"\n")
     k = next(k for k in range(2345, 4000) if len(lines[4 * k + 3]) >= 30)   # (reads shorter than -l are not looked at)

@@ -280,16 +280,20 @@ def test_reference_order_on_the_index_pass(harness, tmp_path):
     from sickle_b200 import synth
     from test_oracle_fuzz_vs_ref import _records
 
-    se, il, var, lng, bad = (str(tmp_path / n) for n in ("se.fq", "il.fq", "var.fq", "long.fq", "bad.fq"))
+    se, il, var, lng, bad, pf, pr = (str(tmp_path / n) for n in ("se.fq", "il.fq", "var.fq", "long.fq", "bad.fq", "f.fq", "r.fq"))
     data = synth.fixed_length_records(3000, 150, "sanger", seed=5).tobytes()
     open(se, "wb").write(data)
-    open(il, "wb").write(synth.paired_records(1200, 150, "sanger", seed=6)[2].tobytes())
+    f2, r2, il2 = synth.paired_records(1200, 150, "sanger", seed=6)
+    open(il, "wb").write(il2.tobytes())
+    open(pf, "wb").write(f2.tobytes())
+    open(pr, "wb").write(r2.tobytes()[:len(r2.tobytes()) * 3 // 4])   # (the second file shorter, ending inside a record)
     open(var, "wb").write(_records(np.random.default_rng(91), 1500, 250, "sanger"))
     open(lng, "wb").write(synth.variable_length_records(12, 6000, 9000, "illumina", 3))
     for k in ("index3", "index5", "index7", "index9"):
         for threads in (1, 2, 3, 8, 32):
             for path, kw in ((se, dict(first=5)), (se, dict(x=True, n=True, q=30, l=5, ctas=2)), (il, dict(mode="pei", first=3)),
-                             (il, dict(mode="pei", singles=False)), (il, dict(mode="peM", singles=False, ctas=2)), (var, dict(n=True, first=9))):
+                             (il, dict(mode="pei", singles=False)), (il, dict(mode="peM", singles=False, ctas=2)), (var, dict(n=True, first=9)),
+                             (pf, dict(mode="pe2", path2=pr, first=7)), (pf, dict(mode="pe2", path2=pr, singles=False, ctas=2))):
                 rc, out, err = run(harness, path, kernel=k, threads=threads, **kw)
                 assert rc == 0 and (out.startswith("OK") or out.startswith("FASTFAIL")), (k, threads, kw, out, err[-400:])
                 if k == "index9" and path != var:
