@@ -5,7 +5,11 @@
 //   H2D(in) -> kernels -> D2H(summary);  sk_wait: wait summary, D2H(out streams, exact sizes).
 // Kernels of a batch are either
 //   fused   : kf_fused (parse+trim+route+emit in one pass) + kf_finalize      [short records, input order]
-//   general : K1 line index (per input) -> K2 trim+route+scan -> K3 emit -> k_finalize   [everything]
+//   two files: kf_fused<CH,1> (verdicts) -> kf2_between -> kf_fused<CH,2> (route + emit) -> kf2_finalize
+//   ordered : kf_fused<CH,3> (index + verdicts) -> kfo_offsets -> kf_fused<CH,4> (emit queue by queue) -> kf_finalize
+//                                                                               [-a N, single end, N <= 32]
+//   hybrid  : kf_fused<CH,3> (line index + verdicts, one or two inputs) -> k2_trim_route<true> -> K3 -> k_finalize   [-a N otherwise]
+//   general : K1 line index (per input) -> K2 trim+route+scan (one or two kernels) -> K3 emit -> k_finalize   [everything]
 // The fused kernel flags what it cannot do exactly (long records, data errors, ...); the batch is then
 // re-run on the general path before the result is returned, and the context backs off for a while.
 // This replaces the reference's two-stage overlap (detached output thread while the main thread

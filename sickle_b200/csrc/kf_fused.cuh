@@ -8,7 +8,8 @@
 //   * sliding_window / get_quality_num          (src/trim.cpp:3-140)
 //   * keep / singles / discard routing          (src/trim_single.cpp:382-404, src/trim_paired.cpp:531-567)
 //   * record formatting                         (src/trim_single.cpp:393-396, src/trim_paired.cpp:506-513)
-// for SK_MODE_SE, SK_MODE_PE_INTER and SK_MODE_PE_INTER_M in input order (emulate_threads == 1).
+// for SK_MODE_SE, SK_MODE_PE_INTER and SK_MODE_PE_INTER_M in input order (emulate_threads == 1); two input files and
+// the reference's -a N order run the kernel twice (template parameter PASS, below).
 //
 // Tile structure (256 threads, persistent CTAs, tiles handed out by an atomic ticket):
 //   S1  region = tile (224 threads x CH x 16 B) + halo (32 threads x CH x 16 B) -> shared memory by
@@ -35,14 +36,25 @@
 //           record's verdict {keep, five, kept bases, bytes of name + line 3} goes into an 8-byte entry of a
 //           per-file table indexed by record number; the files' record counts are summed up.
 //   (kf2_between: units = min of the two record counts; ticket counter back to zero)
-//   PASS 2  the same tiles again: S1-S5, then instead of trimming, a record looks up its own entry and its
-//           mate's, is routed (both kept -> its file's stream; one kept -> singles), and S7-S8 run as for
+//           PASS 1 also leaves every tile's newline positions and line numbers in global memory (kFNlSlot bytes).
+//   PASS 2  the same tiles again: S1 fetches the tile and, with a second bulk copy on the same mbarrier, what PASS 1
+//           saved for it (no S2-S4: no masks, no scan, no look-back #1), S5, then instead of trimming, a record looks
+//           up its own entry and its mate's, is routed (both kept -> its file's stream; one kept -> singles), and S7-S8 run as for
 //           interleaved pairs: stream 0 of a file-f tile is output stream f, flushed flat; the singles stream
 //           is laid out in pair order, so a tile also reserves room for the singles its mates' tiles write
 //           (sizes from the mates' entries) and copies its own singles out one by one.
 // The input is read twice (650 + 280 bytes per read instead of 325 + 280), which a kernel at 30 % of the
 // HBM roofline can afford; in exchange no tile ever waits for another tile's trimming.
 // PASS 0 is the single pass described above.
+// The reference's -a N output order (emulate_threads = N > 1: record k of a batch is dealt to queue (k+1) % N and the
+// queues are written one after the other, src/trim_single.cpp:263,273-274,374-428) is two passes as well:
+//   PASS 3  index + verdict pass: S1-S6 over one input or two; per record {keep, five, kept bases} into the general
+//           path's descriptor table.  Either (tq == nullptr) the line index K1 would have written goes to line_end and
+//           k2_trim_route<true> + k3_emit finish the batch (any mode, any N), or (single end, N <= 32) the tile's newline
+//           positions are saved as in PASS 1 and its kept bytes per queue are counted into tq;
+//   (kfo_offsets: every (tile, queue) segment's place in the output)
+//   PASS 4  ordered emit: tile + saved positions by TMA, verdicts from the table, the tile staged queue by queue and
+//           flushed as up to N segments -- no look-back in this pass.
 //
 // CH (3, 5, 7 or 9: 11 / 18 / 25 / 32 KB tiles) is chosen by the host per batch so that a tile holds at most
 // ~112 records.  Anything this kernel cannot handle exactly -- a record longer than the halo, more
