@@ -105,6 +105,13 @@ void drain_sinks(ByteSink *const *sinks) {
         if (sinks[i] && sinks[i]->is_open()) sinks[i]->drain();
 }
 
+// Whether device / pinned buffers are left to process exit instead of being freed one by one (default: yes).
+static bool keep_context_at_exit() {
+    if (host::batch_mode) return false;   // `sickle batch` runs many commands in one process: nothing may pile up
+    const char *e = getenv("SICKLE_B200_KEEP_CONTEXT");
+    return e && *e ? atoi(e) != 0 : true;
+}
+
 struct Ctx {
     sk_ctx *c = nullptr;
     Totals *tot = nullptr;
@@ -126,8 +133,9 @@ struct Ctx {
         return c != nullptr;
     }
     ~Ctx() {
-        // SICKLE_B200_KEEP_CONTEXT=1: leave buffers and context to process exit (the CLI exits right after)
-        static const bool keep = getenv("SICKLE_B200_KEEP_CONTEXT") && atoi(getenv("SICKLE_B200_KEEP_CONTEXT")) != 0;
+        // Buffers and context are left to process exit (the CLI exits right after; unpinning and freeing a 1 GiB slot by
+        // hand took 0.2-1.4 s of a 2-4 s run, the exit itself is not slower for it).  SICKLE_B200_KEEP_CONTEXT=0: free them.
+        const bool keep = keep_context_at_exit();
         drain_sinks(sinks);
         const double t0 = host::now_s();
         if (c && host::batch_mode && reusable) {
@@ -231,7 +239,7 @@ public:
         }
         for (auto &w : workers_)
             if (w->th.joinable()) w->th.join();
-        static const bool keep = getenv("SICKLE_B200_KEEP_CONTEXT") && atoi(getenv("SICKLE_B200_KEEP_CONTEXT")) != 0;
+        const bool keep = keep_context_at_exit();
         if (!keep)
             for (auto &w : workers_)
                 if (w->c) sk_destroy(w->c);
